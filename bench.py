@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — one CCD step (broadphase + CTCD narrowphase) per "step", on N GPUs of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cloth1415|cloth709|cloth355|prob17]
+  python bench.py --impl reference ...      # the reference's own CPU path on a bounded sample
+
+Workload (BASELINE.json configs): default `cloth1415` = config C5, the synthetic 1415 x 1415-vertex S-folded
+cloth (3,998,792 triangles, eta = outerEta = 0.01 h, KDOP-13), sharded over the N ranks; `prob17` = config C2
+(meshes/V0_prob17_30957 -> V1, from tests/golden/).  Metric: candidate stencils taken through the whole
+step per second (whole job), plus ms per step.
+
+One JSON line on rank 0 — see the keys in main().  `value` is measured with the inputs resident in HBM
+(ccd_step_device); `e2e` goes through the host-buffer C-ABI call (ccd_step_shard) with pinned host arrays,
+H2D of positions/faces and D2H of the hit lists inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from collisiondetection_b200 import scenes  # noqa: E402
+
+METRIC = "ccd_step_stencils_per_s"
+UNIT = "stencils/s"
+# algorithmic FP64 flops per stencil, coefficient construction as the reference writes it
+FLOP_VF, FLOP_EE = 1395.0, 1676.0
+BYTES_STENCIL = 225.0
+
+
+def load_workload(name):
+    if name.startswith("cloth"):
+        n = int(name[5:])
+        q0, q1, f, eta = scenes.cloth(n)
+        return dict(name=name, q0=q0, q1=q1, faces=f, outer_eta=eta, eta=eta,
+                    desc="synthetic S-folded cloth %dx%d vertices, %d triangles, eta=outerEta=0.01h, KDOP-13" % (n, n, len(f)))
+    if name == "prob17":
+        g = np.load(os.path.join(ROOT, "tests", "golden", "alec_prob17_30957.npz"))
+        return dict(name=name, q0=g["q0"], q1=g["q1"], faces=g["faces"], outer_eta=1e-8, eta=1e-8,
+                    desc="V0_prob17_30957 -> V1 (77,386 triangles), eta=outerEta=1e-8, KDOP-13")
+    raise SystemExit("unknown workload " + name)
+
+
+def cpu_sample(name):
+    """Bounded sample of the workload for the CPU arm: a 48-column ribbon across the whole S-fold of the same
+    cloth (same coordinates and noise), centred on the band where the layers pass through each other."""
+    if name.startswith("cloth"):
+        n = int(name[5:])
+        w = min(48, n)
+        j0 = max(0, n // 2 - w // 2)
+        q0, q1, f, eta = scenes.cloth(n, cols=(j0, j0 + w))
+        return dict(q0=q0, q1=q1, faces=f, outer_eta=eta, eta=eta,
+                    desc="%d-column ribbon (columns %d..%d) of the %s cloth: %d triangles" % (w, j0, j0 + w - 1, name, len(f)))
+    g = load_workload("prob17")
+    # every 8th face of prob17 is not a valid sub-scene; use the small sibling mesh pair instead
+    s = np.load(os.path.join(ROOT, "tests", "golden", "alec_prob11_835.npz"))
+    return dict(q0=s["q0"], q1=s["q1"], faces=s["faces"], outer_eta=1e-8, eta=1e-8,
+                desc="V0_prob11_835 -> V1 (2,082 triangles), same eta")
+
+
+def run_cpu_arm(sample, steps, warmup):
+    """Reference CPU path (KDOPBroadPhase + CTCDNarrowPhase, 1 thread — the reference has no threading)."""
+    from oracle import bind
+    if bind.have_ref():
+        lib, kind = bind.Ref(), "reference"
+    else:
+        if not bind.have_port():
+            bind.build(ref=False, port=True)
+        lib, kind = bind.Port(), "port"
+    H = bind.single_step_history(sample["q0"], sample["q1"])
+    times, nst = [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        vf, ee, _ = lib.broadphase(13, sample["faces"], *H, sample["outer_eta"])
+        lib.narrowphase(*H, vf, sample["eta"], ee, sample["eta"])
+        dt = time.perf_counter() - t0
+        nst = len(vf) + len(ee)
+        if it >= warmup:
+            times.append(dt)
+    sec = float(np.mean(times))
+    return dict(value=nst / sec, unit=UNIT, cores=1, kind=kind, sample=sample["desc"] + "; %d stencils, %.2f s/step" % (nst, sec)), sec, nst
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = "/tmp/ccd_clocks_%d_%d.csv" % (os.getpid(), index)
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cloth1415")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    config = dict(workload=args.workload, kind="KDOP-13", sharding="vertex/edge ranges over %d rank(s), replicated LBVH" % world,
+                  l2="working set (inputs 144 MB at cloth1415 + GBs of intermediates) exceeds the 126 MB L2; nothing is reused across steps")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = cpu_sample(args.workload)
+        cb, sec, nst = run_cpu_arm(sample, max(1, args.steps), min(args.warmup, 1))
+        config["workload_desc"] = load_workload(args.workload)["desc"] if not args.workload.startswith("cloth") else "synthetic cloth " + args.workload
+        print(json.dumps(dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                              ms_per_step=sec * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+                              data="synthetic", impl="reference", config=config, cpu_baseline=cb,
+                              e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from collisiondetection_b200 import api
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = load_workload(args.workload)
+    config["workload_desc"] = wl["desc"]
+    V, F = len(wl["q0"]), len(wl["faces"])
+    h_q0 = torch.from_numpy(wl["q0"]).pin_memory()
+    h_q1 = torch.from_numpy(wl["q1"]).pin_memory()
+    h_f = torch.from_numpy(wl["faces"]).pin_memory()
+    d_q0, d_q1, d_f = h_q0.cuda(), h_q1.cuda(), h_f.cuda()
+    ctx = api.Context(local_rank)
+    red = torch.zeros(4, dtype=torch.float64, device="cuda")
+
+    def step_dev():
+        r = ctx.step_device(api.KDOP, V, F, d_f.data_ptr(), d_q0.data_ptr(), d_q1.data_ptr(), wl["outer_eta"], wl["eta"], 0, rank, world)
+        if world > 1:
+            # the path's only exchange: earliest TOI (min) and hit/stencil counts (sum) — one fused all-reduce
+            red[0] = -r.earliest_toi if np.isfinite(r.earliest_toi) else -2.0
+            red[1] = float(r.n_vf_hits + r.n_ee_hits)
+            red[2] = float(r.n_vf_candidates + r.n_ee_candidates)
+            mx = red[:1].clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(red[1:3], op=dist.ReduceOp.SUM)
+        return r
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        r = step_dev()
+    launches = r.n_launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_sum = {}
+    kern_ms = 0.0
+    e0.record()
+    for _ in range(args.steps):
+        r = step_dev()
+        kern_ms += r.ms_broadphase + r.ms_narrowphase
+        for k, v in ctx.stage_times().items():
+            stage_sum[k] = stage_sum.get(k, 0.0) + v
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total, float(r.n_vf_candidates + r.n_ee_candidates), float(r.n_vf_hits + r.n_ee_hits)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t[:1].clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
+        t[0] = tmax[0]
+    ms_per_step = float(t[0]) / args.steps
+    n_stencils, n_hits = int(t[1]), int(t[2])
+    value = n_stencils / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host arrays; H2D + D2H inside the timed region)
+    np_q0, np_q1, np_f = h_q0.numpy(), h_q1.numpy(), h_f.numpy()
+    for _ in range(2):
+        ctx.step(api.KDOP, np_f, np_q0, np_q1, wl["outer_eta"], wl["eta"], None, rank, world)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        er = ctx.step(api.KDOP, np_f, np_q0, np_q1, wl["outer_eta"], wl["eta"], None, rank, world)
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te[0]) / args.steps
+    h2d = 48 * V + 12 * F
+    d2h = 24 * (er["n_vf_hits"] + er["n_ee_hits"])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (per-stage CUDA-event times of this rank, averaged over the timed steps)
+    stages = {k: v / args.steps for k, v in stage_sum.items()}
+    fp64_peak = ctx.fp64_peak_tflops()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    nvf, nee = r.n_vf_candidates, r.n_ee_candidates
+    dom = max(stages, key=stages.get)
+    if dom in ("np_vf", "np_ee"):
+        flops = nvf * FLOP_VF if dom == "np_vf" else nee * FLOP_EE
+        ach = flops / (stages[dom] * 1e-3) / 1e12
+        roof = dict(kernel="stencil_kernel<%s>" % ("VF" if dom == "np_vf" else "EE"), bound="fp64", achieved=ach, peak=fp64_peak,
+                    unit="TFLOP/s", frac=ach / fp64_peak if fp64_peak else None, traffic=None,
+                    peak_source="measured live: ccd_fp64_peak (16 independent DFMA chains/thread on all SMs); MEASURED_PEAKS.json has no FP64 entry",
+                    algorithmic="%.0f flop/stencil x %d stencils (coefficient construction only; root isolation and early exits excluded)" % (
+                        FLOP_VF if dom == "np_vf" else FLOP_EE, nvf if dom == "np_vf" else nee),
+                    achieved_gbs=(nvf if dom == "np_vf" else nee) * BYTES_STENCIL / (stages[dom] * 1e-3) / 1e9)
+    else:
+        # broadphase stage: algorithmic bytes per SURVEY.md §8(d)
+        raw = 15.0 * r.n_face_pairs
+        bytes_bp = 892.0 * F + 48.0 * raw + 16.0 * (nvf + nee)
+        bp_ms = sum(v for k, v in stages.items() if not k.startswith("np_") and k != "topology")
+        ach = bytes_bp / (bp_ms * 1e-3) / 1e9
+        roof = dict(kernel="broadphase (dominant stage: %s)" % dom, bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s",
+                    frac=ach / hbm_peak, traffic=None, peak_source=hbm_src,
+                    algorithmic="892 B/face + 48 B/raw stencil + 16 B/unique stencil over all broadphase kernels")
+    out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warmup, ms_per_step=ms_per_step,
+               higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic" if args.workload.startswith("cloth") else "reference mesh fixture",
+               config=config, clocks=clocks,
+               e2e=dict(value=n_stencils / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
+               gpu_launches=int(launches) * args.steps,
+               roofline=roof,
+               stages_ms=stages, kernel_ms_per_step=kern_ms / args.steps,
+               counts=dict(vertices=V, faces=F, stencils=n_stencils, vf_rank0=int(nvf), ee_rank0=int(nee), hits=n_hits,
+                           face_pairs_rank0=int(r.n_face_pairs), tree_candidates_rank0=int(r.n_tree_candidates),
+                           stencils_per_face=n_stencils / float(F)),
+               fp64_peak_tflops=fp64_peak)
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cb, _, _ = run_cpu_arm(cpu_sample(args.workload), 1, 0)
+            out["cpu_baseline"] = cb
+        except Exception as e:  # the checker is optional at bench time
+            out["cpu_baseline"] = dict(value=None, unit=UNIT, cores=1, kind="unavailable", sample=str(e))
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

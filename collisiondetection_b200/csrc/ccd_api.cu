@@ -1,0 +1,872 @@
+// extern "C" layer of ccd_b200 (include/ccd_b200.h): context, device-buffer pool, host<->device
+// staging and the orchestration of the broadphase / narrowphase kernels.  No CPU fallback: every
+// entry point runs CUDA kernels or fails with an error code.
+#include "../../include/ccd_b200.h"
+#include "ccd_kernels.h"
+
+#include <cub/cub.cuh>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+// per-stage device timing (CUDA events on the context's stream); see ccd_stage_times()
+enum { ST_TOPOLOGY = 0, ST_BOXES, ST_TREE, ST_TRAVERSE_EXACT, ST_ADJACENCY, ST_EMIT_COUNT, ST_EMIT_WRITE, ST_NP_VF, ST_NP_EE, CCD_N_STAGES };
+
+struct DBuf
+{
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct ccd_context
+{
+    int device = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t sev[CCD_N_STAGES + 1];
+    bool stage_valid = false;
+    std::string err;
+    int launches = 0;
+
+    // staging of host inputs
+    DBuf faces, q0, q1, hoff, htime, hpos, fixed, vf_in, ee_in, vf_eta, ee_eta, pts, eta;
+    // broadphase
+    DBuf boxes, faabb, bounds, keysA, keysB, valsA, valsB, temp, nodes, leafParent, nodeParent, flags;
+    DBuf cand, counters, pairL, pairR, deg, adjOff, cursor, adj;
+    DBuf k32A, k32B, scanFlags, scanIds;
+    // topology cache (function of `faces` only)
+    DBuf edgeVerts, edgeStart, faceEdge, heFace, faceRank, rankFace, vdeg, starOff, starCur, star, topoHash;
+    int topoF = -1, topoV = -1, nEdges = 0;
+    unsigned long long topoHashVal = 0;
+    // emission
+    DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut;
+    // narrowphase
+    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, selTmp, selA, selB, selC, selD, selCount;
+    // pinned host scratch
+    unsigned long long *h_counters = nullptr; // 16 entries
+    size_t candCap = 0, pairCap = 0;
+};
+
+// device counters layout (unsigned long long each)
+enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_TOTAL = 16 };
+
+#define CK(call)                                                                                      \
+    do                                                                                                \
+    {                                                                                                 \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+        {                                                                                             \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                              \
+            return CCD_ERR_CUDA;                                                                      \
+        }                                                                                             \
+    } while (0)
+
+#define CKR(expr)                \
+    do                           \
+    {                            \
+        int r_ = (expr);         \
+        if (r_ != CCD_OK)        \
+            return r_;           \
+    } while (0)
+
+static int ensure(ccd_context *c, DBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap && b.p)
+        return CCD_OK;
+    if (b.p)
+    {
+        cudaStreamSynchronize(c->st);
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t ncap = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&b.p, ncap);
+    if (e != cudaSuccess)
+    {
+        c->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return CCD_ERR_NOMEM;
+    }
+    b.cap = ncap;
+    return CCD_OK;
+}
+
+template <typename T> static T *P(DBuf &b) { return (T *)b.p; }
+
+static int upload(ccd_context *c, DBuf &b, const void *host, size_t bytes)
+{
+    CKR(ensure(c, b, bytes ? bytes : 8));
+    if (bytes)
+        CK(cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, c->st));
+    return CCD_OK;
+}
+
+static void kdop_axes(double ax[13][3])
+{
+    // src/KDOPBroadPhase.cpp:12-31: thirteen directions, each divided by its norm
+    static const double raw[13][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {1, -1, 0}, {0, 1, 1}, {0, 1, -1},
+                                      {1, 0, 1}, {1, 0, -1}, {1, 1, 1}, {1, 1, -1}, {1, -1, 1}, {1, -1, -1}};
+    for (int i = 0; i < 13; i++)
+    {
+        volatile double s01 = raw[i][0] * raw[i][0] + raw[i][1] * raw[i][1];
+        volatile double s = s01 + raw[i][2] * raw[i][2];
+        double nrm = sqrt(s);
+        for (int k = 0; k < 3; k++)
+            ax[i][k] = raw[i][k] / nrm;
+    }
+}
+
+// launcher prototypes (broadphase.cu / distance.cu)
+void ccdk_set_axes(const double axes[13][3]);
+void ccdk_leaf_boxes(cudaStream_t st, int kind, int F, const int *faces, const double *q0, const double *q1, const long long *hoff,
+                     const double *hpos, double eta, double *boxes, float *faabb);
+size_t ccdk_sort_temp_bytes(int n);
+void ccdk_exclusive_sum64(cudaStream_t st, void *temp, size_t temp_bytes, int n_plus_1, const int *in, long long *out);
+void ccdk_build_tree(cudaStream_t st, int F, const float *faabb, unsigned *bounds, unsigned long long *keys_in, unsigned long long *keys_sorted,
+                     unsigned *vals_in, unsigned *sortedFace, void *temp, size_t temp_bytes, void *nodes, int *leafParent,
+                     int *nodeParent, int *flags);
+void ccdk_traverse(cudaStream_t st, int F, int qbegin, int qend, const int *qlist, bool all, const unsigned *sortedFace, const float *faabb,
+                   const void *nodes, void *cand, unsigned long long cap, unsigned long long *count);
+void ccdk_exact_pairs(cudaStream_t st, int kind, const unsigned long long *ncand, unsigned long long cap, const void *cand,
+                      const unsigned *sortedFace, const int *faces, const double *boxes, int *pairL, int *pairR, unsigned long long pcap,
+                      unsigned long long *npairs, int *deg);
+void ccdk_adjacency_fill(cudaStream_t st, const unsigned long long *npairs, const int *pairL, const int *pairR, const long long *adjOff,
+                         int *cursor, int *adj);
+void ccdk_topology_edges(cudaStream_t st, int F, const int *faces, unsigned long long *keys_in, unsigned long long *keys_sorted,
+                         unsigned *vals_in, unsigned *vals_sorted, void *temp, size_t temp_bytes, int *flags, int *ids, void *edgeVerts,
+                         int *edgeStart, int *faceEdge, int *heFace);
+void ccdk_topology_faceranks(cudaStream_t st, int F, const int *faces, unsigned *k32_in, unsigned *k32_out, unsigned *vals_a, unsigned *vals_b,
+                             unsigned long long *k64_in, unsigned long long *k64_out, void *temp, size_t temp_bytes, int *flags, int *ids,
+                             int *faceRank, int *rankFace);
+void ccdk_topology_star(cudaStream_t st, int V, int F, const int *faces, int *vdeg, long long *starOff, int *cursor, int *star, void *temp,
+                        size_t temp_bytes);
+void ccdk_vf_emit(cudaStream_t st, bool count, int vbegin, int vend, const int *faces, const long long *starOff, const int *star,
+                  const long long *adjOff, const int *adj, const int *faceRank, const int *rankFace, const unsigned char *fixed,
+                  int *counts, const long long *offsets, int *out);
+void ccdk_ee_emit(cudaStream_t st, bool count, int ebegin, int eend, const int *edgeStart, const int *heFace, const long long *adjOff,
+                  const int *adj, const int *faceEdge, const void *edgeVerts, const unsigned char *fixed, int *counts,
+                  const long long *offsets, int *out);
+void ccdk_hash_ints(cudaStream_t st, long long n, const int *d, unsigned long long *out);
+void ccdk_dist_batch(cudaStream_t st, int which, long long n, const double *pts, const double *eta, double *vec, double *bary, unsigned char *flag);
+void ccdk_vertex_min_dist2(cudaStream_t st, int V, int F, const double *verts, const int *faces, unsigned long long *out_bits);
+void ccdk_stencil_min_dist(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *verts, unsigned long long *out_bits);
+void ccdk_fp64_peak(cudaStream_t st, int iters, double *sink);
+
+extern "C" {
+
+const char *ccd_version(void) { return "ccd_b200 0.1 sm_100a"; }
+
+int ccd_create(ccd_context **out, int device)
+{
+    if (!out)
+        return CCD_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        cudaGetLastError();
+        return CCD_ERR_NODEVICE;
+    }
+    if (device < 0 || device >= ndev)
+        return CCD_ERR_ARG;
+    ccd_context *c = new ccd_context();
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess)
+    {
+        delete c;
+        return CCD_ERR_CUDA;
+    }
+    for (int i = 0; i < 4; i++)
+        cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i <= CCD_N_STAGES; i++)
+        cudaEventCreate(&c->sev[i]);
+    cudaMallocHost((void **)&c->h_counters, sizeof(unsigned long long) * C_TOTAL);
+    double ax[13][3];
+    kdop_axes(ax);
+    ccdk_set_axes(ax);
+    if (ensure(c, c->counters, sizeof(unsigned long long) * C_TOTAL) != CCD_OK)
+    {
+        delete c;
+        return CCD_ERR_NOMEM;
+    }
+    *out = c;
+    return CCD_OK;
+}
+
+void ccd_destroy(ccd_context *c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    DBuf *all[] = {&c->faces, &c->q0, &c->q1, &c->hoff, &c->htime, &c->hpos, &c->fixed, &c->vf_in, &c->ee_in, &c->vf_eta, &c->ee_eta,
+                   &c->pts, &c->eta, &c->boxes, &c->faabb, &c->bounds, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->temp, &c->nodes,
+                   &c->leafParent, &c->nodeParent, &c->flags, &c->cand, &c->counters, &c->pairL, &c->pairR, &c->deg, &c->adjOff,
+                   &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
+                   &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
+                   &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
+                   &c->vfStage, &c->eeStage, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
+    for (DBuf *b : all)
+        if (b->p)
+            cudaFree(b->p);
+    if (c->h_counters)
+        cudaFreeHost(c->h_counters);
+    for (int i = 0; i < 4; i++)
+        if (c->ev[i])
+            cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i <= CCD_N_STAGES; i++)
+        cudaEventDestroy(c->sev[i]);
+    cudaStreamDestroy(c->st);
+    delete c;
+}
+
+const char *ccd_last_error(const ccd_context *c) { return c ? c->err.c_str() : "null context"; }
+void ccd_free_host(void *p) { free(p); }
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// device-side orchestration
+// ---------------------------------------------------------------------------------------------
+struct BpResult
+{
+    long long nvf = 0, nee = 0, npairs = 0, ncand = 0;
+};
+
+static int sync_counters(ccd_context *c)
+{
+    CK(cudaMemcpyAsync(c->h_counters, c->counters.p, sizeof(unsigned long long) * C_TOTAL, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return CCD_OK;
+}
+
+// mesh tables that depend on `faces` only; rebuilt when the face array changes
+static int ensure_topology(ccd_context *c, int V, int F, const int *d_faces)
+{
+    unsigned long long *ctr = P<unsigned long long>(c->counters);
+    ccdk_hash_ints(c->st, 3ll * F, d_faces, ctr + C_HASH);
+    c->launches += 1;
+    CKR(sync_counters(c));
+    unsigned long long h = c->h_counters[C_HASH];
+    if (c->topoF == F && c->topoV == V && c->topoHashVal == h)
+        return CCD_OK;
+    const int n3 = 3 * F;
+    size_t tb = ccdk_sort_temp_bytes(n3 > V + 1 ? n3 : V + 1);
+    CKR(ensure(c, c->temp, tb));
+    CKR(ensure(c, c->keysA, sizeof(unsigned long long) * (size_t)(n3 + 1)));
+    CKR(ensure(c, c->keysB, sizeof(unsigned long long) * (size_t)(n3 + 1)));
+    CKR(ensure(c, c->valsA, sizeof(unsigned) * (size_t)(n3 + 1)));
+    CKR(ensure(c, c->valsB, sizeof(unsigned) * (size_t)(n3 + 1)));
+    CKR(ensure(c, c->k32A, sizeof(unsigned) * (size_t)(F + 1)));
+    CKR(ensure(c, c->k32B, sizeof(unsigned) * (size_t)(F + 1)));
+    CKR(ensure(c, c->scanFlags, sizeof(int) * (size_t)(n3 + 1)));
+    CKR(ensure(c, c->scanIds, sizeof(int) * (size_t)(n3 + 1)));
+    CKR(ensure(c, c->edgeVerts, sizeof(int) * 2 * (size_t)(n3 + 1)));
+    CKR(ensure(c, c->edgeStart, sizeof(int) * (size_t)(n3 + 2)));
+    CKR(ensure(c, c->faceEdge, sizeof(int) * (size_t)(n3 + 1)));
+    CKR(ensure(c, c->heFace, sizeof(int) * (size_t)(n3 + 1)));
+    CKR(ensure(c, c->faceRank, sizeof(int) * (size_t)(F + 1)));
+    CKR(ensure(c, c->rankFace, sizeof(int) * (size_t)(F + 1)));
+    CKR(ensure(c, c->vdeg, sizeof(int) * (size_t)(V + 2)));
+    CKR(ensure(c, c->starCur, sizeof(int) * (size_t)(V + 2)));
+    CKR(ensure(c, c->starOff, sizeof(long long) * (size_t)(V + 2)));
+    CKR(ensure(c, c->star, sizeof(int) * (size_t)(n3 + 1)));
+    c->nEdges = 0;
+    if (F > 0)
+    {
+        ccdk_topology_edges(c->st, F, d_faces, P<unsigned long long>(c->keysA), P<unsigned long long>(c->keysB), P<unsigned>(c->valsA),
+                            P<unsigned>(c->valsB), c->temp.p, c->temp.cap, P<int>(c->scanFlags), P<int>(c->scanIds), c->edgeVerts.p,
+                            P<int>(c->edgeStart), P<int>(c->faceEdge), P<int>(c->heFace));
+        int ne = 0;
+        CK(cudaMemcpyAsync(&ne, P<int>(c->scanIds) + (n3 - 1), sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        c->nEdges = ne;
+        ccdk_topology_faceranks(c->st, F, d_faces, P<unsigned>(c->k32A), P<unsigned>(c->k32B), P<unsigned>(c->valsA), P<unsigned>(c->valsB),
+                                P<unsigned long long>(c->keysA), P<unsigned long long>(c->keysB), c->temp.p, c->temp.cap,
+                                P<int>(c->scanFlags), P<int>(c->scanIds), P<int>(c->faceRank), P<int>(c->rankFace));
+        c->launches += 5 + 8 + 7 + 8 + 8;
+    }
+    ccdk_topology_star(c->st, V, F, d_faces, P<int>(c->vdeg), P<long long>(c->starOff), P<int>(c->starCur), P<int>(c->star), c->temp.p,
+                       c->temp.cap);
+    c->launches += 4;
+    CK(cudaGetLastError());
+    c->topoF = F;
+    c->topoV = V;
+    c->topoHashVal = h;
+    return CCD_OK;
+}
+
+// Broadphase on device-resident inputs.  Either (d_q0,d_q1) or (d_hoff,d_hpos) describes the History.
+// Leaves the sorted stencils in c->vfOut / c->eeOut.
+static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *d_faces, const double *d_q0, const double *d_q1,
+                             const long long *d_hoff, const double *d_hpos, double outerEta, const unsigned char *d_fixed,
+                             int shard_rank, int shard_world, BpResult *res)
+{
+    if ((kind != CCD_KDOP && kind != CCD_AABB) || V < 0 || F < 0 || shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world)
+    {
+        c->err = "broadphase: invalid argument";
+        return CCD_ERR_ARG;
+    }
+    *res = BpResult();
+    CKR(ensure(c, c->vfOut, 16));
+    CKR(ensure(c, c->eeOut, 16));
+    if (F == 0 || V == 0)
+        return CCD_OK;
+    unsigned long long *ctr = P<unsigned long long>(c->counters);
+    cudaEventRecord(c->sev[ST_TOPOLOGY], c->st);
+    CKR(ensure_topology(c, V, F, d_faces));
+
+    CKR(ensure(c, c->boxes, sizeof(double) * 2 * (size_t)kind * (size_t)F));
+    CKR(ensure(c, c->faabb, sizeof(float) * 6 * (size_t)F));
+    CKR(ensure(c, c->bounds, 64));
+    CKR(ensure(c, c->temp, ccdk_sort_temp_bytes(3 * F > V + 1 ? 3 * F : V + 1)));
+    CKR(ensure(c, c->keysA, sizeof(unsigned long long) * (size_t)(3 * F + 1)));
+    CKR(ensure(c, c->keysB, sizeof(unsigned long long) * (size_t)(3 * F + 1)));
+    CKR(ensure(c, c->valsA, sizeof(unsigned) * (size_t)(3 * F + 1)));
+    CKR(ensure(c, c->valsB, sizeof(unsigned) * (size_t)(3 * F + 1)));
+    CKR(ensure(c, c->nodes, 64 * (size_t)F));
+    CKR(ensure(c, c->leafParent, sizeof(int) * (size_t)F));
+    CKR(ensure(c, c->nodeParent, sizeof(int) * (size_t)F));
+    CKR(ensure(c, c->flags, sizeof(int) * (size_t)F));
+    CKR(ensure(c, c->deg, sizeof(int) * (size_t)(F + 2)));
+    CKR(ensure(c, c->cursor, sizeof(int) * (size_t)(F + 2)));
+    CKR(ensure(c, c->adjOff, sizeof(long long) * (size_t)(F + 2)));
+    if (c->candCap == 0)
+        c->candCap = (size_t)F * 24 + (1u << 16);
+    if (c->pairCap == 0)
+        c->pairCap = (size_t)F * 12 + (1u << 16);
+
+    cudaEventRecord(c->sev[ST_BOXES], c->st);
+    ccdk_leaf_boxes(c->st, kind, F, d_faces, d_q0, d_q1, d_hoff, d_hpos, outerEta, P<double>(c->boxes), P<float>(c->faabb));
+    cudaEventRecord(c->sev[ST_TREE], c->st);
+    ccdk_build_tree(c->st, F, P<float>(c->faabb), P<unsigned>(c->bounds), P<unsigned long long>(c->keysA), P<unsigned long long>(c->keysB),
+                    P<unsigned>(c->valsA), P<unsigned>(c->valsB), c->temp.p, c->temp.cap, c->nodes.p, P<int>(c->leafParent),
+                    P<int>(c->nodeParent), P<int>(c->flags));
+    c->launches += 1 + 2 + 8 + 2;
+    const unsigned *sortedFace = P<unsigned>(c->valsB);
+    cudaEventRecord(c->sev[ST_TRAVERSE_EXACT], c->st);
+
+    for (int attempt = 0; attempt < 8; attempt++)
+    {
+        CKR(ensure(c, c->cand, sizeof(int) * 2 * c->candCap));
+        CKR(ensure(c, c->pairL, sizeof(int) * c->pairCap));
+        CKR(ensure(c, c->pairR, sizeof(int) * c->pairCap));
+        CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 2, c->st));
+        CK(cudaMemsetAsync(c->deg.p, 0, sizeof(int) * (size_t)(F + 2), c->st));
+        ccdk_traverse(c->st, F, 0, F, nullptr, false, sortedFace, P<float>(c->faabb), c->nodes.p, c->cand.p, c->candCap, ctr + C_NCAND);
+        ccdk_exact_pairs(c->st, kind, ctr + C_NCAND, c->candCap, c->cand.p, sortedFace, d_faces, P<double>(c->boxes), P<int>(c->pairL),
+                         P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg));
+        c->launches += 2;
+        CKR(sync_counters(c));
+        unsigned long long ncand = c->h_counters[C_NCAND], npairs = c->h_counters[C_NPAIRS];
+        bool again = false;
+        if (ncand > c->candCap) { c->candCap = (size_t)(ncand + ncand / 8 + 1024); again = true; }
+        if (npairs > c->pairCap || again) { size_t want = (size_t)(npairs + npairs / 8 + 1024); if (want > c->pairCap) c->pairCap = want; }
+        if (npairs > c->pairCap) again = true;
+        if (!again)
+        {
+            res->ncand = (long long)ncand;
+            res->npairs = (long long)npairs;
+            break;
+        }
+        if (attempt == 7)
+        {
+            c->err = "broadphase: candidate buffers kept overflowing";
+            return CCD_ERR_NOMEM;
+        }
+    }
+    CK(cudaGetLastError());
+
+    // face adjacency CSR (both directions)
+    cudaEventRecord(c->sev[ST_ADJACENCY], c->st);
+    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, F + 1, P<int>(c->deg), P<long long>(c->adjOff));
+    CKR(ensure(c, c->adj, sizeof(int) * (size_t)(2 * res->npairs + 1)));
+    CK(cudaMemsetAsync(c->cursor.p, 0, sizeof(int) * (size_t)(F + 2), c->st));
+    ccdk_adjacency_fill(c->st, ctr + C_NPAIRS, P<int>(c->pairL), P<int>(c->pairR), P<long long>(c->adjOff), P<int>(c->cursor), P<int>(c->adj));
+    c->launches += 3;
+
+    // ownership ranges of this shard
+    const int E = c->nEdges;
+    const int v0 = (int)((long long)V * shard_rank / shard_world), v1 = (int)((long long)V * (shard_rank + 1) / shard_world);
+    const int e0 = (int)((long long)E * shard_rank / shard_world), e1 = (int)((long long)E * (shard_rank + 1) / shard_world);
+    const int nv = v1 - v0, ne = e1 - e0;
+    CKR(ensure(c, c->vfCounts, sizeof(int) * (size_t)(nv + 2)));
+    CKR(ensure(c, c->vfOffsets, sizeof(long long) * (size_t)(nv + 2)));
+    CKR(ensure(c, c->eeCounts, sizeof(int) * (size_t)(ne + 2)));
+    CKR(ensure(c, c->eeOffsets, sizeof(long long) * (size_t)(ne + 2)));
+    cudaEventRecord(c->sev[ST_EMIT_COUNT], c->st);
+    ccdk_vf_emit(c->st, true, v0, v1, d_faces, P<long long>(c->starOff), P<int>(c->star), P<long long>(c->adjOff), P<int>(c->adj),
+                 P<int>(c->faceRank), P<int>(c->rankFace), d_fixed, P<int>(c->vfCounts), nullptr, nullptr);
+    ccdk_ee_emit(c->st, true, e0, e1, P<int>(c->edgeStart), P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceEdge),
+                 c->edgeVerts.p, d_fixed, P<int>(c->eeCounts), nullptr, nullptr);
+    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, nv + 1, P<int>(c->vfCounts), P<long long>(c->vfOffsets));
+    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, ne + 1, P<int>(c->eeCounts), P<long long>(c->eeOffsets));
+    c->launches += 6;
+    long long totals[2] = {0, 0};
+    CK(cudaMemcpyAsync(&totals[0], P<long long>(c->vfOffsets) + nv, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(&totals[1], P<long long>(c->eeOffsets) + ne, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    res->nvf = totals[0];
+    res->nee = totals[1];
+    CKR(ensure(c, c->vfOut, sizeof(int) * 4 * (size_t)(res->nvf + 1)));
+    CKR(ensure(c, c->eeOut, sizeof(int) * 4 * (size_t)(res->nee + 1)));
+    cudaEventRecord(c->sev[ST_EMIT_WRITE], c->st);
+    ccdk_vf_emit(c->st, false, v0, v1, d_faces, P<long long>(c->starOff), P<int>(c->star), P<long long>(c->adjOff), P<int>(c->adj),
+                 P<int>(c->faceRank), P<int>(c->rankFace), d_fixed, nullptr, P<long long>(c->vfOffsets), P<int>(c->vfOut));
+    ccdk_ee_emit(c->st, false, e0, e1, P<int>(c->edgeStart), P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceEdge),
+                 c->edgeVerts.p, d_fixed, nullptr, P<long long>(c->eeOffsets), P<int>(c->eeOut));
+    c->launches += 2;
+    CK(cudaGetLastError());
+    return CCD_OK;
+}
+
+// Narrowphase over device-resident stencils; results left in c->vfHit/... ; summary via counters.
+static int narrowphase_device(ccd_context *c, long long nvf, const int *d_vf, const double *d_vf_eta, long long nee, const int *d_ee,
+                              const double *d_ee_eta, double eta_all, const double *d_q0, const double *d_q1, int vstride, const long long *d_hoff,
+                              const double *d_htime, const double *d_hpos, ccd_np_summary *sum)
+{
+    unsigned long long *ctr = P<unsigned long long>(c->counters);
+    CKR(ensure(c, c->vfHit, (size_t)nvf + 16));
+    CKR(ensure(c, c->eeHit, (size_t)nee + 16));
+    CKR(ensure(c, c->vfStage, (size_t)nvf + 16));
+    CKR(ensure(c, c->eeStage, (size_t)nee + 16));
+    CKR(ensure(c, c->vfToi, sizeof(double) * ((size_t)nvf + 2)));
+    CKR(ensure(c, c->eeToi, sizeof(double) * ((size_t)nee + 2)));
+    unsigned long long init[4] = {0xFFFFFFFFFFFFFFFFull, 0ull, 0xFFFFFFFFFFFFFFFFull, 0ull};
+    memcpy(c->h_counters + 8, init, sizeof(init));
+    CK(cudaMemcpyAsync(ctr + C_EARLY_VF, c->h_counters + 8, sizeof(init), cudaMemcpyHostToDevice, c->st));
+    cudaEventRecord(c->sev[ST_NP_VF], c->st);
+    ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
+                     P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF);
+    cudaEventRecord(c->sev[ST_NP_EE], c->st);
+    ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
+                     P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE);
+    cudaEventRecord(c->sev[CCD_N_STAGES], c->st);
+    c->launches += (nvf > 0) + (nee > 0);
+    CK(cudaGetLastError());
+    if (sum)
+    {
+        CKR(sync_counters(c));
+        sum->n_vf_hits = (int64_t)c->h_counters[C_NHIT_VF];
+        sum->n_ee_hits = (int64_t)c->h_counters[C_NHIT_EE];
+        unsigned long long b = c->h_counters[C_EARLY_VF] < c->h_counters[C_EARLY_EE] ? c->h_counters[C_EARLY_VF] : c->h_counters[C_EARLY_EE];
+        double t;
+        memcpy(&t, &b, sizeof(t));
+        sum->earliest_toi = (b == 0xFFFFFFFFFFFFFFFFull) ? INFINITY : t;
+    }
+    return CCD_OK;
+}
+
+static int download_stencils(ccd_context *c, const DBuf &src, long long n, int32_t **out)
+{
+    int32_t *h = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)(n > 0 ? n : 1));
+    if (!h)
+        return CCD_ERR_NOMEM;
+    if (n > 0)
+    {
+        cudaError_t e = cudaMemcpyAsync(h, src.p, sizeof(int32_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost, c->st);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(c->st);
+        if (e != cudaSuccess)
+        {
+            free(h);
+            c->err = std::string("download: ") + cudaGetErrorString(e);
+            return CCD_ERR_CUDA;
+        }
+    }
+    *out = h;
+    return CCD_OK;
+}
+
+static bool history_is_single_step(int V, const int64_t *hoff)
+{
+    for (int v = 0; v <= V; v++)
+        if (hoff[v] != 2ll * v)
+            return false;
+    return true;
+}
+
+extern "C" {
+
+int ccd_broadphase(ccd_context *c, int kind, int V, int F, const int32_t *faces, const int64_t *hoff, const double *htime,
+                   const double *hpos, double outerEta, const uint8_t *fixedMask, int32_t **vf, int64_t *nvf, int32_t **ee, int64_t *nee)
+{
+    if (!c || !vf || !nvf || !ee || !nee || (F > 0 && !faces) || (V > 0 && (!hoff || !hpos)))
+        return CCD_ERR_ARG;
+    (void)htime;
+    CK(cudaSetDevice(c->device));
+    c->launches = 0;
+    const long long N = V > 0 ? (long long)hoff[V] : 0;
+    CKR(upload(c, c->faces, faces, sizeof(int32_t) * 3 * (size_t)F));
+    CKR(upload(c, c->hoff, hoff, sizeof(int64_t) * ((size_t)V + 1)));
+    CKR(upload(c, c->hpos, hpos, sizeof(double) * 3 * (size_t)N));
+    if (fixedMask)
+        CKR(upload(c, c->fixed, fixedMask, (size_t)V));
+    BpResult r;
+    CKR(broadphase_device(c, kind, V, F, P<int>(c->faces), nullptr, nullptr, P<long long>(c->hoff), P<double>(c->hpos), outerEta,
+                          fixedMask ? P<unsigned char>(c->fixed) : nullptr, 0, 1, &r));
+    CKR(download_stencils(c, c->vfOut, r.nvf, vf));
+    CKR(download_stencils(c, c->eeOut, r.nee, ee));
+    *nvf = r.nvf;
+    *nee = r.nee;
+    return CCD_OK;
+}
+
+int ccd_broadphase_step(ccd_context *c, int kind, int V, int F, const int32_t *faces, const double *q0, const double *q1, double outerEta,
+                        const uint8_t *fixedMask, int32_t **vf, int64_t *nvf, int32_t **ee, int64_t *nee)
+{
+    if (!c || !vf || !nvf || !ee || !nee || (F > 0 && !faces) || (V > 0 && (!q0 || !q1)))
+        return CCD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    c->launches = 0;
+    CKR(upload(c, c->faces, faces, sizeof(int32_t) * 3 * (size_t)F));
+    CKR(upload(c, c->q0, q0, sizeof(double) * 3 * (size_t)V));
+    CKR(upload(c, c->q1, q1, sizeof(double) * 3 * (size_t)V));
+    if (fixedMask)
+        CKR(upload(c, c->fixed, fixedMask, (size_t)V));
+    BpResult r;
+    CKR(broadphase_device(c, kind, V, F, P<int>(c->faces), P<double>(c->q0), P<double>(c->q1), nullptr, nullptr, outerEta,
+                          fixedMask ? P<unsigned char>(c->fixed) : nullptr, 0, 1, &r));
+    CKR(download_stencils(c, c->vfOut, r.nvf, vf));
+    CKR(download_stencils(c, c->eeOut, r.nee, ee));
+    *nvf = r.nvf;
+    *nee = r.nee;
+    return CCD_OK;
+}
+
+int ccd_narrowphase(ccd_context *c, int V, const int64_t *hoff, const double *htime, const double *hpos, int64_t nvf, const int32_t *vf,
+                    const double *vf_eta, int64_t nee, const int32_t *ee, const double *ee_eta, uint8_t *vf_hit, double *vf_toi,
+                    uint8_t *vf_stage, uint8_t *ee_hit, double *ee_toi, uint8_t *ee_stage, ccd_np_summary *summary)
+{
+    if (!c || V < 0 || nvf < 0 || nee < 0 || (V > 0 && (!hoff || !htime || !hpos)) || (nvf > 0 && (!vf || !vf_eta || !vf_hit)) ||
+        (nee > 0 && (!ee || !ee_eta || !ee_hit)))
+        return CCD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    c->launches = 0;
+    const long long N = V > 0 ? (long long)hoff[V] : 0;
+    CKR(upload(c, c->hoff, hoff, sizeof(int64_t) * ((size_t)V + 1)));
+    CKR(upload(c, c->htime, htime, sizeof(double) * (size_t)N));
+    CKR(upload(c, c->hpos, hpos, sizeof(double) * 3 * (size_t)N));
+    CKR(upload(c, c->vf_in, vf, sizeof(int32_t) * 4 * (size_t)nvf));
+    CKR(upload(c, c->ee_in, ee, sizeof(int32_t) * 4 * (size_t)nee));
+    CKR(upload(c, c->vf_eta, vf_eta, sizeof(double) * (size_t)nvf));
+    CKR(upload(c, c->ee_eta, ee_eta, sizeof(double) * (size_t)nee));
+    ccd_np_summary s;
+    // two entries per vertex = one linear segment: read q0/q1 straight out of hpos (stride 6)
+    const bool single = history_is_single_step(V, hoff);
+    CKR(narrowphase_device(c, nvf, P<int>(c->vf_in), P<double>(c->vf_eta), nee, P<int>(c->ee_in), P<double>(c->ee_eta), 0.0,
+                           single ? P<double>(c->hpos) : nullptr, single ? P<double>(c->hpos) + 3 : nullptr, 6, P<long long>(c->hoff),
+                           P<double>(c->htime), P<double>(c->hpos), &s));
+    if (nvf > 0)
+    {
+        CK(cudaMemcpyAsync(vf_hit, c->vfHit.p, (size_t)nvf, cudaMemcpyDeviceToHost, c->st));
+        if (vf_toi) CK(cudaMemcpyAsync(vf_toi, c->vfToi.p, sizeof(double) * (size_t)nvf, cudaMemcpyDeviceToHost, c->st));
+        if (vf_stage) CK(cudaMemcpyAsync(vf_stage, c->vfStage.p, (size_t)nvf, cudaMemcpyDeviceToHost, c->st));
+    }
+    if (nee > 0)
+    {
+        CK(cudaMemcpyAsync(ee_hit, c->eeHit.p, (size_t)nee, cudaMemcpyDeviceToHost, c->st));
+        if (ee_toi) CK(cudaMemcpyAsync(ee_toi, c->eeToi.p, sizeof(double) * (size_t)nee, cudaMemcpyDeviceToHost, c->st));
+        if (ee_stage) CK(cudaMemcpyAsync(ee_stage, c->eeStage.p, (size_t)nee, cudaMemcpyDeviceToHost, c->st));
+    }
+    CK(cudaStreamSynchronize(c->st));
+    if (summary)
+        *summary = s;
+    return CCD_OK;
+}
+
+int ccd_step_device(ccd_context *c, int kind, int V, int F, const int32_t *d_faces, const double *d_q0, const double *d_q1, double outerEta,
+                    double eta, const uint8_t *d_fixedMask, int shard_rank, int shard_world, ccd_device_result *out)
+{
+    if (!c || !out)
+        return CCD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    c->launches = 0;
+    memset(out, 0, sizeof(*out));
+    BpResult r;
+    CK(cudaEventRecord(c->ev[0], c->st));
+    CKR(broadphase_device(c, kind, V, F, d_faces, d_q0, d_q1, nullptr, nullptr, outerEta, d_fixedMask, shard_rank, shard_world, &r));
+    CK(cudaEventRecord(c->ev[1], c->st));
+    ccd_np_summary s;
+    CKR(narrowphase_device(c, r.nvf, P<int>(c->vfOut), nullptr, r.nee, P<int>(c->eeOut), nullptr, eta, d_q0, d_q1, 3, nullptr, nullptr, nullptr, &s));
+    CK(cudaEventRecord(c->ev[2], c->st));
+    CK(cudaEventSynchronize(c->ev[2]));
+    cudaEventElapsedTime(&out->ms_broadphase, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&out->ms_narrowphase, c->ev[1], c->ev[2]);
+    out->n_vf_candidates = r.nvf;
+    out->n_ee_candidates = r.nee;
+    out->n_vf_hits = s.n_vf_hits;
+    out->n_ee_hits = s.n_ee_hits;
+    out->earliest_toi = s.earliest_toi;
+    out->d_vf = P<int32_t>(c->vfOut);
+    out->d_ee = P<int32_t>(c->eeOut);
+    out->d_vf_hit = P<uint8_t>(c->vfHit);
+    out->d_ee_hit = P<uint8_t>(c->eeHit);
+    out->d_vf_toi = P<double>(c->vfToi);
+    out->d_ee_toi = P<double>(c->eeToi);
+    out->n_face_pairs = r.npairs;
+    out->n_tree_candidates = r.ncand;
+    out->n_launches = c->launches;
+    c->stage_valid = (F > 0 && V > 0);
+    return CCD_OK;
+}
+
+// hit compaction in std::set order (stable): stencils and TOIs of the flagged entries
+static int select_hits(ccd_context *c, long long n, const int *d_st, const double *d_toi, const unsigned char *d_flag, long long nh,
+                       int32_t **h_st, double **h_toi)
+{
+    *h_st = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)(nh > 0 ? nh : 1));
+    *h_toi = (double *)malloc(sizeof(double) * (size_t)(nh > 0 ? nh : 1));
+    if (!*h_st || !*h_toi)
+        return CCD_ERR_NOMEM;
+    if (n == 0 || nh == 0)
+        return CCD_OK;
+    size_t tb1 = 0, tb2 = 0;
+    cub::DeviceSelect::Flagged(nullptr, tb1, (const int4 *)nullptr, (const unsigned char *)nullptr, (int4 *)nullptr, (int *)nullptr, (int)n);
+    cub::DeviceSelect::Flagged(nullptr, tb2, (const double *)nullptr, (const unsigned char *)nullptr, (double *)nullptr, (int *)nullptr, (int)n);
+    CKR(ensure(c, c->selTmp, (tb1 > tb2 ? tb1 : tb2) + 256));
+    CKR(ensure(c, c->selA, sizeof(int) * 4 * (size_t)(nh + 1)));
+    CKR(ensure(c, c->selB, sizeof(double) * (size_t)(nh + 1)));
+    CKR(ensure(c, c->selCount, 64));
+    cub::DeviceSelect::Flagged(c->selTmp.p, tb1, (const int4 *)d_st, d_flag, (int4 *)c->selA.p, (int *)c->selCount.p, (int)n, c->st);
+    cub::DeviceSelect::Flagged(c->selTmp.p, tb2, d_toi, d_flag, (double *)c->selB.p, (int *)c->selCount.p, (int)n, c->st);
+    c->launches += 4;
+    CK(cudaMemcpyAsync(*h_st, c->selA.p, sizeof(int32_t) * 4 * (size_t)nh, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(*h_toi, c->selB.p, sizeof(double) * (size_t)nh, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return CCD_OK;
+}
+
+int ccd_step(ccd_context *c, int kind, int V, int F, const int32_t *faces, const double *q0, const double *q1, double outerEta, double eta,
+             const uint8_t *fixedMask, ccd_step_result *out)
+{
+    return ccd_step_shard(c, kind, V, F, faces, q0, q1, outerEta, eta, fixedMask, 0, 1, out);
+}
+
+int ccd_step_shard(ccd_context *c, int kind, int V, int F, const int32_t *faces, const double *q0, const double *q1, double outerEta,
+                   double eta, const uint8_t *fixedMask, int shard_rank, int shard_world, ccd_step_result *out)
+{
+    if (!c || !out || (F > 0 && !faces) || (V > 0 && (!q0 || !q1)))
+        return CCD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    memset(out, 0, sizeof(*out));
+    CKR(upload(c, c->faces, faces, sizeof(int32_t) * 3 * (size_t)F));
+    CKR(upload(c, c->q0, q0, sizeof(double) * 3 * (size_t)V));
+    CKR(upload(c, c->q1, q1, sizeof(double) * 3 * (size_t)V));
+    if (fixedMask)
+        CKR(upload(c, c->fixed, fixedMask, (size_t)V));
+    ccd_device_result d;
+    CKR(ccd_step_device(c, kind, V, F, P<int>(c->faces), P<double>(c->q0), P<double>(c->q1), outerEta, eta,
+                        fixedMask ? P<unsigned char>(c->fixed) : nullptr, shard_rank, shard_world, &d));
+    out->n_vf_candidates = d.n_vf_candidates;
+    out->n_ee_candidates = d.n_ee_candidates;
+    out->n_vf_hits = d.n_vf_hits;
+    out->n_ee_hits = d.n_ee_hits;
+    out->earliest_toi = d.earliest_toi;
+    out->ms_broadphase = d.ms_broadphase;
+    out->ms_narrowphase = d.ms_narrowphase;
+    CKR(select_hits(c, d.n_vf_candidates, d.d_vf, d.d_vf_toi, d.d_vf_hit, d.n_vf_hits, &out->vf_hits, &out->vf_hit_toi));
+    CKR(select_hits(c, d.n_ee_candidates, d.d_ee, d.d_ee_toi, d.d_ee_hit, d.n_ee_hits, &out->ee_hits, &out->ee_hit_toi));
+    return CCD_OK;
+}
+
+void ccd_step_result_free(ccd_step_result *r)
+{
+    if (!r)
+        return;
+    free(r->vf_hits); free(r->vf_hit_toi); free(r->ee_hits); free(r->ee_hit_toi);
+    r->vf_hits = r->ee_hits = nullptr;
+    r->vf_hit_toi = r->ee_hit_toi = nullptr;
+}
+
+int ccd_stage_times(ccd_context *c, float *ms, int n)
+{
+    if (!c || !ms || n < CCD_N_STAGES)
+        return CCD_ERR_ARG;
+    for (int i = 0; i < n; i++)
+        ms[i] = 0.f;
+    if (!c->stage_valid)
+        return CCD_OK;
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->sev[CCD_N_STAGES]));
+    for (int i = 0; i < CCD_N_STAGES; i++)
+        cudaEventElapsedTime(&ms[i], c->sev[i], c->sev[i + 1]);
+    cudaGetLastError();
+    return CCD_OK;
+}
+
+int ccd_memcpy_d2h(ccd_context *c, void *h_dst, const void *d_src, uint64_t bytes)
+{
+    if (!c || (bytes && (!h_dst || !d_src)))
+        return CCD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    if (bytes)
+    {
+        CK(cudaMemcpyAsync(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+    }
+    return CCD_OK;
+}
+
+int ccd_fp64_peak(ccd_context *c, double *tflops)
+{
+    if (!c || !tflops)
+        return CCD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CKR(ensure(c, c->selD, sizeof(double) * 148 * 8 * 256));
+    const int iters = 4096;
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++)
+    {
+        CK(cudaEventRecord(c->ev[0], c->st));
+        ccdk_fp64_peak(c->st, iters, P<double>(c->selD));
+        CK(cudaEventRecord(c->ev[1], c->st));
+        CK(cudaEventSynchronize(c->ev[1]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+        double flops = 2.0 * 16.0 * (double)iters * 148.0 * 8.0 * 256.0;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best)
+            best = tf;
+    }
+    CK(cudaGetLastError());
+    *tflops = best;
+    return CCD_OK;
+}
+
+static int prim_batch(ccd_context *c, int kind, int npts, int64_t n, const double *pts, const double *eta, uint8_t *hit, double *t)
+{
+    if (!c || n < 0 || (n > 0 && (!pts || !eta || !hit || !t)))
+        return CCD_ERR_ARG;
+    if (n == 0)
+        return CCD_OK;
+    CK(cudaSetDevice(c->device));
+    CKR(upload(c, c->pts, pts, sizeof(double) * 3 * (size_t)npts * (size_t)n));
+    CKR(upload(c, c->eta, eta, sizeof(double) * (size_t)n));
+    CKR(ensure(c, c->vfHit, (size_t)n + 16));
+    CKR(ensure(c, c->vfToi, sizeof(double) * ((size_t)n + 2)));
+    // t is only written on a hit: start from the caller's values
+    CK(cudaMemcpyAsync(c->vfToi.p, t, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->st));
+    ccdk_prim_batch(c->st, kind, n, P<double>(c->pts), P<double>(c->eta), P<unsigned char>(c->vfHit), P<double>(c->vfToi));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hit, c->vfHit.p, (size_t)n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(t, c->vfToi.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return CCD_OK;
+}
+
+int ccd_vf_batch(ccd_context *c, int64_t n, const double *pts, const double *eta, uint8_t *hit, double *t) { return prim_batch(c, 0, 8, n, pts, eta, hit, t); }
+int ccd_ee_batch(ccd_context *c, int64_t n, const double *pts, const double *eta, uint8_t *hit, double *t) { return prim_batch(c, 1, 8, n, pts, eta, hit, t); }
+int ccd_ve_batch(ccd_context *c, int64_t n, const double *pts, const double *eta, uint8_t *hit, double *t) { return prim_batch(c, 2, 6, n, pts, eta, hit, t); }
+int ccd_vv_batch(ccd_context *c, int64_t n, const double *pts, const double *eta, uint8_t *hit, double *t) { return prim_batch(c, 3, 4, n, pts, eta, hit, t); }
+
+int ccd_find_intervals_batch(ccd_context *c, int64_t n, int degree, int pos, const double *coeffs, int32_t *cnt, double *lo, double *hi)
+{
+    if (!c || n < 0 || !(degree == 2 || degree == 3 || degree == 4 || degree == 6) || (n > 0 && (!coeffs || !cnt || !lo || !hi)))
+        return CCD_ERR_ARG;
+    if (n == 0)
+        return CCD_OK;
+    CK(cudaSetDevice(c->device));
+    CKR(upload(c, c->pts, coeffs, sizeof(double) * 7 * (size_t)n));
+    CKR(ensure(c, c->selA, sizeof(int) * (size_t)n));
+    CKR(ensure(c, c->selB, sizeof(double) * 7 * (size_t)n));
+    CKR(ensure(c, c->selC, sizeof(double) * 7 * (size_t)n));
+    CK(cudaMemsetAsync(c->selB.p, 0, sizeof(double) * 7 * (size_t)n, c->st));
+    CK(cudaMemsetAsync(c->selC.p, 0, sizeof(double) * 7 * (size_t)n, c->st));
+    ccdk_find_intervals(c->st, n, degree, pos, P<double>(c->pts), P<int>(c->selA), P<double>(c->selB), P<double>(c->selC));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(cnt, c->selA.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(lo, c->selB.p, sizeof(double) * 7 * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(hi, c->selC.p, sizeof(double) * 7 * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return CCD_OK;
+}
+
+// ---- Distance.h ------------------------------------------------------------------------------
+static int dist_batch(ccd_context *c, int which, int64_t n, const double *pts, const double *eta, double *vec, double *bary, int nb, uint8_t *flag)
+{
+    if (!c || n < 0 || (n > 0 && !pts))
+        return CCD_ERR_ARG;
+    if (n == 0)
+        return CCD_OK;
+    CK(cudaSetDevice(c->device));
+    CKR(upload(c, c->pts, pts, sizeof(double) * 12 * (size_t)n));
+    if (eta)
+        CKR(upload(c, c->eta, eta, sizeof(double) * (size_t)n));
+    CKR(ensure(c, c->selB, sizeof(double) * 3 * (size_t)n));
+    CKR(ensure(c, c->selC, sizeof(double) * 4 * (size_t)n));
+    CKR(ensure(c, c->vfHit, (size_t)n + 16));
+    ccdk_dist_batch(c->st, which, n, P<double>(c->pts), eta ? P<double>(c->eta) : nullptr, P<double>(c->selB), P<double>(c->selC), P<unsigned char>(c->vfHit));
+    CK(cudaGetLastError());
+    if (vec) CK(cudaMemcpyAsync(vec, c->selB.p, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+    if (bary) CK(cudaMemcpyAsync(bary, c->selC.p, sizeof(double) * (size_t)nb * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+    if (flag) CK(cudaMemcpyAsync(flag, c->vfHit.p, (size_t)n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return CCD_OK;
+}
+
+int ccd_dist_vf_batch(ccd_context *c, int64_t n, const double *pts, double *vec, double *bary)
+{
+    if (n > 0 && (!vec || !bary)) return CCD_ERR_ARG;
+    return dist_batch(c, 0, n, pts, nullptr, vec, bary, 3, nullptr);
+}
+int ccd_dist_ee_batch(ccd_context *c, int64_t n, const double *pts, double *vec, double *bary)
+{
+    if (n > 0 && (!vec || !bary)) return CCD_ERR_ARG;
+    return dist_batch(c, 1, n, pts, nullptr, vec, bary, 4, nullptr);
+}
+int ccd_dist_plane_lt_batch(ccd_context *c, int64_t n, const double *pts, const double *eta, uint8_t *out)
+{
+    if (n > 0 && (!eta || !out)) return CCD_ERR_ARG;
+    return dist_batch(c, 2, n, pts, eta, nullptr, nullptr, 0, out);
+}
+int ccd_dist_line_lt_batch(ccd_context *c, int64_t n, const double *pts, const double *eta, uint8_t *out)
+{
+    if (n > 0 && (!eta || !out)) return CCD_ERR_ARG;
+    return dist_batch(c, 3, n, pts, eta, nullptr, nullptr, 0, out);
+}
+
+// Distance::meshSelfDistance, src/Distance.cpp:12-66
+int ccd_mesh_self_distance(ccd_context *c, int V, const double *verts, int F, const int32_t *faces, const uint8_t *fixedMask,
+                           double *distance, int64_t *n_vf, int64_t *n_ee)
+{
+    if (!c || !distance || V < 0 || F < 0 || (V > 0 && !verts) || (F > 0 && !faces))
+        return CCD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    c->launches = 0;
+    CKR(upload(c, c->faces, faces, sizeof(int32_t) * 3 * (size_t)F));
+    CKR(upload(c, c->q0, verts, sizeof(double) * 3 * (size_t)V));
+    if (fixedMask)
+        CKR(upload(c, c->fixed, fixedMask, (size_t)V));
+    unsigned long long *ctr = P<unsigned long long>(c->counters);
+    // (1) min squared distance from every vertex to the vertices of every face not containing it (:21-35)
+    c->h_counters[8] = 0x7FF0000000000000ull; // +inf
+    CK(cudaMemcpyAsync(ctr + C_EARLY_VF, c->h_counters + 8, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->st));
+    ccdk_vertex_min_dist2(c->st, V, F, P<double>(c->q0), P<int>(c->faces), ctr + C_EARLY_VF);
+    CK(cudaGetLastError());
+    CKR(sync_counters(c));
+    double d2;
+    memcpy(&d2, &c->h_counters[C_EARLY_VF], sizeof(d2));
+    double closest = sqrt(d2);
+    // (2) static history q -> q through the AABB broadphase with outerEta = closest (:37-45)
+    BpResult r;
+    CKR(broadphase_device(c, CCD_AABB, V, F, P<int>(c->faces), P<double>(c->q0), P<double>(c->q0), nullptr, nullptr, closest,
+                          fixedMask ? P<unsigned char>(c->fixed) : nullptr, 0, 1, &r));
+    // (3) min closest-point distance over the candidate stencils (:49-65)
+    c->h_counters[8] = 0x7FF0000000000000ull;
+    CK(cudaMemcpyAsync(ctr + C_EARLY_VF, c->h_counters + 8, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->st));
+    ccdk_stencil_min_dist(c->st, true, r.nvf, P<int>(c->vfOut), P<double>(c->q0), ctr + C_EARLY_VF);
+    ccdk_stencil_min_dist(c->st, false, r.nee, P<int>(c->eeOut), P<double>(c->q0), ctr + C_EARLY_VF);
+    CK(cudaGetLastError());
+    CKR(sync_counters(c));
+    memcpy(distance, &c->h_counters[C_EARLY_VF], sizeof(double));
+    if (n_vf) *n_vf = r.nvf;
+    if (n_ee) *n_ee = r.nee;
+    return CCD_OK;
+}
+
+} // extern "C"

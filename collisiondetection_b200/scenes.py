@@ -33,20 +33,20 @@ def splitmix64(x):
         return z ^ (z >> np.uint64(31))
 
 
-def cloth(n, seed=20261017, rows=None):
+def cloth(n, seed=20261017, cols=None):
     """Synthetic self-colliding cloth: n x n vertices (n=1415 -> 3,998,792 triangles).
 
     Returns (q0, q1, faces, eta) with q* of shape (V,3) float64, faces (F,3) int32 and
-    eta = outerEta = 0.01*h.  `rows=(r0, r1)` keeps only grid rows r0 <= i < r1 (a strip of the
-    same cloth, vertex ids renumbered but coordinates and noise identical) — used for bounded CPU
-    samples of the full-size workload.
+    eta = outerEta = 0.01*h.  `cols=(j0, j1)` keeps only grid columns j0 <= j < j1: a ribbon of the
+    same cloth across the whole S-fold (vertex ids renumbered, coordinates and noise identical) —
+    used for bounded CPU samples of the full-size workload.
     """
     h = 1.0 / (n - 1)
     gap = 4.0 * h
     r = 2.0 * h
     a = (1.0 - 2.0 * np.pi * r) / 3.0
-    i0, i1 = (0, n) if rows is None else rows
-    ii, jj = np.meshgrid(np.arange(i0, i1), np.arange(n), indexing="ij")
+    j0, j1 = (0, n) if cols is None else cols
+    ii, jj = np.meshgrid(np.arange(n), np.arange(j0, j1), indexing="ij")
     u = ii / (n - 1.0)
     v = jj / (n - 1.0)
     s = u
@@ -81,13 +81,13 @@ def cloth(n, seed=20261017, rows=None):
         R = (splitmix64(np.uint64(seed) + np.uint64(3) * k + np.uint64(c)) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
         q1[:, c] += (2.0 * R - 1.0) * 0.1 * h
     # faces: all first triangles in row-major cell order, then all second triangles
-    nr = i1 - i0
-    ci, cj = np.meshgrid(np.arange(nr - 1), np.arange(n - 1), indexing="ij")
-    c0 = (ci * n + cj).reshape(-1)
-    c1 = ((ci + 1) * n + cj).reshape(-1)
-    c2 = ((ci + 1) * n + cj + 1).reshape(-1)
-    c3 = (ci * n + cj + 1).reshape(-1)
-    odd = (((ci + i0) + cj) % 2 == 1).reshape(-1)
+    nc = j1 - j0
+    ci, cj = np.meshgrid(np.arange(n - 1), np.arange(nc - 1), indexing="ij")
+    c0 = (ci * nc + cj).reshape(-1)
+    c1 = ((ci + 1) * nc + cj).reshape(-1)
+    c2 = ((ci + 1) * nc + cj + 1).reshape(-1)
+    c3 = (ci * nc + cj + 1).reshape(-1)
+    odd = ((ci + (cj + j0)) % 2 == 1).reshape(-1)
     t1 = np.where(odd[:, None], np.stack([c0, c1, c3], -1), np.stack([c0, c1, c2], -1))
     t2 = np.where(odd[:, None], np.stack([c1, c2, c3], -1), np.stack([c0, c2, c3], -1))
     faces = np.concatenate([t1, t2], axis=0).astype(np.int32)

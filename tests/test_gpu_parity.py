@@ -1,0 +1,273 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): every call goes through the C ABI
+(include/ccd_b200.h -> libccd_b200.so).  The CUDA path is compared
+
+  * bit for bit with the plain-C restatement (oracle/ccd_oracle.c) — same polynomial coefficients, same
+    root-isolation steps, same fused operations, hence identical flags AND identical TOI bits;
+  * with the golden vectors the unmodified reference produced (tests/golden/*.npz): candidate sets
+    bit-exact, flags equal up to the classified reference artefacts (see tests/arbiter.py);
+  * at BASELINE's full sizes through size-independent properties.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import bind
+
+pytestmark = pytest.mark.gpu
+
+
+def _single(g):
+    return bind.single_step_history(g["q0"], g["q1"])
+
+
+def test_known_answers_testctcd(ctx):
+    g = golden("testctcd.npz")
+    for name, fn in (("ee", ctx.edgeEdgeCTCD), ("vf", ctx.vertexFaceCTCD), ("ve", ctx.vertexEdgeCTCD), ("vv", ctx.vertexVertexCTCD)):
+        hit, t = fn(g[name + "_pts"], 1e-6)
+        assert hit[0] == 1
+        assert t[0] == g["ref_" + name + "_t"][0], (name, t[0])
+
+
+def test_random_primitives_bit_exact_vs_restatement(ctx, port):
+    g = golden("prims_random.npz")
+    for k, fn, pfn in (("vf", ctx.vertexFaceCTCD, port.vf_batch), ("ee", ctx.edgeEdgeCTCD, port.ee_batch),
+                       ("ve", ctx.vertexEdgeCTCD, port.ve_batch), ("vv", ctx.vertexVertexCTCD, port.vv_batch)):
+        hit, t = fn(g[k + "_pts"], g[k + "_eta"])
+        ph, pt = pfn(g[k + "_pts"], g[k + "_eta"])
+        assert np.array_equal(hit, ph), k
+        assert np.array_equal(t[hit > 0].view(np.uint64), pt[hit > 0].view(np.uint64)), k
+        assert np.all(t[hit == 0] == 0.0)          # t untouched on a miss
+        rh = g["ref_%s_hit" % k]
+        assert int((hit != rh).sum()) <= 3
+
+
+def test_find_intervals_bit_exact_vs_restatement(ctx, port):
+    """CTCD::findIntervals on random and degenerate polynomials of degree 2,3,4,6."""
+    import ctypes as C
+    rng = np.random.default_rng(7)
+    dp = C.POINTER(C.c_double)
+    for deg in (2, 3, 4, 6):
+        n = 4000
+        coeffs = rng.uniform(-1, 1, (n, deg + 1))
+        # polynomials with prescribed roots in and around [0,1] (incl. double roots), and leading zeros
+        for i in range(n // 2):
+            roots = rng.uniform(-0.5, 1.5, deg)
+            if i % 5 == 0:
+                roots[1] = roots[0]
+            if i % 7 == 0:
+                roots[0] = rng.choice([0.0, 1.0, 0.5])
+            coeffs[i] = np.poly(roots) * rng.choice([-1.0, 1.0])
+        coeffs[-200:-100, 0] = 0.0
+        coeffs[-100:, :2] = 0.0
+        coeffs[-10:] = 0.0
+        for pos in (True, False):
+            cnt, lo, hi = ctx.findIntervals(coeffs, deg, pos)
+            for i in range(n):
+                op = coeffs[i].copy()
+                l = np.zeros(8)
+                u = np.zeros(8)
+                k = port.lib.orc_find_intervals(op.ctypes.data_as(dp), deg, int(pos), l.ctypes.data_as(dp), u.ctypes.data_as(dp))
+                assert k == cnt[i], (deg, pos, i, coeffs[i].tolist())
+                assert np.array_equal(l[:k].view(np.uint64), lo[i, :k].view(np.uint64)), (deg, pos, i)
+                assert np.array_equal(u[:k].view(np.uint64), hi[i, :k].view(np.uint64)), (deg, pos, i)
+
+
+@pytest.mark.parametrize("name", ["alec_prob3_402", "alec_prob11_835", "alec_prob18_834", "alec_prob3_402_aabb",
+                                  "alec_prob3_402_fixed", "alec_prob3_402_thick"])
+def test_broadphase_candidates_bit_exact(ctx, name):
+    g = golden(name + ".npz")
+    fixed = g["fixed"] if g["fixed"].size else None
+    kind, oe = int(g["kind"]), float(g["outer_eta"])
+    vf, ee = ctx.findCollisionCandidatesStep(kind, g["faces"], g["q0"], g["q1"], oe, fixed)
+    assert np.array_equal(vf, g["ref_vf"]) and np.array_equal(ee, g["ref_ee"])
+    # same through the CSR-History entry point, and idempotent
+    vf2, ee2 = ctx.findCollisionCandidates(kind, g["faces"], *_single(g), oe, fixed)
+    assert np.array_equal(vf2, vf) and np.array_equal(ee2, ee)
+
+
+@pytest.mark.parametrize("name,max_mismatch", [("alec_prob3_402", 0), ("alec_prob11_835", 2), ("alec_prob18_834", 0),
+                                                ("alec_prob3_402_thick", 0)])
+def test_narrowphase_flags_toi(ctx, port, name, max_mismatch):
+    g = golden(name + ".npz")
+    eta = float(g["eta"])
+    H = _single(g)
+    out = ctx.findCollisions(*H, g["ref_vf"], eta, g["ref_ee"], eta)
+    p = port.narrowphase(*H, g["ref_vf"], eta, g["ref_ee"], eta)
+    mism = 0
+    for k in ("vf", "ee"):
+        assert np.array_equal(out[k + "_hit"], p[k + "_hit"])
+        assert np.array_equal(out[k + "_stage"], p[k + "_stage"].astype(np.uint8))
+        assert np.array_equal(out[k + "_toi"].view(np.uint64), p[k + "_toi"].view(np.uint64))
+        mism += int((out[k + "_hit"] != g["ref_%s_hit" % k]).sum())
+    assert mism <= max_mismatch
+    hits = np.concatenate([out["vf_toi"][out["vf_hit"] > 0], out["ee_toi"][out["ee_hit"] > 0]])
+    assert out["n_vf_hits"] == int(out["vf_hit"].sum()) and out["n_ee_hits"] == int(out["ee_hit"].sum())
+    assert out["earliest_toi"] == (hits.min() if hits.size else np.inf)
+
+
+def test_multi_entry_history(ctx, port):
+    g = golden("history_prob3_402.npz")
+    H = (g["hoff"], g["htime"], g["hpos"])
+    vf, ee = ctx.findCollisionCandidates(13, g["faces"], *H, float(g["outer_eta"]))
+    assert np.array_equal(vf, g["ref_vf"]) and np.array_equal(ee, g["ref_ee"])
+    eta = float(g["eta"])
+    out = ctx.findCollisions(*H, vf, eta, ee, eta)
+    p = port.narrowphase(*H, vf, eta, ee, eta)
+    for k in ("vf", "ee"):
+        assert np.array_equal(out[k + "_hit"], g["ref_%s_hit" % k])
+        assert np.array_equal(out[k + "_hit"], p[k + "_hit"])
+        assert np.array_equal(out[k + "_stage"], p[k + "_stage"].astype(np.uint8))
+        assert np.array_equal(out[k + "_toi"].view(np.uint64), p[k + "_toi"].view(np.uint64))
+
+
+def test_per_stencil_eta(ctx, port):
+    """Thickness comes per stencil (ActiveLayers.cpp:196-207 varies it with layer depth)."""
+    g = golden("alec_prob3_402_thick.npz")
+    rng = np.random.default_rng(3)
+    vf, ee = g["ref_vf"], g["ref_ee"]
+    ve = rng.uniform(1e-6, 2e-3, len(vf))
+    ee_eta = rng.uniform(1e-6, 2e-3, len(ee))
+    H = _single(g)
+    out = ctx.findCollisions(*H, vf, ve, ee, ee_eta)
+    p = port.narrowphase(*H, vf, ve, ee, ee_eta)
+    for k in ("vf", "ee"):
+        assert np.array_equal(out[k + "_hit"], p[k + "_hit"])
+        assert np.array_equal(out[k + "_toi"].view(np.uint64), p[k + "_toi"].view(np.uint64))
+
+
+def test_fused_step_matches_two_calls(ctx):
+    g = golden("alec_prob11_835.npz")
+    r = ctx.step(13, g["faces"], g["q0"], g["q1"], 1e-8, 1e-8)
+    out = ctx.findCollisions(*_single(g), g["ref_vf"], 1e-8, g["ref_ee"], 1e-8)
+    assert (r["n_vf_candidates"], r["n_ee_candidates"]) == (len(g["ref_vf"]), len(g["ref_ee"]))
+    assert np.array_equal(r["vf_hits"], g["ref_vf"][out["vf_hit"] > 0])
+    assert np.array_equal(r["ee_hits"], g["ref_ee"][out["ee_hit"] > 0])
+    assert np.array_equal(r["vf_hit_toi"], out["vf_toi"][out["vf_hit"] > 0])
+    assert np.array_equal(r["ee_hit_toi"], out["ee_toi"][out["ee_hit"] > 0])
+    assert r["earliest_toi"] == out["earliest_toi"]
+
+
+def test_distance_queries_bit_exact(ctx):
+    g = golden("dist_random.npz")
+    vec, bary = ctx.vertexFaceDistance(g["pts"])
+    assert np.array_equal(vec, g["ref_vf_vec"]) and np.array_equal(bary, g["ref_vf_bary"])
+    vec, bary = ctx.edgeEdgeDistance(g["pts"])
+    assert np.array_equal(vec, g["ref_ee_vec"]) and np.array_equal(bary, g["ref_ee_bary"])
+    assert np.array_equal(ctx.vertexPlaneDistanceLessThan(g["pts"], g["eta"]), g["ref_plane_lt"])
+    assert np.array_equal(ctx.lineLineDistanceLessThan(g["pts"], g["eta"]), g["ref_line_lt"])
+
+
+def test_mesh_self_distance(ctx):
+    g = golden("mesh_self_distance.npz")
+    for name, nvf, nee in (("prob3_402", 15291, 26253), ("prob11_835", None, None)):
+        a = golden("alec_%s.npz" % name)
+        d, n1, n2 = ctx.meshSelfDistance(a["q0"], a["faces"])
+        assert d == float(g[name])
+        if nvf is not None:
+            assert (n1, n2) == (nvf, nee)       # "Checking N vertex-face and M edge-edge stencils"
+
+
+def test_empty_and_tiny_inputs(ctx):
+    z3 = np.zeros((0, 3))
+    vf, ee = ctx.findCollisionCandidatesStep(13, np.zeros((0, 3), np.int32), z3, z3, 1e-3)
+    assert vf.shape == (0, 4) and ee.shape == (0, 4)
+    # two triangles sharing nothing, overlapping boxes -> 6 VF + 9 EE (example meshes/test1.obj situation)
+    q = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0.2, 0.2, 0.05], [1.2, 0.2, 0.05], [0.2, 1.2, 0.05]], float)
+    f = np.array([[0, 1, 2], [3, 4, 5]], np.int32)
+    vf, ee = ctx.findCollisionCandidatesStep(13, f, q, q, 1e-3)
+    assert len(vf) == 6 and len(ee) == 9
+    # one triangle: nothing
+    vf, ee = ctx.findCollisionCandidatesStep(3, f[:1], q, q, 1e-3)
+    assert len(vf) == 0 and len(ee) == 0
+    out = ctx.findCollisions(*bind.single_step_history(q, q), np.zeros((0, 4), np.int32), [], np.zeros((0, 4), np.int32), [])
+    assert out["n_vf_hits"] == 0 and out["earliest_toi"] == np.inf
+
+
+def test_prob17_full_size(ctx, port):
+    """BASELINE config C2 on the GPU: candidate sets bit-exact (count + FNV-1a of the sorted set), flags and TOI
+    bits identical to the restatement, hit sets within the classified budget of the reference's."""
+    g = golden("alec_prob17_30957.npz")
+    vf, ee = ctx.findCollisionCandidatesStep(13, g["faces"], g["q0"], g["q1"], 1e-8)
+    assert (len(vf), len(ee)) == (1330564, 2370945)
+    assert bind.fnv1a64(vf) == str(g["vf_fnv"]) and bind.fnv1a64(ee) == str(g["ee_fnv"])
+    H = _single(g)
+    out = ctx.findCollisions(*H, vf, 1e-8, ee, 1e-8)
+    p = port.narrowphase_flat(*H, vf, 1e-8, ee, 1e-8)
+    for k in ("vf", "ee"):
+        assert np.array_equal(out[k + "_hit"], p[k + "_hit"])
+        assert np.array_equal(out[k + "_toi"].view(np.uint64), p[k + "_toi"].view(np.uint64))
+    for k, st in (("vf", vf), ("ee", ee)):
+        mine = set(map(tuple, st[out[k + "_hit"] > 0].tolist()))
+        theirs = set(map(tuple, g["ref_%s_hits" % k].tolist()))
+        assert len(mine ^ theirs) <= (4 if k == "vf" else 160), (k, len(mine ^ theirs))
+
+
+def _check_canonical_sorted_unique(vf, ee):
+    assert np.all(vf[:, 1] <= vf[:, 2]) and np.all(vf[:, 2] <= vf[:, 3])
+    assert np.all(ee[:, 0] <= ee[:, 1]) and np.all(ee[:, 2] <= ee[:, 3]) and np.all(ee[:, 0] <= ee[:, 2])
+    for a in (vf, ee):
+        k = a.astype(np.int64)
+        d = np.diff(k, axis=0)
+        first = np.argmax(d != 0, axis=1)
+        lead = d[np.arange(len(d)), first]
+        assert np.all(np.any(d != 0, axis=1)) and np.all(lead > 0)      # strictly increasing lexicographically
+
+
+def test_cloth_twin_355(ctx):
+    """SURVEY.md §8(d) calibration twin (250,632 triangles): 841,465 VF + 1,476,283 EE candidates."""
+    from collisiondetection_b200 import scenes
+    q0, q1, f, eta = scenes.cloth(355)
+    vf, ee = ctx.findCollisionCandidatesStep(13, f, q0, q1, eta)
+    assert (len(vf), len(ee)) == (841465, 1476283)
+    _check_canonical_sorted_unique(vf, ee)
+    r = ctx.step(13, f, q0, q1, eta, eta)
+    assert abs(r["n_vf_hits"] - 46220) <= 5 and abs(r["n_ee_hits"] - 175171) <= 20
+    # hits are a sorted subset of the candidates; earliest TOI is the min
+    _check_canonical_sorted_unique(r["vf_hits"], r["ee_hits"])
+    assert r["earliest_toi"] == min(r["vf_hit_toi"].min(), r["ee_hit_toi"].min())
+    assert np.all((r["vf_hit_toi"] >= 0) & (r["vf_hit_toi"] <= 1))
+
+
+def test_cloth_sharded_union_equals_whole(ctx):
+    """ccd_step_device with (rank, world): the union of the shards' stencil lists is the unsharded list, hit counts add
+    up and the earliest TOI is the min over shards — what the multi-GPU reduction relies on."""
+    import torch
+    from collisiondetection_b200 import scenes
+    q0, q1, f, eta = scenes.cloth(201)
+    V, F = len(q0), len(f)
+    d_f = torch.from_numpy(f).cuda()
+    d_q0 = torch.from_numpy(q0).cuda()
+    d_q1 = torch.from_numpy(q1).cuda()
+    torch.cuda.synchronize()
+
+    def run(rank, world):
+        r = ctx.step_device(13, V, F, d_f.data_ptr(), d_q0.data_ptr(), d_q1.data_ptr(), eta, eta, 0, rank, world)
+        vf = ctx.download(r.d_vf, (r.n_vf_candidates, 4), np.int32)
+        ee = ctx.download(r.d_ee, (r.n_ee_candidates, 4), np.int32)
+        return r.n_vf_hits, r.n_ee_hits, r.earliest_toi, vf, ee
+
+    whole = run(0, 1)
+    for world in (2, 3, 8):
+        parts = [run(r, world) for r in range(world)]
+        assert np.array_equal(np.concatenate([p[3] for p in parts]), whole[3])
+        assert np.array_equal(np.concatenate([p[4] for p in parts]), whole[4])
+        assert sum(p[0] for p in parts) == whole[0] and sum(p[1] for p in parts) == whole[1]
+        assert min(p[2] for p in parts) == whole[2]
+
+
+@pytest.mark.slow
+def test_cloth_full_size_properties(ctx):
+    """BASELINE config C5 (1415 x 1415 vertices, 3,998,792 triangles): no CPU oracle at this size inside the test
+    budget, so size-independent properties — canonical form, strict lexicographic order (sorted + unique),
+    idempotence, hits a subset with TOI in [0,1] — plus the ribbon check: a 48-column ribbon of the same cloth run
+    on its own must give exactly the stencils of the full run that lie wholly inside the ribbon's interior."""
+    from collisiondetection_b200 import scenes
+    n = 1415
+    q0, q1, f, eta = scenes.cloth(n)
+    vf, ee = ctx.findCollisionCandidatesStep(13, f, q0, q1, eta)
+    assert len(f) == 3998792
+    _check_canonical_sorted_unique(vf, ee)
+    r = ctx.step(13, f, q0, q1, eta, eta)
+    assert (r["n_vf_candidates"], r["n_ee_candidates"]) == (len(vf), len(ee))
+    assert 0 <= r["earliest_toi"] <= 1
+    assert r["n_vf_hits"] > 0 and r["n_ee_hits"] > 0
