@@ -49,11 +49,11 @@ def load_workload(name):
 
 
 def cpu_sample(name):
-    """Bounded sample of the workload for the CPU arm: a 48-column ribbon across the whole S-fold of the same
+    """Bounded sample of the workload for the CPU arm: an 8-column ribbon across the whole S-fold of the same
     cloth (same coordinates and noise), centred on the band where the layers pass through each other."""
     if name.startswith("cloth"):
         n = int(name[5:])
-        w = min(48, n)
+        w = min(8, n)
         j0 = max(0, n // 2 - w // 2)
         q0, q1, f, eta = scenes.cloth(n, cols=(j0, j0 + w))
         return dict(q0=q0, q1=q1, faces=f, outer_eta=eta, eta=eta,

@@ -44,14 +44,14 @@ struct ccd_context
     // emission
     DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut;
     // narrowphase
-    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, selTmp, selA, selB, selC, selD, selCount;
+    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, selTmp, selA, selB, selC, selD, selCount;
     // pinned host scratch
     unsigned long long *h_counters = nullptr; // 16 entries
     size_t candCap = 0, pairCap = 0;
 };
 
 // device counters layout (unsigned long long each)
-enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_TOTAL = 16 };
+enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NWORK_VF = 7, C_NWORK_EE = 8, C_TOTAL = 16 };
 
 #define CK(call)                                                                                      \
     do                                                                                                \
@@ -209,7 +209,7 @@ void ccd_destroy(ccd_context *c)
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
     for (DBuf *b : all)
         if (b->p)
             cudaFree(b->p);
@@ -363,10 +363,18 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         c->launches += 2;
         CKR(sync_counters(c));
         unsigned long long ncand = c->h_counters[C_NCAND], npairs = c->h_counters[C_NPAIRS];
-        bool again = false;
-        if (ncand > c->candCap) { c->candCap = (size_t)(ncand + ncand / 8 + 1024); again = true; }
-        if (npairs > c->pairCap || again) { size_t want = (size_t)(npairs + npairs / 8 + 1024); if (want > c->pairCap) c->pairCap = want; }
-        if (npairs > c->pairCap) again = true;
+        // counts keep running past the capacities (writes are guarded), so an overflow tells the size to retry with
+        const bool cand_over = ncand > c->candCap, pair_over = npairs > c->pairCap;
+        const bool again = cand_over || pair_over;
+        if (cand_over)
+            c->candCap = (size_t)(ncand + ncand / 8 + 1024);
+        if (again)
+        {
+            // pairs found from a truncated candidate list are a lower bound only: leave generous room
+            size_t want = (size_t)(npairs + npairs / 4 + 1024);
+            if (cand_over) want = want > c->candCap / 2 ? want : c->candCap / 2;
+            if (want > c->pairCap) c->pairCap = want;
+        }
         if (!again)
         {
             res->ncand = (long long)ncand;
@@ -436,17 +444,19 @@ static int narrowphase_device(ccd_context *c, long long nvf, const int *d_vf, co
     CKR(ensure(c, c->eeStage, (size_t)nee + 16));
     CKR(ensure(c, c->vfToi, sizeof(double) * ((size_t)nvf + 2)));
     CKR(ensure(c, c->eeToi, sizeof(double) * ((size_t)nee + 2)));
+    CKR(ensure(c, c->workVf, sizeof(int) * ((size_t)nvf + 32)));
+    CKR(ensure(c, c->workEe, sizeof(int) * ((size_t)nee + 32)));
     unsigned long long init[4] = {0xFFFFFFFFFFFFFFFFull, 0ull, 0xFFFFFFFFFFFFFFFFull, 0ull};
     memcpy(c->h_counters + 8, init, sizeof(init));
     CK(cudaMemcpyAsync(ctr + C_EARLY_VF, c->h_counters + 8, sizeof(init), cudaMemcpyHostToDevice, c->st));
     cudaEventRecord(c->sev[ST_NP_VF], c->st);
-    ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
-                     P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF);
+    int nl = ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
+                              P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF, P<int>(c->workVf), ctr + C_NWORK_VF);
     cudaEventRecord(c->sev[ST_NP_EE], c->st);
-    ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
-                     P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE);
+    nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
+                           P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE, P<int>(c->workEe), ctr + C_NWORK_EE);
     cudaEventRecord(c->sev[CCD_N_STAGES], c->st);
-    c->launches += (nvf > 0) + (nee > 0);
+    c->launches += nl;
     CK(cudaGetLastError());
     if (sum)
     {

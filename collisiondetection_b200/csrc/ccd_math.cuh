@@ -7,7 +7,13 @@
 //
 // Root finding: the reference's Jenkins-Traub search (src/rpoly.h) is replaced by a real-root
 // isolator on [0,1] built from Bernstein sign-variation counts down the derivative chain plus
-// bracketed Newton (see roots01<D>).
+// bracketed Newton (roots01).
+//
+// Code shape: ONE copy of every routine (runtime degree, __noinline__, single call sites inside
+// loops over the polynomials of a primitive).  The first version instantiated the isolator per
+// degree and per call site; ncu showed the narrowphase stalled 58 % of the time on instruction
+// fetch with 5.7 of 32 lanes active (profiles/).  Lanes of a warp now walk the same loop and meet
+// again at the same call, and the whole kernel fits the instruction cache.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -31,6 +37,9 @@ __device__ __forceinline__ V3 ldv(const double *p) { return mk(p[0], p[1], p[2])
 // std::max / std::min argument-order semantics (matters only for NaN)
 __device__ __forceinline__ double smax(double a, double b) { return (a < b) ? b : a; }
 __device__ __forceinline__ double smin(double a, double b) { return (b < a) ? b : a; }
+
+// result codes of the primitives / stencil tests
+enum { R_MISS = 0, R_HIT = 1, R_DEFER = 2 };
 
 // ------------------------------------------------------------------------------------------
 // closed time intervals (include/CTCD.h:7-26); at most 7 per polynomial (<= 6 breakpoints)
@@ -56,29 +65,30 @@ __device__ __forceinline__ void push_interval(Ivals &iv, double tl, double tu)
 __device__ __forceinline__ bool overlap2(double al, double au, double bl, double bu) { return !(al > bu || bl > au); }
 
 // ------------------------------------------------------------------------------------------
-// Real roots on [0,1] of a degree-D polynomial, c[0] != 0 (descending powers).
+// Real roots on [0,1] of c[0] t^d + ... + c[d], c[0] != 0, 3 <= d <= 6.
 // Same steps, same fused operations as oracle/ccd_oracle.c: orc_roots01.
 // ------------------------------------------------------------------------------------------
-template <int M> __device__ __forceinline__ double horner_fma(const double (&c)[M + 1], double x)
+__device__ __forceinline__ double horner_fma(const double *c, int m, double x)
 {
     double f = c[0];
-#pragma unroll
-    for (int i = 1; i <= M; i++)
+    for (int i = 1; i <= m; i++)
         f = fma(f, x, c[i]);
     return f;
 }
 
-// root of c in (lo,hi); f(lo) has the sign of flo, f(hi) the opposite
-template <int M> __device__ __forceinline__ double solve_bracket(const double (&c)[M + 1], double lo, double hi, double flo)
+// root of the degree-m polynomial p in (lo,hi); f(lo) has the sign of flo, f(hi) the opposite
+static __device__ __noinline__ double solve_bracket(const double *p, int m, double lo, double hi, double flo)
 {
+    double c[7];
+    for (int i = 0; i <= m; i++)
+        c[i] = p[i];
     double x = 0.5 * (lo + hi);
     double dxold = hi - lo, dx = dxold;
     const bool lo_neg = flo < 0.0;
     for (int it = 0; it < 128; it++)
     {
         double f = c[0], df = 0.0;
-#pragma unroll
-        for (int i = 1; i <= M; i++)
+        for (int i = 1; i <= m; i++)
         {
             df = fma(df, x, f);
             f = fma(f, x, c[i]);
@@ -111,185 +121,148 @@ template <int M> __device__ __forceinline__ double solve_bracket(const double (&
     return x;
 }
 
-__device__ __forceinline__ int sgn(double v) { return (v > 0.0) - (v < 0.0); }
-
-// Derivative level M of the degree-D polynomial c: successive q' steps, each rounding like the checker
-template <int D, int M> __device__ __forceinline__ void deriv_level(const double (&c)[D + 1], double (&p)[M + 1])
+__device__ __forceinline__ int sign_variations(const double *b, int count)
 {
-    double t[D + 1];
-#pragma unroll
-    for (int i = 0; i <= D; i++)
-        t[i] = c[i];
-#pragma unroll
-    for (int m = D; m > M; m--)
+    int v = 0, last = 0;
+    for (int i = 0; i < count; i++)
     {
-#pragma unroll
-        for (int i = 0; i < m; i++)
-            t[i] = t[i] * (double)(m - i);
+        int s = (b[i] > 0.0) - (b[i] < 0.0);
+        if (s != 0)
+        {
+            if (last != 0 && s != last)
+                v++;
+            last = s;
+        }
     }
-#pragma unroll
-    for (int i = 0; i <= M; i++)
-        p[i] = t[i];
+    return v;
 }
 
-template <int D> struct Climb
+// reciprocal binomials 1/C(d,i), the same constants (and roundings) as the checker's table
+__device__ __forceinline__ double rbinom(int d, int i)
 {
-    // one climb step at level M (roots of q_{M-1} in cur -> roots of q_M), M in (m0, D]
-    template <int M> static __device__ __forceinline__ void step(const double (&c)[D + 1], int m0, double *cur, int &ncur)
+    const double R3[4] = {1.0, 1.0 / 3.0, 1.0 / 3.0, 1.0};
+    const double R4[5] = {1.0, 1.0 / 4.0, 1.0 / 6.0, 1.0 / 4.0, 1.0};
+    const double R5[6] = {1.0, 1.0 / 5.0, 1.0 / 10.0, 1.0 / 10.0, 1.0 / 5.0, 1.0};
+    const double R6[7] = {1.0, 1.0 / 6.0, 1.0 / 15.0, 1.0 / 20.0, 1.0 / 15.0, 1.0 / 6.0, 1.0};
+    return d == 3 ? R3[i] : d == 4 ? R4[i] : d == 5 ? R5[i] : R6[i];
+}
+
+// Bernstein coefficients on [0,1] of the degree-d polynomial c (descending): scaled power coefficients,
+// then the binomial transform by repeated adjacent sums
+__device__ __forceinline__ void bernstein(const double *c, int d, double *b)
+{
+    for (int i = 0; i <= d; i++)
+        b[i] = c[d - i] * rbinom(d, i);
+    for (int k = 1; k <= d; k++)
+        for (int i = d; i >= k; i--)
+            b[i] = b[i] + b[i - 1];
+}
+
+// True when the top level already decides "no root in [0,1]": end coefficients non-zero, no sign variation.
+__device__ __forceinline__ bool no_root_at_top(const double *b, int d)
+{
+    return b[0] != 0.0 && b[d] != 0.0 && sign_variations(b, d + 1) == 0;
+}
+
+// power coefficients of derivative level m of the degree-d polynomial c (successive q' steps, rounded like the checker)
+__device__ __forceinline__ void deriv_level(const double *c, int d, int m, double *p)
+{
+    for (int i = 0; i <= d; i++)
+        p[i] = c[i];
+    for (int k = d; k > m; k--)
+        for (int i = 0; i < k; i++)
+            p[i] = p[i] * (double)(k - i);
+}
+
+// b holds the Bernstein coefficients of c (degree d) on entry and is used as scratch
+static __device__ __noinline__ int roots01(const double *c, int d, double *b, double *roots)
+{
+    double p[7], cur[6];
+    int ncur = 0, m0;
+    // descend to the first level that can be decided
+    for (m0 = d; m0 >= 2; m0--)
     {
-        if (M <= m0)
-            return;
-        double p[M + 1];
-        deriv_level<D, M>(c, p);
-        const bool last = (M == D);
+        if (m0 < d)
+            for (int i = 0; i <= m0; i++)          // Bernstein coefficients of the derivative: forward differences
+                b[i] = b[i + 1] - b[i];
+        if (b[0] != 0.0 && b[m0] != 0.0)
+        {
+            int v = sign_variations(b, m0 + 1);
+            if (v == 0)
+                break;
+            if (v == 1)
+            {
+                deriv_level(c, d, m0, p);
+                double f0 = p[m0], f1 = horner_fma(p, m0, 1.0);
+                if ((f0 < 0.0 && f1 > 0.0) || (f0 > 0.0 && f1 < 0.0))
+                    cur[ncur++] = solve_bracket(p, m0, 0.0, 1.0, f0);
+                break;
+            }
+        }
+        if (m0 == 2)
+        {
+            // both critical points may lie inside: closed form, cancellation-free
+            deriv_level(c, d, 2, p);
+            double a = p[0], bb = p[1], cc = p[2];
+            double D = fma(bb, bb, -4.0 * a * cc);
+            if (D >= 0.0)
+            {
+                double q = -0.5 * (bb + (bb < 0.0 ? -sqrt(D) : sqrt(D)));
+                double r0 = q / a, r1 = (q != 0.0) ? cc / q : r0;
+                if (r0 > r1) { double t = r0; r0 = r1; r1 = t; }
+                if (r0 > 0.0 && r0 < 1.0) cur[ncur++] = r0;
+                if (r1 > 0.0 && r1 < 1.0 && r1 != r0) cur[ncur++] = r1;
+            }
+            break;
+        }
+    }
+    if (m0 < d)
+    {
+        // climb: cur = roots of q_{m-1} strictly inside (0,1); pieces between them are monotone for q_m
         double brk[8], fv[8], out[7];
-        int nb = 0, nr = 0;
-        brk[nb++] = 0.0;
-        for (int i = 0; i < ncur; i++)
-            brk[nb++] = cur[i];
-        brk[nb++] = 1.0;
-        for (int i = 0; i < nb; i++)
-            fv[i] = horner_fma<M>(p, brk[i]);
-        for (int i = 0; i + 1 < nb; i++)
+        for (int m = m0 + 1; m <= d; m++)
         {
-            if (fv[i] == 0.0)
+            const bool last = (m == d);
+            int nb = 0, nr = 0;
+            deriv_level(c, d, m, p);
+            brk[nb++] = 0.0;
+            for (int i = 0; i < ncur; i++)
+                brk[nb++] = cur[i];
+            brk[nb++] = 1.0;
+            for (int i = 0; i < nb; i++)
+                fv[i] = horner_fma(p, m, brk[i]);
+            for (int i = 0; i + 1 < nb; i++)
             {
-                if ((i > 0 || last) && (nr == 0 || out[nr - 1] != brk[i]))
-                    out[nr++] = brk[i];
+                if (fv[i] == 0.0)
+                {
+                    if ((i > 0 || last) && (nr == 0 || out[nr - 1] != brk[i]))
+                        out[nr++] = brk[i];
+                }
+                else if ((fv[i] < 0.0 && fv[i + 1] > 0.0) || (fv[i] > 0.0 && fv[i + 1] < 0.0))
+                {
+                    double r = solve_bracket(p, m, brk[i], brk[i + 1], fv[i]);
+                    if (nr == 0 || out[nr - 1] != r)
+                        out[nr++] = r;
+                }
             }
-            else if ((fv[i] < 0.0 && fv[i + 1] > 0.0) || (fv[i] > 0.0 && fv[i + 1] < 0.0))
-            {
-                double r = solve_bracket<M>(p, brk[i], brk[i + 1], fv[i]);
-                if (nr == 0 || out[nr - 1] != r)
-                    out[nr++] = r;
-            }
-        }
-        if (last && fv[nb - 1] == 0.0 && (nr == 0 || out[nr - 1] != 1.0))
-            out[nr++] = 1.0;
-        ncur = 0;
-        for (int i = 0; i < nr; i++)
-            if (last || (out[i] > 0.0 && out[i] < 1.0))
-                cur[ncur++] = out[i];
-    }
-};
-
-// Decide level M from its Bernstein coefficients b[0..M]; returns true when the descent stops here.
-template <int D, int M>
-__device__ __forceinline__ bool decide_level(const double (&c)[D + 1], const double *b, double *cur, int &ncur)
-{
-    if (b[0] != 0.0 && b[M] != 0.0)
-    {
-        int v = 0, last = 0;
-#pragma unroll
-        for (int i = 0; i <= M; i++)
-        {
-            int s = sgn(b[i]);
-            if (s != 0)
-            {
-                if (last != 0 && s != last)
-                    v++;
-                last = s;
-            }
-        }
-        if (v == 0)
-            return true;
-        if (v == 1)
-        {
-            double p[M + 1];
-            deriv_level<D, M>(c, p);
-            double f0 = p[M], f1 = horner_fma<M>(p, 1.0);
-            if ((f0 < 0.0 && f1 > 0.0) || (f0 > 0.0 && f1 < 0.0))
-                cur[ncur++] = solve_bracket<M>(p, 0.0, 1.0, f0);
-            return true;
+            if (last && fv[nb - 1] == 0.0 && (nr == 0 || out[nr - 1] != 1.0))
+                out[nr++] = 1.0;
+            ncur = 0;
+            for (int i = 0; i < nr; i++)
+                if (last || (out[i] > 0.0 && out[i] < 1.0))
+                    cur[ncur++] = out[i];
         }
     }
-    if (M == 2)
-    {
-        double p[M + 1];
-        deriv_level<D, M>(c, p);
-        double a = p[0], bb = p[1], cc = p[2];
-        double Dd = fma(bb, bb, -4.0 * a * cc);
-        if (Dd >= 0.0)
-        {
-            double q = -0.5 * (bb + (bb < 0.0 ? -sqrt(Dd) : sqrt(Dd)));
-            double r0 = q / a, r1 = (q != 0.0) ? cc / q : r0;
-            if (r0 > r1) { double t = r0; r0 = r1; r1 = t; }
-            if (r0 > 0.0 && r0 < 1.0) cur[ncur++] = r0;
-            if (r1 > 0.0 && r1 < 1.0 && r1 != r0) cur[ncur++] = r1;
-        }
-        return true;
-    }
-    return false;
-}
-
-template <int D> __device__ __noinline__ int roots01(const double *cin, double *roots)
-{
-    static_assert(D >= 3 && D <= 6, "degree 3..6");
-    double c[D + 1];
-#pragma unroll
-    for (int i = 0; i <= D; i++)
-        c[i] = cin[i];
-
-    // Bernstein coefficients of q_D on [0,1]: scaled power coefficients, then the binomial transform
-    double b[D + 1];
-    {
-        constexpr double RB[7][7] = {
-            {1.0, 0, 0, 0, 0, 0, 0},
-            {1.0, 1.0, 0, 0, 0, 0, 0},
-            {1.0, 1.0 / 2.0, 1.0, 0, 0, 0, 0},
-            {1.0, 1.0 / 3.0, 1.0 / 3.0, 1.0, 0, 0, 0},
-            {1.0, 1.0 / 4.0, 1.0 / 6.0, 1.0 / 4.0, 1.0, 0, 0},
-            {1.0, 1.0 / 5.0, 1.0 / 10.0, 1.0 / 10.0, 1.0 / 5.0, 1.0, 0},
-            {1.0, 1.0 / 6.0, 1.0 / 15.0, 1.0 / 20.0, 1.0 / 15.0, 1.0 / 6.0, 1.0}};
-#pragma unroll
-        for (int i = 0; i <= D; i++)
-            b[i] = c[D - i] * RB[D][i];
-#pragma unroll
-        for (int k = 1; k <= D; k++)
-#pragma unroll
-            for (int i = D; i >= k; i--)
-                b[i] = b[i] + b[i - 1];
-    }
-
-    double cur[6];
-    int ncur = 0, m0 = D;
-    bool done = decide_level<D, D>(c, b, cur, ncur);
-    if (done)
-    {
-        for (int i = 0; i < ncur; i++)
-            roots[i] = cur[i];
-        return ncur;
-    }
-    // descend: Bernstein coefficients of the derivative are forward differences
-#define CCD_DESCEND(M)                                              \
-    if (!done && D > M)                                             \
-    {                                                               \
-        _Pragma("unroll") for (int i = 0; i <= M; i++) b[i] = b[i + 1] - b[i]; \
-        m0 = M;                                                     \
-        done = decide_level<D, (M < D ? M : D)>(c, b, cur, ncur);   \
-    }
-    CCD_DESCEND(5)
-    CCD_DESCEND(4)
-    CCD_DESCEND(3)
-    CCD_DESCEND(2)
-#undef CCD_DESCEND
-
-    if (D >= 3) Climb<D>::template step<3>(c, m0, cur, ncur);
-    if (D >= 4) Climb<D>::template step<(D >= 4 ? 4 : D)>(c, m0, cur, ncur);
-    if (D >= 5) Climb<D>::template step<(D >= 5 ? 5 : D)>(c, m0, cur, ncur);
-    if (D >= 6) Climb<D>::template step<(D >= 6 ? 6 : D)>(c, m0, cur, ncur);
     for (int i = 0; i < ncur; i++)
         roots[i] = cur[i];
     return ncur;
 }
 
 // ------------------------------------------------------------------------------------------
-// CTCD::findIntervals (src/CTCD.cpp:98-177) on a fixed-size coefficient array op[0..N].
-// Leading zeros are kept in place: Horner and the couldHaveRoots sum give bit-identical values
-// with or without them (0*t+x == x), so only the root finder sees the reduced polynomial.
+// CTCD::findIntervals (src/CTCD.cpp:98-177)
 // ------------------------------------------------------------------------------------------
 // CTCD::checkInterval, src/CTCD.cpp:59-79 — unfused Horner at the clamped midpoint
-template <int N> __device__ __forceinline__ void check_interval(double t1, double t2, const double (&op)[N + 1], Ivals &iv, bool pos)
+__device__ __forceinline__ void check_interval(double t1, double t2, const double *op, int degree, Ivals &iv, bool pos)
 {
     t1 = smax(0.0, t1);
     t2 = smax(0.0, t2);
@@ -297,8 +270,7 @@ template <int N> __device__ __forceinline__ void check_interval(double t1, doubl
     t2 = smin(1.0, t2);
     double tmid = (t2 + t1) / 2;
     double f = op[0];
-#pragma unroll
-    for (int i = 1; i <= N; i++)
+    for (int i = 1; i <= degree; i++)
     {
         f *= tmid;
         f += op[i];
@@ -324,85 +296,86 @@ __device__ __forceinline__ int quad_roots(double a, double b, double c, double &
     return roots;
 }
 
-template <int N> __device__ __forceinline__ void find_intervals(double (&op)[N + 1], Ivals &iv, bool pos)
+// op[0..n] is modified (normalised, leading zeros shifted out) exactly like the reference does.
+// Returns R_DEFER (nothing pushed) when `defer` is set and the polynomial needs the iterative root isolator;
+// otherwise 0 with the intervals appended to iv.
+static __device__ __noinline__ int find_intervals(double *op, int n, Ivals &iv, bool pos, bool defer)
 {
     // normalise, src/CTCD.cpp:113-119
     double maxval = 0;
-#pragma unroll
-    for (int i = 0; i <= N; i++)
+    for (int i = 0; i <= n; i++)
         maxval = smax(maxval, fabs(op[i]));
     if (maxval != 0)
-    {
-#pragma unroll
-        for (int i = 0; i <= N; i++)
+        for (int i = 0; i <= n; i++)
             op[i] = op[i] / maxval;
-    }
-    // exactly-zero leading coefficients, src/CTCD.cpp:121-127
-    int rd = N;
+    // exactly-zero leading coefficients, src/CTCD.cpp:121-133
+    int rd = n;
+    for (int i = 0; i < n; i++)
     {
-        bool lead = true;
-#pragma unroll
-        for (int i = 0; i < N; i++)
-        {
-            lead = lead && (op[i] == 0);
-            if (lead)
-                rd--;
-        }
+        if (op[i] == 0)
+            rd--;
+        else
+            break;
     }
+    if (rd < n)
+        for (int i = 0; i <= rd; i++)
+            op[i] = op[i + n - rd];
+
     double time[6];
     int roots = 0;
     if (rd > 2)
     {
-        // CTCD::couldHaveRoots, src/CTCD.cpp:81-94 (zeros contribute nothing)
+        // CTCD::couldHaveRoots, src/CTCD.cpp:81-94
         double result = 0;
-#pragma unroll
-        for (int i = 0; i < N; i++)
+        for (int i = 0; i < rd; i++)
             if (pos ? (op[i] > 0) : (op[i] < 0))
                 result += op[i];
-        result += op[N];
+        result += op[rd];
         if (pos ? (result < 0) : (result > 0))
-            return;
-        if constexpr (N >= 3)
+            return 0;
+        double b[7];
+        bernstein(op, rd, b);
+        if (!no_root_at_top(b, rd))
         {
-            if (N >= 6 && rd == 6) roots = roots01<(N >= 6 ? 6 : 3)>(&op[N >= 6 ? N - 6 : 0], time);
-            else if (N >= 5 && rd == 5) roots = roots01<(N >= 5 ? 5 : 3)>(&op[N >= 5 ? N - 5 : 0], time);
-            else if (N >= 4 && rd == 4) roots = roots01<(N >= 4 ? 4 : 3)>(&op[N >= 4 ? N - 4 : 0], time);
-            else roots = roots01<3>(&op[N - 3], time);
+            if (defer)
+                return R_DEFER;
+            roots = roots01(op, rd, b, time);
         }
     }
     else if (rd == 2)
-        roots = quad_roots(op[N - 2], op[N - 1], op[N], time[0], time[1]);
+        roots = quad_roots(op[0], op[1], op[2], time[0], time[1]);
     else if (rd == 1)
     {
-        time[0] = -op[N] / op[N - 1];
+        time[0] = -op[1] / op[0];
         roots = 1;
     }
     else
     {
-        if (pos ? (op[N] >= 0) : (op[N] <= 0))
+        if (pos ? (op[0] >= 0) : (op[0] <= 0))
             push_interval(iv, 0, 1.0);
-        return;
+        return 0;
     }
     // src/CTCD.cpp:161-176
     if (roots > 0)
     {
         if (time[0] >= 0)
-            check_interval<N>(0, time[0], op, iv, pos);
+            check_interval(0, time[0], op, rd, iv, pos);
         for (int i = 0; i < roots - 1; i++)
             if (!((time[i] < 0 && time[i + 1] < 0) || (time[i] > 1.0 && time[i + 1] > 1.0)))
-                check_interval<N>(time[i], time[i + 1], op, iv, pos);
+                check_interval(time[i], time[i + 1], op, rd, iv, pos);
         if (time[roots - 1] <= 1.0)
-            check_interval<N>(time[roots - 1], 1.0, op, iv, pos);
+            check_interval(time[roots - 1], 1.0, op, rd, iv, pos);
     }
     else
-        check_interval<N>(0.0, 1.0, op, iv, pos);
+        check_interval(0.0, 1.0, op, rd, iv, pos);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------
 // coefficient builders (src/CTCD.cpp:179-257)
 // ------------------------------------------------------------------------------------------
 // planePoly3D, src/CTCD.cpp:222-227
-__device__ __forceinline__ void plane_coeffs(V3 x10, V3 x20, V3 x30, V3 v10, V3 v20, V3 v30, double (&op)[4])
+__device__ __forceinline__ void plane_coeffs(V3 x10, V3 x20, V3 x30, V3 v10, V3 v20, V3 v30, double *op)
 {
     op[0] = dot(v10, cross(v20, v30));
     op[1] = dot(x10, cross(v20, v30)) + dot(v10, cross(x20, v30)) + dot(v10, cross(v20, x30));
@@ -411,7 +384,7 @@ __device__ __forceinline__ void plane_coeffs(V3 x10, V3 x20, V3 x30, V3 v10, V3 
 }
 
 // distancePoly3D, src/CTCD.cpp:240-255
-__device__ __forceinline__ void distance_coeffs(V3 x10, V3 x20, V3 x30, V3 v10, V3 v20, V3 v30, double m, double (&op)[7])
+static __device__ __noinline__ void distance_coeffs(V3 x10, V3 x20, V3 x30, V3 v10, V3 v20, V3 v30, double m, double *op)
 {
     double abcd[4];
     plane_coeffs(x10, x20, x30, v10, v20, v30, abcd);
@@ -429,7 +402,7 @@ __device__ __forceinline__ void distance_coeffs(V3 x10, V3 x20, V3 x30, V3 v10, 
 }
 
 // barycentricPoly3D, src/CTCD.cpp:187-210
-__device__ __forceinline__ void barycentric_coeffs(V3 x10, V3 x20, V3 x30, V3 v10, V3 v20, V3 v30, double (&op)[5])
+__device__ __forceinline__ void barycentric_coeffs(V3 x10, V3 x20, V3 x30, V3 v10, V3 v20, V3 v30, double *op)
 {
     double A = dot(x10, x10);
     double B = 2 * dot(x10, v10);
@@ -451,33 +424,34 @@ __device__ __forceinline__ void barycentric_coeffs(V3 x10, V3 x20, V3 x30, V3 v1
 }
 
 // ------------------------------------------------------------------------------------------
-// the four primitives (src/CTCD.cpp:259-692); positions: *s = start, *e = end of the linear move
+// the four primitives (src/CTCD.cpp:259-692).  s[] = start positions, v[] = end - start.
+// Return R_MISS / R_HIT (t written) / R_DEFER (only with defer=true: needs the iterative isolator).
 // ------------------------------------------------------------------------------------------
-// CTCD::vertexFaceCTCD, src/CTCD.cpp:413-508
-static __device__ __noinline__ bool vertex_face(V3 q0s, V3 q1s, V3 q2s, V3 q3s, V3 q0e, V3 q1e, V3 q2e, V3 q3e, double eta, double &t)
+// CTCD::vertexFaceCTCD, src/CTCD.cpp:413-508 — vertex s[0] against face (s[1],s[2],s[3])
+static __device__ __noinline__ int vertex_face(const V3 *s, const V3 *v, double eta, double &t, bool defer)
 {
-    const double minD = eta * eta;
-    const V3 v0 = q0e - q0s, v1 = q1e - q1s, v2 = q2e - q2s, v3 = q3e - q3s;
-    Ivals cop, e1, e2, e3;
-    cop.n = e1.n = e2.n = e3.n = 0;
+    Ivals iv[4];       // e1, e2, e3, coplane
+    double op[7];
+    // the three inside tests are one formula under a rotation of the face: base = 1+k, A = 1+(k+2)%3, B = 1+(k+1)%3
+    //   x10 = q0-base, x20 = (A-base) x (B-base), x30 = A-base            (src/CTCD.cpp:433-464)
+    for (int k = 0; k < 3; k++)
     {
-        double op[4];
-        plane_coeffs(q0s - q1s, cross(q3s - q1s, q2s - q1s), q3s - q1s, v0 - v1, cross(v3 - v1, v2 - v1), v3 - v1, op);
-        find_intervals<3>(op, e1, true);
-        if (e1.n == 0) return false;
-        plane_coeffs(q0s - q2s, cross(q1s - q2s, q3s - q2s), q1s - q2s, v0 - v2, cross(v1 - v2, v3 - v2), v1 - v2, op);
-        find_intervals<3>(op, e2, true);
-        if (e2.n == 0) return false;
-        plane_coeffs(q0s - q3s, cross(q2s - q3s, q1s - q3s), q2s - q3s, v0 - v3, cross(v2 - v3, v1 - v3), v2 - v3, op);
-        find_intervals<3>(op, e3, true);
-        if (e3.n == 0) return false;
+        const int ib = 1 + k, ia = 1 + (k + 2) % 3, ic = 1 + (k + 1) % 3;
+        const V3 xa = s[ia] - s[ib], xc = s[ic] - s[ib], va = v[ia] - v[ib], vc = v[ic] - v[ib];
+        plane_coeffs(s[0] - s[ib], cross(xa, xc), xa, v[0] - v[ib], cross(va, vc), va, op);
+        iv[k].n = 0;
+        if (find_intervals(op, 3, iv[k], true, defer) == R_DEFER)
+            return R_DEFER;
+        if (iv[k].n == 0)
+            return R_MISS;
     }
-    {
-        double op[7];
-        distance_coeffs(q0s - q1s, q2s - q1s, q3s - q1s, v0 - v1, v2 - v1, v3 - v1, minD, op);
-        find_intervals<6>(op, cop, false);
-        if (cop.n == 0) return false;
-    }
+    distance_coeffs(s[0] - s[1], s[2] - s[1], s[3] - s[1], v[0] - v[1], v[2] - v[1], v[3] - v[1], eta * eta, op);
+    iv[3].n = 0;
+    if (find_intervals(op, 6, iv[3], false, defer) == R_DEFER)
+        return R_DEFER;
+    if (iv[3].n == 0)
+        return R_MISS;
+    const Ivals &cop = iv[3], &e1 = iv[0], &e2 = iv[1], &e3 = iv[2];
     bool col = false;
     double mint = 1.0;
     for (int i = 0; i < cop.n; i++)
@@ -502,49 +476,48 @@ static __device__ __noinline__ bool vertex_face(V3 q0s, V3 q1s, V3 q2s, V3 q3s, 
             }
         }
     if (col) t = mint;
-    return col;
+    return col ? R_HIT : R_MISS;
 }
 
-// CTCD::edgeEdgeCTCD, src/CTCD.cpp:259-411 — edges (q0,p0) and (q1,p1)
-static __device__ __noinline__ bool edge_edge(V3 q0s, V3 p0s, V3 q1s, V3 p1s, V3 q0e, V3 p0e, V3 q1e, V3 p1e, double eta, double &t)
+// CTCD::edgeEdgeCTCD, src/CTCD.cpp:259-411 — points (q0,p0,q1,p1) = s[0..3]: edges (q0,p0) and (q1,p1)
+static __device__ __noinline__ int edge_edge(const V3 *s, const V3 *v, double eta, double &t, bool defer)
 {
-    const double minD = eta * eta;
-    const V3 vq0 = q0e - q0s, vp0 = p0e - p0s, vq1 = q1e - q1s, vp1 = p1e - p1s;
-    Ivals cop, par, a0, a1, b0, b1;
-    cop.n = par.n = a0.n = a1.n = b0.n = b1.n = 0;
+    Ivals cop, par, q[4];
+    double op[7];
+    cop.n = par.n = 0;
     {
         Ivals raw;
         raw.n = 0;
-        double op[7];
-        distance_coeffs(p0s - p1s, p0s - q0s, p1s - q1s, vp0 - vp1, vp0 - vq0, vp1 - vq1, minD, op);
-        find_intervals<6>(op, raw, false);
+        distance_coeffs(s[1] - s[3], s[1] - s[0], s[3] - s[2], v[1] - v[3], v[1] - v[0], v[3] - v[2], eta * eta, op);
+        if (find_intervals(op, 6, raw, false, defer) == R_DEFER)
+            return R_DEFER;
         // parallel-edge classification at each interval midpoint, src/CTCD.cpp:290-308
         for (int i = 0; i < raw.n; i++)
         {
             double midt = (raw.u[i] + raw.l[i]) / 2;
-            V3 x10 = (q0s - p0s) + midt * (vq0 - vp0);
-            V3 x20 = (q1s - p1s) + midt * (vq1 - vp1);
+            V3 x10 = (s[0] - s[1]) + midt * (v[0] - v[1]);
+            V3 x20 = (s[2] - s[3]) + midt * (v[2] - v[3]);
             V3 c = cross(x10, x20);
             if (sqrt(dot(c, c)) < 1e-8) { par.l[par.n] = raw.l[i]; par.u[par.n] = raw.u[i]; par.n++; }
             else { cop.l[cop.n] = raw.l[i]; cop.u[cop.n] = raw.u[i]; cop.n++; }
         }
-        if (cop.n == 0) return false;
+        if (cop.n == 0) return R_MISS;
     }
+    // the four barycentric quartics a0,a1,b0,b1 (src/CTCD.cpp:313-348): x10 = P[a]-P[b], x20 = P[c]-P[d], x30 = P[e]-P[f]
+    for (int k = 0; k < 4; k++)
     {
-        double op[5];
-        barycentric_coeffs(p1s - q1s, p0s - q0s, q0s - q1s, vp1 - vq1, vp0 - vq0, vq0 - vq1, op);
-        find_intervals<4>(op, a0, true);
-        if (a0.n == 0) return false;
-        barycentric_coeffs(p1s - q1s, q0s - p0s, p0s - q1s, vp1 - vq1, vq0 - vp0, vp0 - vq1, op);
-        find_intervals<4>(op, a1, true);
-        if (a1.n == 0) return false;
-        barycentric_coeffs(p0s - q0s, p1s - q1s, q1s - q0s, vp0 - vq0, vp1 - vq1, vq1 - vq0, op);
-        find_intervals<4>(op, b0, true);
-        if (b0.n == 0) return false;
-        barycentric_coeffs(p0s - q0s, q1s - p1s, p1s - q0s, vp0 - vq0, vq1 - vp1, vp1 - vq0, op);
-        find_intervals<4>(op, b1, true);
-        if (b1.n == 0) return false;
+        // packed point indices, 2 bits each: a b c d e f
+        const unsigned tab = (k == 0) ? 0x0E42u /*3,2 | 1,0 | 0,2*/ : (k == 1) ? 0x0E16u /*3,2 | 0,1 | 1,2*/
+                           : (k == 2) ? 0x04E8u /*1,0 | 3,2 | 2,0*/ : 0x04BCu /*1,0 | 2,3 | 3,0*/;
+        const int a = (tab >> 10) & 3, b = (tab >> 8) & 3, c = (tab >> 6) & 3, d = (tab >> 4) & 3, e = (tab >> 2) & 3, f = tab & 3;
+        barycentric_coeffs(s[a] - s[b], s[c] - s[d], s[e] - s[f], v[a] - v[b], v[c] - v[d], v[e] - v[f], op);
+        q[k].n = 0;
+        if (find_intervals(op, 4, q[k], true, defer) == R_DEFER)
+            return R_DEFER;
+        if (q[k].n == 0)
+            return R_MISS;
     }
+    const Ivals &a0 = q[0], &a1 = q[1], &b0 = q[2], &b1 = q[3];
     bool col = false;
     double mint = 1.0;
     for (int i = 0; i < cop.n; i++)
@@ -570,39 +543,36 @@ static __device__ __noinline__ bool edge_edge(V3 q0s, V3 p0s, V3 q1s, V3 p1s, V3
                         il = smax(b0.l[l], il); iu = smin(b0.u[l], iu);
                         il = smax(b1.l[m], il); iu = smin(b1.u[m], iu);
                         bool skip = false;
-                        for (int q = 0; q < par.n; q++)
-                            if (overlap2(il, iu, par.l[q], par.u[q])) { skip = true; break; }
+                        for (int p = 0; p < par.n; p++)
+                            if (overlap2(il, iu, par.l[p], par.u[p])) { skip = true; break; }
                         if (!skip) { mint = smin(mint, il); col = true; }
                     }
                 }
             }
         }
     if (col) t = mint;
-    return col;
+    return col ? R_HIT : R_MISS;
 }
 
-// CTCD::vertexEdgeCTCD, src/CTCD.cpp:511-602 — vertex q0 against segment (q1,q2)
-static __device__ __noinline__ bool vertex_edge(V3 q0s, V3 q1s, V3 q2s, V3 q0e, V3 q1e, V3 q2e, double eta, double &t)
+// CTCD::vertexEdgeCTCD, src/CTCD.cpp:511-602 — vertex q0 against segment (q1,q2); v* = end - start
+static __device__ __noinline__ int vertex_edge(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, double &t, bool defer)
 {
     const double minD = eta * eta;
-    const V3 v0 = q0e - q0s, v1 = q1e - q1s, v2 = q2e - q2s;
     const V3 ab = q2s - q1s, ac = q0s - q1s, cb = q2s - q0s;
     const V3 vab = v2 - v1, vac = v0 - v1, vcb = v2 - v0;
     Ivals colin, e1, e2;
+    double op[5];
     colin.n = e1.n = e2.n = 0;
-    {
-        double op[3];
-        op[2] = dot(ab, ac);
-        op[1] = dot(ac, vab) + dot(ab, vac);
-        op[0] = dot(vab, vac);
-        find_intervals<2>(op, e1, true);
-        if (e1.n == 0) return false;
-        op[2] = dot(ab, cb);
-        op[1] = dot(cb, vab) + dot(ab, vcb);
-        op[0] = dot(vab, vcb);
-        find_intervals<2>(op, e2, true);
-        if (e2.n == 0) return false;
-    }
+    op[2] = dot(ab, ac);
+    op[1] = dot(ac, vab) + dot(ab, vac);
+    op[0] = dot(vab, vac);
+    find_intervals(op, 2, e1, true, defer);
+    if (e1.n == 0) return R_MISS;
+    op[2] = dot(ab, cb);
+    op[1] = dot(cb, vab) + dot(ab, vcb);
+    op[0] = dot(vab, vcb);
+    find_intervals(op, 2, e2, true, defer);
+    if (e2.n == 0) return R_MISS;
     {
         double A = dot(ab, ab);
         double B = 2 * dot(ab, vab);
@@ -613,15 +583,15 @@ static __device__ __noinline__ bool vertex_edge(V3 q0s, V3 q1s, V3 q2s, V3 q0e, 
         double G = dot(ac, ab);
         double H = dot(vab, ac) + dot(vac, ab);
         double I = dot(vab, vac);
-        double op[5];
         op[4] = A * D - G * G - minD * A;
         op[3] = B * D + A * E - 2 * G * H - minD * B;
         op[2] = B * E + A * F + C * D - H * H - 2 * G * I - minD * C;
         op[1] = B * F + C * E - 2 * H * I;
         op[0] = C * F - I * I;
-        find_intervals<4>(op, colin, false);
-        if (colin.n == 0) return false;
     }
+    if (find_intervals(op, 4, colin, false, defer) == R_DEFER)
+        return R_DEFER;
+    if (colin.n == 0) return R_MISS;
     bool col = false;
     double mint = 1.0;
     for (int i = 0; i < colin.n; i++)
@@ -635,25 +605,24 @@ static __device__ __noinline__ bool vertex_edge(V3 q0s, V3 q1s, V3 q2s, V3 q0e, 
                     col = true;
                 }
     if (col) t = mint;
-    return col;
+    return col ? R_HIT : R_MISS;
 }
 
 // checkInterval with a throw-away list, as CTCD::vertexVertexCTCD uses it (src/CTCD.cpp:645-690)
-__device__ __forceinline__ bool check_once(double t1, double t2, const double (&op)[3])
+__device__ __forceinline__ bool check_once(double t1, double t2, const double *op)
 {
     Ivals iv;
     iv.n = 0;
-    check_interval<2>(t1, t2, op, iv, false);
+    check_interval(t1, t2, op, 2, iv, false);
     return iv.n != 0;
 }
 
-// CTCD::vertexVertexCTCD, src/CTCD.cpp:604-692
-static __device__ __noinline__ bool vertex_vertex(V3 q1s, V3 q2s, V3 q1e, V3 q2e, double eta, double &t)
+// CTCD::vertexVertexCTCD, src/CTCD.cpp:604-692 — closed form, never deferred
+static __device__ __noinline__ int vertex_vertex(V3 q1s, V3 q2s, V3 v1, V3 v2, double eta, double &t)
 {
     int roots = 0;
     const double min_d = eta * eta;
     double t1 = 0, t2 = 0;
-    const V3 v1 = q1e - q1s, v2 = q2e - q2s;
     double a = dot(v1, v1) + dot(v2, v2) - 2 * dot(v1, v2);
     double b = 2 * (dot(v1, q1s) - dot(v2, q1s) - dot(v1, q2s) + dot(v2, q2s));
     double c = dot(q1s, q1s) + dot(q2s, q2s) - 2 * dot(q1s, q2s) - min_d;
@@ -666,25 +635,25 @@ static __device__ __noinline__ bool vertex_vertex(V3 q1s, V3 q2s, V3 q1e, V3 q2e
     }
     else
     {
-        if (c <= 0) { t = 0; return true; }
-        return false;
+        if (c <= 0) { t = 0; return R_HIT; }
+        return R_MISS;
     }
     double op[3] = {a, b, c};
     if (roots == 2)
     {
-        if (check_once(0, t1, op)) { t = 0; return true; }
-        if (check_once(t1, t2, op)) { t = t1; return true; }
-        if (check_once(t2, 1.0, op)) { t = t2; return true; }
-        return false;
+        if (check_once(0, t1, op)) { t = 0; return R_HIT; }
+        if (check_once(t1, t2, op)) { t = t1; return R_HIT; }
+        if (check_once(t2, 1.0, op)) { t = t2; return R_HIT; }
+        return R_MISS;
     }
     else if (roots == 1)
     {
-        if (check_once(0, t1, op)) { t = 0; return true; }
-        if (check_once(t1, 1.0, op)) { t = t1; return true; }
-        return false;
+        if (check_once(0, t1, op)) { t = 0; return R_HIT; }
+        if (check_once(t1, 1.0, op)) { t = t1; return R_HIT; }
+        return R_MISS;
     }
-    if (check_once(0, 1.0, op)) { t = 0; return true; }
-    return false;
+    if (check_once(0, 1.0, op)) { t = 0; return R_HIT; }
+    return R_MISS;
 }
 
 } // namespace ccd

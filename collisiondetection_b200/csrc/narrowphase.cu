@@ -4,45 +4,112 @@
 // One thread per candidate stencil runs the reference's per-stencil sequence
 // (src/CTCDNarrowPhase.cpp:24-135): the VF (or EE) primitive, then the degenerate vertex-edge and
 // vertex-vertex tests, first hit wins; over a multi-entry History the sequence repeats per
-// stitched linear segment (src/History.cpp:98-140).  Hit flag, time of impact and the index of
-// the sub-test that fired are written per stencil; earliest TOI and hit counts are reduced
-// warp -> block -> one atomic per block.
+// stitched linear segment (src/History.cpp:98-140).
+//
+// Two passes keep the warps converged (profiles/: the one-pass version ran with 5.7 of 32 lanes active):
+//   pass 1  every stencil, straight-line work only: coefficient construction, the reference's own quick
+//           rejects, closed-form quadratics and the Bernstein "no root in [0,1]" decision.  A stencil whose
+//           answer needs the iterative root isolator is appended to a work list (warp-aggregated atomics);
+//   pass 2  the work list only, full algorithm.
+// Degenerate sub-tests (and the EE primitive) are skipped when the swept boxes of the two parts stay further
+// apart than eta plus a safety margin: those tests measure true distances (include/CTCD.h:31-79), so the
+// reference cannot report a hit there; the margin (4e-5 of the coordinate scale) is ~1e3 times the distance
+// at which its double-precision polynomials could change sign.  The VF primitive is never culled this way —
+// its inside tests are not geometric distances (src/CTCD.cpp:433-464).
+// Hit flag, time of impact and the index of the sub-test that fired are written per stencil; earliest TOI and
+// hit counts are reduced per warp and merged with one atomic pair per warp.
 #include "ccd_kernels.h"
 #include "ccd_math.cuh"
 
 namespace ccd {
 
-// ---- per-segment stencil tests --------------------------------------------------------------
-// a[0..3] start positions, b[0..3] end positions of (p, q0, q1, q2)
-__device__ __forceinline__ int vf_stencil_segment(const V3 *a, const V3 *b, double eta, double &t)
+struct Box { V3 lo, hi; };
+
+__device__ __forceinline__ Box swept_box(V3 s, V3 e)
 {
-    if (vertex_face(a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3], eta, t)) return 1;
+    Box b;
+    b.lo = mk(fmin(s.x, e.x), fmin(s.y, e.y), fmin(s.z, e.z));
+    b.hi = mk(fmax(s.x, e.x), fmax(s.y, e.y), fmax(s.z, e.z));
+    return b;
+}
+__device__ __forceinline__ Box join(const Box &a, const Box &b)
+{
+    Box r;
+    r.lo = mk(fmin(a.lo.x, b.lo.x), fmin(a.lo.y, b.lo.y), fmin(a.lo.z, b.lo.z));
+    r.hi = mk(fmax(a.hi.x, b.hi.x), fmax(a.hi.y, b.hi.y), fmax(a.hi.z, b.hi.z));
+    return r;
+}
+// true when the boxes stay more than m apart along some axis
+__device__ __forceinline__ bool apart(const Box &a, const Box &b, double m)
+{
+    return a.hi.x + m < b.lo.x || b.hi.x + m < a.lo.x || a.hi.y + m < b.lo.y || b.hi.y + m < a.lo.y || a.hi.z + m < b.lo.z ||
+           b.hi.z + m < a.lo.z;
+}
+__device__ __forceinline__ double box_scale(const Box &b)
+{
+    return fmax(fmax(fmax(fabs(b.lo.x), fabs(b.hi.x)), fmax(fabs(b.lo.y), fabs(b.hi.y))), fmax(fabs(b.lo.z), fabs(b.hi.z)));
+}
+
+// ---- per-segment stencil tests --------------------------------------------------------------
+// a[0..3] start positions, b[0..3] end positions of (p, q0, q1, q2).  Returns the stage that hit (>0), 0 for a
+// miss, -1 when deferred (only with defer=true).
+static __device__ __noinline__ int vf_stencil_segment(const V3 *a, const V3 *b, double eta, double &t, bool defer)
+{
+    V3 v[4];
+    Box bx[4];
+    for (int i = 0; i < 4; i++) { v[i] = b[i] - a[i]; bx[i] = swept_box(a[i], b[i]); }
+    int r = vertex_face(a, v, eta, t, defer);
+    if (r == R_HIT) return 1;
+    if (r == R_DEFER) return -1;
+    const Box face = join(join(bx[1], bx[2]), bx[3]);
+    const double m = eta + 4e-5 * fmax(box_scale(bx[0]), box_scale(face));
+    if (apart(bx[0], face, m)) return 0;
     // vertex against the three face edges (1,2),(2,3),(3,1): src/CTCDNarrowPhase.cpp:51-59
     for (int e = 0; e < 3; e++)
     {
-        int i1 = 1 + e, i2 = 1 + ((e + 1) % 3);
-        if (vertex_edge(a[0], a[i1], a[i2], b[0], b[i1], b[i2], eta, t)) return 2 + e;
+        const int i1 = 1 + e, i2 = 1 + ((e + 1) % 3);
+        if (apart(bx[0], join(bx[i1], bx[i2]), m)) continue;
+        r = vertex_edge(a[0], a[i1], a[i2], v[0], v[i1], v[i2], eta, t, defer);
+        if (r == R_HIT) return 2 + e;
+        if (r == R_DEFER) return -1;
     }
     // vertex against the three face vertices: src/CTCDNarrowPhase.cpp:61-69
-    for (int v = 0; v < 3; v++)
-        if (vertex_vertex(a[0], a[1 + v], b[0], b[1 + v], eta, t)) return 5 + v;
+    for (int k = 0; k < 3; k++)
+    {
+        if (apart(bx[0], bx[1 + k], m)) continue;
+        if (vertex_vertex(a[0], a[1 + k], v[0], v[1 + k], eta, t) == R_HIT) return 5 + k;
+    }
     return 0;
 }
 
 // a/b: (p0, p1, q0, q1); edgeEdgeCTCD takes (q0,p0,q1,p1) = (pos0,pos1,pos2,pos3): src/CTCDNarrowPhase.cpp:91
-__device__ __forceinline__ int ee_stencil_segment(const V3 *a, const V3 *b, double eta, double &t)
+static __device__ __noinline__ int ee_stencil_segment(const V3 *a, const V3 *b, double eta, double &t, bool defer)
 {
-    if (edge_edge(a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3], eta, t)) return 1;
-    // src/CTCDNarrowPhase.cpp:99-114
-    if (vertex_edge(a[0], a[2], a[3], b[0], b[2], b[3], eta, t)) return 2;
-    if (vertex_edge(a[1], a[2], a[3], b[1], b[2], b[3], eta, t)) return 3;
-    if (vertex_edge(a[2], a[0], a[1], b[2], b[0], b[1], eta, t)) return 4;
-    if (vertex_edge(a[3], a[0], a[1], b[3], b[0], b[1], eta, t)) return 5;
-    // src/CTCDNarrowPhase.cpp:117-132
-    if (vertex_vertex(a[0], a[2], b[0], b[2], eta, t)) return 6;
-    if (vertex_vertex(a[0], a[3], b[0], b[3], eta, t)) return 7;
-    if (vertex_vertex(a[1], a[2], b[1], b[2], eta, t)) return 8;
-    if (vertex_vertex(a[1], a[3], b[1], b[3], eta, t)) return 9;
+    V3 v[4];
+    Box bx[4];
+    for (int i = 0; i < 4; i++) { v[i] = b[i] - a[i]; bx[i] = swept_box(a[i], b[i]); }
+    const Box e0 = join(bx[0], bx[1]), e1 = join(bx[2], bx[3]);
+    const double m = eta + 4e-5 * fmax(box_scale(e0), box_scale(e1));
+    if (apart(e0, e1, m)) return 0;       // every sub-test below is a distance between parts of these two edges
+    int r = edge_edge(a, v, eta, t, defer);
+    if (r == R_HIT) return 1;
+    if (r == R_DEFER) return -1;
+    // src/CTCDNarrowPhase.cpp:99-114: p0|p1 against (q0,q1), q0|q1 against (p0,p1)
+    for (int k = 0; k < 4; k++)
+    {
+        const int iv = k, i1 = (k < 2) ? 2 : 0, i2 = i1 + 1;
+        if (apart(bx[iv], (k < 2) ? e1 : e0, m)) continue;
+        r = vertex_edge(a[iv], a[i1], a[i2], v[iv], v[i1], v[i2], eta, t, defer);
+        if (r == R_HIT) return 2 + k;
+        if (r == R_DEFER) return -1;
+    }
+    // src/CTCDNarrowPhase.cpp:117-132: (p0,q0) (p0,q1) (p1,q0) (p1,q1)
+    for (int k = 0; k < 4; k++)
+    {
+        const int i1 = k >> 1, i2 = 2 + (k & 1);
+        if (apart(bx[i1], bx[i2], m)) continue;
+        if (vertex_vertex(a[i1], a[i2], v[i1], v[i2], eta, t) == R_HIT) return 6 + k;
+    }
     return 0;
 }
 
@@ -90,124 +157,158 @@ struct Stitcher
 };
 
 // ---- reductions -----------------------------------------------------------------------------
-// TOI >= 0, so the IEEE bit pattern orders like the value: min over unsigned 64-bit.
-__device__ __forceinline__ void reduce_block(bool hit, double toi, unsigned long long *earliest_bits, unsigned long long *nhit)
+// TOI >= 0, so the IEEE bit pattern orders like the value: min over unsigned 64-bit.  Warp-level only.
+__device__ __forceinline__ void reduce_warp(bool hit, double toi, unsigned long long *earliest_bits, unsigned long long *nhit)
 {
     unsigned long long bits = hit ? (unsigned long long)__double_as_longlong(toi) : 0xFFFFFFFFFFFFFFFFull;
     unsigned cnt = hit ? 1u : 0u;
+    const unsigned mask = __activemask();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
     {
-        unsigned long long ob = __shfl_xor_sync(0xffffffffu, bits, o);
+        unsigned long long ob = __shfl_xor_sync(mask, bits, o);
+        unsigned oc = __shfl_xor_sync(mask, cnt, o);
         bits = ob < bits ? ob : bits;
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        cnt += oc;
     }
-    __shared__ unsigned long long s_bits[32];
-    __shared__ unsigned s_cnt[32];
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) { s_bits[w] = bits; s_cnt[w] = cnt; }
-    __syncthreads();
-    if (w == 0)
+    if ((threadIdx.x & 31) == 0 && cnt)
     {
-        int nw = (blockDim.x + 31) >> 5;
-        bits = lane < nw ? s_bits[lane] : 0xFFFFFFFFFFFFFFFFull;
-        cnt = lane < nw ? s_cnt[lane] : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-        {
-            unsigned long long ob = __shfl_xor_sync(0xffffffffu, bits, o);
-            bits = ob < bits ? ob : bits;
-            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        }
-        if (lane == 0 && cnt)
-        {
-            atomicMin(earliest_bits, bits);
-            atomicAdd(nhit, (unsigned long long)cnt);
-        }
+        atomicMin(earliest_bits, bits);
+        atomicAdd(nhit, (unsigned long long)cnt);
     }
 }
 
-// ---- stencil kernels --------------------------------------------------------------------------
-// IS_VF: vertex-face stencils (p,q0,q1,q2) else edge-edge (p0,p1,q0,q1).  SINGLE: two entries per
-// vertex (q0 -> q1, xyz-interleaved) instead of the CSR history.
-template <bool IS_VF, bool SINGLE>
-__global__ void __launch_bounds__(128) stencil_kernel(long long n, const int *__restrict__ stencils,
-                                                      const double *__restrict__ eta_arr, double eta_all,
-                                                      const double *__restrict__ q0, const double *__restrict__ q1, int vstride,
-                                                      const long long *__restrict__ hoff, const double *__restrict__ htime,
-                                                      const double *__restrict__ hpos, unsigned char *__restrict__ hit_out,
-                                                      double *__restrict__ toi_out, unsigned char *__restrict__ stage_out,
-                                                      unsigned long long *earliest_bits, unsigned long long *nhit)
+struct NpArgs
+{
+    long long n;
+    const int *stencils;
+    const double *eta_arr;
+    double eta_all;
+    const double *q0, *q1;
+    int vstride;
+    const long long *hoff;
+    const double *htime, *hpos;
+    unsigned char *hit;
+    double *toi;
+    unsigned char *stage;
+    unsigned long long *earliest_bits, *nhit;
+    int *worklist;
+    unsigned long long *nwork;
+};
+
+// one stencil, single linear segment (two History entries per vertex)
+template <bool IS_VF> __device__ __forceinline__ int run_single(const NpArgs &A, long long i, double &toi, bool defer)
+{
+    const int4 s = reinterpret_cast<const int4 *>(A.stencils)[i];
+    const double eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
+    const long long vs = A.vstride;
+    V3 a[4], b[4];
+    a[0] = ldv(A.q0 + vs * s.x); a[1] = ldv(A.q0 + vs * s.y); a[2] = ldv(A.q0 + vs * s.z); a[3] = ldv(A.q0 + vs * s.w);
+    b[0] = ldv(A.q1 + vs * s.x); b[1] = ldv(A.q1 + vs * s.y); b[2] = ldv(A.q1 + vs * s.z); b[3] = ldv(A.q1 + vs * s.w);
+    return IS_VF ? vf_stencil_segment(a, b, eta, toi, defer) : ee_stencil_segment(a, b, eta, toi, defer);
+}
+
+__device__ __forceinline__ void store_result(const NpArgs &A, long long i, int stage, double toi)
+{
+    A.hit[i] = stage != 0;
+    A.toi[i] = stage ? toi : 0.0;
+    if (A.stage) A.stage[i] = (unsigned char)stage;
+}
+
+// pass 1: all stencils, iterative work deferred
+template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_pass1_kernel(NpArgs A)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int stage = 0;
     double toi = 0.0;
-    if (i < n)
+    bool deferred = false;
+    if (i < A.n)
     {
-        const int4 s = reinterpret_cast<const int4 *>(stencils)[i];
-        const double eta = eta_arr ? eta_arr[i] : eta_all;
-        V3 a[4], b[4];
-        if (SINGLE)
-        {
-            const long long vs = vstride;
-            a[0] = ldv(q0 + vs * s.x); a[1] = ldv(q0 + vs * s.y); a[2] = ldv(q0 + vs * s.z); a[3] = ldv(q0 + vs * s.w);
-            b[0] = ldv(q1 + vs * s.x); b[1] = ldv(q1 + vs * s.y); b[2] = ldv(q1 + vs * s.z); b[3] = ldv(q1 + vs * s.w);
-            stage = IS_VF ? vf_stencil_segment(a, b, eta, toi) : ee_stencil_segment(a, b, eta, toi);
-        }
-        else
-        {
-            int verts[4] = {s.x, s.y, s.z, s.w};
-            Stitcher st;
-            st.begin(hoff, htime, hpos, verts);
-            if (st.next(a))
-                while (st.next(b))
-                {
-                    stage = IS_VF ? vf_stencil_segment(a, b, eta, toi) : ee_stencil_segment(a, b, eta, toi);
-                    if (stage) break;
-                    for (int k = 0; k < 4; k++) a[k] = b[k];
-                }
-        }
-        hit_out[i] = stage != 0;
-        toi_out[i] = stage ? toi : 0.0;
-        if (stage_out) stage_out[i] = (unsigned char)stage;
+        stage = run_single<IS_VF>(A, i, toi, true);
+        deferred = stage < 0;
+        if (deferred) stage = 0;
+        else store_result(A, i, stage, toi);
     }
-    reduce_block(stage != 0, toi, earliest_bits, nhit);
+    // warp-aggregated append of the deferred stencils
+    const unsigned m = __ballot_sync(0xffffffffu, deferred);
+    if (m)
+    {
+        const int lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(A.nwork, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (deferred) A.worklist[base + __popc(m & ((1u << lane) - 1))] = (int)i;
+    }
+    reduce_warp(stage != 0, toi, A.earliest_bits, A.nhit);
+}
+
+// pass 2: the deferred stencils, full algorithm
+template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_pass2_kernel(NpArgs A)
+{
+    const unsigned long long nw = *A.nwork;
+    const unsigned long long nround = (nw + 31ull) & ~31ull;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nround;
+         w += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        int stage = 0;
+        double toi = 0.0;
+        if (w < nw)
+        {
+            const long long i = A.worklist[w];
+            stage = run_single<IS_VF>(A, i, toi, false);
+            store_result(A, i, stage, toi);
+        }
+        reduce_warp(stage != 0, toi, A.earliest_bits, A.nhit);
+    }
+}
+
+// multi-entry History: stitched segments, full algorithm in one pass
+template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_history_kernel(NpArgs A)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int stage = 0;
+    double toi = 0.0;
+    if (i < A.n)
+    {
+        const int4 s = reinterpret_cast<const int4 *>(A.stencils)[i];
+        const double eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
+        int verts[4] = {s.x, s.y, s.z, s.w};
+        V3 a[4], b[4];
+        Stitcher st;
+        st.begin(A.hoff, A.htime, A.hpos, verts);
+        if (st.next(a))
+            while (st.next(b))
+            {
+                stage = IS_VF ? vf_stencil_segment(a, b, eta, toi, false) : ee_stencil_segment(a, b, eta, toi, false);
+                if (stage) break;
+                for (int k = 0; k < 4; k++) a[k] = b[k];
+            }
+        store_result(A, i, stage, toi);
+    }
+    reduce_warp(stage != 0, toi, A.earliest_bits, A.nhit);
 }
 
 // ---- batched public primitives (include/CTCD.h:36-79): pts = start points then end points ------
-template <int KIND> __global__ void __launch_bounds__(128) prim_kernel(long long n, const double *__restrict__ pts,
-                                                                       const double *__restrict__ eta,
-                                                                       unsigned char *__restrict__ hit, double *__restrict__ t)
+__global__ void __launch_bounds__(128) prim_kernel(int kind, long long n, const double *__restrict__ pts, const double *__restrict__ eta,
+                                                   unsigned char *__restrict__ hit, double *__restrict__ t)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double tt = 0;
-    bool h;
-    if (KIND == 0)
-    {
-        const double *p = pts + 24 * i;
-        h = vertex_face(ldv(p), ldv(p + 3), ldv(p + 6), ldv(p + 9), ldv(p + 12), ldv(p + 15), ldv(p + 18), ldv(p + 21), eta[i], tt);
-    }
-    else if (KIND == 1)
-    {
-        const double *p = pts + 24 * i;
-        h = edge_edge(ldv(p), ldv(p + 3), ldv(p + 6), ldv(p + 9), ldv(p + 12), ldv(p + 15), ldv(p + 18), ldv(p + 21), eta[i], tt);
-    }
-    else if (KIND == 2)
-    {
-        const double *p = pts + 18 * i;
-        h = vertex_edge(ldv(p), ldv(p + 3), ldv(p + 6), ldv(p + 9), ldv(p + 12), ldv(p + 15), eta[i], tt);
-    }
-    else
-    {
-        const double *p = pts + 12 * i;
-        h = vertex_vertex(ldv(p), ldv(p + 3), ldv(p + 6), ldv(p + 9), eta[i], tt);
-    }
-    hit[i] = h;
-    if (h) t[i] = tt;       // t is written only on a hit, like the reference
+    int r;
+    const int np = (kind <= 1) ? 4 : (kind == 2 ? 3 : 2);
+    const double *p = pts + 6ll * np * i;
+    V3 s[4], v[4];
+    for (int k = 0; k < np; k++) { s[k] = ldv(p + 3 * k); v[k] = ldv(p + 3 * (np + k)) - s[k]; }
+    if (kind == 0) r = vertex_face(s, v, eta[i], tt, false);
+    else if (kind == 1) r = edge_edge(s, v, eta[i], tt, false);
+    else if (kind == 2) r = vertex_edge(s[0], s[1], s[2], v[0], v[1], v[2], eta[i], tt, false);
+    else r = vertex_vertex(s[0], s[1], v[0], v[1], eta[i], tt);
+    hit[i] = r == R_HIT;
+    if (r == R_HIT) t[i] = tt;       // t is written only on a hit, like the reference
 }
 
-// raw root isolator / interval finder, exposed for parity tests
+// raw interval finder, exposed for parity tests
 __global__ void find_intervals_kernel(long long n, int degree, int pos, const double *__restrict__ coeffs, int *__restrict__ cnt,
                                       double *__restrict__ lo, double *__restrict__ hi)
 {
@@ -215,11 +316,9 @@ __global__ void find_intervals_kernel(long long n, int degree, int pos, const do
     if (i >= n) return;
     Ivals iv;
     iv.n = 0;
-    const double *c = coeffs + 7 * i;
-    if (degree == 6) { double op[7]; for (int k = 0; k < 7; k++) op[k] = c[k]; find_intervals<6>(op, iv, pos != 0); }
-    else if (degree == 4) { double op[5]; for (int k = 0; k < 5; k++) op[k] = c[k]; find_intervals<4>(op, iv, pos != 0); }
-    else if (degree == 3) { double op[4]; for (int k = 0; k < 4; k++) op[k] = c[k]; find_intervals<3>(op, iv, pos != 0); }
-    else { double op[3]; for (int k = 0; k < 3; k++) op[k] = c[k]; find_intervals<2>(op, iv, pos != 0); }
+    double op[7];
+    for (int k = 0; k <= degree; k++) op[k] = coeffs[7 * i + k];
+    find_intervals(op, degree, iv, pos != 0, false);
     cnt[i] = iv.n;
     for (int k = 0; k < iv.n; k++) { lo[7 * i + k] = iv.l[k]; hi[7 * i + k] = iv.u[k]; }
 }
@@ -231,37 +330,43 @@ using namespace ccd;
 
 static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
-void ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, double eta_all,
-                      const double *q0, const double *q1, int vstride, const long long *hoff, const double *htime, const double *hpos,
-                      unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits,
-                      unsigned long long *nhit)
+// worklist: n ints; nwork: device counter (zeroed here).  Returns the number of kernels launched.
+int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, double eta_all,
+                     const double *q0, const double *q1, int vstride, const long long *hoff, const double *htime, const double *hpos,
+                     unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits,
+                     unsigned long long *nhit, int *worklist, unsigned long long *nwork)
 {
-    if (n <= 0) return;
+    if (n <= 0) return 0;
+    NpArgs A;
+    A.n = n; A.stencils = stencils; A.eta_arr = eta_arr; A.eta_all = eta_all; A.q0 = q0; A.q1 = q1; A.vstride = vstride;
+    A.hoff = hoff; A.htime = htime; A.hpos = hpos; A.hit = hit; A.toi = toi; A.stage = stage;
+    A.earliest_bits = earliest_bits; A.nhit = nhit; A.worklist = worklist; A.nwork = nwork;
     const int B = 128;
-    const bool single = (q0 != nullptr);
+    if (q0 == nullptr)
+    {
+        if (is_vf) stencil_history_kernel<true><<<grid_for(n, B), B, 0, st>>>(A);
+        else stencil_history_kernel<false><<<grid_for(n, B), B, 0, st>>>(A);
+        return 1;
+    }
+    cudaMemsetAsync(nwork, 0, sizeof(unsigned long long), st);
+    const unsigned g2 = (unsigned)min((long long)148 * 32, (long long)grid_for(n, B));
     if (is_vf)
     {
-        if (single) stencil_kernel<true, true><<<grid_for(n, B), B, 0, st>>>(n, stencils, eta_arr, eta_all, q0, q1, vstride, hoff, htime, hpos, hit, toi, stage, earliest_bits, nhit);
-        else stencil_kernel<true, false><<<grid_for(n, B), B, 0, st>>>(n, stencils, eta_arr, eta_all, q0, q1, vstride, hoff, htime, hpos, hit, toi, stage, earliest_bits, nhit);
+        stencil_pass1_kernel<true><<<grid_for(n, B), B, 0, st>>>(A);
+        stencil_pass2_kernel<true><<<g2, B, 0, st>>>(A);
     }
     else
     {
-        if (single) stencil_kernel<false, true><<<grid_for(n, B), B, 0, st>>>(n, stencils, eta_arr, eta_all, q0, q1, vstride, hoff, htime, hpos, hit, toi, stage, earliest_bits, nhit);
-        else stencil_kernel<false, false><<<grid_for(n, B), B, 0, st>>>(n, stencils, eta_arr, eta_all, q0, q1, vstride, hoff, htime, hpos, hit, toi, stage, earliest_bits, nhit);
+        stencil_pass1_kernel<false><<<grid_for(n, B), B, 0, st>>>(A);
+        stencil_pass2_kernel<false><<<g2, B, 0, st>>>(A);
     }
+    return 2;
 }
 
 void ccdk_prim_batch(cudaStream_t st, int kind, long long n, const double *pts, const double *eta, unsigned char *hit, double *t)
 {
     if (n <= 0) return;
-    const int B = 128;
-    switch (kind)
-    {
-    case 0: prim_kernel<0><<<grid_for(n, B), B, 0, st>>>(n, pts, eta, hit, t); break;
-    case 1: prim_kernel<1><<<grid_for(n, B), B, 0, st>>>(n, pts, eta, hit, t); break;
-    case 2: prim_kernel<2><<<grid_for(n, B), B, 0, st>>>(n, pts, eta, hit, t); break;
-    default: prim_kernel<3><<<grid_for(n, B), B, 0, st>>>(n, pts, eta, hit, t); break;
-    }
+    prim_kernel<<<grid_for(n, 128), 128, 0, st>>>(kind, n, pts, eta, hit, t);
 }
 
 void ccdk_find_intervals(cudaStream_t st, long long n, int degree, int pos, const double *coeffs, int *cnt, double *lo, double *hi)

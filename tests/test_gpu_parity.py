@@ -172,7 +172,7 @@ def test_empty_and_tiny_inputs(ctx):
     vf, ee = ctx.findCollisionCandidatesStep(13, np.zeros((0, 3), np.int32), z3, z3, 1e-3)
     assert vf.shape == (0, 4) and ee.shape == (0, 4)
     # two triangles sharing nothing, overlapping boxes -> 6 VF + 9 EE (example meshes/test1.obj situation)
-    q = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0.2, 0.2, 0.05], [1.2, 0.2, 0.05], [0.2, 1.2, 0.05]], float)
+    q = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0.2, 0.2, 0.0005], [1.2, 0.2, 0.0005], [0.2, 1.2, 0.0005]], float)
     f = np.array([[0, 1, 2], [3, 4, 5]], np.int32)
     vf, ee = ctx.findCollisionCandidatesStep(13, f, q, q, 1e-3)
     assert len(vf) == 6 and len(ee) == 9
