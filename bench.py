@@ -287,7 +287,7 @@ def main():
                roofline=roof,
                stages_ms=stages, kernel_ms_per_step=kern_ms / args.steps,
                counts=dict(vertices=V, faces=F, stencils=n_stencils, vf_rank0=int(nvf), ee_rank0=int(nee), hits=n_hits,
-                           face_pairs_rank0=int(r.n_face_pairs), tree_candidates_rank0=int(r.n_tree_candidates),
+                           face_pairs_rank0=int(r.n_face_pairs), tree_candidates_rank0=int(r.n_tree_candidates), vf_deferred_rank0=int(r.n_vf_deferred), ee_deferred_rank0=int(r.n_ee_deferred),
                            stencils_per_face=n_stencils / float(F)),
                fp64_peak_tflops=fp64_peak)
     if world == 1 and not args.no_cpu_baseline:

@@ -43,7 +43,7 @@ class DeviceResult(C.Structure):
                 ("n_ee_hits", C.c_int64), ("earliest_toi", C.c_double), ("d_vf", C.c_void_p), ("d_ee", C.c_void_p),
                 ("d_vf_hit", C.c_void_p), ("d_ee_hit", C.c_void_p), ("d_vf_toi", C.c_void_p), ("d_ee_toi", C.c_void_p),
                 ("n_face_pairs", C.c_int64), ("n_tree_candidates", C.c_int64), ("ms_broadphase", C.c_float),
-                ("ms_narrowphase", C.c_float), ("n_launches", C.c_int32)]
+                ("ms_narrowphase", C.c_float), ("n_launches", C.c_int32), ("n_vf_deferred", C.c_int64), ("n_ee_deferred", C.c_int64)]
 
 
 EXPORTS = [

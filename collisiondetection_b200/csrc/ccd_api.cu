@@ -44,14 +44,14 @@ struct ccd_context
     // emission
     DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut;
     // narrowphase
-    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, selTmp, selA, selB, selC, selD, selCount;
+    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, tasksVf, tasksEe, selTmp, selA, selB, selC, selD, selCount;
     // pinned host scratch
     unsigned long long *h_counters = nullptr; // 16 entries
-    size_t candCap = 0, pairCap = 0;
+    size_t candCap = 0, pairCap = 0, taskCapVf = 0, taskCapEe = 0;
 };
 
 // device counters layout (unsigned long long each)
-enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NWORK_VF = 7, C_NWORK_EE = 8, C_TOTAL = 16 };
+enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NWORK_VF = 7, C_NWORK_EE = 8, C_NTASK_VF = 9, C_NTASK_EE = 10, C_TOTAL = 16 };
 
 #define CK(call)                                                                                      \
     do                                                                                                \
@@ -209,7 +209,7 @@ void ccd_destroy(ccd_context *c)
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
     for (DBuf *b : all)
         if (b->p)
             cudaFree(b->p);
@@ -446,21 +446,44 @@ static int narrowphase_device(ccd_context *c, long long nvf, const int *d_vf, co
     CKR(ensure(c, c->eeToi, sizeof(double) * ((size_t)nee + 2)));
     CKR(ensure(c, c->workVf, sizeof(int) * ((size_t)nvf + 32)));
     CKR(ensure(c, c->workEe, sizeof(int) * ((size_t)nee + 32)));
-    unsigned long long init[4] = {0xFFFFFFFFFFFFFFFFull, 0ull, 0xFFFFFFFFFFFFFFFFull, 0ull};
-    memcpy(c->h_counters + 8, init, sizeof(init));
-    CK(cudaMemcpyAsync(ctr + C_EARLY_VF, c->h_counters + 8, sizeof(init), cudaMemcpyHostToDevice, c->st));
-    cudaEventRecord(c->sev[ST_NP_VF], c->st);
-    int nl = ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
-                              P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF, P<int>(c->workVf), ctr + C_NWORK_VF);
-    cudaEventRecord(c->sev[ST_NP_EE], c->st);
-    nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
-                           P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE, P<int>(c->workEe), ctr + C_NWORK_EE);
-    cudaEventRecord(c->sev[CCD_N_STAGES], c->st);
+    CKR(ensure(c, c->workTaskVf, sizeof(int) * ((size_t)nvf + 32)));
+    CKR(ensure(c, c->workTaskEe, sizeof(int) * ((size_t)nee + 32)));
+    CKR(ensure(c, c->workSubVf, (size_t)nvf + 32));
+    CKR(ensure(c, c->workSubEe, (size_t)nee + 32));
+    int nl = 0;
+    for (int attempt = 0; attempt < 4; attempt++)
+    {
+        // task records: one per polynomial that needs the root isolator; grown on demand (count known after pass 1)
+        if (c->taskCapVf < (size_t)nvf / 2 + 1024) c->taskCapVf = (size_t)nvf / 2 + 1024;
+        if (c->taskCapEe < (size_t)nee + 1024) c->taskCapEe = (size_t)nee + 1024;
+        CKR(ensure(c, c->tasksVf, 64 * c->taskCapVf));
+        CKR(ensure(c, c->tasksEe, 64 * c->taskCapEe));
+        unsigned long long init[4] = {0xFFFFFFFFFFFFFFFFull, 0ull, 0xFFFFFFFFFFFFFFFFull, 0ull};
+        memcpy(c->h_counters + 8, init, sizeof(init));
+        CK(cudaMemcpyAsync(ctr + C_EARLY_VF, c->h_counters + 8, sizeof(init), cudaMemcpyHostToDevice, c->st));
+        cudaEventRecord(c->sev[ST_NP_VF], c->st);
+        nl += ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
+                               P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF, P<int>(c->workVf),
+                               P<int>(c->workTaskVf), P<unsigned char>(c->workSubVf), P<double>(c->tasksVf), c->taskCapVf, ctr + C_NWORK_VF,
+                               ctr + C_NTASK_VF);
+        cudaEventRecord(c->sev[ST_NP_EE], c->st);
+        nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
+                               P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE, P<int>(c->workEe),
+                               P<int>(c->workTaskEe), P<unsigned char>(c->workSubEe), P<double>(c->tasksEe), c->taskCapEe, ctr + C_NWORK_EE,
+                               ctr + C_NTASK_EE);
+        cudaEventRecord(c->sev[CCD_N_STAGES], c->st);
+        CK(cudaGetLastError());
+        CKR(sync_counters(c));
+        const bool single = d_q0 != nullptr;
+        const unsigned long long tv = single ? c->h_counters[C_NTASK_VF] : 0, te = single ? c->h_counters[C_NTASK_EE] : 0;
+        if (tv <= c->taskCapVf && te <= c->taskCapEe)
+            break;
+        if (tv > c->taskCapVf) c->taskCapVf = (size_t)(tv + tv / 8 + 1024);
+        if (te > c->taskCapEe) c->taskCapEe = (size_t)(te + te / 8 + 1024);
+    }
     c->launches += nl;
-    CK(cudaGetLastError());
     if (sum)
     {
-        CKR(sync_counters(c));
         sum->n_vf_hits = (int64_t)c->h_counters[C_NHIT_VF];
         sum->n_ee_hits = (int64_t)c->h_counters[C_NHIT_EE];
         unsigned long long b = c->h_counters[C_EARLY_VF] < c->h_counters[C_EARLY_EE] ? c->h_counters[C_EARLY_VF] : c->h_counters[C_EARLY_EE];
@@ -621,6 +644,8 @@ int ccd_step_device(ccd_context *c, int kind, int V, int F, const int32_t *d_fac
     out->n_face_pairs = r.npairs;
     out->n_tree_candidates = r.ncand;
     out->n_launches = c->launches;
+    out->n_vf_deferred = (int64_t)c->h_counters[C_NWORK_VF];
+    out->n_ee_deferred = (int64_t)c->h_counters[C_NWORK_EE];
     c->stage_valid = (F > 0 && V > 0);
     return CCD_OK;
 }

@@ -40,6 +40,18 @@ __device__ __forceinline__ double smin(double a, double b) { return (b < a) ? b 
 
 // result codes of the primitives / stencil tests
 enum { R_MISS = 0, R_HIT = 1, R_DEFER = 2 };
+// how a primitive treats polynomials that need the iterative root isolator:
+//   FULL   isolate in place;   DEFER  export them (Pend) and return R_DEFER;
+//   RESUME take their roots from task records computed by the root kernel (narrowphase.cu)
+enum { MODE_FULL = 0, MODE_DEFER = 1, MODE_RESUME = 2 };
+
+// the polynomials of one primitive that still need root isolation: normalised, reduced coefficients
+struct Pend
+{
+    double ops[5][7];
+    int rds[5];
+    unsigned mask;
+};
 
 // ------------------------------------------------------------------------------------------
 // closed time intervals (include/CTCD.h:7-26); at most 7 per polynomial (<= 6 breakpoints)
@@ -296,10 +308,11 @@ __device__ __forceinline__ int quad_roots(double a, double b, double c, double &
     return roots;
 }
 
-// op[0..n] is modified (normalised, leading zeros shifted out) exactly like the reference does.
-// Returns R_DEFER (nothing pushed) when `defer` is set and the polynomial needs the iterative root isolator;
-// otherwise 0 with the intervals appended to iv.
-static __device__ __noinline__ int find_intervals(double *op, int n, Ivals &iv, bool pos, bool defer)
+// First half of findIntervals: normalise, drop exactly-zero leading coefficients, and settle everything that
+// needs no iteration (quick reject, closed forms for degree <= 2, Bernstein "no root in [0,1]").
+// op[0..n] is modified exactly like the reference does.  Returns 0 when iv is final, 1 when the reduced
+// polynomial op[0..rd] (rd >= 3) still needs the root isolator (finish_poly).
+static __device__ __noinline__ int prepare_poly(double *op, int n, Ivals &iv, bool pos, int &rd_out)
 {
     // normalise, src/CTCD.cpp:113-119
     double maxval = 0;
@@ -320,8 +333,9 @@ static __device__ __noinline__ int find_intervals(double *op, int n, Ivals &iv, 
     if (rd < n)
         for (int i = 0; i <= rd; i++)
             op[i] = op[i + n - rd];
+    rd_out = rd;
 
-    double time[6];
+    double time[2];
     int roots = 0;
     if (rd > 2)
     {
@@ -336,11 +350,7 @@ static __device__ __noinline__ int find_intervals(double *op, int n, Ivals &iv, 
         double b[7];
         bernstein(op, rd, b);
         if (!no_root_at_top(b, rd))
-        {
-            if (defer)
-                return R_DEFER;
-            roots = roots01(op, rd, b, time);
-        }
+            return 1;
     }
     else if (rd == 2)
         roots = quad_roots(op[0], op[1], op[2], time[0], time[1]);
@@ -355,7 +365,24 @@ static __device__ __noinline__ int find_intervals(double *op, int n, Ivals &iv, 
             push_interval(iv, 0, 1.0);
         return 0;
     }
-    // src/CTCD.cpp:161-176
+    // src/CTCD.cpp:161-176 (at most two breakpoints here)
+    if (roots > 0)
+    {
+        if (time[0] >= 0)
+            check_interval(0, time[0], op, rd, iv, pos);
+        if (roots == 2 && !((time[0] < 0 && time[1] < 0) || (time[0] > 1.0 && time[1] > 1.0)))
+            check_interval(time[0], time[1], op, rd, iv, pos);
+        if (time[roots - 1] <= 1.0)
+            check_interval(time[roots - 1], 1.0, op, rd, iv, pos);
+    }
+    else
+        check_interval(0.0, 1.0, op, rd, iv, pos);
+    return 0;
+}
+
+// the interval rules of src/CTCD.cpp:161-176 for the prepared polynomial and its real roots in [0,1]
+__device__ __forceinline__ void intervals_from_roots(const double *op, int rd, const double *time, int roots, Ivals &iv, bool pos)
+{
     if (roots > 0)
     {
         if (time[0] >= 0)
@@ -368,7 +395,51 @@ static __device__ __noinline__ int find_intervals(double *op, int n, Ivals &iv, 
     }
     else
         check_interval(0.0, 1.0, op, rd, iv, pos);
-    return 0;
+}
+
+// Second half of findIntervals: real roots of the prepared polynomial in [0,1], then the interval rules.
+static __device__ __noinline__ void finish_poly(const double *op, int rd, Ivals &iv, bool pos)
+{
+    double time[6], b[7];
+    bernstein(op, rd, b);
+    const int roots = roots01(op, rd, b, time);
+    intervals_from_roots(op, rd, time, roots, iv, pos);
+}
+
+// CTCD::findIntervals for a single polynomial (FULL mode).
+__device__ __forceinline__ void find_intervals(double *op, int n, Ivals &iv, bool pos)
+{
+    int rd;
+    if (prepare_poly(op, n, iv, pos, rd))
+        finish_poly(op, rd, iv, pos);
+}
+
+// Settle the pending polynomials of a primitive: lists[k] receives the intervals of polynomial k (bit k of P.mask),
+// posmask bit k = the reference's `pos` flag.  RESUME reads 64-byte task records {roots[6], -, count} in bit order.
+// Returns false as soon as a list comes out empty (the primitive misses), else true.
+static __device__ __noinline__ bool resolve_pending(Pend &P, Ivals *lists, unsigned posmask, int mode, const double *trec)
+{
+    int j = 0;
+    while (P.mask)
+    {
+        const int k = __ffs(P.mask) - 1;
+        P.mask &= P.mask - 1;
+        const bool pos = (posmask >> k) & 1u;
+        if (mode == MODE_RESUME)
+        {
+            double r[6];
+            const double *rec = trec + 8 * j;
+            j++;
+            const int nr = (int)rec[7];
+            for (int i = 0; i < nr; i++) r[i] = rec[i];
+            intervals_from_roots(P.ops[k], P.rds[k], r, nr, lists[k], pos);
+        }
+        else
+            finish_poly(P.ops[k], P.rds[k], lists[k], pos);
+        if (lists[k].n == 0)
+            return false;
+    }
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -428,29 +499,38 @@ __device__ __forceinline__ void barycentric_coeffs(V3 x10, V3 x20, V3 x30, V3 v1
 // Return R_MISS / R_HIT (t written) / R_DEFER (only with defer=true: needs the iterative isolator).
 // ------------------------------------------------------------------------------------------
 // CTCD::vertexFaceCTCD, src/CTCD.cpp:413-508 — vertex s[0] against face (s[1],s[2],s[3])
-static __device__ __noinline__ int vertex_face(const V3 *s, const V3 *v, double eta, double &t, bool defer)
+static __device__ __noinline__ int vertex_face(const V3 *s, const V3 *v, double eta, double &t, int mode, Pend &P, const double *trec)
 {
     Ivals iv[4];       // e1, e2, e3, coplane
-    double op[7];
+    P.mask = 0;
     // the three inside tests are one formula under a rotation of the face: base = 1+k, A = 1+(k+2)%3, B = 1+(k+1)%3
     //   x10 = q0-base, x20 = (A-base) x (B-base), x30 = A-base            (src/CTCD.cpp:433-464)
+    // Every polynomial is built and settled as far as straight-line code goes before any root is isolated: an empty
+    // list anywhere is a miss (src/CTCD.cpp:441,452,463,474), and the lanes of a warp then run the isolator together.
     for (int k = 0; k < 3; k++)
     {
         const int ib = 1 + k, ia = 1 + (k + 2) % 3, ic = 1 + (k + 1) % 3;
         const V3 xa = s[ia] - s[ib], xc = s[ic] - s[ib], va = v[ia] - v[ib], vc = v[ic] - v[ib];
-        plane_coeffs(s[0] - s[ib], cross(xa, xc), xa, v[0] - v[ib], cross(va, vc), va, op);
+        plane_coeffs(s[0] - s[ib], cross(xa, xc), xa, v[0] - v[ib], cross(va, vc), va, P.ops[k]);
         iv[k].n = 0;
-        if (find_intervals(op, 3, iv[k], true, defer) == R_DEFER)
-            return R_DEFER;
-        if (iv[k].n == 0)
+        if (prepare_poly(P.ops[k], 3, iv[k], true, P.rds[k]))
+            P.mask |= 1u << k;
+        else if (iv[k].n == 0)
             return R_MISS;
     }
-    distance_coeffs(s[0] - s[1], s[2] - s[1], s[3] - s[1], v[0] - v[1], v[2] - v[1], v[3] - v[1], eta * eta, op);
+    distance_coeffs(s[0] - s[1], s[2] - s[1], s[3] - s[1], v[0] - v[1], v[2] - v[1], v[3] - v[1], eta * eta, P.ops[3]);
     iv[3].n = 0;
-    if (find_intervals(op, 6, iv[3], false, defer) == R_DEFER)
-        return R_DEFER;
-    if (iv[3].n == 0)
+    if (prepare_poly(P.ops[3], 6, iv[3], false, P.rds[3]))
+        P.mask |= 8u;
+    else if (iv[3].n == 0)
         return R_MISS;
+    if (P.mask)
+    {
+        if (mode == MODE_DEFER)
+            return R_DEFER;
+        if (!resolve_pending(P, iv, 0x7u, mode, trec))
+            return R_MISS;
+    }
     const Ivals &cop = iv[3], &e1 = iv[0], &e2 = iv[1], &e3 = iv[2];
     bool col = false;
     double mint = 1.0;
@@ -480,18 +560,41 @@ static __device__ __noinline__ int vertex_face(const V3 *s, const V3 *v, double 
 }
 
 // CTCD::edgeEdgeCTCD, src/CTCD.cpp:259-411 — points (q0,p0,q1,p1) = s[0..3]: edges (q0,p0) and (q1,p1)
-static __device__ __noinline__ int edge_edge(const V3 *s, const V3 *v, double eta, double &t, bool defer)
+static __device__ __noinline__ int edge_edge(const V3 *s, const V3 *v, double eta, double &t, int mode, Pend &P, const double *trec)
 {
-    Ivals cop, par, q[4];
-    double op[7];
+    Ivals cop, par, q[5];      // q[0..3] = a0,a1,b0,b1 ; q[4] = raw coplanarity intervals
+    P.mask = 0;
     cop.n = par.n = 0;
+    distance_coeffs(s[1] - s[3], s[1] - s[0], s[3] - s[2], v[1] - v[3], v[1] - v[0], v[3] - v[2], eta * eta, P.ops[4]);
+    q[4].n = 0;
+    if (prepare_poly(P.ops[4], 6, q[4], false, P.rds[4]))
+        P.mask |= 16u;
+    else if (q[4].n == 0)
+        return R_MISS;
+    // the four barycentric quartics a0,a1,b0,b1 (src/CTCD.cpp:313-348): x10 = P[a]-P[b], x20 = P[c]-P[d], x30 = P[e]-P[f]
+    for (int k = 0; k < 4; k++)
     {
-        Ivals raw;
-        raw.n = 0;
-        distance_coeffs(s[1] - s[3], s[1] - s[0], s[3] - s[2], v[1] - v[3], v[1] - v[0], v[3] - v[2], eta * eta, op);
-        if (find_intervals(op, 6, raw, false, defer) == R_DEFER)
+        // packed point indices, 2 bits each: a b c d e f
+        const unsigned tab = (k == 0) ? 0x0E42u /*3,2 | 1,0 | 0,2*/ : (k == 1) ? 0x0E16u /*3,2 | 0,1 | 1,2*/
+                           : (k == 2) ? 0x04E8u /*1,0 | 3,2 | 2,0*/ : 0x04BCu /*1,0 | 2,3 | 3,0*/;
+        const int a = (tab >> 10) & 3, b = (tab >> 8) & 3, c = (tab >> 6) & 3, d = (tab >> 4) & 3, e = (tab >> 2) & 3, f = tab & 3;
+        barycentric_coeffs(s[a] - s[b], s[c] - s[d], s[e] - s[f], v[a] - v[b], v[c] - v[d], v[e] - v[f], P.ops[k]);
+        q[k].n = 0;
+        if (prepare_poly(P.ops[k], 4, q[k], true, P.rds[k]))
+            P.mask |= 1u << k;
+        else if (q[k].n == 0)
+            return R_MISS;
+    }
+    if (P.mask)
+    {
+        if (mode == MODE_DEFER)
             return R_DEFER;
+        if (!resolve_pending(P, q, 0xFu, mode, trec))
+            return R_MISS;
+    }
+    {
         // parallel-edge classification at each interval midpoint, src/CTCD.cpp:290-308
+        const Ivals &raw = q[4];
         for (int i = 0; i < raw.n; i++)
         {
             double midt = (raw.u[i] + raw.l[i]) / 2;
@@ -502,20 +605,6 @@ static __device__ __noinline__ int edge_edge(const V3 *s, const V3 *v, double et
             else { cop.l[cop.n] = raw.l[i]; cop.u[cop.n] = raw.u[i]; cop.n++; }
         }
         if (cop.n == 0) return R_MISS;
-    }
-    // the four barycentric quartics a0,a1,b0,b1 (src/CTCD.cpp:313-348): x10 = P[a]-P[b], x20 = P[c]-P[d], x30 = P[e]-P[f]
-    for (int k = 0; k < 4; k++)
-    {
-        // packed point indices, 2 bits each: a b c d e f
-        const unsigned tab = (k == 0) ? 0x0E42u /*3,2 | 1,0 | 0,2*/ : (k == 1) ? 0x0E16u /*3,2 | 0,1 | 1,2*/
-                           : (k == 2) ? 0x04E8u /*1,0 | 3,2 | 2,0*/ : 0x04BCu /*1,0 | 2,3 | 3,0*/;
-        const int a = (tab >> 10) & 3, b = (tab >> 8) & 3, c = (tab >> 6) & 3, d = (tab >> 4) & 3, e = (tab >> 2) & 3, f = tab & 3;
-        barycentric_coeffs(s[a] - s[b], s[c] - s[d], s[e] - s[f], v[a] - v[b], v[c] - v[d], v[e] - v[f], op);
-        q[k].n = 0;
-        if (find_intervals(op, 4, q[k], true, defer) == R_DEFER)
-            return R_DEFER;
-        if (q[k].n == 0)
-            return R_MISS;
     }
     const Ivals &a0 = q[0], &a1 = q[1], &b0 = q[2], &b1 = q[3];
     bool col = false;
@@ -555,23 +644,24 @@ static __device__ __noinline__ int edge_edge(const V3 *s, const V3 *v, double et
 }
 
 // CTCD::vertexEdgeCTCD, src/CTCD.cpp:511-602 — vertex q0 against segment (q1,q2); v* = end - start
-static __device__ __noinline__ int vertex_edge(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, double &t, bool defer)
+static __device__ __noinline__ int vertex_edge(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, double &t, int mode, Pend &P, const double *trec)
 {
     const double minD = eta * eta;
     const V3 ab = q2s - q1s, ac = q0s - q1s, cb = q2s - q0s;
     const V3 vab = v2 - v1, vac = v0 - v1, vcb = v2 - v0;
     Ivals colin, e1, e2;
-    double op[5];
+    double *op = P.ops[0];
+    P.mask = 0;
     colin.n = e1.n = e2.n = 0;
     op[2] = dot(ab, ac);
     op[1] = dot(ac, vab) + dot(ab, vac);
     op[0] = dot(vab, vac);
-    find_intervals(op, 2, e1, true, defer);
+    find_intervals(op, 2, e1, true);
     if (e1.n == 0) return R_MISS;
     op[2] = dot(ab, cb);
     op[1] = dot(cb, vab) + dot(ab, vcb);
     op[0] = dot(vab, vcb);
-    find_intervals(op, 2, e2, true, defer);
+    find_intervals(op, 2, e2, true);
     if (e2.n == 0) return R_MISS;
     {
         double A = dot(ab, ab);
@@ -589,8 +679,13 @@ static __device__ __noinline__ int vertex_edge(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3
         op[1] = B * F + C * E - 2 * H * I;
         op[0] = C * F - I * I;
     }
-    if (find_intervals(op, 4, colin, false, defer) == R_DEFER)
-        return R_DEFER;
+    if (prepare_poly(op, 4, colin, false, P.rds[0]))
+    {
+        P.mask = 1u;
+        if (mode == MODE_DEFER)
+            return R_DEFER;
+        resolve_pending(P, &colin, 0u, mode, trec);
+    }
     if (colin.n == 0) return R_MISS;
     bool col = false;
     double mint = 1.0;

@@ -6,11 +6,13 @@
 // vertex-vertex tests, first hit wins; over a multi-entry History the sequence repeats per
 // stitched linear segment (src/History.cpp:98-140).
 //
-// Two passes keep the warps converged (profiles/: the one-pass version ran with 5.7 of 32 lanes active):
+// Three kernels keep the warps converged (profiles/: the one-pass version ran with 5.7 of 32 lanes active):
 //   pass 1  every stencil, straight-line work only: coefficient construction, the reference's own quick
 //           rejects, closed-form quadratics and the Bernstein "no root in [0,1]" decision.  A stencil whose
-//           answer needs the iterative root isolator is appended to a work list (warp-aggregated atomics);
-//   pass 2  the work list only, full algorithm.
+//           next sub-test needs the iterative root isolator goes on a work list, with one 64-byte task
+//           record per pending polynomial (warp-aggregated allocation);
+//   roots   one thread per pending polynomial: dense warps, every lane inside the isolator;
+//   pass 3  the work list only: resumes at the deferred sub-test with its roots, finishes the sequence.
 // Degenerate sub-tests (and the EE primitive) are skipped when the swept boxes of the two parts stay further
 // apart than eta plus a safety margin: those tests measure true distances (include/CTCD.h:31-79), so the
 // reference cannot report a hit there; the margin (4e-5 of the coordinate scale) is ~1e3 times the distance
@@ -51,27 +53,37 @@ __device__ __forceinline__ double box_scale(const Box &b)
 }
 
 // ---- per-segment stencil tests --------------------------------------------------------------
-// a[0..3] start positions, b[0..3] end positions of (p, q0, q1, q2).  Returns the stage that hit (>0), 0 for a
-// miss, -1 when deferred (only with defer=true).
-static __device__ __noinline__ int vf_stencil_segment(const V3 *a, const V3 *b, double eta, double &t, bool defer)
+// Sub-tests are numbered in the reference's order: 0 = the VF / EE primitive, then the vertex-edge tests, then
+// the vertex-vertex tests.  a[0..3] start positions, b[0..3] end positions.
+// Return: stage that hit (sub-test index + 1), 0 for a miss, -(sub+1) when sub-test `sub` was deferred (DEFER mode;
+// its pending polynomials are in P).  RESUME mode starts at sub-test `start` (everything before it is known to
+// miss), feeds it the roots in trec and finishes the remaining sub-tests in FULL mode.
+static __device__ __noinline__ int vf_stencil_segment(const V3 *a, const V3 *b, double eta, double &t, int mode, int start, Pend &P,
+                                                      const double *trec)
 {
     V3 v[4];
     Box bx[4];
     for (int i = 0; i < 4; i++) { v[i] = b[i] - a[i]; bx[i] = swept_box(a[i], b[i]); }
-    int r = vertex_face(a, v, eta, t, defer);
-    if (r == R_HIT) return 1;
-    if (r == R_DEFER) return -1;
+    int r;
+    if (start <= 0)
+    {
+        r = vertex_face(a, v, eta, t, mode, P, trec);
+        if (r == R_HIT) return 1;
+        if (r == R_DEFER) return -1;
+    }
+    const int later = (mode == MODE_RESUME) ? MODE_FULL : mode;
     const Box face = join(join(bx[1], bx[2]), bx[3]);
     const double m = eta + 4e-5 * fmax(box_scale(bx[0]), box_scale(face));
     if (apart(bx[0], face, m)) return 0;
     // vertex against the three face edges (1,2),(2,3),(3,1): src/CTCDNarrowPhase.cpp:51-59
     for (int e = 0; e < 3; e++)
     {
-        const int i1 = 1 + e, i2 = 1 + ((e + 1) % 3);
+        const int sub = 1 + e, i1 = 1 + e, i2 = 1 + ((e + 1) % 3);
+        if (sub < start) continue;
         if (apart(bx[0], join(bx[i1], bx[i2]), m)) continue;
-        r = vertex_edge(a[0], a[i1], a[i2], v[0], v[i1], v[i2], eta, t, defer);
-        if (r == R_HIT) return 2 + e;
-        if (r == R_DEFER) return -1;
+        r = vertex_edge(a[0], a[i1], a[i2], v[0], v[i1], v[i2], eta, t, sub == start ? mode : later, P, trec);
+        if (r == R_HIT) return sub + 1;
+        if (r == R_DEFER) return -(sub + 1);
     }
     // vertex against the three face vertices: src/CTCDNarrowPhase.cpp:61-69
     for (int k = 0; k < 3; k++)
@@ -83,7 +95,8 @@ static __device__ __noinline__ int vf_stencil_segment(const V3 *a, const V3 *b, 
 }
 
 // a/b: (p0, p1, q0, q1); edgeEdgeCTCD takes (q0,p0,q1,p1) = (pos0,pos1,pos2,pos3): src/CTCDNarrowPhase.cpp:91
-static __device__ __noinline__ int ee_stencil_segment(const V3 *a, const V3 *b, double eta, double &t, bool defer)
+static __device__ __noinline__ int ee_stencil_segment(const V3 *a, const V3 *b, double eta, double &t, int mode, int start, Pend &P,
+                                                      const double *trec)
 {
     V3 v[4];
     Box bx[4];
@@ -91,17 +104,23 @@ static __device__ __noinline__ int ee_stencil_segment(const V3 *a, const V3 *b, 
     const Box e0 = join(bx[0], bx[1]), e1 = join(bx[2], bx[3]);
     const double m = eta + 4e-5 * fmax(box_scale(e0), box_scale(e1));
     if (apart(e0, e1, m)) return 0;       // every sub-test below is a distance between parts of these two edges
-    int r = edge_edge(a, v, eta, t, defer);
-    if (r == R_HIT) return 1;
-    if (r == R_DEFER) return -1;
+    int r;
+    if (start <= 0)
+    {
+        r = edge_edge(a, v, eta, t, mode, P, trec);
+        if (r == R_HIT) return 1;
+        if (r == R_DEFER) return -1;
+    }
+    const int later = (mode == MODE_RESUME) ? MODE_FULL : mode;
     // src/CTCDNarrowPhase.cpp:99-114: p0|p1 against (q0,q1), q0|q1 against (p0,p1)
     for (int k = 0; k < 4; k++)
     {
-        const int iv = k, i1 = (k < 2) ? 2 : 0, i2 = i1 + 1;
+        const int sub = 1 + k, iv = k, i1 = (k < 2) ? 2 : 0, i2 = i1 + 1;
+        if (sub < start) continue;
         if (apart(bx[iv], (k < 2) ? e1 : e0, m)) continue;
-        r = vertex_edge(a[iv], a[i1], a[i2], v[iv], v[i1], v[i2], eta, t, defer);
-        if (r == R_HIT) return 2 + k;
-        if (r == R_DEFER) return -1;
+        r = vertex_edge(a[iv], a[i1], a[i2], v[iv], v[i1], v[i2], eta, t, sub == start ? mode : later, P, trec);
+        if (r == R_HIT) return sub + 1;
+        if (r == R_DEFER) return -(sub + 1);
     }
     // src/CTCDNarrowPhase.cpp:117-132: (p0,q0) (p0,q1) (p1,q0) (p1,q1)
     for (int k = 0; k < 4; k++)
@@ -192,12 +211,18 @@ struct NpArgs
     double *toi;
     unsigned char *stage;
     unsigned long long *earliest_bits, *nhit;
-    int *worklist;
-    unsigned long long *nwork;
+    // deferred work: entry w = {stencil index, first task record, sub-test that deferred}; tasks are 64-byte records
+    int *work_stencil;
+    int *work_task;
+    unsigned char *work_sub;
+    double *tasks;
+    unsigned long long *nwork, *ntask;
+    unsigned long long task_cap;
 };
 
 // one stencil, single linear segment (two History entries per vertex)
-template <bool IS_VF> __device__ __forceinline__ int run_single(const NpArgs &A, long long i, double &toi, bool defer)
+template <bool IS_VF>
+__device__ __forceinline__ int run_single(const NpArgs &A, long long i, double &toi, int mode, int start, Pend &P, const double *trec)
 {
     const int4 s = reinterpret_cast<const int4 *>(A.stencils)[i];
     const double eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
@@ -205,7 +230,7 @@ template <bool IS_VF> __device__ __forceinline__ int run_single(const NpArgs &A,
     V3 a[4], b[4];
     a[0] = ldv(A.q0 + vs * s.x); a[1] = ldv(A.q0 + vs * s.y); a[2] = ldv(A.q0 + vs * s.z); a[3] = ldv(A.q0 + vs * s.w);
     b[0] = ldv(A.q1 + vs * s.x); b[1] = ldv(A.q1 + vs * s.y); b[2] = ldv(A.q1 + vs * s.z); b[3] = ldv(A.q1 + vs * s.w);
-    return IS_VF ? vf_stencil_segment(a, b, eta, toi, defer) : ee_stencil_segment(a, b, eta, toi, defer);
+    return IS_VF ? vf_stencil_segment(a, b, eta, toi, mode, start, P, trec) : ee_stencil_segment(a, b, eta, toi, mode, start, P, trec);
 }
 
 __device__ __forceinline__ void store_result(const NpArgs &A, long long i, int stage, double toi)
@@ -215,35 +240,91 @@ __device__ __forceinline__ void store_result(const NpArgs &A, long long i, int s
     if (A.stage) A.stage[i] = (unsigned char)stage;
 }
 
-// pass 1: all stencils, iterative work deferred
+// pass 1: all stencils, straight-line work only.  A stencil whose next sub-test needs the root isolator is put on the
+// work list together with one task record per pending polynomial (coefficients + reduced degree).
 template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_pass1_kernel(NpArgs A)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int stage = 0;
+    int stage = 0, ntask = 0;
     double toi = 0.0;
-    bool deferred = false;
+    Pend P;
+    P.mask = 0;
     if (i < A.n)
     {
-        stage = run_single<IS_VF>(A, i, toi, true);
-        deferred = stage < 0;
-        if (deferred) stage = 0;
+        stage = run_single<IS_VF>(A, i, toi, MODE_DEFER, 0, P, nullptr);
+        if (stage < 0) ntask = __popc(P.mask);
         else store_result(A, i, stage, toi);
     }
-    // warp-aggregated append of the deferred stencils
+    const int lane = threadIdx.x & 31;
+    const bool deferred = stage < 0;
     const unsigned m = __ballot_sync(0xffffffffu, deferred);
     if (m)
     {
-        const int lane = threadIdx.x & 31;
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(A.nwork, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (deferred) A.worklist[base + __popc(m & ((1u << lane) - 1))] = (int)i;
+        // warp-aggregated allocation: one atomic for the work-list slots, one for the task records
+        int pre = ntask;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            int x = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += x;
+        }
+        const int total = __shfl_sync(0xffffffffu, pre, 31);
+        unsigned long long wbase = 0, tbase = 0;
+        if (lane == 0)
+        {
+            wbase = atomicAdd(A.nwork, (unsigned long long)__popc(m));
+            tbase = atomicAdd(A.ntask, (unsigned long long)total);
+        }
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        tbase = __shfl_sync(0xffffffffu, tbase, 0);
+        if (deferred)
+        {
+            const unsigned long long w = wbase + __popc(m & ((1u << lane) - 1));
+            const unsigned long long t0 = tbase + (unsigned long long)(pre - ntask);
+            A.work_stencil[w] = (int)i;
+            A.work_task[w] = (int)t0;
+            A.work_sub[w] = (unsigned char)(-stage - 1);
+            int j = 0;
+            unsigned mask = P.mask;
+            while (mask)
+            {
+                const int k = __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (t0 + j < A.task_cap)
+                {
+                    double *rec = A.tasks + 8 * (t0 + j);
+                    const int rd = P.rds[k];
+                    for (int c = 0; c <= rd; c++) rec[c] = P.ops[k][c];
+                    rec[7] = (double)rd;
+                }
+                j++;
+            }
+        }
     }
-    reduce_warp(stage != 0, toi, A.earliest_bits, A.nhit);
+    reduce_warp(stage > 0, toi, A.earliest_bits, A.nhit);
 }
 
-// pass 2: the deferred stencils, full algorithm
-template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_pass2_kernel(NpArgs A)
+// root kernel: one thread per pending polynomial; the record's coefficients are replaced by its roots in [0,1]
+__global__ void __launch_bounds__(128) roots_kernel(double *tasks, const unsigned long long *ntask_ptr, unsigned long long cap)
+{
+    unsigned long long nt = *ntask_ptr;
+    if (nt > cap) nt = cap;
+    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < nt;
+         j += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        double *rec = tasks + 8 * j;
+        double op[7], b[7], roots[6];
+        const int rd = (int)rec[7];
+        for (int c = 0; c <= rd; c++) op[c] = rec[c];
+        bernstein(op, rd, b);
+        const int nr = roots01(op, rd, b, roots);
+        for (int c = 0; c < nr; c++) rec[c] = roots[c];
+        rec[7] = (double)nr;
+    }
+}
+
+// pass 3: the deferred stencils resume at the sub-test that deferred, with its roots read from the task records
+template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_pass3_kernel(NpArgs A)
 {
     const unsigned long long nw = *A.nwork;
     const unsigned long long nround = (nw + 31ull) & ~31ull;
@@ -254,8 +335,9 @@ template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_pass2_kerne
         double toi = 0.0;
         if (w < nw)
         {
-            const long long i = A.worklist[w];
-            stage = run_single<IS_VF>(A, i, toi, false);
+            Pend P;
+            const long long i = A.work_stencil[w];
+            stage = run_single<IS_VF>(A, i, toi, MODE_RESUME, A.work_sub[w], P, A.tasks + 8ll * A.work_task[w]);
             store_result(A, i, stage, toi);
         }
         reduce_warp(stage != 0, toi, A.earliest_bits, A.nhit);
@@ -274,12 +356,13 @@ template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_history_ker
         const double eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
         int verts[4] = {s.x, s.y, s.z, s.w};
         V3 a[4], b[4];
+        Pend P;
         Stitcher st;
         st.begin(A.hoff, A.htime, A.hpos, verts);
         if (st.next(a))
             while (st.next(b))
             {
-                stage = IS_VF ? vf_stencil_segment(a, b, eta, toi, false) : ee_stencil_segment(a, b, eta, toi, false);
+                stage = IS_VF ? vf_stencil_segment(a, b, eta, toi, MODE_FULL, 0, P, nullptr) : ee_stencil_segment(a, b, eta, toi, MODE_FULL, 0, P, nullptr);
                 if (stage) break;
                 for (int k = 0; k < 4; k++) a[k] = b[k];
             }
@@ -300,9 +383,10 @@ __global__ void __launch_bounds__(128) prim_kernel(int kind, long long n, const 
     const double *p = pts + 6ll * np * i;
     V3 s[4], v[4];
     for (int k = 0; k < np; k++) { s[k] = ldv(p + 3 * k); v[k] = ldv(p + 3 * (np + k)) - s[k]; }
-    if (kind == 0) r = vertex_face(s, v, eta[i], tt, false);
-    else if (kind == 1) r = edge_edge(s, v, eta[i], tt, false);
-    else if (kind == 2) r = vertex_edge(s[0], s[1], s[2], v[0], v[1], v[2], eta[i], tt, false);
+    Pend P;
+    if (kind == 0) r = vertex_face(s, v, eta[i], tt, MODE_FULL, P, nullptr);
+    else if (kind == 1) r = edge_edge(s, v, eta[i], tt, MODE_FULL, P, nullptr);
+    else if (kind == 2) r = vertex_edge(s[0], s[1], s[2], v[0], v[1], v[2], eta[i], tt, MODE_FULL, P, nullptr);
     else r = vertex_vertex(s[0], s[1], v[0], v[1], eta[i], tt);
     hit[i] = r == R_HIT;
     if (r == R_HIT) t[i] = tt;       // t is written only on a hit, like the reference
@@ -318,7 +402,7 @@ __global__ void find_intervals_kernel(long long n, int degree, int pos, const do
     iv.n = 0;
     double op[7];
     for (int k = 0; k <= degree; k++) op[k] = coeffs[7 * i + k];
-    find_intervals(op, degree, iv, pos != 0, false);
+    find_intervals(op, degree, iv, pos != 0);
     cnt[i] = iv.n;
     for (int k = 0; k < iv.n; k++) { lo[7 * i + k] = iv.l[k]; hi[7 * i + k] = iv.u[k]; }
 }
@@ -330,17 +414,22 @@ using namespace ccd;
 
 static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
-// worklist: n ints; nwork: device counter (zeroed here).  Returns the number of kernels launched.
+// Buffers: work_stencil/work_task (n ints each), work_sub (n bytes), tasks (task_cap records of 8 doubles), counters
+// nwork/ntask (zeroed here).  Returns the number of kernels launched.  If *ntask ends above task_cap the caller must
+// grow the task buffer and call again (the stencils whose records did not fit resume with garbage otherwise).
 int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, double eta_all,
                      const double *q0, const double *q1, int vstride, const long long *hoff, const double *htime, const double *hpos,
                      unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits,
-                     unsigned long long *nhit, int *worklist, unsigned long long *nwork)
+                     unsigned long long *nhit, int *work_stencil, int *work_task, unsigned char *work_sub, double *tasks,
+                     unsigned long long task_cap, unsigned long long *nwork, unsigned long long *ntask)
 {
     if (n <= 0) return 0;
     NpArgs A;
     A.n = n; A.stencils = stencils; A.eta_arr = eta_arr; A.eta_all = eta_all; A.q0 = q0; A.q1 = q1; A.vstride = vstride;
     A.hoff = hoff; A.htime = htime; A.hpos = hpos; A.hit = hit; A.toi = toi; A.stage = stage;
-    A.earliest_bits = earliest_bits; A.nhit = nhit; A.worklist = worklist; A.nwork = nwork;
+    A.earliest_bits = earliest_bits; A.nhit = nhit;
+    A.work_stencil = work_stencil; A.work_task = work_task; A.work_sub = work_sub; A.tasks = tasks;
+    A.nwork = nwork; A.ntask = ntask; A.task_cap = task_cap;
     const int B = 128;
     if (q0 == nullptr)
     {
@@ -349,18 +438,14 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
         return 1;
     }
     cudaMemsetAsync(nwork, 0, sizeof(unsigned long long), st);
+    cudaMemsetAsync(ntask, 0, sizeof(unsigned long long), st);
     const unsigned g2 = (unsigned)min((long long)148 * 32, (long long)grid_for(n, B));
-    if (is_vf)
-    {
-        stencil_pass1_kernel<true><<<grid_for(n, B), B, 0, st>>>(A);
-        stencil_pass2_kernel<true><<<g2, B, 0, st>>>(A);
-    }
-    else
-    {
-        stencil_pass1_kernel<false><<<grid_for(n, B), B, 0, st>>>(A);
-        stencil_pass2_kernel<false><<<g2, B, 0, st>>>(A);
-    }
-    return 2;
+    if (is_vf) stencil_pass1_kernel<true><<<grid_for(n, B), B, 0, st>>>(A);
+    else stencil_pass1_kernel<false><<<grid_for(n, B), B, 0, st>>>(A);
+    roots_kernel<<<g2, B, 0, st>>>(tasks, ntask, task_cap);
+    if (is_vf) stencil_pass3_kernel<true><<<g2, B, 0, st>>>(A);
+    else stencil_pass3_kernel<false><<<g2, B, 0, st>>>(A);
+    return 3;
 }
 
 void ccdk_prim_batch(cudaStream_t st, int kind, long long n, const double *pts, const double *eta, unsigned char *hit, double *t)

@@ -120,6 +120,7 @@ typedef struct
     int64_t n_tree_candidates; /* pairs that survived the float AABB tree before the exact test */
     float ms_broadphase, ms_narrowphase;
     int32_t n_launches; /* kernels launched by this call (ours + CUB passes) */
+    int64_t n_vf_deferred, n_ee_deferred; /* stencils that needed the iterative root isolator (narrowphase pass 2) */
 } ccd_device_result;
 
 int ccd_step_device(ccd_context *ctx, int kind, int V, int F, const int32_t *d_faces, const double *d_q0,
