@@ -44,14 +44,15 @@ struct ccd_context
     // emission
     DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut;
     // narrowphase
-    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, tasksVf, tasksEe, selTmp, selA, selB, selC, selD, selCount;
+    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, work2Vf, work2Ee, work2TaskVf, work2TaskEe, work2SubVf, work2SubEe, tasksVf, tasksEe, selTmp, selA, selB, selC, selD, selCount;
     // pinned host scratch
     unsigned long long *h_counters = nullptr; // 16 entries
     size_t candCap = 0, pairCap = 0, taskCapVf = 0, taskCapEe = 0;
 };
 
 // device counters layout (unsigned long long each)
-enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NWORK_VF = 7, C_NWORK_EE = 8, C_NTASK_VF = 9, C_NTASK_EE = 10, C_TOTAL = 16 };
+enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NP_VF = 16 /* 4 counters: list 1, list 2, task records, records after pass 1 */, C_NP_EE = 20, C_TOTAL = 24 };
+enum { C_NWORK_VF = C_NP_VF, C_NTASK_VF = C_NP_VF + 2, C_NWORK_EE = C_NP_EE, C_NTASK_EE = C_NP_EE + 2 };
 
 #define CK(call)                                                                                      \
     do                                                                                                \
@@ -209,7 +210,7 @@ void ccd_destroy(ccd_context *c)
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->work2Vf, &c->work2Ee, &c->work2TaskVf, &c->work2TaskEe, &c->work2SubVf, &c->work2SubEe, &c->tasksVf, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
     for (DBuf *b : all)
         if (b->p)
             cudaFree(b->p);
@@ -450,6 +451,12 @@ static int narrowphase_device(ccd_context *c, long long nvf, const int *d_vf, co
     CKR(ensure(c, c->workTaskEe, sizeof(int) * ((size_t)nee + 32)));
     CKR(ensure(c, c->workSubVf, (size_t)nvf + 32));
     CKR(ensure(c, c->workSubEe, (size_t)nee + 32));
+    CKR(ensure(c, c->work2Vf, sizeof(int) * ((size_t)nvf + 32)));
+    CKR(ensure(c, c->work2Ee, sizeof(int) * ((size_t)nee + 32)));
+    CKR(ensure(c, c->work2TaskVf, sizeof(int) * ((size_t)nvf + 32)));
+    CKR(ensure(c, c->work2TaskEe, sizeof(int) * ((size_t)nee + 32)));
+    CKR(ensure(c, c->work2SubVf, (size_t)nvf + 32));
+    CKR(ensure(c, c->work2SubEe, (size_t)nee + 32));
     int nl = 0;
     for (int attempt = 0; attempt < 4; attempt++)
     {
@@ -464,22 +471,22 @@ static int narrowphase_device(ccd_context *c, long long nvf, const int *d_vf, co
         cudaEventRecord(c->sev[ST_NP_VF], c->st);
         nl += ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
                                P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF, P<int>(c->workVf),
-                               P<int>(c->workTaskVf), P<unsigned char>(c->workSubVf), P<double>(c->tasksVf), c->taskCapVf, ctr + C_NWORK_VF,
-                               ctr + C_NTASK_VF);
+                               P<int>(c->workTaskVf), P<unsigned char>(c->workSubVf), P<int>(c->work2Vf), P<int>(c->work2TaskVf),
+                               P<unsigned char>(c->work2SubVf), P<double>(c->tasksVf), c->taskCapVf, ctr + C_NP_VF);
         cudaEventRecord(c->sev[ST_NP_EE], c->st);
         nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
                                P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE, P<int>(c->workEe),
-                               P<int>(c->workTaskEe), P<unsigned char>(c->workSubEe), P<double>(c->tasksEe), c->taskCapEe, ctr + C_NWORK_EE,
-                               ctr + C_NTASK_EE);
+                               P<int>(c->workTaskEe), P<unsigned char>(c->workSubEe), P<int>(c->work2Ee), P<int>(c->work2TaskEe),
+                               P<unsigned char>(c->work2SubEe), P<double>(c->tasksEe), c->taskCapEe, ctr + C_NP_EE);
         cudaEventRecord(c->sev[CCD_N_STAGES], c->st);
         CK(cudaGetLastError());
         CKR(sync_counters(c));
         const bool single = d_q0 != nullptr;
         const unsigned long long tv = single ? c->h_counters[C_NTASK_VF] : 0, te = single ? c->h_counters[C_NTASK_EE] : 0;
-        if (tv <= c->taskCapVf && te <= c->taskCapEe)
+        if (tv + 5 <= c->taskCapVf && te + 5 <= c->taskCapEe)
             break;
-        if (tv > c->taskCapVf) c->taskCapVf = (size_t)(tv + tv / 8 + 1024);
-        if (te > c->taskCapEe) c->taskCapEe = (size_t)(te + te / 8 + 1024);
+        if (tv + 5 > c->taskCapVf) c->taskCapVf = (size_t)(tv + tv / 8 + 1024);
+        if (te + 5 > c->taskCapEe) c->taskCapEe = (size_t)(te + te / 8 + 1024);
     }
     c->launches += nl;
     if (sum)

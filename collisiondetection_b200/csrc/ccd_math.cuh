@@ -191,6 +191,7 @@ static __device__ __noinline__ int roots01(const double *c, int d, double *b, do
 {
     double p[7], cur[6];
     int ncur = 0, m0;
+    bool one = false;      // level m0 has exactly one sign variation: one root, bracketed by [0,1]
     // descend to the first level that can be decided
     for (m0 = d; m0 >= 2; m0--)
     {
@@ -204,10 +205,7 @@ static __device__ __noinline__ int roots01(const double *c, int d, double *b, do
                 break;
             if (v == 1)
             {
-                deriv_level(c, d, m0, p);
-                double f0 = p[m0], f1 = horner_fma(p, m0, 1.0);
-                if ((f0 < 0.0 && f1 > 0.0) || (f0 > 0.0 && f1 < 0.0))
-                    cur[ncur++] = solve_bracket(p, m0, 0.0, 1.0, f0);
+                one = true;
                 break;
             }
         }
@@ -228,42 +226,44 @@ static __device__ __noinline__ int roots01(const double *c, int d, double *b, do
             break;
         }
     }
-    if (m0 < d)
+    // climb: cur = roots of q_{m-1} strictly inside (0,1); pieces between them are monotone for q_m.
+    // A level decided by "one sign variation" is handled by the same loop as a single piece [0,1] in which only a
+    // strict sign change counts (zeros at the ends are not roots there), so every bracketed solve of every lane of
+    // the warp is issued from the one call below.
+    double brk[8], fv[8], out[7];
+    for (int m = one ? m0 : m0 + 1; m <= d; m++)
     {
-        // climb: cur = roots of q_{m-1} strictly inside (0,1); pieces between them are monotone for q_m
-        double brk[8], fv[8], out[7];
-        for (int m = m0 + 1; m <= d; m++)
-        {
-            const bool last = (m == d);
-            int nb = 0, nr = 0;
-            deriv_level(c, d, m, p);
-            brk[nb++] = 0.0;
+        const bool plain = one && m == m0;
+        const bool last = (m == d);
+        int nb = 0, nr = 0;
+        deriv_level(c, d, m, p);
+        brk[nb++] = 0.0;
+        if (!plain)
             for (int i = 0; i < ncur; i++)
                 brk[nb++] = cur[i];
-            brk[nb++] = 1.0;
-            for (int i = 0; i < nb; i++)
-                fv[i] = horner_fma(p, m, brk[i]);
-            for (int i = 0; i + 1 < nb; i++)
+        brk[nb++] = 1.0;
+        for (int i = 0; i < nb; i++)
+            fv[i] = horner_fma(p, m, brk[i]);
+        for (int i = 0; i + 1 < nb; i++)
+        {
+            if (fv[i] == 0.0)
             {
-                if (fv[i] == 0.0)
-                {
-                    if ((i > 0 || last) && (nr == 0 || out[nr - 1] != brk[i]))
-                        out[nr++] = brk[i];
-                }
-                else if ((fv[i] < 0.0 && fv[i + 1] > 0.0) || (fv[i] > 0.0 && fv[i + 1] < 0.0))
-                {
-                    double r = solve_bracket(p, m, brk[i], brk[i + 1], fv[i]);
-                    if (nr == 0 || out[nr - 1] != r)
-                        out[nr++] = r;
-                }
+                if (!plain && (i > 0 || last) && (nr == 0 || out[nr - 1] != brk[i]))
+                    out[nr++] = brk[i];
             }
-            if (last && fv[nb - 1] == 0.0 && (nr == 0 || out[nr - 1] != 1.0))
-                out[nr++] = 1.0;
-            ncur = 0;
-            for (int i = 0; i < nr; i++)
-                if (last || (out[i] > 0.0 && out[i] < 1.0))
-                    cur[ncur++] = out[i];
+            else if ((fv[i] < 0.0 && fv[i + 1] > 0.0) || (fv[i] > 0.0 && fv[i + 1] < 0.0))
+            {
+                double r = solve_bracket(p, m, brk[i], brk[i + 1], fv[i]);
+                if (nr == 0 || out[nr - 1] != r)
+                    out[nr++] = r;
+            }
         }
+        if (!plain && last && fv[nb - 1] == 0.0 && (nr == 0 || out[nr - 1] != 1.0))
+            out[nr++] = 1.0;
+        ncur = 0;
+        for (int i = 0; i < nr; i++)
+            if ((last && !plain) || (out[i] > 0.0 && out[i] < 1.0))
+                cur[ncur++] = out[i];
     }
     for (int i = 0; i < ncur; i++)
         roots[i] = cur[i];
@@ -274,7 +274,7 @@ static __device__ __noinline__ int roots01(const double *c, int d, double *b, do
 // CTCD::findIntervals (src/CTCD.cpp:98-177)
 // ------------------------------------------------------------------------------------------
 // CTCD::checkInterval, src/CTCD.cpp:59-79 — unfused Horner at the clamped midpoint
-__device__ __forceinline__ void check_interval(double t1, double t2, const double *op, int degree, Ivals &iv, bool pos)
+static __device__ __noinline__ void check_interval(double t1, double t2, const double *op, int degree, Ivals &iv, bool pos)
 {
     t1 = smax(0.0, t1);
     t2 = smax(0.0, t2);
@@ -292,7 +292,7 @@ __device__ __forceinline__ void check_interval(double t1, double t2, const doubl
 }
 
 // CTCD::getQuadRoots, src/CTCD.cpp:38-56
-__device__ __forceinline__ int quad_roots(double a, double b, double c, double &t0, double &t1)
+static __device__ __noinline__ int quad_roots(double a, double b, double c, double &t0, double &t1)
 {
     int roots = 0;
     double sign = (b < 0) ? -1.0 : 1.0;
@@ -417,7 +417,7 @@ __device__ __forceinline__ void find_intervals(double *op, int n, Ivals &iv, boo
 // Settle the pending polynomials of a primitive: lists[k] receives the intervals of polynomial k (bit k of P.mask),
 // posmask bit k = the reference's `pos` flag.  RESUME reads 64-byte task records {roots[6], -, count} in bit order.
 // Returns false as soon as a list comes out empty (the primitive misses), else true.
-static __device__ __noinline__ bool resolve_pending(Pend &P, Ivals *lists, unsigned posmask, int mode, const double *trec)
+template <int MODE> static __device__ __noinline__ bool resolve_pending(Pend &P, Ivals *lists, unsigned posmask, const double *trec)
 {
     int j = 0;
     while (P.mask)
@@ -425,7 +425,7 @@ static __device__ __noinline__ bool resolve_pending(Pend &P, Ivals *lists, unsig
         const int k = __ffs(P.mask) - 1;
         P.mask &= P.mask - 1;
         const bool pos = (posmask >> k) & 1u;
-        if (mode == MODE_RESUME)
+        if (MODE == MODE_RESUME)
         {
             double r[6];
             const double *rec = trec + 8 * j;
@@ -499,7 +499,7 @@ __device__ __forceinline__ void barycentric_coeffs(V3 x10, V3 x20, V3 x30, V3 v1
 // Return R_MISS / R_HIT (t written) / R_DEFER (only with defer=true: needs the iterative isolator).
 // ------------------------------------------------------------------------------------------
 // CTCD::vertexFaceCTCD, src/CTCD.cpp:413-508 — vertex s[0] against face (s[1],s[2],s[3])
-static __device__ __noinline__ int vertex_face(const V3 *s, const V3 *v, double eta, double &t, int mode, Pend &P, const double *trec)
+template <int MODE> static __device__ __noinline__ int vertex_face(const V3 *s, const V3 *v, double eta, double &t, Pend &P, const double *trec)
 {
     Ivals iv[4];       // e1, e2, e3, coplane
     P.mask = 0;
@@ -526,9 +526,9 @@ static __device__ __noinline__ int vertex_face(const V3 *s, const V3 *v, double 
         return R_MISS;
     if (P.mask)
     {
-        if (mode == MODE_DEFER)
+        if (MODE == MODE_DEFER)
             return R_DEFER;
-        if (!resolve_pending(P, iv, 0x7u, mode, trec))
+        if (!resolve_pending<MODE>(P, iv, 0x7u, trec))
             return R_MISS;
     }
     const Ivals &cop = iv[3], &e1 = iv[0], &e2 = iv[1], &e3 = iv[2];
@@ -560,7 +560,7 @@ static __device__ __noinline__ int vertex_face(const V3 *s, const V3 *v, double 
 }
 
 // CTCD::edgeEdgeCTCD, src/CTCD.cpp:259-411 — points (q0,p0,q1,p1) = s[0..3]: edges (q0,p0) and (q1,p1)
-static __device__ __noinline__ int edge_edge(const V3 *s, const V3 *v, double eta, double &t, int mode, Pend &P, const double *trec)
+template <int MODE> static __device__ __noinline__ int edge_edge(const V3 *s, const V3 *v, double eta, double &t, Pend &P, const double *trec)
 {
     Ivals cop, par, q[5];      // q[0..3] = a0,a1,b0,b1 ; q[4] = raw coplanarity intervals
     P.mask = 0;
@@ -587,9 +587,9 @@ static __device__ __noinline__ int edge_edge(const V3 *s, const V3 *v, double et
     }
     if (P.mask)
     {
-        if (mode == MODE_DEFER)
+        if (MODE == MODE_DEFER)
             return R_DEFER;
-        if (!resolve_pending(P, q, 0xFu, mode, trec))
+        if (!resolve_pending<MODE>(P, q, 0xFu, trec))
             return R_MISS;
     }
     {
@@ -644,7 +644,7 @@ static __device__ __noinline__ int edge_edge(const V3 *s, const V3 *v, double et
 }
 
 // CTCD::vertexEdgeCTCD, src/CTCD.cpp:511-602 — vertex q0 against segment (q1,q2); v* = end - start
-static __device__ __noinline__ int vertex_edge(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, double &t, int mode, Pend &P, const double *trec)
+template <int MODE> static __device__ __noinline__ int vertex_edge(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, double &t, Pend &P, const double *trec)
 {
     const double minD = eta * eta;
     const V3 ab = q2s - q1s, ac = q0s - q1s, cb = q2s - q0s;
@@ -682,9 +682,9 @@ static __device__ __noinline__ int vertex_edge(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3
     if (prepare_poly(op, 4, colin, false, P.rds[0]))
     {
         P.mask = 1u;
-        if (mode == MODE_DEFER)
+        if (MODE == MODE_DEFER)
             return R_DEFER;
-        resolve_pending(P, &colin, 0u, mode, trec);
+        resolve_pending<MODE>(P, &colin, 0u, trec);
     }
     if (colin.n == 0) return R_MISS;
     bool col = false;

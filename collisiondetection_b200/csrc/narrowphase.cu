@@ -12,7 +12,9 @@
 //           next sub-test needs the iterative root isolator goes on a work list, with one 64-byte task
 //           record per pending polynomial (warp-aggregated allocation);
 //   roots   one thread per pending polynomial: dense warps, every lane inside the isolator;
-//   pass 3  the work list only: resumes at the deferred sub-test with its roots, finishes the sequence.
+//   resume  the work list only: continues at the deferred sub-test with its roots; a later sub-test that needs
+//           roots again is deferred once more (second, tiny round) so that only the last, rare-work kernel
+//           carries the isolator inline — the big kernels stay small enough for the instruction cache.
 // Degenerate sub-tests (and the EE primitive) are skipped when the swept boxes of the two parts stay further
 // apart than eta plus a safety margin: those tests measure true distances (include/CTCD.h:31-79), so the
 // reference cannot report a hit there; the margin (4e-5 of the coordinate scale) is ~1e3 times the distance
@@ -55,11 +57,11 @@ __device__ __forceinline__ double box_scale(const Box &b)
 // ---- per-segment stencil tests --------------------------------------------------------------
 // Sub-tests are numbered in the reference's order: 0 = the VF / EE primitive, then the vertex-edge tests, then
 // the vertex-vertex tests.  a[0..3] start positions, b[0..3] end positions.
-// Return: stage that hit (sub-test index + 1), 0 for a miss, -(sub+1) when sub-test `sub` was deferred (DEFER mode;
-// its pending polynomials are in P).  RESUME mode starts at sub-test `start` (everything before it is known to
-// miss), feeds it the roots in trec and finishes the remaining sub-tests in FULL mode.
-static __device__ __noinline__ int vf_stencil_segment(const V3 *a, const V3 *b, double eta, double &t, int mode, int start, Pend &P,
-                                                      const double *trec)
+// Return: stage that hit (sub-test index + 1), 0 for a miss, -(sub+1) when sub-test `sub` was deferred (its pending
+// polynomials are in P).  The walk starts at sub-test `start` (everything before it is known to miss); that sub-test
+// runs in mode FIRST (RESUME: its roots come from trec), the ones after it in mode LATER.
+template <int FIRST, int LATER>
+static __device__ __noinline__ int vf_stencil_segment(const V3 *a, const V3 *b, double eta, double &t, int start, Pend &P, const double *trec)
 {
     V3 v[4];
     Box bx[4];
@@ -67,11 +69,10 @@ static __device__ __noinline__ int vf_stencil_segment(const V3 *a, const V3 *b, 
     int r;
     if (start <= 0)
     {
-        r = vertex_face(a, v, eta, t, mode, P, trec);
+        r = vertex_face<FIRST>(a, v, eta, t, P, trec);
         if (r == R_HIT) return 1;
         if (r == R_DEFER) return -1;
     }
-    const int later = (mode == MODE_RESUME) ? MODE_FULL : mode;
     const Box face = join(join(bx[1], bx[2]), bx[3]);
     const double m = eta + 4e-5 * fmax(box_scale(bx[0]), box_scale(face));
     if (apart(bx[0], face, m)) return 0;
@@ -81,7 +82,8 @@ static __device__ __noinline__ int vf_stencil_segment(const V3 *a, const V3 *b, 
         const int sub = 1 + e, i1 = 1 + e, i2 = 1 + ((e + 1) % 3);
         if (sub < start) continue;
         if (apart(bx[0], join(bx[i1], bx[i2]), m)) continue;
-        r = vertex_edge(a[0], a[i1], a[i2], v[0], v[i1], v[i2], eta, t, sub == start ? mode : later, P, trec);
+        r = (FIRST != LATER && sub == start) ? vertex_edge<FIRST>(a[0], a[i1], a[i2], v[0], v[i1], v[i2], eta, t, P, trec)
+                                              : vertex_edge<LATER>(a[0], a[i1], a[i2], v[0], v[i1], v[i2], eta, t, P, trec);
         if (r == R_HIT) return sub + 1;
         if (r == R_DEFER) return -(sub + 1);
     }
@@ -95,8 +97,8 @@ static __device__ __noinline__ int vf_stencil_segment(const V3 *a, const V3 *b, 
 }
 
 // a/b: (p0, p1, q0, q1); edgeEdgeCTCD takes (q0,p0,q1,p1) = (pos0,pos1,pos2,pos3): src/CTCDNarrowPhase.cpp:91
-static __device__ __noinline__ int ee_stencil_segment(const V3 *a, const V3 *b, double eta, double &t, int mode, int start, Pend &P,
-                                                      const double *trec)
+template <int FIRST, int LATER>
+static __device__ __noinline__ int ee_stencil_segment(const V3 *a, const V3 *b, double eta, double &t, int start, Pend &P, const double *trec)
 {
     V3 v[4];
     Box bx[4];
@@ -107,18 +109,18 @@ static __device__ __noinline__ int ee_stencil_segment(const V3 *a, const V3 *b, 
     int r;
     if (start <= 0)
     {
-        r = edge_edge(a, v, eta, t, mode, P, trec);
+        r = edge_edge<FIRST>(a, v, eta, t, P, trec);
         if (r == R_HIT) return 1;
         if (r == R_DEFER) return -1;
     }
-    const int later = (mode == MODE_RESUME) ? MODE_FULL : mode;
     // src/CTCDNarrowPhase.cpp:99-114: p0|p1 against (q0,q1), q0|q1 against (p0,p1)
     for (int k = 0; k < 4; k++)
     {
         const int sub = 1 + k, iv = k, i1 = (k < 2) ? 2 : 0, i2 = i1 + 1;
         if (sub < start) continue;
         if (apart(bx[iv], (k < 2) ? e1 : e0, m)) continue;
-        r = vertex_edge(a[iv], a[i1], a[i2], v[iv], v[i1], v[i2], eta, t, sub == start ? mode : later, P, trec);
+        r = (FIRST != LATER && sub == start) ? vertex_edge<FIRST>(a[iv], a[i1], a[i2], v[iv], v[i1], v[i2], eta, t, P, trec)
+                                              : vertex_edge<LATER>(a[iv], a[i1], a[i2], v[iv], v[i1], v[i2], eta, t, P, trec);
         if (r == R_HIT) return sub + 1;
         if (r == R_DEFER) return -(sub + 1);
     }
@@ -197,6 +199,15 @@ __device__ __forceinline__ void reduce_warp(bool hit, double toi, unsigned long 
     }
 }
 
+// one list of deferred stencils: entry w = {stencil index, first task record, sub-test that deferred}
+struct WorkList
+{
+    int *stencil;
+    int *task;
+    unsigned char *sub;
+    unsigned long long *count;
+};
+
 struct NpArgs
 {
     long long n;
@@ -211,18 +222,15 @@ struct NpArgs
     double *toi;
     unsigned char *stage;
     unsigned long long *earliest_bits, *nhit;
-    // deferred work: entry w = {stencil index, first task record, sub-test that deferred}; tasks are 64-byte records
-    int *work_stencil;
-    int *work_task;
-    unsigned char *work_sub;
-    double *tasks;
-    unsigned long long *nwork, *ntask;
+    WorkList in, out;           // pass 1 fills `out`; a resume pass reads `in` and may fill `out`
+    double *tasks;              // 64-byte records: coefficients + reduced degree in, roots + count out
+    unsigned long long *ntask;  // running number of task records
     unsigned long long task_cap;
 };
 
 // one stencil, single linear segment (two History entries per vertex)
-template <bool IS_VF>
-__device__ __forceinline__ int run_single(const NpArgs &A, long long i, double &toi, int mode, int start, Pend &P, const double *trec)
+template <bool IS_VF, int FIRST, int LATER>
+__device__ __forceinline__ int run_single(const NpArgs &A, long long i, double &toi, int start, Pend &P, const double *trec)
 {
     const int4 s = reinterpret_cast<const int4 *>(A.stencils)[i];
     const double eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
@@ -230,7 +238,7 @@ __device__ __forceinline__ int run_single(const NpArgs &A, long long i, double &
     V3 a[4], b[4];
     a[0] = ldv(A.q0 + vs * s.x); a[1] = ldv(A.q0 + vs * s.y); a[2] = ldv(A.q0 + vs * s.z); a[3] = ldv(A.q0 + vs * s.w);
     b[0] = ldv(A.q1 + vs * s.x); b[1] = ldv(A.q1 + vs * s.y); b[2] = ldv(A.q1 + vs * s.z); b[3] = ldv(A.q1 + vs * s.w);
-    return IS_VF ? vf_stencil_segment(a, b, eta, toi, mode, start, P, trec) : ee_stencil_segment(a, b, eta, toi, mode, start, P, trec);
+    return IS_VF ? vf_stencil_segment<FIRST, LATER>(a, b, eta, toi, start, P, trec) : ee_stencil_segment<FIRST, LATER>(a, b, eta, toi, start, P, trec);
 }
 
 __device__ __forceinline__ void store_result(const NpArgs &A, long long i, int stage, double toi)
@@ -240,76 +248,78 @@ __device__ __forceinline__ void store_result(const NpArgs &A, long long i, int s
     if (A.stage) A.stage[i] = (unsigned char)stage;
 }
 
-// pass 1: all stencils, straight-line work only.  A stencil whose next sub-test needs the root isolator is put on the
-// work list together with one task record per pending polynomial (coefficients + reduced degree).
+// Whole-warp call.  Lanes with `deferred` set put stencil i on the out list with one task record per pending polynomial
+// of P (coefficients + reduced degree): one atomic for the list slots and one for the records per warp.
+__device__ __forceinline__ void defer_stencil(const NpArgs &A, bool deferred, long long i, int sub, const Pend &P)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned m = __ballot_sync(0xffffffffu, deferred);
+    if (!m) return;
+    const int ntask = deferred ? __popc(P.mask) : 0;
+    int pre = ntask;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        int x = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += x;
+    }
+    const int total = __shfl_sync(0xffffffffu, pre, 31);
+    unsigned long long wbase = 0, tbase = 0;
+    if (lane == 0)
+    {
+        wbase = atomicAdd(A.out.count, (unsigned long long)__popc(m));
+        tbase = atomicAdd(A.ntask, (unsigned long long)total);
+    }
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    tbase = __shfl_sync(0xffffffffu, tbase, 0);
+    if (!deferred) return;
+    const unsigned long long w = wbase + __popc(m & ((1u << lane) - 1));
+    const unsigned long long t0 = tbase + (unsigned long long)(pre - ntask);
+    A.out.stencil[w] = (int)i;
+    A.out.task[w] = (int)t0;
+    A.out.sub[w] = (unsigned char)sub;
+    int j = 0;
+    unsigned mask = P.mask;
+    while (mask)
+    {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        if (t0 + j < A.task_cap)
+        {
+            double *rec = A.tasks + 8 * (t0 + j);
+            const int rd = P.rds[k];
+            for (int c = 0; c <= rd; c++) rec[c] = P.ops[k][c];
+            rec[7] = (double)rd;
+        }
+        j++;
+    }
+}
+
+// pass 1: all stencils, straight-line work only.  A stencil whose next sub-test needs the root isolator is deferred.
 template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_pass1_kernel(NpArgs A)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int stage = 0, ntask = 0;
+    int stage = 0;
     double toi = 0.0;
     Pend P;
     P.mask = 0;
     if (i < A.n)
     {
-        stage = run_single<IS_VF>(A, i, toi, MODE_DEFER, 0, P, nullptr);
-        if (stage < 0) ntask = __popc(P.mask);
-        else store_result(A, i, stage, toi);
+        stage = run_single<IS_VF, MODE_DEFER, MODE_DEFER>(A, i, toi, 0, P, nullptr);
+        if (stage >= 0) store_result(A, i, stage, toi);
     }
-    const int lane = threadIdx.x & 31;
-    const bool deferred = stage < 0;
-    const unsigned m = __ballot_sync(0xffffffffu, deferred);
-    if (m)
-    {
-        // warp-aggregated allocation: one atomic for the work-list slots, one for the task records
-        int pre = ntask;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            int x = __shfl_up_sync(0xffffffffu, pre, o);
-            if (lane >= o) pre += x;
-        }
-        const int total = __shfl_sync(0xffffffffu, pre, 31);
-        unsigned long long wbase = 0, tbase = 0;
-        if (lane == 0)
-        {
-            wbase = atomicAdd(A.nwork, (unsigned long long)__popc(m));
-            tbase = atomicAdd(A.ntask, (unsigned long long)total);
-        }
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        tbase = __shfl_sync(0xffffffffu, tbase, 0);
-        if (deferred)
-        {
-            const unsigned long long w = wbase + __popc(m & ((1u << lane) - 1));
-            const unsigned long long t0 = tbase + (unsigned long long)(pre - ntask);
-            A.work_stencil[w] = (int)i;
-            A.work_task[w] = (int)t0;
-            A.work_sub[w] = (unsigned char)(-stage - 1);
-            int j = 0;
-            unsigned mask = P.mask;
-            while (mask)
-            {
-                const int k = __ffs(mask) - 1;
-                mask &= mask - 1;
-                if (t0 + j < A.task_cap)
-                {
-                    double *rec = A.tasks + 8 * (t0 + j);
-                    const int rd = P.rds[k];
-                    for (int c = 0; c <= rd; c++) rec[c] = P.ops[k][c];
-                    rec[7] = (double)rd;
-                }
-                j++;
-            }
-        }
-    }
+    defer_stencil(A, stage < 0, i, -stage - 1, P);
     reduce_warp(stage > 0, toi, A.earliest_bits, A.nhit);
 }
 
-// root kernel: one thread per pending polynomial; the record's coefficients are replaced by its roots in [0,1]
-__global__ void __launch_bounds__(128) roots_kernel(double *tasks, const unsigned long long *ntask_ptr, unsigned long long cap)
+// root kernel: one thread per pending polynomial of records [*begin, *end); coefficients are replaced by the roots in [0,1]
+__global__ void __launch_bounds__(128) roots_kernel(double *tasks, const unsigned long long *begin_ptr, const unsigned long long *end_ptr,
+                                                    unsigned long long cap)
 {
-    unsigned long long nt = *ntask_ptr;
+    unsigned long long nt = *end_ptr;
+    const unsigned long long t0 = begin_ptr ? *begin_ptr : 0ull;
     if (nt > cap) nt = cap;
-    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < nt;
+    for (unsigned long long j = t0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < nt;
          j += (unsigned long long)gridDim.x * blockDim.x)
     {
         double *rec = tasks + 8 * j;
@@ -323,24 +333,30 @@ __global__ void __launch_bounds__(128) roots_kernel(double *tasks, const unsigne
     }
 }
 
-// pass 3: the deferred stencils resume at the sub-test that deferred, with its roots read from the task records
-template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_pass3_kernel(NpArgs A)
+// resume pass: the stencils of the `in` list continue at the sub-test that deferred, with its roots read from the task
+// records.  LATER = DEFER: a later sub-test that needs the isolator again goes on the `out` list (second round);
+// LATER = FULL: everything is finished in place (last round; rare work, the only kernel that carries the isolator inline).
+template <bool IS_VF, int LATER> __global__ void __launch_bounds__(128) stencil_resume_kernel(NpArgs A)
 {
-    const unsigned long long nw = *A.nwork;
+    const unsigned long long nw = *A.in.count;
     const unsigned long long nround = (nw + 31ull) & ~31ull;
     for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nround;
          w += (unsigned long long)gridDim.x * blockDim.x)
     {
         int stage = 0;
+        long long i = 0;
         double toi = 0.0;
-        if (w < nw)
+        Pend P;
+        P.mask = 0;
+        // records past the capacity were never written: the caller grows the buffer and reruns the whole narrowphase
+        if (w < nw && (unsigned long long)A.in.task[w] + 5ull <= A.task_cap)
         {
-            Pend P;
-            const long long i = A.work_stencil[w];
-            stage = run_single<IS_VF>(A, i, toi, MODE_RESUME, A.work_sub[w], P, A.tasks + 8ll * A.work_task[w]);
-            store_result(A, i, stage, toi);
+            i = A.in.stencil[w];
+            stage = run_single<IS_VF, MODE_RESUME, LATER>(A, i, toi, A.in.sub[w], P, A.tasks + 8ll * A.in.task[w]);
+            if (stage >= 0) store_result(A, i, stage, toi);
         }
-        reduce_warp(stage != 0, toi, A.earliest_bits, A.nhit);
+        if (LATER == MODE_DEFER) defer_stencil(A, stage < 0, i, -stage - 1, P);
+        reduce_warp(stage > 0, toi, A.earliest_bits, A.nhit);
     }
 }
 
@@ -362,7 +378,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_history_ker
         if (st.next(a))
             while (st.next(b))
             {
-                stage = IS_VF ? vf_stencil_segment(a, b, eta, toi, MODE_FULL, 0, P, nullptr) : ee_stencil_segment(a, b, eta, toi, MODE_FULL, 0, P, nullptr);
+                stage = IS_VF ? vf_stencil_segment<MODE_FULL, MODE_FULL>(a, b, eta, toi, 0, P, nullptr) : ee_stencil_segment<MODE_FULL, MODE_FULL>(a, b, eta, toi, 0, P, nullptr);
                 if (stage) break;
                 for (int k = 0; k < 4; k++) a[k] = b[k];
             }
@@ -384,9 +400,9 @@ __global__ void __launch_bounds__(128) prim_kernel(int kind, long long n, const 
     V3 s[4], v[4];
     for (int k = 0; k < np; k++) { s[k] = ldv(p + 3 * k); v[k] = ldv(p + 3 * (np + k)) - s[k]; }
     Pend P;
-    if (kind == 0) r = vertex_face(s, v, eta[i], tt, MODE_FULL, P, nullptr);
-    else if (kind == 1) r = edge_edge(s, v, eta[i], tt, MODE_FULL, P, nullptr);
-    else if (kind == 2) r = vertex_edge(s[0], s[1], s[2], v[0], v[1], v[2], eta[i], tt, MODE_FULL, P, nullptr);
+    if (kind == 0) r = vertex_face<MODE_FULL>(s, v, eta[i], tt, P, nullptr);
+    else if (kind == 1) r = edge_edge<MODE_FULL>(s, v, eta[i], tt, P, nullptr);
+    else if (kind == 2) r = vertex_edge<MODE_FULL>(s[0], s[1], s[2], v[0], v[1], v[2], eta[i], tt, P, nullptr);
     else r = vertex_vertex(s[0], s[1], v[0], v[1], eta[i], tt);
     hit[i] = r == R_HIT;
     if (r == R_HIT) t[i] = tt;       // t is written only on a hit, like the reference
@@ -414,38 +430,49 @@ using namespace ccd;
 
 static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
-// Buffers: work_stencil/work_task (n ints each), work_sub (n bytes), tasks (task_cap records of 8 doubles), counters
-// nwork/ntask (zeroed here).  Returns the number of kernels launched.  If *ntask ends above task_cap the caller must
-// grow the task buffer and call again (the stencils whose records did not fit resume with garbage otherwise).
+// Buffers: two work lists w1/w2 = {n ints, n ints, n bytes}, tasks (task_cap records of 8 doubles), counters
+// ctr[0] = entries of list 1, ctr[1] = entries of list 2, ctr[2] = task records, ctr[3] = task records after pass 1
+// (all zeroed here).  Returns the number of kernels launched.  If ctr[2] ends above task_cap the caller must grow the
+// task buffer and call again.
 int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, double eta_all,
                      const double *q0, const double *q1, int vstride, const long long *hoff, const double *htime, const double *hpos,
                      unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits,
-                     unsigned long long *nhit, int *work_stencil, int *work_task, unsigned char *work_sub, double *tasks,
-                     unsigned long long task_cap, unsigned long long *nwork, unsigned long long *ntask)
+                     unsigned long long *nhit, int *w1_stencil, int *w1_task, unsigned char *w1_sub, int *w2_stencil, int *w2_task,
+                     unsigned char *w2_sub, double *tasks, unsigned long long task_cap, unsigned long long *ctr)
 {
     if (n <= 0) return 0;
     NpArgs A;
     A.n = n; A.stencils = stencils; A.eta_arr = eta_arr; A.eta_all = eta_all; A.q0 = q0; A.q1 = q1; A.vstride = vstride;
     A.hoff = hoff; A.htime = htime; A.hpos = hpos; A.hit = hit; A.toi = toi; A.stage = stage;
     A.earliest_bits = earliest_bits; A.nhit = nhit;
-    A.work_stencil = work_stencil; A.work_task = work_task; A.work_sub = work_sub; A.tasks = tasks;
-    A.nwork = nwork; A.ntask = ntask; A.task_cap = task_cap;
+    A.tasks = tasks; A.ntask = ctr + 2; A.task_cap = task_cap;
+    const WorkList L1 = {w1_stencil, w1_task, w1_sub, ctr + 0}, L2 = {w2_stencil, w2_task, w2_sub, ctr + 1}, none = {nullptr, nullptr, nullptr, nullptr};
     const int B = 128;
     if (q0 == nullptr)
     {
+        A.in = none; A.out = none;
         if (is_vf) stencil_history_kernel<true><<<grid_for(n, B), B, 0, st>>>(A);
         else stencil_history_kernel<false><<<grid_for(n, B), B, 0, st>>>(A);
         return 1;
     }
-    cudaMemsetAsync(nwork, 0, sizeof(unsigned long long), st);
-    cudaMemsetAsync(ntask, 0, sizeof(unsigned long long), st);
+    cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned long long), st);
     const unsigned g2 = (unsigned)min((long long)148 * 32, (long long)grid_for(n, B));
+    // pass 1 -> list 1
+    A.in = none; A.out = L1;
     if (is_vf) stencil_pass1_kernel<true><<<grid_for(n, B), B, 0, st>>>(A);
     else stencil_pass1_kernel<false><<<grid_for(n, B), B, 0, st>>>(A);
-    roots_kernel<<<g2, B, 0, st>>>(tasks, ntask, task_cap);
-    if (is_vf) stencil_pass3_kernel<true><<<g2, B, 0, st>>>(A);
-    else stencil_pass3_kernel<false><<<g2, B, 0, st>>>(A);
-    return 3;
+    cudaMemcpyAsync(ctr + 3, ctr + 2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st);
+    roots_kernel<<<g2, B, 0, st>>>(tasks, nullptr, ctr + 3, task_cap);
+    // resume list 1; sub-tests that need roots again -> list 2
+    A.in = L1; A.out = L2;
+    if (is_vf) stencil_resume_kernel<true, MODE_DEFER><<<g2, B, 0, st>>>(A);
+    else stencil_resume_kernel<false, MODE_DEFER><<<g2, B, 0, st>>>(A);
+    roots_kernel<<<148, B, 0, st>>>(tasks, ctr + 3, ctr + 2, task_cap);
+    // resume list 2 and finish in place
+    A.in = L2; A.out = none;
+    if (is_vf) stencil_resume_kernel<true, MODE_FULL><<<148 * 4, B, 0, st>>>(A);
+    else stencil_resume_kernel<false, MODE_FULL><<<148 * 4, B, 0, st>>>(A);
+    return 5;
 }
 
 void ccdk_prim_batch(cudaStream_t st, int kind, long long n, const double *pts, const double *eta, unsigned char *hit, double *t)
