@@ -178,18 +178,17 @@ def main():
     h_f = torch.from_numpy(wl["faces"]).pin_memory()
     d_q0, d_q1, d_f = h_q0.cuda(), h_q1.cuda(), h_f.cuda()
     ctx = api.Context(local_rank)
-    red = torch.zeros(4, dtype=torch.float64, device="cuda")
+    from collisiondetection_b200 import distributed as D
+    if world > 1:
+        # replicated positions: rank 0's arrays are the step's input on every GPU (NCCL broadcast over NVLink)
+        D.broadcast_positions(d_q0, d_q1, src=0)
+    summary = {}
 
     def step_dev():
         r = ctx.step_device(api.KDOP, V, F, d_f.data_ptr(), d_q0.data_ptr(), d_q1.data_ptr(), wl["outer_eta"], wl["eta"], 0, rank, world)
-        if world > 1:
-            # the path's only exchange: earliest TOI (min) and hit/stencil counts (sum) — one fused all-reduce
-            red[0] = -r.earliest_toi if np.isfinite(r.earliest_toi) else -2.0
-            red[1] = float(r.n_vf_hits + r.n_ee_hits)
-            red[2] = float(r.n_vf_candidates + r.n_ee_candidates)
-            mx = red[:1].clone()
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            dist.all_reduce(red[1:3], op=dist.ReduceOp.SUM)
+        # the path's only exchange: earliest TOI (min) and hit / stencil counts (sum) — one fused all-reduce
+        summary["toi"], summary["hits"], summary["stencils"] = D.reduce_step_summary(
+            r.earliest_toi, r.n_vf_hits + r.n_ee_hits, r.n_vf_candidates + r.n_ee_candidates, device="cuda")
         return r
 
     def barrier():
@@ -218,14 +217,11 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total, float(r.n_vf_candidates + r.n_ee_candidates), float(r.n_vf_hits + r.n_ee_hits)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
-        tmax = t[:1].clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
-        t[0] = tmax[0]
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t[0]) / args.steps
-    n_stencils, n_hits = int(t[1]), int(t[2])
+    n_stencils, n_hits = summary["stencils"], summary["hits"]
     value = n_stencils / (ms_per_step * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call (pinned host arrays; H2D + D2H inside the timed region)
@@ -289,7 +285,7 @@ def main():
                counts=dict(vertices=V, faces=F, stencils=n_stencils, vf_rank0=int(nvf), ee_rank0=int(nee), hits=n_hits,
                            face_pairs_rank0=int(r.n_face_pairs), tree_candidates_rank0=int(r.n_tree_candidates), vf_deferred_rank0=int(r.n_vf_deferred), ee_deferred_rank0=int(r.n_ee_deferred),
                            stencils_per_face=n_stencils / float(F)),
-               fp64_peak_tflops=fp64_peak)
+               earliest_toi=summary["toi"], fp64_peak_tflops=fp64_peak)
     if world == 1 and not args.no_cpu_baseline:
         try:
             cb, _, _ = run_cpu_arm(cpu_sample(args.workload), 1, 0)

@@ -1,0 +1,75 @@
+"""world_size-2 (and 3) gloo runs of the host-side multi-GPU logic on CPU: ownership ranges partition the stencil
+lists exactly, and the fused summary all-reduce reproduces the single-process result."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, golden
+
+sys.path.insert(0, ROOT)
+
+
+def _worker(rank, world, port_no, vf, ee, vf_hit, vf_toi, ee_hit, ee_toi, V, edges, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from collisiondetection_b200 import distributed as D
+    # the stencils this rank owns: VF by vertex range, EE by rank range of the first edge (ids are lexicographic)
+    v0, v1 = D.shard_range(V, rank, world)
+    e0, e1 = D.shard_range(len(edges), rank, world)
+    own_vf = (vf[:, 0] >= v0) & (vf[:, 0] < v1)
+    first_edge = np.searchsorted(edges, vf_key(ee[:, 0], ee[:, 1]))
+    own_ee = (first_edge >= e0) & (first_edge < e1)
+    hits = int(vf_hit[own_vf].sum() + ee_hit[own_ee].sum())
+    tois = np.concatenate([vf_toi[own_vf][vf_hit[own_vf] > 0], ee_toi[own_ee][ee_hit[own_ee] > 0]])
+    earliest = tois.min() if tois.size else np.inf
+    q = torch.arange(6, dtype=torch.float64) * (1.0 if rank == 0 else 0.0)
+    q2 = q.clone()
+    D.broadcast_positions(q, q2)
+    assert torch.equal(q, torch.arange(6, dtype=torch.float64))
+    toi, nh, ns = D.reduce_step_summary(earliest, hits, int(own_vf.sum() + own_ee.sum()))
+    results[rank] = (toi, nh, ns, int(own_vf.sum()), int(own_ee.sum()))
+    dist.destroy_process_group()
+
+
+def vf_key(a, b):
+    return a.astype(np.int64) << 32 | b.astype(np.int64)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_summary_matches_whole(world):
+    g = golden("alec_prob11_835.npz")
+    vf, ee = g["ref_vf"], g["ref_ee"]
+    V = len(g["q0"])
+    f = g["faces"]
+    he = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+    edges = np.unique(vf_key(he.min(1), he.max(1)))
+    mgr = mp.get_context("spawn").Manager()
+    results = mgr.dict()
+    port_no = 29600 + world
+    mp.spawn(_worker, args=(world, port_no, vf, ee, g["ref_vf_hit"], g["ref_vf_toi"], g["ref_ee_hit"], g["ref_ee_toi"], V, edges, results),
+             nprocs=world, join=True)
+    hits = np.concatenate([g["ref_vf_toi"][g["ref_vf_hit"] > 0], g["ref_ee_toi"][g["ref_ee_hit"] > 0]])
+    for r in range(world):
+        toi, nh, ns, _, _ = results[r]
+        assert toi == hits.min()
+        assert nh == int(g["ref_vf_hit"].sum() + g["ref_ee_hit"].sum())
+        assert ns == len(vf) + len(ee)
+    assert sum(results[r][3] for r in range(world)) == len(vf)
+    assert sum(results[r][4] for r in range(world)) == len(ee)
+
+
+def test_shard_ranges_partition():
+    from collisiondetection_b200.distributed import shard_range
+    for n in (0, 1, 7, 1000, 2002225):
+        for world in (1, 2, 3, 4, 8):
+            ranges = [shard_range(n, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in ranges]
+            assert max(sizes) - min(sizes) <= 1
