@@ -42,7 +42,7 @@ struct ccd_context
     int topoF = -1, topoV = -1, nEdges = 0;
     unsigned long long topoHashVal = 0;
     // emission
-    DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut;
+    DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut, shardBounds;
     // narrowphase
     DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, work2Vf, work2Ee, work2TaskVf, work2TaskEe, work2SubVf, work2SubEe, tasksVf, tasksEe, selTmp, selA, selB, selC, selD, selCount;
     // pinned host scratch
@@ -152,6 +152,7 @@ void ccdk_ee_emit(cudaStream_t st, bool count, int ebegin, int eend, const int *
                   const int *adj, const int *faceEdge, const void *edgeVerts, const unsigned char *fixed, int *counts,
                   const long long *offsets, int *out);
 void ccdk_hash_ints(cudaStream_t st, long long n, const int *d, unsigned long long *out);
+void ccdk_shard_bounds(cudaStream_t st, const long long *offsets, int n, int rank, int world, int *out);
 void ccdk_dist_batch(cudaStream_t st, int which, long long n, const double *pts, const double *eta, double *vec, double *bary, unsigned char *flag);
 void ccdk_vertex_min_dist2(cudaStream_t st, int V, int F, const double *verts, const int *faces, unsigned long long *out_bits);
 void ccdk_stencil_min_dist(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *verts, unsigned long long *out_bits);
@@ -209,7 +210,7 @@ void ccd_destroy(ccd_context *c)
                    &c->leafParent, &c->nodeParent, &c->flags, &c->cand, &c->counters, &c->pairL, &c->pairR, &c->deg, &c->adjOff,
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
-                   &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
+                   &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->shardBounds, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
                    &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->work2Vf, &c->work2Ee, &c->work2TaskVf, &c->work2TaskEe, &c->work2SubVf, &c->work2SubEe, &c->tasksVf, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
     for (DBuf *b : all)
         if (b->p)
@@ -398,29 +399,36 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     ccdk_adjacency_fill(c->st, ctr + C_NPAIRS, P<int>(c->pairL), P<int>(c->pairR), P<long long>(c->adjOff), P<int>(c->cursor), P<int>(c->adj));
     c->launches += 3;
 
-    // ownership ranges of this shard
+    // Stencil counts for every vertex / unique edge (replicated on all ranks), then ownership ranges balanced by the
+    // number of stencils: rank r owns the items whose first stencil falls in [T*r/W, T*(r+1)/W).
     const int E = c->nEdges;
-    const int v0 = (int)((long long)V * shard_rank / shard_world), v1 = (int)((long long)V * (shard_rank + 1) / shard_world);
-    const int e0 = (int)((long long)E * shard_rank / shard_world), e1 = (int)((long long)E * (shard_rank + 1) / shard_world);
-    const int nv = v1 - v0, ne = e1 - e0;
-    CKR(ensure(c, c->vfCounts, sizeof(int) * (size_t)(nv + 2)));
-    CKR(ensure(c, c->vfOffsets, sizeof(long long) * (size_t)(nv + 2)));
-    CKR(ensure(c, c->eeCounts, sizeof(int) * (size_t)(ne + 2)));
-    CKR(ensure(c, c->eeOffsets, sizeof(long long) * (size_t)(ne + 2)));
+    CKR(ensure(c, c->vfCounts, sizeof(int) * (size_t)(V + 2)));
+    CKR(ensure(c, c->vfOffsets, sizeof(long long) * (size_t)(V + 2)));
+    CKR(ensure(c, c->eeCounts, sizeof(int) * (size_t)(E + 2)));
+    CKR(ensure(c, c->eeOffsets, sizeof(long long) * (size_t)(E + 2)));
+    CKR(ensure(c, c->shardBounds, 64));
     cudaEventRecord(c->sev[ST_EMIT_COUNT], c->st);
-    ccdk_vf_emit(c->st, true, v0, v1, d_faces, P<long long>(c->starOff), P<int>(c->star), P<long long>(c->adjOff), P<int>(c->adj),
+    ccdk_vf_emit(c->st, true, 0, V, d_faces, P<long long>(c->starOff), P<int>(c->star), P<long long>(c->adjOff), P<int>(c->adj),
                  P<int>(c->faceRank), P<int>(c->rankFace), d_fixed, P<int>(c->vfCounts), nullptr, nullptr);
-    ccdk_ee_emit(c->st, true, e0, e1, P<int>(c->edgeStart), P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceEdge),
+    ccdk_ee_emit(c->st, true, 0, E, P<int>(c->edgeStart), P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceEdge),
                  c->edgeVerts.p, d_fixed, P<int>(c->eeCounts), nullptr, nullptr);
-    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, nv + 1, P<int>(c->vfCounts), P<long long>(c->vfOffsets));
-    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, ne + 1, P<int>(c->eeCounts), P<long long>(c->eeOffsets));
-    c->launches += 6;
-    long long totals[2] = {0, 0};
-    CK(cudaMemcpyAsync(&totals[0], P<long long>(c->vfOffsets) + nv, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaMemcpyAsync(&totals[1], P<long long>(c->eeOffsets) + ne, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, V + 1, P<int>(c->vfCounts), P<long long>(c->vfOffsets));
+    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, E + 1, P<int>(c->eeCounts), P<long long>(c->eeOffsets));
+    ccdk_shard_bounds(c->st, P<long long>(c->vfOffsets), V, shard_rank, shard_world, P<int>(c->shardBounds));
+    ccdk_shard_bounds(c->st, P<long long>(c->eeOffsets), E, shard_rank, shard_world, P<int>(c->shardBounds) + 2);
+    c->launches += 8;
+    int bounds[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(bounds, c->shardBounds.p, sizeof(bounds), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    res->nvf = totals[0];
-    res->nee = totals[1];
+    const int v0 = bounds[0], v1 = bounds[1], e0 = bounds[2], e1 = bounds[3];
+    long long range[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(&range[0], P<long long>(c->vfOffsets) + v0, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(&range[1], P<long long>(c->vfOffsets) + v1, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(&range[2], P<long long>(c->eeOffsets) + e0, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(&range[3], P<long long>(c->eeOffsets) + e1, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    res->nvf = range[1] - range[0];
+    res->nee = range[3] - range[2];
     CKR(ensure(c, c->vfOut, sizeof(int) * 4 * (size_t)(res->nvf + 1)));
     CKR(ensure(c, c->eeOut, sizeof(int) * 4 * (size_t)(res->nee + 1)));
     cudaEventRecord(c->sev[ST_EMIT_WRITE], c->st);

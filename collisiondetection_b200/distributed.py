@@ -2,7 +2,8 @@
 
 The path shards without a data-path collective: positions and faces are replicated (every rank uploads or receives
 the same q0/q1 — `broadcast_positions`), every rank builds the same LBVH, and rank r emits and tests only the stencils
-it owns (vertex range for VF, unique-edge range for EE — `shard_range`, the same arithmetic as ccd_step_device).
+it owns: a contiguous vertex range for VF and unique-edge range for EE, balanced by stencil count inside
+ccd_step_device (`shard_range` is the plain index split used for other per-item work).
 The only exchange is the step summary: earliest TOI (min) and hit / stencil counts (sum), fused into ONE all-reduce
 by carrying the minimum as a negated maximum next to sums that are kept on their own rank's slot.
 """
@@ -12,7 +13,7 @@ import torch.distributed as dist
 
 
 def shard_range(n, rank, world):
-    """Contiguous ownership range [begin, end) of rank `rank` over n items — matches csrc/ccd_api.cu."""
+    """Contiguous range [begin, end) of rank `rank` over n equally weighted items."""
     return (n * rank) // world, (n * (rank + 1)) // world
 
 

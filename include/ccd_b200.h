@@ -102,8 +102,9 @@ int ccd_step_shard(ccd_context *ctx, int kind, int V, int F, const int32_t *face
 
 /* Device-resident variant: inputs already in HBM, results stay in HBM (pointers valid until the next
  * call on this context).  shard_rank / shard_world partition the step across GPUs of one job: every
- * rank builds the (replicated) tree, rank r owns the r-th contiguous range of vertices (VF stencils)
- * and of unique edges (EE stencils); world = 1 means the whole step.  The union over ranks of the
+ * rank builds the (replicated) tree and counts the stencils of every vertex / unique edge; rank r then owns
+ * a contiguous range of vertices (VF stencils) and of unique edges (EE stencils) chosen so that every rank
+ * gets the same number of stencils.  world = 1 means the whole step.  The concatenation over ranks of the
  * stencil lists equals the single-GPU lists exactly. */
 typedef struct
 {
