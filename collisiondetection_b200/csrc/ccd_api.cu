@@ -51,8 +51,8 @@ struct ccd_context
 };
 
 // device counters layout (unsigned long long each)
-enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NP_VF = 16 /* 4 counters: list 1, list 2, task records, records after pass 1 */, C_NP_EE = 20, C_TOTAL = 24 };
-enum { C_NWORK_VF = C_NP_VF, C_NTASK_VF = C_NP_VF + 2, C_NWORK_EE = C_NP_EE, C_NTASK_EE = C_NP_EE + 2 };
+enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NP_VF = 16 /* 2 counters: work-list entries, task records */, C_NP_EE = 20, C_TOTAL = 24 };
+enum { C_NWORK_VF = C_NP_VF, C_NTASK_VF = C_NP_VF + 1, C_NWORK_EE = C_NP_EE, C_NTASK_EE = C_NP_EE + 1 };
 
 #define CK(call)                                                                                      \
     do                                                                                                \
@@ -457,14 +457,8 @@ static int narrowphase_device(ccd_context *c, long long nvf, const int *d_vf, co
     CKR(ensure(c, c->workEe, sizeof(int) * ((size_t)nee + 32)));
     CKR(ensure(c, c->workTaskVf, sizeof(int) * ((size_t)nvf + 32)));
     CKR(ensure(c, c->workTaskEe, sizeof(int) * ((size_t)nee + 32)));
-    CKR(ensure(c, c->workSubVf, (size_t)nvf + 32));
-    CKR(ensure(c, c->workSubEe, (size_t)nee + 32));
-    CKR(ensure(c, c->work2Vf, sizeof(int) * ((size_t)nvf + 32)));
-    CKR(ensure(c, c->work2Ee, sizeof(int) * ((size_t)nee + 32)));
-    CKR(ensure(c, c->work2TaskVf, sizeof(int) * ((size_t)nvf + 32)));
-    CKR(ensure(c, c->work2TaskEe, sizeof(int) * ((size_t)nee + 32)));
-    CKR(ensure(c, c->work2SubVf, (size_t)nvf + 32));
-    CKR(ensure(c, c->work2SubEe, (size_t)nee + 32));
+    CKR(ensure(c, c->workSubVf, sizeof(int) * 5 * ((size_t)nvf + 32)));
+    CKR(ensure(c, c->workSubEe, sizeof(int) * 5 * ((size_t)nee + 32)));
     int nl = 0;
     for (int attempt = 0; attempt < 4; attempt++)
     {
@@ -479,13 +473,11 @@ static int narrowphase_device(ccd_context *c, long long nvf, const int *d_vf, co
         cudaEventRecord(c->sev[ST_NP_VF], c->st);
         nl += ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
                                P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF, P<int>(c->workVf),
-                               P<int>(c->workTaskVf), P<unsigned char>(c->workSubVf), P<int>(c->work2Vf), P<int>(c->work2TaskVf),
-                               P<unsigned char>(c->work2SubVf), P<double>(c->tasksVf), c->taskCapVf, ctr + C_NP_VF);
+                               P<int>(c->workTaskVf), P<int>(c->workSubVf), P<double>(c->tasksVf), c->taskCapVf, ctr + C_NP_VF);
         cudaEventRecord(c->sev[ST_NP_EE], c->st);
         nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
                                P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE, P<int>(c->workEe),
-                               P<int>(c->workTaskEe), P<unsigned char>(c->workSubEe), P<int>(c->work2Ee), P<int>(c->work2TaskEe),
-                               P<unsigned char>(c->work2SubEe), P<double>(c->tasksEe), c->taskCapEe, ctr + C_NP_EE);
+                               P<int>(c->workTaskEe), P<int>(c->workSubEe), P<double>(c->tasksEe), c->taskCapEe, ctr + C_NP_EE);
         cudaEventRecord(c->sev[CCD_N_STAGES], c->st);
         CK(cudaGetLastError());
         CKR(sync_counters(c));

@@ -12,9 +12,8 @@
 //           next sub-test needs the iterative root isolator goes on a work list, with one 64-byte task
 //           record per pending polynomial (warp-aggregated allocation);
 //   roots   one thread per pending polynomial: dense warps, every lane inside the isolator;
-//   resume  the work list only: continues at the deferred sub-test with its roots; a later sub-test that needs
-//           roots again is deferred once more (second, tiny round) so that only the last, rare-work kernel
-//           carries the isolator inline — the big kernels stay small enough for the instruction cache.
+//           (the walk goes on past a deferring sub-test, so one round collects everything a stencil needs);
+//   pass 3  the work list only: re-evaluates just the deferred sub-tests, in order, with their roots.
 // Degenerate sub-tests (and the EE primitive) are skipped when the swept boxes of the two parts stay further
 // apart than eta plus a safety margin: those tests measure true distances (include/CTCD.h:31-79), so the
 // reference cannot report a hit there; the margin (4e-5 of the coordinate scale) is ~1e3 times the distance
@@ -23,7 +22,13 @@
 // Hit flag, time of impact and the index of the sub-test that fired are written per stencil; earliest TOI and
 // hit counts are reduced per warp and merged with one atomic pair per warp.
 #include "ccd_kernels.h"
+#ifndef NP_MINB
+#define NP_MINB 3      // resident blocks of 128 threads per SM the stencil kernels are compiled for
+#endif
 #include "ccd_math.cuh"
+#include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
+namespace cg = cooperative_groups;
 
 namespace ccd {
 
@@ -55,81 +60,88 @@ __device__ __forceinline__ double box_scale(const Box &b)
 }
 
 // ---- per-segment stencil tests --------------------------------------------------------------
-// Sub-tests are numbered in the reference's order: 0 = the VF / EE primitive, then the vertex-edge tests, then
-// the vertex-vertex tests.  a[0..3] start positions, b[0..3] end positions.
-// Return: stage that hit (sub-test index + 1), 0 for a miss, -(sub+1) when sub-test `sub` was deferred (its pending
-// polynomials are in P).  The walk starts at sub-test `start` (everything before it is known to miss); that sub-test
-// runs in mode FIRST (RESUME: its roots come from trec), the ones after it in mode LATER.
-template <int FIRST, int LATER>
-static __device__ __noinline__ int vf_stencil_segment(const V3 *a, const V3 *b, double eta, double &t, int start, Pend &P, const double *trec)
+// Sub-tests are numbered in the reference's order: 0 = the VF / EE primitive, 1.. = the vertex-edge tests (3 for a VF
+// stencil: face edges (1,2),(2,3),(3,1), src/CTCDNarrowPhase.cpp:51-59; 4 for an EE stencil: p0|p1 against (q0,q1),
+// q0|q1 against (p0,p1), :99-114), then the vertex-vertex tests (:61-69, :117-132).  stage = sub-test index + 1.
+// a[0..3] start positions of (p,q0,q1,q2) / (p0,p1,q0,q1), v[] = end - start.
+template <bool IS_VF> struct Subs
 {
-    V3 v[4];
-    Box bx[4];
-    for (int i = 0; i < 4; i++) { v[i] = b[i] - a[i]; bx[i] = swept_box(a[i], b[i]); }
-    int r;
-    if (start <= 0)
+    static constexpr int NVE = IS_VF ? 3 : 4;
+    static constexpr int NVV = IS_VF ? 3 : 4;
+    // vertex / edge endpoints of vertex-edge sub-test `sub` (1-based)
+    static __device__ __forceinline__ void ve(int sub, int &iv, int &i1, int &i2)
     {
-        r = vertex_face<FIRST>(a, v, eta, t, P, trec);
-        if (r == R_HIT) return 1;
-        if (r == R_DEFER) return -1;
+        if (IS_VF) { iv = 0; i1 = sub; i2 = 1 + (sub % 3); }
+        else { iv = sub - 1; i1 = (sub <= 2) ? 2 : 0; i2 = i1 + 1; }
     }
-    const Box face = join(join(bx[1], bx[2]), bx[3]);
-    const double m = eta + 4e-5 * fmax(box_scale(bx[0]), box_scale(face));
-    if (apart(bx[0], face, m)) return 0;
-    // vertex against the three face edges (1,2),(2,3),(3,1): src/CTCDNarrowPhase.cpp:51-59
-    for (int e = 0; e < 3; e++)
+    static __device__ __forceinline__ void vv(int k, int &i1, int &i2)
     {
-        const int sub = 1 + e, i1 = 1 + e, i2 = 1 + ((e + 1) % 3);
-        if (sub < start) continue;
-        if (apart(bx[0], join(bx[i1], bx[i2]), m)) continue;
-        r = (FIRST != LATER && sub == start) ? vertex_edge<FIRST>(a[0], a[i1], a[i2], v[0], v[i1], v[i2], eta, t, P, trec)
-                                              : vertex_edge<LATER>(a[0], a[i1], a[i2], v[0], v[i1], v[i2], eta, t, P, trec);
-        if (r == R_HIT) return sub + 1;
-        if (r == R_DEFER) return -(sub + 1);
+        if (IS_VF) { i1 = 0; i2 = 1 + k; }
+        else { i1 = k >> 1; i2 = 2 + (k & 1); }
     }
-    // vertex against the three face vertices: src/CTCDNarrowPhase.cpp:61-69
-    for (int k = 0; k < 3; k++)
-    {
-        if (apart(bx[0], bx[1 + k], m)) continue;
-        if (vertex_vertex(a[0], a[1 + k], v[0], v[1 + k], eta, t) == R_HIT) return 5 + k;
-    }
-    return 0;
+};
+
+// the primitive or one vertex-edge test (sub <= NVE)
+template <bool IS_VF, int MODE>
+__device__ __forceinline__ int eval_sub(int sub, const V3 *a, const V3 *v, double eta, double &t, Pend &P, const double *trec)
+{
+    if (sub == 0)
+        return IS_VF ? vertex_face<MODE>(a, v, eta, t, P, trec) : edge_edge<MODE>(a, v, eta, t, P, trec);
+    int iv, i1, i2;
+    Subs<IS_VF>::ve(sub, iv, i1, i2);
+    return vertex_edge<MODE>(a[iv], a[i1], a[i2], v[iv], v[i1], v[i2], eta, t, P, trec);
 }
 
-// a/b: (p0, p1, q0, q1); edgeEdgeCTCD takes (q0,p0,q1,p1) = (pos0,pos1,pos2,pos3): src/CTCDNarrowPhase.cpp:91
-template <int FIRST, int LATER>
-static __device__ __noinline__ int ee_stencil_segment(const V3 *a, const V3 *b, double eta, double &t, int start, Pend &P, const double *trec)
+// swept boxes of the four vertices and the culling margin of the stencil
+template <bool IS_VF> struct Cull
+{
+    Box bx[4], g0, g1;      // VF: g0 = vertex, g1 = face ; EE: g0 = edge (0,1), g1 = edge (2,3)
+    double m;
+    __device__ __forceinline__ void init(const V3 *a, const V3 *b, double eta)
+    {
+        for (int i = 0; i < 4; i++) bx[i] = swept_box(a[i], b[i]);
+        if (IS_VF) { g0 = bx[0]; g1 = join(join(bx[1], bx[2]), bx[3]); }
+        else { g0 = join(bx[0], bx[1]); g1 = join(bx[2], bx[3]); }
+        m = eta + 4e-5 * fmax(box_scale(g0), box_scale(g1));
+    }
+    __device__ __forceinline__ bool stencil_apart() const { return apart(g0, g1, m); }
+    __device__ __forceinline__ bool ve_apart(int sub) const
+    {
+        int iv, i1, i2;
+        Subs<IS_VF>::ve(sub, iv, i1, i2);
+        return apart(bx[iv], join(bx[i1], bx[i2]), m);
+    }
+    __device__ __forceinline__ bool vv_apart(int k) const
+    {
+        int i1, i2;
+        Subs<IS_VF>::vv(k, i1, i2);
+        return apart(bx[i1], bx[i2], m);
+    }
+};
+
+// Whole sequence in place (FULL mode): multi-entry History segments and the reference-order semantics in one walk.
+// Returns the stage that hit, 0 for a miss.
+template <bool IS_VF> static __device__ __noinline__ int stencil_segment_full(const V3 *a, const V3 *b, double eta, double &t)
 {
     V3 v[4];
-    Box bx[4];
-    for (int i = 0; i < 4; i++) { v[i] = b[i] - a[i]; bx[i] = swept_box(a[i], b[i]); }
-    const Box e0 = join(bx[0], bx[1]), e1 = join(bx[2], bx[3]);
-    const double m = eta + 4e-5 * fmax(box_scale(e0), box_scale(e1));
-    if (apart(e0, e1, m)) return 0;       // every sub-test below is a distance between parts of these two edges
-    int r;
-    if (start <= 0)
+    for (int i = 0; i < 4; i++) v[i] = b[i] - a[i];
+    Cull<IS_VF> c;
+    c.init(a, b, eta);
+    Pend P;
+    if (!IS_VF && c.stencil_apart()) return 0;      // every EE sub-test is a distance between parts of the two edges
+    if (eval_sub<IS_VF, MODE_FULL>(0, a, v, eta, t, P, nullptr) == R_HIT) return 1;
+    if (IS_VF && c.stencil_apart()) return 0;
+    for (int sub = 1; sub <= Subs<IS_VF>::NVE; sub++)
     {
-        r = edge_edge<FIRST>(a, v, eta, t, P, trec);
-        if (r == R_HIT) return 1;
-        if (r == R_DEFER) return -1;
+        if (c.ve_apart(sub)) continue;
+        if (eval_sub<IS_VF, MODE_FULL>(sub, a, v, eta, t, P, nullptr) == R_HIT) return sub + 1;
     }
-    // src/CTCDNarrowPhase.cpp:99-114: p0|p1 against (q0,q1), q0|q1 against (p0,p1)
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < Subs<IS_VF>::NVV; k++)
     {
-        const int sub = 1 + k, iv = k, i1 = (k < 2) ? 2 : 0, i2 = i1 + 1;
-        if (sub < start) continue;
-        if (apart(bx[iv], (k < 2) ? e1 : e0, m)) continue;
-        r = (FIRST != LATER && sub == start) ? vertex_edge<FIRST>(a[iv], a[i1], a[i2], v[iv], v[i1], v[i2], eta, t, P, trec)
-                                              : vertex_edge<LATER>(a[iv], a[i1], a[i2], v[iv], v[i1], v[i2], eta, t, P, trec);
-        if (r == R_HIT) return sub + 1;
-        if (r == R_DEFER) return -(sub + 1);
-    }
-    // src/CTCDNarrowPhase.cpp:117-132: (p0,q0) (p0,q1) (p1,q0) (p1,q1)
-    for (int k = 0; k < 4; k++)
-    {
-        const int i1 = k >> 1, i2 = 2 + (k & 1);
-        if (apart(bx[i1], bx[i2], m)) continue;
-        if (vertex_vertex(a[i1], a[i2], v[i1], v[i2], eta, t) == R_HIT) return 6 + k;
+        if (c.vv_apart(k)) continue;
+        int i1, i2;
+        Subs<IS_VF>::vv(k, i1, i2);
+        if (vertex_vertex(a[i1], a[i2], v[i1], v[i2], eta, t) == R_HIT) return Subs<IS_VF>::NVE + 2 + k;
     }
     return 0;
 }
@@ -199,15 +211,6 @@ __device__ __forceinline__ void reduce_warp(bool hit, double toi, unsigned long 
     }
 }
 
-// one list of deferred stencils: entry w = {stencil index, first task record, sub-test that deferred}
-struct WorkList
-{
-    int *stencil;
-    int *task;
-    unsigned char *sub;
-    unsigned long long *count;
-};
-
 struct NpArgs
 {
     long long n;
@@ -222,23 +225,30 @@ struct NpArgs
     double *toi;
     unsigned char *stage;
     unsigned long long *earliest_bits, *nhit;
-    WorkList in, out;           // pass 1 fills `out`; a resume pass reads `in` and may fill `out`
+    // deferred stencils: entry w = {stencil index, meta = deferred-sub-test mask | decided later hit << 8, first task
+    // record of each deferred sub-test (<= 5: the primitive and the vertex-edge tests)}
+    int *w_stencil;
+    int *w_meta;
+    int *w_base;                // 5 ints per entry
+    unsigned long long *nwork;
     double *tasks;              // 64-byte records: coefficients + reduced degree in, roots + count out
     unsigned long long *ntask;  // running number of task records
     unsigned long long task_cap;
 };
 
-// one stencil, single linear segment (two History entries per vertex)
-template <bool IS_VF, int FIRST, int LATER>
-__device__ __forceinline__ int run_single(const NpArgs &A, long long i, double &toi, int start, Pend &P, const double *trec)
+struct StencilIn
+{
+    V3 a[4], b[4];
+    double eta;
+};
+
+template <bool IS_VF> __device__ __forceinline__ void load_single(const NpArgs &A, long long i, StencilIn &S)
 {
     const int4 s = reinterpret_cast<const int4 *>(A.stencils)[i];
-    const double eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
+    S.eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
     const long long vs = A.vstride;
-    V3 a[4], b[4];
-    a[0] = ldv(A.q0 + vs * s.x); a[1] = ldv(A.q0 + vs * s.y); a[2] = ldv(A.q0 + vs * s.z); a[3] = ldv(A.q0 + vs * s.w);
-    b[0] = ldv(A.q1 + vs * s.x); b[1] = ldv(A.q1 + vs * s.y); b[2] = ldv(A.q1 + vs * s.z); b[3] = ldv(A.q1 + vs * s.w);
-    return IS_VF ? vf_stencil_segment<FIRST, LATER>(a, b, eta, toi, start, P, trec) : ee_stencil_segment<FIRST, LATER>(a, b, eta, toi, start, P, trec);
+    S.a[0] = ldv(A.q0 + vs * s.x); S.a[1] = ldv(A.q0 + vs * s.y); S.a[2] = ldv(A.q0 + vs * s.z); S.a[3] = ldv(A.q0 + vs * s.w);
+    S.b[0] = ldv(A.q1 + vs * s.x); S.b[1] = ldv(A.q1 + vs * s.y); S.b[2] = ldv(A.q1 + vs * s.z); S.b[3] = ldv(A.q1 + vs * s.w);
 }
 
 __device__ __forceinline__ void store_result(const NpArgs &A, long long i, int stage, double toi)
@@ -248,36 +258,17 @@ __device__ __forceinline__ void store_result(const NpArgs &A, long long i, int s
     if (A.stage) A.stage[i] = (unsigned char)stage;
 }
 
-// Whole-warp call.  Lanes with `deferred` set put stencil i on the out list with one task record per pending polynomial
-// of P (coefficients + reduced degree): one atomic for the list slots and one for the records per warp.
-__device__ __forceinline__ void defer_stencil(const NpArgs &A, bool deferred, long long i, int sub, const Pend &P)
+// One task record per pending polynomial of P (coefficients + reduced degree); returns the first record's index.
+// Called from divergent code: the lanes that happen to be here together share one atomic (coalesced group).
+__device__ __forceinline__ int alloc_tasks(const NpArgs &A, const Pend &P)
 {
-    const int lane = threadIdx.x & 31;
-    const unsigned m = __ballot_sync(0xffffffffu, deferred);
-    if (!m) return;
-    const int ntask = deferred ? __popc(P.mask) : 0;
-    int pre = ntask;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-        int x = __shfl_up_sync(0xffffffffu, pre, o);
-        if (lane >= o) pre += x;
-    }
-    const int total = __shfl_sync(0xffffffffu, pre, 31);
-    unsigned long long wbase = 0, tbase = 0;
-    if (lane == 0)
-    {
-        wbase = atomicAdd(A.out.count, (unsigned long long)__popc(m));
-        tbase = atomicAdd(A.ntask, (unsigned long long)total);
-    }
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    tbase = __shfl_sync(0xffffffffu, tbase, 0);
-    if (!deferred) return;
-    const unsigned long long w = wbase + __popc(m & ((1u << lane) - 1));
-    const unsigned long long t0 = tbase + (unsigned long long)(pre - ntask);
-    A.out.stencil[w] = (int)i;
-    A.out.task[w] = (int)t0;
-    A.out.sub[w] = (unsigned char)sub;
+    cg::coalesced_group g = cg::coalesced_threads();
+    const int n = __popc(P.mask);
+    const int pre = cg::exclusive_scan(g, n);
+    unsigned long long base = 0;
+    if (g.thread_rank() == g.size() - 1) base = atomicAdd(A.ntask, (unsigned long long)(pre + n));
+    base = g.shfl(base, g.size() - 1);
+    const unsigned long long t0 = base + (unsigned long long)pre;
     int j = 0;
     unsigned mask = P.mask;
     while (mask)
@@ -293,33 +284,152 @@ __device__ __forceinline__ void defer_stencil(const NpArgs &A, bool deferred, lo
         }
         j++;
     }
+    return (int)t0;
 }
 
-// pass 1: all stencils, straight-line work only.  A stencil whose next sub-test needs the root isolator is deferred.
-template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_pass1_kernel(NpArgs A)
+// pass 1: every stencil, straight-line work only, as a block-synchronous pipeline over a tile of NP_TILE stencils so that
+// the lanes of a warp do the same kind of work at the same time:
+//   phase 0  one thread per stencil: gather the 8 positions into shared memory, swept-box culling -> the set of sub-tests
+//            that have to be evaluated at all;
+//   phase 1  the sub-tests become items of three shared-memory queues (primitive / vertex-edge / vertex-vertex);
+//   phase 2  the queues are drained densely, one item per thread: each item ends as miss, hit (+ t) or deferred (its
+//            polynomials exported as task records);
+//   phase 3  one thread per stencil: first hit in the reference's order wins if nothing before it is deferred; a stencil
+//            with deferred sub-tests goes on the work list with the later hit (if any) pass 1 already knows.
+// Evaluating every culling survivor instead of stopping at the first hit costs little (hits are ~10 %) and changes no
+// result: the winner is still the first hit in order.
+#define NP_TILE 128
+struct TileShared
 {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int stage = 0;
-    double toi = 0.0;
-    Pend P;
-    P.mask = 0;
+    V3 a[NP_TILE][4], v[NP_TILE][4];
+    double eta[NP_TILE];
+    double rtoi[NP_TILE][9];
+    int rbase[NP_TILE][5];
+    unsigned short todo[NP_TILE];
+    unsigned char res[NP_TILE][9];       // per sub-test: 0 miss / not needed, 1 hit, 2 deferred
+    unsigned short qprim[NP_TILE], qve[NP_TILE * 4], qvv[NP_TILE * 4];
+    int nprim, nve, nvv;
+};
+
+template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) stencil_pass1_kernel(NpArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileShared &T = *reinterpret_cast<TileShared *>(smem_raw);
+    const int tid = threadIdx.x;
+    const long long i = (long long)blockIdx.x * NP_TILE + tid;
+    constexpr int NVE = Subs<IS_VF>::NVE, NVV = Subs<IS_VF>::NVV;
+    if (tid == 0) { T.nprim = 0; T.nve = 0; T.nvv = 0; }
+    // ---- phase 0
+    unsigned todo = 0;
     if (i < A.n)
     {
-        stage = run_single<IS_VF, MODE_DEFER, MODE_DEFER>(A, i, toi, 0, P, nullptr);
-        if (stage >= 0) store_result(A, i, stage, toi);
+        StencilIn S;
+        load_single<IS_VF>(A, i, S);
+        Cull<IS_VF> c;
+        c.init(S.a, S.b, S.eta);
+        const bool far = c.stencil_apart();
+        if (IS_VF || !far) todo = 1u;
+        if (!far)
+        {
+            for (int sub = 1; sub <= NVE; sub++)
+                if (!c.ve_apart(sub)) todo |= 1u << sub;
+            for (int k = 0; k < NVV; k++)
+                if (!c.vv_apart(k)) todo |= 1u << (NVE + 1 + k);
+        }
+        for (int k = 0; k < 4; k++) { T.a[tid][k] = S.a[k]; T.v[tid][k] = S.b[k] - S.a[k]; }
+        T.eta[tid] = S.eta;
     }
-    defer_stencil(A, stage < 0, i, -stage - 1, P);
+    T.todo[tid] = (unsigned short)todo;
+    for (int k = 0; k < 9; k++) T.res[tid][k] = 0;
+    __syncthreads();
+    // ---- phase 1: queues
+    if (todo & 1u) T.qprim[atomicAdd(&T.nprim, 1)] = (unsigned short)tid;
+    for (int sub = 1; sub <= NVE; sub++)
+        if (todo & (1u << sub)) T.qve[atomicAdd(&T.nve, 1)] = (unsigned short)(tid | (sub << 8));
+    for (int k = 0; k < NVV; k++)
+        if (todo & (1u << (NVE + 1 + k))) T.qvv[atomicAdd(&T.nvv, 1)] = (unsigned short)(tid | (k << 8));
+    __syncthreads();
+    // ---- phase 2: drain the queues densely
+    {
+        Pend P;
+        for (int it = tid; it < T.nprim; it += blockDim.x)
+        {
+            const int s = T.qprim[it];
+            double t = 0.0;
+            const int r = eval_sub<IS_VF, MODE_DEFER>(0, T.a[s], T.v[s], T.eta[s], t, P, nullptr);
+            if (r == R_HIT) { T.res[s][0] = 1; T.rtoi[s][0] = t; }
+            else if (r == R_DEFER) { T.res[s][0] = 2; T.rbase[s][0] = alloc_tasks(A, P); }
+        }
+        for (int it = tid; it < T.nve; it += blockDim.x)
+        {
+            const int s = T.qve[it] & 0xff, sub = T.qve[it] >> 8;
+            double t = 0.0;
+            const int r = eval_sub<IS_VF, MODE_DEFER>(sub, T.a[s], T.v[s], T.eta[s], t, P, nullptr);
+            if (r == R_HIT) { T.res[s][sub] = 1; T.rtoi[s][sub] = t; }
+            else if (r == R_DEFER) { T.res[s][sub] = 2; T.rbase[s][sub] = alloc_tasks(A, P); }
+        }
+        for (int it = tid; it < T.nvv; it += blockDim.x)
+        {
+            const int s = T.qvv[it] & 0xff, k = T.qvv[it] >> 8;
+            int i1, i2;
+            Subs<IS_VF>::vv(k, i1, i2);
+            double t = 0.0;
+            if (vertex_vertex(T.a[s][i1], T.a[s][i2], T.v[s][i1], T.v[s][i2], T.eta[s], t) == R_HIT)
+            {
+                T.res[s][NVE + 1 + k] = 1;
+                T.rtoi[s][NVE + 1 + k] = t;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 3: per-stencil decision
+    int stage = 0, meta = 0, nd = 0;
+    int base[5] = {0, 0, 0, 0, 0};
+    double toi = 0.0;
+    if (i < A.n)
+    {
+        unsigned submask = 0;
+        int later_hit = 255;
+        for (int sub = 0; sub < 1 + NVE + NVV; sub++)
+        {
+            const int r = T.res[tid][sub];
+            if (r == 1)
+            {
+                if (nd == 0) { stage = sub + 1; toi = T.rtoi[tid][sub]; }
+                else later_hit = sub;
+                break;
+            }
+            if (r == 2) { base[nd++] = T.rbase[tid][sub]; submask |= 1u << sub; }
+        }
+        if (nd == 0) store_result(A, i, stage, toi);
+        else { stage = -1; meta = (int)(submask | ((unsigned)later_hit << 8)); }
+    }
+    // warp-aggregated append to the work list
+    const bool deferred = stage < 0;
+    const unsigned m = __ballot_sync(0xffffffffu, deferred);
+    if (m)
+    {
+        const int lane = tid & 31;
+        unsigned long long wbase = 0;
+        if (lane == 0) wbase = atomicAdd(A.nwork, (unsigned long long)__popc(m));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (deferred)
+        {
+            const unsigned long long w = wbase + __popc(m & ((1u << lane) - 1));
+            A.w_stencil[w] = (int)i;
+            A.w_meta[w] = meta;
+            for (int j = 0; j < 5; j++) A.w_base[5 * w + j] = base[j];
+        }
+    }
     reduce_warp(stage > 0, toi, A.earliest_bits, A.nhit);
 }
 
-// root kernel: one thread per pending polynomial of records [*begin, *end); coefficients are replaced by the roots in [0,1]
-__global__ void __launch_bounds__(128) roots_kernel(double *tasks, const unsigned long long *begin_ptr, const unsigned long long *end_ptr,
-                                                    unsigned long long cap)
+// root kernel: one thread per pending polynomial; the record's coefficients are replaced by its roots in [0,1]
+__global__ void __launch_bounds__(128, NP_MINB) roots_kernel(double *tasks, const unsigned long long *ntask_ptr, unsigned long long cap)
 {
-    unsigned long long nt = *end_ptr;
-    const unsigned long long t0 = begin_ptr ? *begin_ptr : 0ull;
+    unsigned long long nt = *ntask_ptr;
     if (nt > cap) nt = cap;
-    for (unsigned long long j = t0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < nt;
+    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < nt;
          j += (unsigned long long)gridDim.x * blockDim.x)
     {
         double *rec = tasks + 8 * j;
@@ -333,29 +443,58 @@ __global__ void __launch_bounds__(128) roots_kernel(double *tasks, const unsigne
     }
 }
 
-// resume pass: the stencils of the `in` list continue at the sub-test that deferred, with its roots read from the task
-// records.  LATER = DEFER: a later sub-test that needs the isolator again goes on the `out` list (second round);
-// LATER = FULL: everything is finished in place (last round; rare work, the only kernel that carries the isolator inline).
-template <bool IS_VF, int LATER> __global__ void __launch_bounds__(128) stencil_resume_kernel(NpArgs A)
+// pass 3: the deferred stencils.  Only the sub-tests that exported polynomials are evaluated again, in order, with
+// their roots read from the task records; the first one that hits wins, else the hit pass 1 found later (if any).
+template <bool IS_VF> static __device__ __noinline__ int resume_walk(const NpArgs &A, const StencilIn &S, double &t, int meta, const int *base)
 {
-    const unsigned long long nw = *A.in.count;
+    V3 v[4];
+    for (int i = 0; i < 4; i++) v[i] = S.b[i] - S.a[i];
+    Pend P;
+    unsigned submask = (unsigned)meta & 0xffu;
+    const int later_hit = (meta >> 8) & 0xff;
+    int j = 0;
+    while (submask)
+    {
+        const int sub = __ffs(submask) - 1;
+        submask &= submask - 1;
+        if (eval_sub<IS_VF, MODE_RESUME>(sub, S.a, v, S.eta, t, P, A.tasks + 8ll * base[j]) == R_HIT) return sub + 1;
+        j++;
+    }
+    if (later_hit == 255) return 0;
+    if (later_hit <= Subs<IS_VF>::NVE)
+        eval_sub<IS_VF, MODE_DEFER>(later_hit, S.a, v, S.eta, t, P, nullptr);      // decided hit: recompute its t
+    else
+    {
+        int i1, i2;
+        Subs<IS_VF>::vv(later_hit - Subs<IS_VF>::NVE - 1, i1, i2);
+        vertex_vertex(S.a[i1], S.a[i2], v[i1], v[i2], S.eta, t);
+    }
+    return later_hit + 1;
+}
+
+template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) stencil_resume_kernel(NpArgs A)
+{
+    const unsigned long long nw = *A.nwork;
     const unsigned long long nround = (nw + 31ull) & ~31ull;
     for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nround;
          w += (unsigned long long)gridDim.x * blockDim.x)
     {
         int stage = 0;
-        long long i = 0;
         double toi = 0.0;
-        Pend P;
-        P.mask = 0;
-        // records past the capacity were never written: the caller grows the buffer and reruns the whole narrowphase
-        if (w < nw && (unsigned long long)A.in.task[w] + 5ull <= A.task_cap)
+        if (w < nw)
         {
-            i = A.in.stencil[w];
-            stage = run_single<IS_VF, MODE_RESUME, LATER>(A, i, toi, A.in.sub[w], P, A.tasks + 8ll * A.in.task[w]);
-            if (stage >= 0) store_result(A, i, stage, toi);
+            int base[5];
+            bool ok = true;      // records past the capacity were never written: the caller grows the buffer and reruns
+            for (int j = 0; j < 5; j++) { base[j] = A.w_base[5 * w + j]; ok = ok && ((unsigned long long)base[j] + 5ull <= A.task_cap); }
+            if (ok)
+            {
+                const long long i = A.w_stencil[w];
+                StencilIn S;
+                load_single<IS_VF>(A, i, S);
+                stage = resume_walk<IS_VF>(A, S, toi, A.w_meta[w], base);
+                store_result(A, i, stage, toi);
+            }
         }
-        if (LATER == MODE_DEFER) defer_stencil(A, stage < 0, i, -stage - 1, P);
         reduce_warp(stage > 0, toi, A.earliest_bits, A.nhit);
     }
 }
@@ -372,13 +511,12 @@ template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_history_ker
         const double eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
         int verts[4] = {s.x, s.y, s.z, s.w};
         V3 a[4], b[4];
-        Pend P;
         Stitcher st;
         st.begin(A.hoff, A.htime, A.hpos, verts);
         if (st.next(a))
             while (st.next(b))
             {
-                stage = IS_VF ? vf_stencil_segment<MODE_FULL, MODE_FULL>(a, b, eta, toi, 0, P, nullptr) : ee_stencil_segment<MODE_FULL, MODE_FULL>(a, b, eta, toi, 0, P, nullptr);
+                stage = stencil_segment_full<IS_VF>(a, b, eta, toi);
                 if (stage) break;
                 for (int k = 0; k < 4; k++) a[k] = b[k];
             }
@@ -430,49 +568,44 @@ using namespace ccd;
 
 static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
-// Buffers: two work lists w1/w2 = {n ints, n ints, n bytes}, tasks (task_cap records of 8 doubles), counters
-// ctr[0] = entries of list 1, ctr[1] = entries of list 2, ctr[2] = task records, ctr[3] = task records after pass 1
-// (all zeroed here).  Returns the number of kernels launched.  If ctr[2] ends above task_cap the caller must grow the
-// task buffer and call again.
+// Buffers: work list {w_stencil: n ints, w_meta: n ints, w_base: 5n ints}, tasks (task_cap records of 8 doubles),
+// counters ctr[0] = work-list entries, ctr[1] = task records (zeroed here).  Returns the number of kernels launched.
+// If ctr[1] ends above task_cap - 5 the caller must grow the task buffer and call again.
 int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, double eta_all,
                      const double *q0, const double *q1, int vstride, const long long *hoff, const double *htime, const double *hpos,
                      unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits,
-                     unsigned long long *nhit, int *w1_stencil, int *w1_task, unsigned char *w1_sub, int *w2_stencil, int *w2_task,
-                     unsigned char *w2_sub, double *tasks, unsigned long long task_cap, unsigned long long *ctr)
+                     unsigned long long *nhit, int *w_stencil, int *w_meta, int *w_base, double *tasks, unsigned long long task_cap,
+                     unsigned long long *ctr)
 {
     if (n <= 0) return 0;
     NpArgs A;
     A.n = n; A.stencils = stencils; A.eta_arr = eta_arr; A.eta_all = eta_all; A.q0 = q0; A.q1 = q1; A.vstride = vstride;
     A.hoff = hoff; A.htime = htime; A.hpos = hpos; A.hit = hit; A.toi = toi; A.stage = stage;
     A.earliest_bits = earliest_bits; A.nhit = nhit;
-    A.tasks = tasks; A.ntask = ctr + 2; A.task_cap = task_cap;
-    const WorkList L1 = {w1_stencil, w1_task, w1_sub, ctr + 0}, L2 = {w2_stencil, w2_task, w2_sub, ctr + 1}, none = {nullptr, nullptr, nullptr, nullptr};
+    A.w_stencil = w_stencil; A.w_meta = w_meta; A.w_base = w_base; A.nwork = ctr + 0;
+    A.tasks = tasks; A.ntask = ctr + 1; A.task_cap = task_cap;
     const int B = 128;
     if (q0 == nullptr)
     {
-        A.in = none; A.out = none;
         if (is_vf) stencil_history_kernel<true><<<grid_for(n, B), B, 0, st>>>(A);
         else stencil_history_kernel<false><<<grid_for(n, B), B, 0, st>>>(A);
         return 1;
     }
-    cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned long long), st);
+    cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), st);
     const unsigned g2 = (unsigned)min((long long)148 * 32, (long long)grid_for(n, B));
-    // pass 1 -> list 1
-    A.in = none; A.out = L1;
-    if (is_vf) stencil_pass1_kernel<true><<<grid_for(n, B), B, 0, st>>>(A);
-    else stencil_pass1_kernel<false><<<grid_for(n, B), B, 0, st>>>(A);
-    cudaMemcpyAsync(ctr + 3, ctr + 2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st);
-    roots_kernel<<<g2, B, 0, st>>>(tasks, nullptr, ctr + 3, task_cap);
-    // resume list 1; sub-tests that need roots again -> list 2
-    A.in = L1; A.out = L2;
-    if (is_vf) stencil_resume_kernel<true, MODE_DEFER><<<g2, B, 0, st>>>(A);
-    else stencil_resume_kernel<false, MODE_DEFER><<<g2, B, 0, st>>>(A);
-    roots_kernel<<<148, B, 0, st>>>(tasks, ctr + 3, ctr + 2, task_cap);
-    // resume list 2 and finish in place
-    A.in = L2; A.out = none;
-    if (is_vf) stencil_resume_kernel<true, MODE_FULL><<<148 * 4, B, 0, st>>>(A);
-    else stencil_resume_kernel<false, MODE_FULL><<<148 * 4, B, 0, st>>>(A);
-    return 5;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        cudaFuncSetAttribute(stencil_pass1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
+        cudaFuncSetAttribute(stencil_pass1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
+        attr_set = true;
+    }
+    if (is_vf) stencil_pass1_kernel<true><<<grid_for(n, NP_TILE), NP_TILE, sizeof(TileShared), st>>>(A);
+    else stencil_pass1_kernel<false><<<grid_for(n, NP_TILE), NP_TILE, sizeof(TileShared), st>>>(A);
+    roots_kernel<<<g2, B, 0, st>>>(tasks, ctr + 1, task_cap);
+    if (is_vf) stencil_resume_kernel<true><<<g2, B, 0, st>>>(A);
+    else stencil_resume_kernel<false><<<g2, B, 0, st>>>(A);
+    return 3;
 }
 
 void ccdk_prim_batch(cudaStream_t st, int kind, long long n, const double *pts, const double *eta, unsigned char *hit, double *t)
