@@ -26,6 +26,7 @@
 #define NP_MINB 3      // resident blocks of 128 threads per SM the stencil kernels are compiled for
 #endif
 #include "ccd_math.cuh"
+#include "ccd_roots_t.cuh"
 #include <cooperative_groups.h>
 #include <cooperative_groups/scan.h>
 namespace cg = cooperative_groups;
@@ -424,21 +425,50 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) stencil_pa
     reduce_warp(stage > 0, toi, A.earliest_bits, A.nhit);
 }
 
-// root kernel: one thread per pending polynomial; the record's coefficients are replaced by its roots in [0,1]
-__global__ void __launch_bounds__(128, NP_MINB) roots_kernel(double *tasks, const unsigned long long *ntask_ptr, unsigned long long cap)
+// Root stage.  Task records are bucketed by reduced degree (3..6) so that each root kernel is specialised for one degree:
+// compile-time array sizes, everything in registers (ccd_roots_t.cuh), dense warps of identical work.
+__global__ void __launch_bounds__(256) bucket_tasks_kernel(const double *__restrict__ tasks, const unsigned long long *ntask_ptr,
+                                                           unsigned long long cap, int *__restrict__ lists, unsigned long long *counts)
 {
     unsigned long long nt = *ntask_ptr;
     if (nt > cap) nt = cap;
-    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < nt;
+    const unsigned long long nround = (nt + 31ull) & ~31ull;
+    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < nround;
          j += (unsigned long long)gridDim.x * blockDim.x)
     {
-        double *rec = tasks + 8 * j;
-        double op[7], b[7], roots[6];
-        const int rd = (int)rec[7];
-        for (int c = 0; c <= rd; c++) op[c] = rec[c];
-        bernstein(op, rd, b);
-        const int nr = roots01(op, rd, b, roots);
-        for (int c = 0; c < nr; c++) rec[c] = roots[c];
+        const int rd = (j < nt) ? (int)tasks[8 * j + 7] : 0;
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int d = 3; d <= 6; d++)
+        {
+            const unsigned m = __ballot_sync(0xffffffffu, rd == d);
+            if (m)
+            {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&counts[d - 3], (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (rd == d) lists[(size_t)(d - 3) * cap + base + __popc(m & ((1u << lane) - 1))] = (int)j;
+            }
+        }
+    }
+}
+
+// one thread per pending polynomial of degree D; the record's coefficients are replaced by its roots in [0,1]
+template <int D>
+__global__ void __launch_bounds__(128) roots_kernel(double *tasks, const int *__restrict__ list, const unsigned long long *count_ptr)
+{
+    const unsigned long long nt = *count_ptr;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nt;
+         w += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        double *rec = tasks + 8ll * list[w];
+        double op[D + 1], roots[6];
+#pragma unroll
+        for (int c = 0; c <= D; c++) op[c] = rec[c];
+        const int nr = roots01_t<D>(op, roots);
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+            if (c < nr) rec[c] = roots[c];
         rec[7] = (double)nr;
     }
 }
@@ -569,13 +599,14 @@ using namespace ccd;
 static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
 // Buffers: work list {w_stencil: n ints, w_meta: n ints, w_base: 5n ints}, tasks (task_cap records of 8 doubles),
-// counters ctr[0] = work-list entries, ctr[1] = task records (zeroed here).  Returns the number of kernels launched.
+// tlists (4 x task_cap ints: task indices by degree), counters ctr[0] = work-list entries, ctr[1] = task records,
+// ctr[2..5] = tasks of degree 3..6 (all zeroed here).  Returns the number of kernels launched.
 // If ctr[1] ends above task_cap - 5 the caller must grow the task buffer and call again.
 int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, double eta_all,
                      const double *q0, const double *q1, int vstride, const long long *hoff, const double *htime, const double *hpos,
                      unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits,
-                     unsigned long long *nhit, int *w_stencil, int *w_meta, int *w_base, double *tasks, unsigned long long task_cap,
-                     unsigned long long *ctr)
+                     unsigned long long *nhit, int *w_stencil, int *w_meta, int *w_base, double *tasks, int *tlists,
+                     unsigned long long task_cap, unsigned long long *ctr)
 {
     if (n <= 0) return 0;
     NpArgs A;
@@ -591,7 +622,7 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
         else stencil_history_kernel<false><<<grid_for(n, B), B, 0, st>>>(A);
         return 1;
     }
-    cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), st);
+    cudaMemsetAsync(ctr, 0, 6 * sizeof(unsigned long long), st);
     const unsigned g2 = (unsigned)min((long long)148 * 32, (long long)grid_for(n, B));
     static bool attr_set = false;
     if (!attr_set)
@@ -602,10 +633,14 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
     }
     if (is_vf) stencil_pass1_kernel<true><<<grid_for(n, NP_TILE), NP_TILE, sizeof(TileShared), st>>>(A);
     else stencil_pass1_kernel<false><<<grid_for(n, NP_TILE), NP_TILE, sizeof(TileShared), st>>>(A);
-    roots_kernel<<<g2, B, 0, st>>>(tasks, ctr + 1, task_cap);
+    bucket_tasks_kernel<<<148 * 4, 256, 0, st>>>(tasks, ctr + 1, task_cap, tlists, ctr + 2);
+    roots_kernel<3><<<g2, B, 0, st>>>(tasks, tlists + 0 * task_cap, ctr + 2);
+    roots_kernel<4><<<g2, B, 0, st>>>(tasks, tlists + 1 * task_cap, ctr + 3);
+    roots_kernel<5><<<g2, B, 0, st>>>(tasks, tlists + 2 * task_cap, ctr + 4);
+    roots_kernel<6><<<g2, B, 0, st>>>(tasks, tlists + 3 * task_cap, ctr + 5);
     if (is_vf) stencil_resume_kernel<true><<<g2, B, 0, st>>>(A);
     else stencil_resume_kernel<false><<<g2, B, 0, st>>>(A);
-    return 3;
+    return 7;
 }
 
 void ccdk_prim_batch(cudaStream_t st, int kind, long long n, const double *pts, const double *eta, unsigned char *hit, double *t)
