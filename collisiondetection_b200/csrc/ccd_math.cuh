@@ -494,6 +494,37 @@ __device__ __forceinline__ void barycentric_coeffs(V3 x10, V3 x20, V3 x30, V3 v1
     op[4] = D * J - A * G;
 }
 
+// polynomial k of the VF primitive: k = 0,1,2 the inside cubics e1,e2,e3 — one formula under a rotation of the face,
+// base = 1+k, A = 1+(k+2)%3, B = 1+(k+1)%3: x10 = q0-base, x20 = (A-base) x (B-base), x30 = A-base (src/CTCD.cpp:433-464);
+// k = 3 the coplanarity sextic (src/CTCD.cpp:466-472)
+__device__ __forceinline__ void build_vf_poly(int k, const V3 *s, const V3 *v, double eta, double *op)
+{
+    if (k < 3)
+    {
+        const int ib = 1 + k, ia = 1 + (k + 2) % 3, ic = 1 + (k + 1) % 3;
+        const V3 xa = s[ia] - s[ib], xc = s[ic] - s[ib], va = v[ia] - v[ib], vc = v[ic] - v[ib];
+        plane_coeffs(s[0] - s[ib], cross(xa, xc), xa, v[0] - v[ib], cross(va, vc), va, op);
+    }
+    else
+        distance_coeffs(s[0] - s[1], s[2] - s[1], s[3] - s[1], v[0] - v[1], v[2] - v[1], v[3] - v[1], eta * eta, op);
+}
+
+// polynomial k of the EE primitive on points (q0,p0,q1,p1) = s[0..3]: k = 0..3 the barycentric quartics a0,a1,b0,b1
+// (src/CTCD.cpp:313-348: x10 = P[a]-P[b], x20 = P[c]-P[d], x30 = P[e]-P[f]); k = 4 the line-distance sextic (:266-288)
+__device__ __forceinline__ void build_ee_poly(int k, const V3 *s, const V3 *v, double eta, double *op)
+{
+    if (k < 4)
+    {
+        // packed point indices, 2 bits each: a b c d e f
+        const unsigned tab = (k == 0) ? 0x0E42u /*3,2 | 1,0 | 0,2*/ : (k == 1) ? 0x0E16u /*3,2 | 0,1 | 1,2*/
+                           : (k == 2) ? 0x04E8u /*1,0 | 3,2 | 2,0*/ : 0x04BCu /*1,0 | 2,3 | 3,0*/;
+        const int a = (tab >> 10) & 3, b = (tab >> 8) & 3, c = (tab >> 6) & 3, d = (tab >> 4) & 3, e = (tab >> 2) & 3, f = tab & 3;
+        barycentric_coeffs(s[a] - s[b], s[c] - s[d], s[e] - s[f], v[a] - v[b], v[c] - v[d], v[e] - v[f], op);
+    }
+    else
+        distance_coeffs(s[1] - s[3], s[1] - s[0], s[3] - s[2], v[1] - v[3], v[1] - v[0], v[3] - v[2], eta * eta, op);
+}
+
 // ------------------------------------------------------------------------------------------
 // the four primitives (src/CTCD.cpp:259-692).  s[] = start positions, v[] = end - start.
 // Return R_MISS / R_HIT (t written) / R_DEFER (only with defer=true: needs the iterative isolator).
@@ -509,16 +540,14 @@ template <int MODE> static __device__ __noinline__ int vertex_face(const V3 *s, 
     // list anywhere is a miss (src/CTCD.cpp:441,452,463,474), and the lanes of a warp then run the isolator together.
     for (int k = 0; k < 3; k++)
     {
-        const int ib = 1 + k, ia = 1 + (k + 2) % 3, ic = 1 + (k + 1) % 3;
-        const V3 xa = s[ia] - s[ib], xc = s[ic] - s[ib], va = v[ia] - v[ib], vc = v[ic] - v[ib];
-        plane_coeffs(s[0] - s[ib], cross(xa, xc), xa, v[0] - v[ib], cross(va, vc), va, P.ops[k]);
+        build_vf_poly(k, s, v, eta, P.ops[k]);
         iv[k].n = 0;
         if (prepare_poly(P.ops[k], 3, iv[k], true, P.rds[k]))
             P.mask |= 1u << k;
         else if (iv[k].n == 0)
             return R_MISS;
     }
-    distance_coeffs(s[0] - s[1], s[2] - s[1], s[3] - s[1], v[0] - v[1], v[2] - v[1], v[3] - v[1], eta * eta, P.ops[3]);
+    build_vf_poly(3, s, v, eta, P.ops[3]);
     iv[3].n = 0;
     if (prepare_poly(P.ops[3], 6, iv[3], false, P.rds[3]))
         P.mask |= 8u;
@@ -565,7 +594,7 @@ template <int MODE> static __device__ __noinline__ int edge_edge(const V3 *s, co
     Ivals cop, par, q[5];      // q[0..3] = a0,a1,b0,b1 ; q[4] = raw coplanarity intervals
     P.mask = 0;
     cop.n = par.n = 0;
-    distance_coeffs(s[1] - s[3], s[1] - s[0], s[3] - s[2], v[1] - v[3], v[1] - v[0], v[3] - v[2], eta * eta, P.ops[4]);
+    build_ee_poly(4, s, v, eta, P.ops[4]);
     q[4].n = 0;
     if (prepare_poly(P.ops[4], 6, q[4], false, P.rds[4]))
         P.mask |= 16u;
@@ -574,11 +603,7 @@ template <int MODE> static __device__ __noinline__ int edge_edge(const V3 *s, co
     // the four barycentric quartics a0,a1,b0,b1 (src/CTCD.cpp:313-348): x10 = P[a]-P[b], x20 = P[c]-P[d], x30 = P[e]-P[f]
     for (int k = 0; k < 4; k++)
     {
-        // packed point indices, 2 bits each: a b c d e f
-        const unsigned tab = (k == 0) ? 0x0E42u /*3,2 | 1,0 | 0,2*/ : (k == 1) ? 0x0E16u /*3,2 | 0,1 | 1,2*/
-                           : (k == 2) ? 0x04E8u /*1,0 | 3,2 | 2,0*/ : 0x04BCu /*1,0 | 2,3 | 3,0*/;
-        const int a = (tab >> 10) & 3, b = (tab >> 8) & 3, c = (tab >> 6) & 3, d = (tab >> 4) & 3, e = (tab >> 2) & 3, f = tab & 3;
-        barycentric_coeffs(s[a] - s[b], s[c] - s[d], s[e] - s[f], v[a] - v[b], v[c] - v[d], v[e] - v[f], P.ops[k]);
+        build_ee_poly(k, s, v, eta, P.ops[k]);
         q[k].n = 0;
         if (prepare_poly(P.ops[k], 4, q[k], true, P.rds[k]))
             P.mask |= 1u << k;

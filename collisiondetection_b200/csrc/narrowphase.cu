@@ -27,6 +27,7 @@
 #endif
 #include "ccd_math.cuh"
 #include "ccd_roots_t.cuh"
+#include "ccd_classify.cuh"
 #include <cooperative_groups.h>
 #include <cooperative_groups/scan.h>
 namespace cg = cooperative_groups;
@@ -259,17 +260,22 @@ __device__ __forceinline__ void store_result(const NpArgs &A, long long i, int s
     if (A.stage) A.stage[i] = (unsigned char)stage;
 }
 
-// One task record per pending polynomial of P (coefficients + reduced degree); returns the first record's index.
-// Called from divergent code: the lanes that happen to be here together share one atomic (coalesced group).
-__device__ __forceinline__ int alloc_tasks(const NpArgs &A, const Pend &P)
+// Reserve n consecutive task records; returns the index of the first.  Called from divergent code: the lanes that
+// happen to be here together share one atomic (coalesced group).
+__device__ __forceinline__ unsigned long long alloc_task_slots(const NpArgs &A, int n)
 {
     cg::coalesced_group g = cg::coalesced_threads();
-    const int n = __popc(P.mask);
     const int pre = cg::exclusive_scan(g, n);
     unsigned long long base = 0;
     if (g.thread_rank() == g.size() - 1) base = atomicAdd(A.ntask, (unsigned long long)(pre + n));
     base = g.shfl(base, g.size() - 1);
-    const unsigned long long t0 = base + (unsigned long long)pre;
+    return base + (unsigned long long)pre;
+}
+
+// One task record per pending polynomial of P (coefficients + reduced degree); returns the first record's index.
+__device__ __forceinline__ int alloc_tasks(const NpArgs &A, const Pend &P)
+{
+    const unsigned long long t0 = alloc_task_slots(A, __popc(P.mask));
     int j = 0;
     unsigned mask = P.mask;
     while (mask)
@@ -355,11 +361,29 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) stencil_pa
         Pend P;
         for (int it = tid; it < T.nprim; it += blockDim.x)
         {
+            // the primitive: register-resident classification of its polynomials (ccd_classify.cuh); only when every
+            // list is already known and non-empty (rare) is the general routine run for the interval combination
             const int s = T.qprim[it];
-            double t = 0.0;
-            const int r = eval_sub<IS_VF, MODE_DEFER>(0, T.a[s], T.v[s], T.eta[s], t, P, nullptr);
-            if (r == R_HIT) { T.res[s][0] = 1; T.rtoi[s][0] = t; }
-            else if (r == R_DEFER) { T.res[s][0] = 2; T.rbase[s][0] = alloc_tasks(A, P); }
+            unsigned pend;
+            if (!classify_primitive<IS_VF>(T.a[s], T.v[s], T.eta[s], pend))
+                continue;
+            if (pend == 0)
+            {
+                double t = 0.0;
+                if (eval_sub<IS_VF, MODE_DEFER>(0, T.a[s], T.v[s], T.eta[s], t, P, nullptr) == R_HIT) { T.res[s][0] = 1; T.rtoi[s][0] = t; }
+                continue;
+            }
+            const unsigned long long t0 = alloc_task_slots(A, __popc(pend));
+            int j = 0;
+            while (pend)
+            {
+                const int k = __ffs(pend) - 1;
+                pend &= pend - 1;
+                if (t0 + j < A.task_cap) export_poly<IS_VF>(k, T.a[s], T.v[s], T.eta[s], A.tasks + 8 * (t0 + j));
+                j++;
+            }
+            T.res[s][0] = 2;
+            T.rbase[s][0] = (int)t0;
         }
         for (int it = tid; it < T.nve; it += blockDim.x)
         {
