@@ -388,10 +388,30 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) stencil_pa
         for (int it = tid; it < T.nve; it += blockDim.x)
         {
             const int s = T.qve[it] & 0xff, sub = T.qve[it] >> 8;
-            double t = 0.0;
-            const int r = eval_sub<IS_VF, MODE_DEFER>(sub, T.a[s], T.v[s], T.eta[s], t, P, nullptr);
-            if (r == R_HIT) { T.res[s][sub] = 1; T.rtoi[s][sub] = t; }
-            else if (r == R_DEFER) { T.res[s][sub] = 2; T.rbase[s][sub] = alloc_tasks(A, P); }
+            int iv, i1, i2;
+            Subs<IS_VF>::ve(sub, iv, i1, i2);
+            double rec[8];
+            bool want_rec;
+            const int c = classify_ve(T.a[s][iv], T.a[s][i1], T.a[s][i2], T.v[s][iv], T.v[s][i1], T.v[s][i2], T.eta[s], rec, want_rec);
+            if (c == VE_MISS)
+                continue;
+            if (c == VE_FULL)
+            {
+                double t = 0.0;
+                if (eval_sub<IS_VF, MODE_DEFER>(sub, T.a[s], T.v[s], T.eta[s], t, P, nullptr) == R_HIT) { T.res[s][sub] = 1; T.rtoi[s][sub] = t; }
+                continue;
+            }
+            const unsigned long long t0 = alloc_task_slots(A, 1);
+            if (t0 < A.task_cap)
+            {
+                double *out = A.tasks + 8 * t0;
+                const int rd = (int)rec[7];
+                out[0] = rec[0]; out[1] = rec[1]; out[2] = rec[2]; out[3] = rec[3];
+                if (rd == 4) out[4] = rec[4];
+                out[7] = rec[7];
+            }
+            T.res[s][sub] = 2;
+            T.rbase[s][sub] = (int)t0;
         }
         for (int it = tid; it < T.nvv; it += blockDim.x)
         {
