@@ -23,7 +23,7 @@
 // hit counts are reduced per warp and merged with one atomic pair per warp.
 #include "ccd_kernels.h"
 #ifndef NP_MINB
-#define NP_MINB 3      // resident blocks of 128 threads per SM the stencil kernels are compiled for
+#define NP_MINB 4      // resident blocks of 128 threads per SM the stencil kernels are compiled for
 #endif
 #include "ccd_math.cuh"
 #include "ccd_roots_t.cuh"
@@ -294,39 +294,41 @@ __device__ __forceinline__ int alloc_tasks(const NpArgs &A, const Pend &P)
     return (int)t0;
 }
 
-// pass 1: every stencil, straight-line work only, as a block-synchronous pipeline over a tile of NP_TILE stencils so that
-// the lanes of a warp do the same kind of work at the same time:
-//   phase 0  one thread per stencil: gather the 8 positions into shared memory, swept-box culling -> the set of sub-tests
-//            that have to be evaluated at all;
-//   phase 1  the sub-tests become items of three shared-memory queues (primitive / vertex-edge / vertex-vertex);
-//   phase 2  the queues are drained densely, one item per thread: each item ends as miss, hit (+ t) or deferred (its
-//            polynomials exported as task records);
-//   phase 3  one thread per stencil: first hit in the reference's order wins if nothing before it is deferred; a stencil
+// pass 1: every stencil, straight-line work only, as a chain of dense kernels connected by queues in HBM, so that the
+// lanes of a warp do the same kind of work at the same time and every kernel is small:
+//   cull     one thread per stencil: gather the 8 positions, swept-box culling -> the sub-tests that have to be
+//            evaluated at all become items of three queues (primitive / vertex-edge / vertex-vertex);
+//   prim, ve, vv   one thread per queue item: the item ends as miss, hit or deferred (its pending polynomials exported
+//            as task records); 2 bits per sub-test are OR-ed into the stencil's status word;
+//   decide   one thread per stencil: first hit in the reference's order wins if nothing before it is deferred; a stencil
 //            with deferred sub-tests goes on the work list with the later hit (if any) pass 1 already knows.
 // Evaluating every culling survivor instead of stopping at the first hit costs little (hits are ~10 %) and changes no
 // result: the winner is still the first hit in order.
-#define NP_TILE 128
-struct TileShared
+struct P1Args
 {
-    V3 a[NP_TILE][4], v[NP_TILE][4];
-    double eta[NP_TILE];
-    double rtoi[NP_TILE][9];
-    int rbase[NP_TILE][5];
-    unsigned short todo[NP_TILE];
-    unsigned char res[NP_TILE][9];       // per sub-test: 0 miss / not needed, 1 hit, 2 deferred
-    unsigned short qprim[NP_TILE], qve[NP_TILE * 4], qvv[NP_TILE * 4];
-    int nprim, nve, nvv;
+    NpArgs A;
+    unsigned *status;            // per stencil: 2 bits per sub-test (1 hit, 2 deferred)
+    int *sbase;                  // per stencil: first task record of deferred sub-test 0..4
+    int *qprim, *qve, *qvv;      // queues: stencil index | sub-test << 28
+    unsigned long long *nq;      // queue lengths: prim, ve, vv
 };
 
-template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) stencil_pass1_kernel(NpArgs A)
+__device__ __forceinline__ void queue_push(bool want, int value, int *queue, unsigned long long *count)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileShared &T = *reinterpret_cast<TileShared *>(smem_raw);
-    const int tid = threadIdx.x;
-    const long long i = (long long)blockIdx.x * NP_TILE + tid;
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (want) queue[base + __popc(m & ((1u << lane) - 1))] = value;
+}
+
+template <bool IS_VF> __global__ void __launch_bounds__(256) np_cull_kernel(P1Args Q)
+{
+    const NpArgs &A = Q.A;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     constexpr int NVE = Subs<IS_VF>::NVE, NVV = Subs<IS_VF>::NVV;
-    if (tid == 0) { T.nprim = 0; T.nve = 0; T.nvv = 0; }
-    // ---- phase 0
     unsigned todo = 0;
     if (i < A.n)
     {
@@ -343,110 +345,176 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) stencil_pa
             for (int k = 0; k < NVV; k++)
                 if (!c.vv_apart(k)) todo |= 1u << (NVE + 1 + k);
         }
-        for (int k = 0; k < 4; k++) { T.a[tid][k] = S.a[k]; T.v[tid][k] = S.b[k] - S.a[k]; }
-        T.eta[tid] = S.eta;
+        Q.status[i] = 0u;
     }
-    T.todo[tid] = (unsigned short)todo;
-    for (int k = 0; k < 9; k++) T.res[tid][k] = 0;
-    __syncthreads();
-    // ---- phase 1: queues
-    if (todo & 1u) T.qprim[atomicAdd(&T.nprim, 1)] = (unsigned short)tid;
+    queue_push((todo & 1u) != 0, (int)i, Q.qprim, Q.nq + 0);
+#pragma unroll
     for (int sub = 1; sub <= NVE; sub++)
-        if (todo & (1u << sub)) T.qve[atomicAdd(&T.nve, 1)] = (unsigned short)(tid | (sub << 8));
+        queue_push((todo >> sub) & 1u, (int)i | (sub << 28), Q.qve, Q.nq + 1);
+#pragma unroll
     for (int k = 0; k < NVV; k++)
-        if (todo & (1u << (NVE + 1 + k))) T.qvv[atomicAdd(&T.nvv, 1)] = (unsigned short)(tid | (k << 8));
-    __syncthreads();
-    // ---- phase 2: drain the queues densely
+        queue_push((todo >> (NVE + 1 + k)) & 1u, (int)i | (k << 28), Q.qvv, Q.nq + 2);
+}
+
+template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_prim_kernel(P1Args Q)
+{
+    const NpArgs &A = Q.A;
+    const unsigned long long n = Q.nq[0];
+    for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < n; it += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        // register-resident classification of the primitive's polynomials (ccd_classify.cuh); only when every list is
+        // already known and non-empty (rare) is the general routine run for the interval combination
+        const long long i = Q.qprim[it];
+        StencilIn S;
+        load_single<IS_VF>(A, i, S);
+        V3 v[4];
+        for (int k = 0; k < 4; k++) v[k] = S.b[k] - S.a[k];
+        unsigned pend;
+        if (!classify_primitive<IS_VF>(S.a, v, S.eta, pend))
+            continue;
+        if (pend == 0)
+        {
+            double t = 0.0;
+            Pend P;
+            if (eval_sub<IS_VF, MODE_DEFER>(0, S.a, v, S.eta, t, P, nullptr) == R_HIT) atomicOr(&Q.status[i], 1u);
+            continue;
+        }
+        const unsigned long long t0 = alloc_task_slots(A, __popc(pend));
+        int j = 0;
+        while (pend)
+        {
+            const int k = __ffs(pend) - 1;
+            pend &= pend - 1;
+            if (t0 + j < A.task_cap) export_poly<IS_VF>(k, S.a, v, S.eta, A.tasks + 8 * (t0 + j));
+            j++;
+        }
+        Q.sbase[5 * i + 0] = (int)t0;
+        atomicOr(&Q.status[i], 2u);
+    }
+}
+
+template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_ve_kernel(P1Args Q)
+{
+    const NpArgs &A = Q.A;
+    const unsigned long long n = Q.nq[1];
+    for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < n; it += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        const int item = Q.qve[it];
+        const long long i = item & 0x0fffffff;
+        const int sub = (unsigned)item >> 28;
+        int iv, i1, i2;
+        Subs<IS_VF>::ve(sub, iv, i1, i2);
+        const int4 s4 = reinterpret_cast<const int4 *>(A.stencils)[i];
+        const int idx[4] = {s4.x, s4.y, s4.z, s4.w};
+        const double eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
+        const long long vs = A.vstride;
+        const V3 a0 = ldv(A.q0 + vs * idx[iv]), a1 = ldv(A.q0 + vs * idx[i1]), a2 = ldv(A.q0 + vs * idx[i2]);
+        const V3 v0 = ldv(A.q1 + vs * idx[iv]) - a0, v1 = ldv(A.q1 + vs * idx[i1]) - a1, v2 = ldv(A.q1 + vs * idx[i2]) - a2;
+        double rec[8];
+        bool want_rec;
+        const int c = classify_ve(a0, a1, a2, v0, v1, v2, eta, rec, want_rec);
+        if (c == VE_MISS)
+            continue;
+        if (c == VE_FULL)
+        {
+            double t = 0.0;
+            Pend P;
+            if (vertex_edge<MODE_DEFER>(a0, a1, a2, v0, v1, v2, eta, t, P, nullptr) == R_HIT) atomicOr(&Q.status[i], 1u << (2 * sub));
+            continue;
+        }
+        const unsigned long long t0 = alloc_task_slots(A, 1);
+        if (t0 < A.task_cap)
+        {
+            double *out = A.tasks + 8 * t0;
+            const int rd = (int)rec[7];
+            out[0] = rec[0]; out[1] = rec[1]; out[2] = rec[2]; out[3] = rec[3];
+            if (rd == 4) out[4] = rec[4];
+            out[7] = rec[7];
+        }
+        Q.sbase[5 * i + sub] = (int)t0;
+        atomicOr(&Q.status[i], 2u << (2 * sub));
+    }
+}
+
+template <bool IS_VF> __global__ void __launch_bounds__(256) np_vv_kernel(P1Args Q)
+{
+    const NpArgs &A = Q.A;
+    const unsigned long long n = Q.nq[2];
+    constexpr int NVE = Subs<IS_VF>::NVE;
+    for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < n; it += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        const int item = Q.qvv[it];
+        const long long i = item & 0x0fffffff;
+        const int k = (unsigned)item >> 28;
+        int i1, i2;
+        Subs<IS_VF>::vv(k, i1, i2);
+        const int4 s4 = reinterpret_cast<const int4 *>(A.stencils)[i];
+        const int idx[4] = {s4.x, s4.y, s4.z, s4.w};
+        const double eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
+        const long long vs = A.vstride;
+        const V3 a1 = ldv(A.q0 + vs * idx[i1]), a2 = ldv(A.q0 + vs * idx[i2]);
+        const V3 v1 = ldv(A.q1 + vs * idx[i1]) - a1, v2 = ldv(A.q1 + vs * idx[i2]) - a2;
+        double t = 0.0;
+        if (vertex_vertex(a1, a2, v1, v2, eta, t) == R_HIT) atomicOr(&Q.status[i], 1u << (2 * (NVE + 1 + k)));
+    }
+}
+
+// the t of a sub-test pass 1 decided as a hit (recomputed: only the first such hit of a stencil is ever needed)
+template <bool IS_VF> static __device__ __noinline__ double decided_toi(const StencilIn &S, int sub)
+{
+    V3 v[4];
+    for (int k = 0; k < 4; k++) v[k] = S.b[k] - S.a[k];
+    double t = 0.0;
+    if (sub <= Subs<IS_VF>::NVE)
     {
         Pend P;
-        for (int it = tid; it < T.nprim; it += blockDim.x)
-        {
-            // the primitive: register-resident classification of its polynomials (ccd_classify.cuh); only when every
-            // list is already known and non-empty (rare) is the general routine run for the interval combination
-            const int s = T.qprim[it];
-            unsigned pend;
-            if (!classify_primitive<IS_VF>(T.a[s], T.v[s], T.eta[s], pend))
-                continue;
-            if (pend == 0)
-            {
-                double t = 0.0;
-                if (eval_sub<IS_VF, MODE_DEFER>(0, T.a[s], T.v[s], T.eta[s], t, P, nullptr) == R_HIT) { T.res[s][0] = 1; T.rtoi[s][0] = t; }
-                continue;
-            }
-            const unsigned long long t0 = alloc_task_slots(A, __popc(pend));
-            int j = 0;
-            while (pend)
-            {
-                const int k = __ffs(pend) - 1;
-                pend &= pend - 1;
-                if (t0 + j < A.task_cap) export_poly<IS_VF>(k, T.a[s], T.v[s], T.eta[s], A.tasks + 8 * (t0 + j));
-                j++;
-            }
-            T.res[s][0] = 2;
-            T.rbase[s][0] = (int)t0;
-        }
-        for (int it = tid; it < T.nve; it += blockDim.x)
-        {
-            const int s = T.qve[it] & 0xff, sub = T.qve[it] >> 8;
-            int iv, i1, i2;
-            Subs<IS_VF>::ve(sub, iv, i1, i2);
-            double rec[8];
-            bool want_rec;
-            const int c = classify_ve(T.a[s][iv], T.a[s][i1], T.a[s][i2], T.v[s][iv], T.v[s][i1], T.v[s][i2], T.eta[s], rec, want_rec);
-            if (c == VE_MISS)
-                continue;
-            if (c == VE_FULL)
-            {
-                double t = 0.0;
-                if (eval_sub<IS_VF, MODE_DEFER>(sub, T.a[s], T.v[s], T.eta[s], t, P, nullptr) == R_HIT) { T.res[s][sub] = 1; T.rtoi[s][sub] = t; }
-                continue;
-            }
-            const unsigned long long t0 = alloc_task_slots(A, 1);
-            if (t0 < A.task_cap)
-            {
-                double *out = A.tasks + 8 * t0;
-                const int rd = (int)rec[7];
-                out[0] = rec[0]; out[1] = rec[1]; out[2] = rec[2]; out[3] = rec[3];
-                if (rd == 4) out[4] = rec[4];
-                out[7] = rec[7];
-            }
-            T.res[s][sub] = 2;
-            T.rbase[s][sub] = (int)t0;
-        }
-        for (int it = tid; it < T.nvv; it += blockDim.x)
-        {
-            const int s = T.qvv[it] & 0xff, k = T.qvv[it] >> 8;
-            int i1, i2;
-            Subs<IS_VF>::vv(k, i1, i2);
-            double t = 0.0;
-            if (vertex_vertex(T.a[s][i1], T.a[s][i2], T.v[s][i1], T.v[s][i2], T.eta[s], t) == R_HIT)
-            {
-                T.res[s][NVE + 1 + k] = 1;
-                T.rtoi[s][NVE + 1 + k] = t;
-            }
-        }
+        eval_sub<IS_VF, MODE_DEFER>(sub, S.a, v, S.eta, t, P, nullptr);
     }
-    __syncthreads();
-    // ---- phase 3: per-stencil decision
+    else
+    {
+        int i1, i2;
+        Subs<IS_VF>::vv(sub - Subs<IS_VF>::NVE - 1, i1, i2);
+        vertex_vertex(S.a[i1], S.a[i2], v[i1], v[i2], S.eta, t);
+    }
+    return t;
+}
+
+template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_decide_kernel(P1Args Q)
+{
+    const NpArgs &A = Q.A;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int NSUB = 1 + Subs<IS_VF>::NVE + Subs<IS_VF>::NVV;
     int stage = 0, meta = 0, nd = 0;
     int base[5] = {0, 0, 0, 0, 0};
     double toi = 0.0;
     if (i < A.n)
     {
+        const unsigned st = Q.status[i];
         unsigned submask = 0;
         int later_hit = 255;
-        for (int sub = 0; sub < 1 + NVE + NVV; sub++)
+        if (st)
         {
-            const int r = T.res[tid][sub];
-            if (r == 1)
+            for (int sub = 0; sub < NSUB; sub++)
             {
-                if (nd == 0) { stage = sub + 1; toi = T.rtoi[tid][sub]; }
-                else later_hit = sub;
-                break;
+                const unsigned r = (st >> (2 * sub)) & 3u;
+                if (r == 1u)
+                {
+                    if (nd == 0) stage = sub + 1; else later_hit = sub;
+                    break;
+                }
+                if (r == 2u) { base[nd++] = Q.sbase[5 * i + sub]; submask |= 1u << sub; }
             }
-            if (r == 2) { base[nd++] = T.rbase[tid][sub]; submask |= 1u << sub; }
         }
-        if (nd == 0) store_result(A, i, stage, toi);
+        if (nd == 0)
+        {
+            if (stage)
+            {
+                StencilIn S;
+                load_single<IS_VF>(A, i, S);
+                toi = decided_toi<IS_VF>(S, stage - 1);
+            }
+            store_result(A, i, stage, toi);
+        }
         else { stage = -1; meta = (int)(submask | ((unsigned)later_hit << 8)); }
     }
     // warp-aggregated append to the work list
@@ -454,7 +522,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) stencil_pa
     const unsigned m = __ballot_sync(0xffffffffu, deferred);
     if (m)
     {
-        const int lane = tid & 31;
+        const int lane = threadIdx.x & 31;
         unsigned long long wbase = 0;
         if (lane == 0) wbase = atomicAdd(A.nwork, (unsigned long long)__popc(m));
         wbase = __shfl_sync(0xffffffffu, wbase, 0);
@@ -643,14 +711,15 @@ using namespace ccd;
 static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
 // Buffers: work list {w_stencil: n ints, w_meta: n ints, w_base: 5n ints}, tasks (task_cap records of 8 doubles),
-// tlists (4 x task_cap ints: task indices by degree), counters ctr[0] = work-list entries, ctr[1] = task records,
-// ctr[2..5] = tasks of degree 3..6 (all zeroed here).  Returns the number of kernels launched.
+// tlists (4 x task_cap ints: task indices by degree), pass-1 scratch {status: n u32, sbase: 5n ints, queues: 9n ints},
+// counters ctr[0] = work-list entries, ctr[1] = task records, ctr[2..5] = tasks of degree 3..6, ctr[6..8] = queue
+// lengths (all zeroed here).  Returns the number of kernels launched.
 // If ctr[1] ends above task_cap - 5 the caller must grow the task buffer and call again.
 int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, double eta_all,
                      const double *q0, const double *q1, int vstride, const long long *hoff, const double *htime, const double *hpos,
                      unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits,
                      unsigned long long *nhit, int *w_stencil, int *w_meta, int *w_base, double *tasks, int *tlists,
-                     unsigned long long task_cap, unsigned long long *ctr)
+                     unsigned long long task_cap, unsigned *status, int *sbase, int *queues, unsigned long long *ctr)
 {
     if (n <= 0) return 0;
     NpArgs A;
@@ -666,17 +735,28 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
         else stencil_history_kernel<false><<<grid_for(n, B), B, 0, st>>>(A);
         return 1;
     }
-    cudaMemsetAsync(ctr, 0, 6 * sizeof(unsigned long long), st);
+    cudaMemsetAsync(ctr, 0, 9 * sizeof(unsigned long long), st);
     const unsigned g2 = (unsigned)min((long long)148 * 32, (long long)grid_for(n, B));
-    static bool attr_set = false;
-    if (!attr_set)
+    P1Args Q;
+    Q.A = A; Q.status = status; Q.sbase = sbase;
+    Q.qprim = queues; Q.qve = queues + n; Q.qvv = queues + 5 * n; Q.nq = ctr + 6;
+    const unsigned gq = 148 * 16;
+    if (is_vf)
     {
-        cudaFuncSetAttribute(stencil_pass1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
-        cudaFuncSetAttribute(stencil_pass1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
-        attr_set = true;
+        np_cull_kernel<true><<<grid_for(n, 256), 256, 0, st>>>(Q);
+        np_prim_kernel<true><<<gq, B, 0, st>>>(Q);
+        np_ve_kernel<true><<<gq, B, 0, st>>>(Q);
+        np_vv_kernel<true><<<gq, 256, 0, st>>>(Q);
+        np_decide_kernel<true><<<grid_for(n, B), B, 0, st>>>(Q);
     }
-    if (is_vf) stencil_pass1_kernel<true><<<grid_for(n, NP_TILE), NP_TILE, sizeof(TileShared), st>>>(A);
-    else stencil_pass1_kernel<false><<<grid_for(n, NP_TILE), NP_TILE, sizeof(TileShared), st>>>(A);
+    else
+    {
+        np_cull_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(Q);
+        np_prim_kernel<false><<<gq, B, 0, st>>>(Q);
+        np_ve_kernel<false><<<gq, B, 0, st>>>(Q);
+        np_vv_kernel<false><<<gq, 256, 0, st>>>(Q);
+        np_decide_kernel<false><<<grid_for(n, B), B, 0, st>>>(Q);
+    }
     bucket_tasks_kernel<<<148 * 4, 256, 0, st>>>(tasks, ctr + 1, task_cap, tlists, ctr + 2);
     roots_kernel<3><<<g2, B, 0, st>>>(tasks, tlists + 0 * task_cap, ctr + 2);
     roots_kernel<4><<<g2, B, 0, st>>>(tasks, tlists + 1 * task_cap, ctr + 3);
@@ -684,7 +764,7 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
     roots_kernel<6><<<g2, B, 0, st>>>(tasks, tlists + 3 * task_cap, ctr + 5);
     if (is_vf) stencil_resume_kernel<true><<<g2, B, 0, st>>>(A);
     else stencil_resume_kernel<false><<<g2, B, 0, st>>>(A);
-    return 7;
+    return 11;
 }
 
 void ccdk_prim_batch(cudaStream_t st, int kind, long long n, const double *pts, const double *eta, unsigned char *hit, double *t)
