@@ -34,7 +34,7 @@ struct ccd_context
     // staging of host inputs
     DBuf faces, q0, q1, hoff, htime, hpos, fixed, vf_in, ee_in, vf_eta, ee_eta, pts, eta;
     // broadphase
-    DBuf boxes, faabb, bounds, keysA, keysB, valsA, valsB, temp, nodes, leafParent, nodeParent, flags;
+    DBuf boxes, faabb, fkdop, bounds, keysA, keysB, valsA, valsB, temp, nodes, leafParent, nodeParent, flags;
     DBuf cand, counters, pairL, pairR, deg, adjOff, cursor, adj;
     DBuf k32A, k32B, scanFlags, scanIds;
     // topology cache (function of `faces` only)
@@ -124,14 +124,15 @@ static void kdop_axes(double ax[13][3])
 // launcher prototypes (broadphase.cu / distance.cu)
 void ccdk_set_axes(const double axes[13][3]);
 void ccdk_leaf_boxes(cudaStream_t st, int kind, int F, const int *faces, const double *q0, const double *q1, const long long *hoff,
-                     const double *hpos, double eta, double *boxes, float *faabb);
+                     const double *hpos, double eta, double *boxes, float *faabb, float *fkdop);
 size_t ccdk_sort_temp_bytes(int n);
 void ccdk_exclusive_sum64(cudaStream_t st, void *temp, size_t temp_bytes, int n_plus_1, const int *in, long long *out);
 void ccdk_build_tree(cudaStream_t st, int F, const float *faabb, unsigned *bounds, unsigned long long *keys_in, unsigned long long *keys_sorted,
                      unsigned *vals_in, unsigned *sortedFace, void *temp, size_t temp_bytes, void *nodes, int *leafParent,
                      int *nodeParent, int *flags);
-void ccdk_traverse(cudaStream_t st, int F, int qbegin, int qend, const int *qlist, bool all, const unsigned *sortedFace, const float *faabb,
-                   const void *nodes, void *cand, unsigned long long cap, unsigned long long *count);
+void ccdk_traverse(cudaStream_t st, int kind, int F, int qbegin, int qend, const int *qlist, bool all, const unsigned *sortedFace,
+                   const float *faabb, const int *faces, const float *fkdop, const void *nodes, void *cand, unsigned long long cap,
+                   unsigned long long *count);
 void ccdk_exact_pairs(cudaStream_t st, int kind, const unsigned long long *ncand, unsigned long long cap, const void *cand,
                       const unsigned *sortedFace, const int *faces, const double *boxes, int *pairL, int *pairR, unsigned long long pcap,
                       unsigned long long *npairs, int *deg);
@@ -206,7 +207,7 @@ void ccd_destroy(ccd_context *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     DBuf *all[] = {&c->faces, &c->q0, &c->q1, &c->hoff, &c->htime, &c->hpos, &c->fixed, &c->vf_in, &c->ee_in, &c->vf_eta, &c->ee_eta,
-                   &c->pts, &c->eta, &c->boxes, &c->faabb, &c->bounds, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->temp, &c->nodes,
+                   &c->pts, &c->eta, &c->boxes, &c->faabb, &c->fkdop, &c->bounds, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->temp, &c->nodes,
                    &c->leafParent, &c->nodeParent, &c->flags, &c->cand, &c->counters, &c->pairL, &c->pairR, &c->deg, &c->adjOff,
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
@@ -324,6 +325,7 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
 
     CKR(ensure(c, c->boxes, sizeof(double) * 2 * (size_t)kind * (size_t)F));
     CKR(ensure(c, c->faabb, sizeof(float) * 6 * (size_t)F));
+    CKR(ensure(c, c->fkdop, sizeof(float) * 2 * (size_t)kind * (size_t)F));
     CKR(ensure(c, c->bounds, 64));
     CKR(ensure(c, c->temp, ccdk_sort_temp_bytes(3 * F > V + 1 ? 3 * F : V + 1)));
     CKR(ensure(c, c->keysA, sizeof(unsigned long long) * (size_t)(3 * F + 1)));
@@ -343,7 +345,7 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         c->pairCap = (size_t)F * 12 + (1u << 16);
 
     cudaEventRecord(c->sev[ST_BOXES], c->st);
-    ccdk_leaf_boxes(c->st, kind, F, d_faces, d_q0, d_q1, d_hoff, d_hpos, outerEta, P<double>(c->boxes), P<float>(c->faabb));
+    ccdk_leaf_boxes(c->st, kind, F, d_faces, d_q0, d_q1, d_hoff, d_hpos, outerEta, P<double>(c->boxes), P<float>(c->faabb), P<float>(c->fkdop));
     cudaEventRecord(c->sev[ST_TREE], c->st);
     ccdk_build_tree(c->st, F, P<float>(c->faabb), P<unsigned>(c->bounds), P<unsigned long long>(c->keysA), P<unsigned long long>(c->keysB),
                     P<unsigned>(c->valsA), P<unsigned>(c->valsB), c->temp.p, c->temp.cap, c->nodes.p, P<int>(c->leafParent),
@@ -359,7 +361,8 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         CKR(ensure(c, c->pairR, sizeof(int) * c->pairCap));
         CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 2, c->st));
         CK(cudaMemsetAsync(c->deg.p, 0, sizeof(int) * (size_t)(F + 2), c->st));
-        ccdk_traverse(c->st, F, 0, F, nullptr, false, sortedFace, P<float>(c->faabb), c->nodes.p, c->cand.p, c->candCap, ctr + C_NCAND);
+        ccdk_traverse(c->st, kind, F, 0, F, nullptr, false, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p, c->cand.p,
+                      c->candCap, ctr + C_NCAND);
         ccdk_exact_pairs(c->st, kind, ctr + C_NCAND, c->candCap, c->cand.p, sortedFace, d_faces, P<double>(c->boxes), P<int>(c->pairL),
                          P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg));
         c->launches += 2;
