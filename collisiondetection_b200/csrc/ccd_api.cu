@@ -51,7 +51,7 @@ struct ccd_context
 };
 
 // device counters layout (unsigned long long each)
-enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NP_VF = 16 /* 9 counters: work-list entries, task records, tasks of degree 3..6, 3 queue lengths */, C_NP_EE = 32, C_TOTAL = 48 };
+enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NP_VF = 16 /* 10 counters: work-list entries, task records, tasks of degree 3..6, 3 queue lengths, general-resume list */, C_NP_EE = 32, C_TOTAL = 48 };
 enum { C_NWORK_VF = C_NP_VF, C_NTASK_VF = C_NP_VF + 1, C_NWORK_EE = C_NP_EE, C_NTASK_EE = C_NP_EE + 1 };
 
 #define CK(call)                                                                                      \

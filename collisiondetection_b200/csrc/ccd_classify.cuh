@@ -140,6 +140,7 @@ template <int N> __device__ __forceinline__ int classify_poly(double (&op)[N + 1
         }
     }
     rd_out = rd;
+    if constexpr (N >= 3)
     if (rd > 2)
     {
         // CTCD::couldHaveRoots, src/CTCD.cpp:81-94 (zeros contribute nothing)

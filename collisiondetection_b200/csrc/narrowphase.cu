@@ -28,6 +28,7 @@
 #include "ccd_math.cuh"
 #include "ccd_roots_t.cuh"
 #include "ccd_classify.cuh"
+#include "ccd_resume.cuh"
 #include <cooperative_groups.h>
 #include <cooperative_groups/scan.h>
 namespace cg = cooperative_groups;
@@ -587,11 +588,14 @@ __global__ void __launch_bounds__(128) roots_kernel(double *tasks, const int *__
 
 // pass 3: the deferred stencils.  Only the sub-tests that exported polynomials are evaluated again, in order, with
 // their roots read from the task records; the first one that hits wins, else the hit pass 1 found later (if any).
-template <bool IS_VF> static __device__ __noinline__ int resume_walk(const NpArgs &A, const StencilIn &S, double &t, int meta, const int *base)
+// GENERAL = false: register-resident finish (ccd_resume.cuh); returns -1 when a sub-test needs the general routine —
+// the stencil is then redone by the GENERAL = true instance in a separate, rarely needed kernel, so that the hot
+// kernel does not carry the general code.
+template <bool IS_VF, bool GENERAL>
+static __device__ __noinline__ int resume_walk(const NpArgs &A, const StencilIn &S, double &t, int meta, const int *base)
 {
     V3 v[4];
     for (int i = 0; i < 4; i++) v[i] = S.b[i] - S.a[i];
-    Pend P;
     unsigned submask = (unsigned)meta & 0xffu;
     const int later_hit = (meta >> 8) & 0xff;
     int j = 0;
@@ -599,32 +603,48 @@ template <bool IS_VF> static __device__ __noinline__ int resume_walk(const NpArg
     {
         const int sub = __ffs(submask) - 1;
         submask &= submask - 1;
-        if (eval_sub<IS_VF, MODE_RESUME>(sub, S.a, v, S.eta, t, P, A.tasks + 8ll * base[j]) == R_HIT) return sub + 1;
+        const double *rec = A.tasks + 8ll * base[j];
+        int r;
+        if (GENERAL)
+        {
+            Pend P;
+            r = (eval_sub<IS_VF, MODE_RESUME>(sub, S.a, v, S.eta, t, P, rec) == R_HIT) ? RS_HIT : RS_MISS;
+        }
+        else if (sub == 0)
+            r = resume_primitive<IS_VF>(S.a, v, S.eta, rec, t);
+        else
+        {
+            int iv, i1, i2;
+            Subs<IS_VF>::ve(sub, iv, i1, i2);
+            r = resume_ve(S.a[iv], S.a[i1], S.a[i2], v[iv], v[i1], v[i2], S.eta, rec, t);
+        }
+        if (r == RS_FALLBACK) return -1;
+        if (r == RS_HIT) return sub + 1;
         j++;
     }
     if (later_hit == 255) return 0;
-    if (later_hit <= Subs<IS_VF>::NVE)
-        eval_sub<IS_VF, MODE_DEFER>(later_hit, S.a, v, S.eta, t, P, nullptr);      // decided hit: recompute its t
-    else
-    {
-        int i1, i2;
-        Subs<IS_VF>::vv(later_hit - Subs<IS_VF>::NVE - 1, i1, i2);
-        vertex_vertex(S.a[i1], S.a[i2], v[i1], v[i2], S.eta, t);
-    }
+    if (!GENERAL) return -1;        // a decided later hit: its t is recomputed by the general routine (rare)
+    t = decided_toi<IS_VF>(S, later_hit);
     return later_hit + 1;
 }
 
-template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) stencil_resume_kernel(NpArgs A)
+// work: list of work-list entries to process (nullptr = all nwork entries); fb_list/fb_count: entries to redo generally
+template <bool IS_VF, bool GENERAL>
+__global__ void __launch_bounds__(128, NP_MINB) stencil_resume_kernel(NpArgs A, const int *work, const unsigned long long *work_count,
+                                                                      int *fb_list, unsigned long long *fb_count)
 {
-    const unsigned long long nw = *A.nwork;
+    const unsigned long long nw = *work_count;
     const unsigned long long nround = (nw + 31ull) & ~31ull;
-    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nround;
-         w += (unsigned long long)gridDim.x * blockDim.x)
+    for (unsigned long long x = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; x < nround;
+         x += (unsigned long long)gridDim.x * blockDim.x)
     {
         int stage = 0;
         double toi = 0.0;
-        if (w < nw)
+        bool fb = false;
+        unsigned long long w = 0;
+        if (x < nw)
         {
+            w = work ? (unsigned long long)work[x] : x;
             int base[5];
             bool ok = true;      // records past the capacity were never written: the caller grows the buffer and reruns
             for (int j = 0; j < 5; j++) { base[j] = A.w_base[5 * w + j]; ok = ok && ((unsigned long long)base[j] + 5ull <= A.task_cap); }
@@ -633,10 +653,12 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) stencil_re
                 const long long i = A.w_stencil[w];
                 StencilIn S;
                 load_single<IS_VF>(A, i, S);
-                stage = resume_walk<IS_VF>(A, S, toi, A.w_meta[w], base);
-                store_result(A, i, stage, toi);
+                stage = resume_walk<IS_VF, GENERAL>(A, S, toi, A.w_meta[w], base);
+                if (stage >= 0) store_result(A, i, stage, toi);
+                else { fb = true; stage = 0; }
             }
         }
+        if (!GENERAL) queue_push(fb, (int)w, fb_list, fb_count);
         reduce_warp(stage > 0, toi, A.earliest_bits, A.nhit);
     }
 }
@@ -713,7 +735,7 @@ static inline unsigned grid_for(long long n, int block) { return (unsigned)((n +
 // Buffers: work list {w_stencil: n ints, w_meta: n ints, w_base: 5n ints}, tasks (task_cap records of 8 doubles),
 // tlists (4 x task_cap ints: task indices by degree), pass-1 scratch {status: n u32, sbase: 5n ints, queues: 9n ints},
 // counters ctr[0] = work-list entries, ctr[1] = task records, ctr[2..5] = tasks of degree 3..6, ctr[6..8] = queue
-// lengths (all zeroed here).  Returns the number of kernels launched.
+// lengths, ctr[9] = stencils for the general resume kernel (all zeroed here).  Returns the number of kernels launched.
 // If ctr[1] ends above task_cap - 5 the caller must grow the task buffer and call again.
 int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, double eta_all,
                      const double *q0, const double *q1, int vstride, const long long *hoff, const double *htime, const double *hpos,
@@ -735,7 +757,7 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
         else stencil_history_kernel<false><<<grid_for(n, B), B, 0, st>>>(A);
         return 1;
     }
-    cudaMemsetAsync(ctr, 0, 9 * sizeof(unsigned long long), st);
+    cudaMemsetAsync(ctr, 0, 10 * sizeof(unsigned long long), st);
     const unsigned g2 = (unsigned)min((long long)148 * 32, (long long)grid_for(n, B));
     P1Args Q;
     Q.A = A; Q.status = status; Q.sbase = sbase;
@@ -762,9 +784,18 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
     roots_kernel<4><<<g2, B, 0, st>>>(tasks, tlists + 1 * task_cap, ctr + 3);
     roots_kernel<5><<<g2, B, 0, st>>>(tasks, tlists + 2 * task_cap, ctr + 4);
     roots_kernel<6><<<g2, B, 0, st>>>(tasks, tlists + 3 * task_cap, ctr + 5);
-    if (is_vf) stencil_resume_kernel<true><<<g2, B, 0, st>>>(A);
-    else stencil_resume_kernel<false><<<g2, B, 0, st>>>(A);
-    return 11;
+    // the queues of pass 1 are free again: their buffer holds the (short) list of stencils for the general routine
+    if (is_vf)
+    {
+        stencil_resume_kernel<true, false><<<g2, B, 0, st>>>(A, nullptr, ctr + 0, queues, ctr + 9);
+        stencil_resume_kernel<true, true><<<148 * 2, B, 0, st>>>(A, queues, ctr + 9, nullptr, nullptr);
+    }
+    else
+    {
+        stencil_resume_kernel<false, false><<<g2, B, 0, st>>>(A, nullptr, ctr + 0, queues, ctr + 9);
+        stencil_resume_kernel<false, true><<<148 * 2, B, 0, st>>>(A, queues, ctr + 9, nullptr, nullptr);
+    }
+    return 12;
 }
 
 void ccdk_prim_batch(cudaStream_t st, int kind, long long n, const double *pts, const double *eta, unsigned char *hit, double *t)
