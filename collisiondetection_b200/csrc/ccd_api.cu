@@ -46,7 +46,10 @@ struct ccd_context
     // narrowphase
     DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, work2Vf, work2Ee, work2TaskVf, work2TaskEe, work2SubVf, work2SubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, selTmp, selA, selB, selC, selD, selCount;
     // pinned host scratch
-    unsigned long long *h_counters = nullptr; // 16 entries
+    unsigned long long *h_counters = nullptr; // C_TOTAL entries
+    // pinned host buffers for the hit lists returned by ccd_step (valid until the next call on the context)
+    void *h_res[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t h_res_cap[4] = {0, 0, 0, 0};
     size_t candCap = 0, pairCap = 0, taskCapVf = 0, taskCapEe = 0;
 };
 
@@ -218,6 +221,9 @@ void ccd_destroy(ccd_context *c)
             cudaFree(b->p);
     if (c->h_counters)
         cudaFreeHost(c->h_counters);
+    for (int i = 0; i < 4; i++)
+        if (c->h_res[i])
+            cudaFreeHost(c->h_res[i]);
     for (int i = 0; i < 4; i++)
         if (c->ev[i])
             cudaEventDestroy(c->ev[i]);
@@ -671,14 +677,33 @@ int ccd_step_device(ccd_context *c, int kind, int V, int F, const int32_t *d_fac
     return CCD_OK;
 }
 
-// hit compaction in std::set order (stable): stencils and TOIs of the flagged entries
-static int select_hits(ccd_context *c, long long n, const int *d_st, const double *d_toi, const unsigned char *d_flag, long long nh,
+static int ensure_pinned(ccd_context *c, int slot, size_t bytes)
+{
+    if (bytes <= c->h_res_cap[slot] && c->h_res[slot])
+        return CCD_OK;
+    if (c->h_res[slot])
+        cudaFreeHost(c->h_res[slot]);
+    c->h_res[slot] = nullptr;
+    c->h_res_cap[slot] = 0;
+    const size_t ncap = bytes + bytes / 4 + 4096;
+    if (cudaMallocHost(&c->h_res[slot], ncap) != cudaSuccess)
+    {
+        cudaGetLastError();
+        c->err = "cudaMallocHost failed";
+        return CCD_ERR_NOMEM;
+    }
+    c->h_res_cap[slot] = ncap;
+    return CCD_OK;
+}
+
+// hit compaction in std::set order (stable) into the context's pinned host buffers `slot`, `slot+1`
+static int select_hits(ccd_context *c, int slot, long long n, const int *d_st, const double *d_toi, const unsigned char *d_flag, long long nh,
                        int32_t **h_st, double **h_toi)
 {
-    *h_st = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)(nh > 0 ? nh : 1));
-    *h_toi = (double *)malloc(sizeof(double) * (size_t)(nh > 0 ? nh : 1));
-    if (!*h_st || !*h_toi)
-        return CCD_ERR_NOMEM;
+    CKR(ensure_pinned(c, slot, sizeof(int32_t) * 4 * (size_t)(nh > 0 ? nh : 1)));
+    CKR(ensure_pinned(c, slot + 1, sizeof(double) * (size_t)(nh > 0 ? nh : 1)));
+    *h_st = (int32_t *)c->h_res[slot];
+    *h_toi = (double *)c->h_res[slot + 1];
     if (n == 0 || nh == 0)
         return CCD_OK;
     size_t tb1 = 0, tb2 = 0;
@@ -725,8 +750,8 @@ int ccd_step_shard(ccd_context *c, int kind, int V, int F, const int32_t *faces,
     out->earliest_toi = d.earliest_toi;
     out->ms_broadphase = d.ms_broadphase;
     out->ms_narrowphase = d.ms_narrowphase;
-    CKR(select_hits(c, d.n_vf_candidates, d.d_vf, d.d_vf_toi, d.d_vf_hit, d.n_vf_hits, &out->vf_hits, &out->vf_hit_toi));
-    CKR(select_hits(c, d.n_ee_candidates, d.d_ee, d.d_ee_toi, d.d_ee_hit, d.n_ee_hits, &out->ee_hits, &out->ee_hit_toi));
+    CKR(select_hits(c, 0, d.n_vf_candidates, d.d_vf, d.d_vf_toi, d.d_vf_hit, d.n_vf_hits, &out->vf_hits, &out->vf_hit_toi));
+    CKR(select_hits(c, 2, d.n_ee_candidates, d.d_ee, d.d_ee_toi, d.d_ee_hit, d.n_ee_hits, &out->ee_hits, &out->ee_hit_toi));
     return CCD_OK;
 }
 
@@ -734,7 +759,7 @@ void ccd_step_result_free(ccd_step_result *r)
 {
     if (!r)
         return;
-    free(r->vf_hits); free(r->vf_hit_toi); free(r->ee_hits); free(r->ee_hit_toi);
+    // the arrays live in pinned buffers owned by the context: nothing to release, just forget them
     r->vf_hits = r->ee_hits = nullptr;
     r->vf_hit_toi = r->ee_hit_toi = nullptr;
 }

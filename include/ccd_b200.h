@@ -85,7 +85,7 @@ typedef struct
     int64_t n_vf_candidates, n_ee_candidates;
     int64_t n_vf_hits, n_ee_hits;
     double earliest_toi;
-    int32_t *vf_hits;   /* 4*n_vf_hits, malloc'ed */
+    int32_t *vf_hits;   /* 4*n_vf_hits; pinned host memory owned by the context, valid until its next call */
     double *vf_hit_toi; /* n_vf_hits */
     int32_t *ee_hits;
     double *ee_hit_toi;
