@@ -44,7 +44,7 @@ struct ccd_context
     // emission
     DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut, shardBounds;
     // narrowphase
-    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, work2Vf, work2Ee, work2TaskVf, work2TaskEe, work2SubVf, work2SubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, selTmp, selA, selB, selC, selD, selCount;
+    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, work2Vf, work2Ee, work2TaskVf, work2TaskEe, work2SubVf, work2SubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, selTmp, selA, selB, selC, selD, selCount;
     // pinned host scratch
     unsigned long long *h_counters = nullptr; // C_TOTAL entries
     // pinned host buffers for the hit lists returned by ccd_step (valid until the next call on the context)
@@ -54,7 +54,7 @@ struct ccd_context
 };
 
 // device counters layout (unsigned long long each)
-enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NP_VF = 16 /* 10 counters: work-list entries, task records, tasks of degree 3..6, 3 queue lengths, general-resume list */, C_NP_EE = 32, C_TOTAL = 48 };
+enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NP_VF = 16 /* CCD_NP_COUNTERS counters per run: work-list entries, records, ... (narrowphase.cu K_*) */, C_NP_EE = 16 + CCD_NP_COUNTERS, C_TOTAL = 16 + 2 * CCD_NP_COUNTERS };
 enum { C_NWORK_VF = C_NP_VF, C_NTASK_VF = C_NP_VF + 1, C_NWORK_EE = C_NP_EE, C_NTASK_EE = C_NP_EE + 1 };
 
 #define CK(call)                                                                                      \
@@ -215,7 +215,7 @@ void ccd_destroy(ccd_context *c)
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->shardBounds, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->work2Vf, &c->work2Ee, &c->work2TaskVf, &c->work2TaskEe, &c->work2SubVf, &c->work2SubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->work2Vf, &c->work2Ee, &c->work2TaskVf, &c->work2TaskEe, &c->work2SubVf, &c->work2SubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
     for (DBuf *b : all)
         if (b->p)
             cudaFree(b->p);
@@ -474,6 +474,8 @@ static int narrowphase_device(ccd_context *c, long long nvf, const int *d_vf, co
         CKR(ensure(c, c->p1Status, sizeof(unsigned) * nmax));
         CKR(ensure(c, c->p1Sbase, sizeof(int) * 5 * nmax));
         CKR(ensure(c, c->p1Queues, sizeof(int) * 9 * nmax));
+        CKR(ensure(c, c->p1Sq, sizeof(int) * 4 * nmax));
+        CKR(ensure(c, c->p1Xq, sizeof(int) * 10 * nmax));
     }
     int nl = 0;
     for (int attempt = 0; attempt < 4; attempt++)
@@ -492,12 +494,12 @@ static int narrowphase_device(ccd_context *c, long long nvf, const int *d_vf, co
         nl += ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
                                P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF, P<int>(c->workVf),
                                P<int>(c->workTaskVf), P<int>(c->workSubVf), P<double>(c->tasksVf), P<int>(c->tlistVf), c->taskCapVf, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
-                               P<int>(c->p1Queues), ctr + C_NP_VF);
+                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_VF);
         cudaEventRecord(c->sev[ST_NP_EE], c->st);
         nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
                                P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE, P<int>(c->workEe),
                                P<int>(c->workTaskEe), P<int>(c->workSubEe), P<double>(c->tasksEe), P<int>(c->tlistEe), c->taskCapEe, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
-                               P<int>(c->p1Queues), ctr + C_NP_EE);
+                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_EE);
         cudaEventRecord(c->sev[CCD_N_STAGES], c->st);
         CK(cudaGetLastError());
         CKR(sync_counters(c));
@@ -507,6 +509,11 @@ static int narrowphase_device(ccd_context *c, long long nvf, const int *d_vf, co
             break;
         if (tv + 5 > c->taskCapVf) c->taskCapVf = (size_t)(tv + tv / 8 + 1024);
         if (te + 5 > c->taskCapEe) c->taskCapEe = (size_t)(te + te / 8 + 1024);
+        if (c->taskCapVf >= (1u << 28) - 8 || c->taskCapEe >= (1u << 28) - 8)
+        {
+            c->err = "narrowphase: more than 2^28 polynomial records in one call; split the stencil list";
+            return CCD_ERR_NOMEM;
+        }
     }
     c->launches += nl;
     if (sum)

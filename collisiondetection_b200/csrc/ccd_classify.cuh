@@ -11,7 +11,7 @@ enum { PC_EMPTY = 0, PC_DECIDED = 1, PC_PENDING = 2 };
 
 // "no root in [0,1]" from the Bernstein coefficients of the reduced polynomial c[0..RD] (descending): end
 // coefficients non-zero and no sign variation (no_root_at_top)
-template <int RD> __device__ __forceinline__ bool no_root_static(const double *c)
+template <int RD> CCD_FN bool no_root_static(const double *c)
 {
     double b[RD + 1];
 #pragma unroll
@@ -46,7 +46,7 @@ template <int RD> __device__ __forceinline__ bool no_root_static(const double *c
 // lies in their convex hull, so the polynomial has that sign on the whole closed eighth).  If the masks of a
 // primitive's polynomials have no common bit, no time satisfies all of them, whatever the exact roots are: the
 // interval lists the reference would build cannot overlap, and the primitive misses without any root being isolated.
-template <int RD, int LEVEL> __device__ __forceinline__ unsigned dyadic_sub(const double (&b)[RD + 1], bool pos)
+template <int RD, int LEVEL> CCD_FN unsigned dyadic_sub(const double (&b)[RD + 1], bool pos)
 {
     bool possible = false;
 #pragma unroll
@@ -74,7 +74,7 @@ template <int RD, int LEVEL> __device__ __forceinline__ unsigned dyadic_sub(cons
     return ml | (mr << (1 << (LEVEL > 0 ? LEVEL - 1 : 0)));
 }
 
-template <int RD> __device__ __forceinline__ unsigned dyadic_mask(const double *c, bool pos)
+template <int RD> CCD_FN unsigned dyadic_mask(const double *c, bool pos)
 {
     double b[RD + 1];
 #pragma unroll
@@ -89,7 +89,7 @@ template <int RD> __device__ __forceinline__ unsigned dyadic_mask(const double *
 }
 
 // mask for the normalised polynomial op[0..N] of reduced degree rd >= 3
-template <int N> __device__ __forceinline__ unsigned dyadic_mask_reduced(const double (&op)[N + 1], int rd, bool pos)
+template <int N> CCD_FN unsigned dyadic_mask_reduced(const double (&op)[N + 1], int rd, bool pos)
 {
     if (N >= 6 && rd == 6) return dyadic_mask<(N >= 6 ? 6 : 3)>(&op[N >= 6 ? N - 6 : 0], pos);
     if (N >= 5 && rd == 5) return dyadic_mask<(N >= 5 ? 5 : 3)>(&op[N >= 5 ? N - 5 : 0], pos);
@@ -99,7 +99,7 @@ template <int N> __device__ __forceinline__ unsigned dyadic_mask_reduced(const d
 
 // would CTCD::checkInterval(t1,t2) push an interval?  Unfused Horner over op[0..N] (exactly-zero leading coefficients
 // change nothing: 0*t + x == x)
-template <int N> __device__ __forceinline__ bool interval_ok(double t1, double t2, const double (&op)[N + 1], bool pos)
+template <int N> CCD_FN bool interval_ok(double t1, double t2, const double (&op)[N + 1], bool pos)
 {
     t1 = smax(0.0, t1);
     t2 = smax(0.0, t2);
@@ -117,7 +117,7 @@ template <int N> __device__ __forceinline__ bool interval_ok(double t1, double t
 }
 
 // op[0..N] raw coefficients in; normalised in place (leading zeros stay where they are); rd = reduced degree out
-template <int N> __device__ __forceinline__ int classify_poly(double (&op)[N + 1], bool pos, int &rd_out)
+template <int N> CCD_FN int classify_poly(double (&op)[N + 1], bool pos, int &rd_out)
 {
     double maxval = 0;
 #pragma unroll
@@ -194,7 +194,7 @@ template <int N> __device__ __forceinline__ int classify_poly(double (&op)[N + 1
 // Straight-line classification of a whole VF / EE primitive: false when some polynomial is EMPTY (the primitive
 // misses), else true with the mask of pending polynomials (bit k as in build_vf_poly / build_ee_poly).  pendmask == 0 means every list is known
 // and non-empty: the caller runs the full primitive for the interval combination (rare).
-template <bool IS_VF> __device__ __forceinline__ bool classify_primitive(const V3 *s, const V3 *v, double eta, unsigned &pendmask)
+template <bool IS_VF> CCD_FN bool classify_primitive(const V3 *s, const V3 *v, double eta, unsigned &pendmask)
 {
     pendmask = 0;
     unsigned occupancy = 0xffu;      // eighths of [0,1] on which every pending polynomial seen so far can be satisfied
@@ -238,7 +238,7 @@ template <bool IS_VF> __device__ __forceinline__ bool classify_primitive(const V
 }
 
 // eighths of [0,1] touched by the closed interval [l,u] (already clamped to [0,1])
-__device__ __forceinline__ unsigned interval_mask(double l, double u)
+CCD_FN unsigned interval_mask(double l, double u)
 {
     int a = (int)(l * 8.0), b = (int)(u * 8.0);
     if (a > 0 && (double)a * 0.125 == l) a--;       // a boundary point belongs to both neighbours
@@ -249,7 +249,7 @@ __device__ __forceinline__ unsigned interval_mask(double l, double u)
 
 // occupancy mask of a polynomial of degree <= 2 (op[0..2], not yet normalised; normalised in place): the intervals the
 // reference's rules give (src/CTCD.cpp:145-176), each widened to the eighths it touches.  0 = EMPTY.
-__device__ __forceinline__ unsigned lowdeg_mask(double (&op)[3], bool pos)
+CCD_FN unsigned lowdeg_mask(double (&op)[3], bool pos)
 {
     double maxval = smax(smax(smax(0.0, fabs(op[0])), fabs(op[1])), fabs(op[2]));
     if (maxval != 0) { op[0] = op[0] / maxval; op[1] = op[1] / maxval; op[2] = op[2] / maxval; }
@@ -293,7 +293,7 @@ enum { VE_MISS = 0, VE_PENDING = 1, VE_FULL = 2 };
 // Straight-line classification of CTCD::vertexEdgeCTCD (src/CTCD.cpp:511-602): VE_MISS when one of its three lists is
 // empty or their occupancy masks share no eighth of [0,1]; VE_PENDING when the distance quartic needs the root isolator
 // (rec receives its task record); VE_FULL when every list is known and the general routine has to combine them.
-__device__ __forceinline__ int classify_ve(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, double *rec_out, bool &want_rec)
+CCD_FN int classify_ve(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, double *rec_out, bool &want_rec)
 {
     const double minD = eta * eta;
     const V3 ab = q2s - q1s, ac = q0s - q1s, cb = q2s - q0s;
@@ -345,7 +345,7 @@ __device__ __forceinline__ int classify_ve(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1,
 
 // Rebuild pending polynomial k of the primitive and write its task record: normalised coefficients of the reduced
 // polynomial + reduced degree — the same values prepare_poly() leaves in Pend.
-template <bool IS_VF> __device__ __forceinline__ void export_poly(int k, const V3 *s, const V3 *v, double eta, double *rec)
+template <bool IS_VF> CCD_FN void export_poly(int k, const V3 *s, const V3 *v, double eta, double *rec)
 {
     double op[7];
     int n;

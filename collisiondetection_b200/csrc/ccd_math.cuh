@@ -18,25 +18,47 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+// Every routine here is plain arithmetic and is also compiled for the host (tests/np_emul.cu runs the same code on the
+// CPU against the checker); device-only intrinsics are wrapped.
+#define CCD_HD __host__ __device__
+#define CCD_FN CCD_HD __forceinline__
+
 namespace ccd {
+
+CCD_FN int ccd_ffs(unsigned x)
+{
+#ifdef __CUDA_ARCH__
+    return __ffs(x);
+#else
+    return __builtin_ffs((int)x);
+#endif
+}
+CCD_FN int ccd_popc(unsigned x)
+{
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
 
 struct V3 { double x, y, z; };
 
-__device__ __forceinline__ V3 mk(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
-__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ V3 operator*(double s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+CCD_FN V3 mk(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+CCD_FN V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+CCD_FN V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+CCD_FN V3 operator*(double s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
 // dot = (x0*y0 + x1*y1) + x2*y2 ; cross in the usual component order — the order the CPU checker uses
-__device__ __forceinline__ double dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
-__device__ __forceinline__ V3 cross(V3 a, V3 b)
+CCD_FN double dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+CCD_FN V3 cross(V3 a, V3 b)
 {
     return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
-__device__ __forceinline__ V3 ldv(const double *p) { return mk(p[0], p[1], p[2]); }
+CCD_FN V3 ldv(const double *p) { return mk(p[0], p[1], p[2]); }
 
 // std::max / std::min argument-order semantics (matters only for NaN)
-__device__ __forceinline__ double smax(double a, double b) { return (a < b) ? b : a; }
-__device__ __forceinline__ double smin(double a, double b) { return (b < a) ? b : a; }
+CCD_FN double smax(double a, double b) { return (a < b) ? b : a; }
+CCD_FN double smin(double a, double b) { return (b < a) ? b : a; }
 
 // result codes of the primitives / stencil tests
 enum { R_MISS = 0, R_HIT = 1, R_DEFER = 2 };
@@ -63,7 +85,7 @@ struct Ivals
 };
 
 // TimeInterval ctor, include/CTCD.h:9-14
-__device__ __forceinline__ void push_interval(Ivals &iv, double tl, double tu)
+CCD_FN void push_interval(Ivals &iv, double tl, double tu)
 {
     double l = tl, u = tu;
     if (l > u) { double t = l; l = u; u = t; }
@@ -74,13 +96,13 @@ __device__ __forceinline__ void push_interval(Ivals &iv, double tl, double tu)
     iv.n++;
 }
 
-__device__ __forceinline__ bool overlap2(double al, double au, double bl, double bu) { return !(al > bu || bl > au); }
+CCD_FN bool overlap2(double al, double au, double bl, double bu) { return !(al > bu || bl > au); }
 
 // ------------------------------------------------------------------------------------------
 // Real roots on [0,1] of c[0] t^d + ... + c[d], c[0] != 0, 3 <= d <= 6.
 // Same steps, same fused operations as oracle/ccd_oracle.c: orc_roots01.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double horner_fma(const double *c, int m, double x)
+CCD_FN double horner_fma(const double *c, int m, double x)
 {
     double f = c[0];
     for (int i = 1; i <= m; i++)
@@ -89,7 +111,7 @@ __device__ __forceinline__ double horner_fma(const double *c, int m, double x)
 }
 
 // root of the degree-m polynomial p in (lo,hi); f(lo) has the sign of flo, f(hi) the opposite
-static __device__ __noinline__ double solve_bracket(const double *p, int m, double lo, double hi, double flo)
+static CCD_HD __noinline__ double solve_bracket(const double *p, int m, double lo, double hi, double flo)
 {
     double c[7];
     for (int i = 0; i <= m; i++)
@@ -133,7 +155,7 @@ static __device__ __noinline__ double solve_bracket(const double *p, int m, doub
     return x;
 }
 
-__device__ __forceinline__ int sign_variations(const double *b, int count)
+CCD_FN int sign_variations(const double *b, int count)
 {
     int v = 0, last = 0;
     for (int i = 0; i < count; i++)
@@ -150,7 +172,7 @@ __device__ __forceinline__ int sign_variations(const double *b, int count)
 }
 
 // reciprocal binomials 1/C(d,i), the same constants (and roundings) as the checker's table
-__device__ __forceinline__ double rbinom(int d, int i)
+CCD_FN double rbinom(int d, int i)
 {
     const double R3[4] = {1.0, 1.0 / 3.0, 1.0 / 3.0, 1.0};
     const double R4[5] = {1.0, 1.0 / 4.0, 1.0 / 6.0, 1.0 / 4.0, 1.0};
@@ -161,7 +183,7 @@ __device__ __forceinline__ double rbinom(int d, int i)
 
 // Bernstein coefficients on [0,1] of the degree-d polynomial c (descending): scaled power coefficients,
 // then the binomial transform by repeated adjacent sums
-__device__ __forceinline__ void bernstein(const double *c, int d, double *b)
+CCD_FN void bernstein(const double *c, int d, double *b)
 {
     for (int i = 0; i <= d; i++)
         b[i] = c[d - i] * rbinom(d, i);
@@ -171,13 +193,13 @@ __device__ __forceinline__ void bernstein(const double *c, int d, double *b)
 }
 
 // True when the top level already decides "no root in [0,1]": end coefficients non-zero, no sign variation.
-__device__ __forceinline__ bool no_root_at_top(const double *b, int d)
+CCD_FN bool no_root_at_top(const double *b, int d)
 {
     return b[0] != 0.0 && b[d] != 0.0 && sign_variations(b, d + 1) == 0;
 }
 
 // power coefficients of derivative level m of the degree-d polynomial c (successive q' steps, rounded like the checker)
-__device__ __forceinline__ void deriv_level(const double *c, int d, int m, double *p)
+CCD_FN void deriv_level(const double *c, int d, int m, double *p)
 {
     for (int i = 0; i <= d; i++)
         p[i] = c[i];
@@ -187,7 +209,7 @@ __device__ __forceinline__ void deriv_level(const double *c, int d, int m, doubl
 }
 
 // b holds the Bernstein coefficients of c (degree d) on entry and is used as scratch
-static __device__ __noinline__ int roots01(const double *c, int d, double *b, double *roots)
+static CCD_HD __noinline__ int roots01(const double *c, int d, double *b, double *roots)
 {
     double p[7], cur[6];
     int ncur = 0, m0;
@@ -274,7 +296,7 @@ static __device__ __noinline__ int roots01(const double *c, int d, double *b, do
 // CTCD::findIntervals (src/CTCD.cpp:98-177)
 // ------------------------------------------------------------------------------------------
 // CTCD::checkInterval, src/CTCD.cpp:59-79 — unfused Horner at the clamped midpoint
-static __device__ __noinline__ void check_interval(double t1, double t2, const double *op, int degree, Ivals &iv, bool pos)
+static CCD_HD __noinline__ void check_interval(double t1, double t2, const double *op, int degree, Ivals &iv, bool pos)
 {
     t1 = smax(0.0, t1);
     t2 = smax(0.0, t2);
@@ -292,7 +314,7 @@ static __device__ __noinline__ void check_interval(double t1, double t2, const d
 }
 
 // CTCD::getQuadRoots, src/CTCD.cpp:38-56
-static __device__ __noinline__ int quad_roots(double a, double b, double c, double &t0, double &t1)
+static CCD_HD __noinline__ int quad_roots(double a, double b, double c, double &t0, double &t1)
 {
     int roots = 0;
     double sign = (b < 0) ? -1.0 : 1.0;
@@ -312,7 +334,7 @@ static __device__ __noinline__ int quad_roots(double a, double b, double c, doub
 // needs no iteration (quick reject, closed forms for degree <= 2, Bernstein "no root in [0,1]").
 // op[0..n] is modified exactly like the reference does.  Returns 0 when iv is final, 1 when the reduced
 // polynomial op[0..rd] (rd >= 3) still needs the root isolator (finish_poly).
-static __device__ __noinline__ int prepare_poly(double *op, int n, Ivals &iv, bool pos, int &rd_out)
+static CCD_HD __noinline__ int prepare_poly(double *op, int n, Ivals &iv, bool pos, int &rd_out)
 {
     // normalise, src/CTCD.cpp:113-119
     double maxval = 0;
@@ -381,7 +403,7 @@ static __device__ __noinline__ int prepare_poly(double *op, int n, Ivals &iv, bo
 }
 
 // the interval rules of src/CTCD.cpp:161-176 for the prepared polynomial and its real roots in [0,1]
-__device__ __forceinline__ void intervals_from_roots(const double *op, int rd, const double *time, int roots, Ivals &iv, bool pos)
+CCD_FN void intervals_from_roots(const double *op, int rd, const double *time, int roots, Ivals &iv, bool pos)
 {
     if (roots > 0)
     {
@@ -398,7 +420,7 @@ __device__ __forceinline__ void intervals_from_roots(const double *op, int rd, c
 }
 
 // Second half of findIntervals: real roots of the prepared polynomial in [0,1], then the interval rules.
-static __device__ __noinline__ void finish_poly(const double *op, int rd, Ivals &iv, bool pos)
+static CCD_HD __noinline__ void finish_poly(const double *op, int rd, Ivals &iv, bool pos)
 {
     double time[6], b[7];
     bernstein(op, rd, b);
@@ -407,7 +429,7 @@ static __device__ __noinline__ void finish_poly(const double *op, int rd, Ivals 
 }
 
 // CTCD::findIntervals for a single polynomial (FULL mode).
-__device__ __forceinline__ void find_intervals(double *op, int n, Ivals &iv, bool pos)
+CCD_FN void find_intervals(double *op, int n, Ivals &iv, bool pos)
 {
     int rd;
     if (prepare_poly(op, n, iv, pos, rd))
@@ -417,12 +439,12 @@ __device__ __forceinline__ void find_intervals(double *op, int n, Ivals &iv, boo
 // Settle the pending polynomials of a primitive: lists[k] receives the intervals of polynomial k (bit k of P.mask),
 // posmask bit k = the reference's `pos` flag.  RESUME reads 64-byte task records {roots[6], -, count} in bit order.
 // Returns false as soon as a list comes out empty (the primitive misses), else true.
-template <int MODE> static __device__ __noinline__ bool resolve_pending(Pend &P, Ivals *lists, unsigned posmask, const double *trec)
+template <int MODE> static CCD_HD __noinline__ bool resolve_pending(Pend &P, Ivals *lists, unsigned posmask, const double *trec)
 {
     int j = 0;
     while (P.mask)
     {
-        const int k = __ffs(P.mask) - 1;
+        const int k = ccd_ffs(P.mask) - 1;
         P.mask &= P.mask - 1;
         const bool pos = (posmask >> k) & 1u;
         if (MODE == MODE_RESUME)
@@ -446,7 +468,7 @@ template <int MODE> static __device__ __noinline__ bool resolve_pending(Pend &P,
 // coefficient builders (src/CTCD.cpp:179-257)
 // ------------------------------------------------------------------------------------------
 // planePoly3D, src/CTCD.cpp:222-227
-__device__ __forceinline__ void plane_coeffs(V3 x10, V3 x20, V3 x30, V3 v10, V3 v20, V3 v30, double *op)
+CCD_FN void plane_coeffs(V3 x10, V3 x20, V3 x30, V3 v10, V3 v20, V3 v30, double *op)
 {
     op[0] = dot(v10, cross(v20, v30));
     op[1] = dot(x10, cross(v20, v30)) + dot(v10, cross(x20, v30)) + dot(v10, cross(v20, x30));
@@ -455,7 +477,7 @@ __device__ __forceinline__ void plane_coeffs(V3 x10, V3 x20, V3 x30, V3 v10, V3 
 }
 
 // distancePoly3D, src/CTCD.cpp:240-255
-static __device__ __noinline__ void distance_coeffs(V3 x10, V3 x20, V3 x30, V3 v10, V3 v20, V3 v30, double m, double *op)
+static CCD_HD __noinline__ void distance_coeffs(V3 x10, V3 x20, V3 x30, V3 v10, V3 v20, V3 v30, double m, double *op)
 {
     double abcd[4];
     plane_coeffs(x10, x20, x30, v10, v20, v30, abcd);
@@ -473,7 +495,7 @@ static __device__ __noinline__ void distance_coeffs(V3 x10, V3 x20, V3 x30, V3 v
 }
 
 // barycentricPoly3D, src/CTCD.cpp:187-210
-__device__ __forceinline__ void barycentric_coeffs(V3 x10, V3 x20, V3 x30, V3 v10, V3 v20, V3 v30, double *op)
+CCD_FN void barycentric_coeffs(V3 x10, V3 x20, V3 x30, V3 v10, V3 v20, V3 v30, double *op)
 {
     double A = dot(x10, x10);
     double B = 2 * dot(x10, v10);
@@ -497,7 +519,7 @@ __device__ __forceinline__ void barycentric_coeffs(V3 x10, V3 x20, V3 x30, V3 v1
 // polynomial k of the VF primitive: k = 0,1,2 the inside cubics e1,e2,e3 — one formula under a rotation of the face,
 // base = 1+k, A = 1+(k+2)%3, B = 1+(k+1)%3: x10 = q0-base, x20 = (A-base) x (B-base), x30 = A-base (src/CTCD.cpp:433-464);
 // k = 3 the coplanarity sextic (src/CTCD.cpp:466-472)
-__device__ __forceinline__ void build_vf_poly(int k, const V3 *s, const V3 *v, double eta, double *op)
+CCD_FN void build_vf_poly(int k, const V3 *s, const V3 *v, double eta, double *op)
 {
     if (k < 3)
     {
@@ -511,7 +533,7 @@ __device__ __forceinline__ void build_vf_poly(int k, const V3 *s, const V3 *v, d
 
 // polynomial k of the EE primitive on points (q0,p0,q1,p1) = s[0..3]: k = 0..3 the barycentric quartics a0,a1,b0,b1
 // (src/CTCD.cpp:313-348: x10 = P[a]-P[b], x20 = P[c]-P[d], x30 = P[e]-P[f]); k = 4 the line-distance sextic (:266-288)
-__device__ __forceinline__ void build_ee_poly(int k, const V3 *s, const V3 *v, double eta, double *op)
+CCD_FN void build_ee_poly(int k, const V3 *s, const V3 *v, double eta, double *op)
 {
     if (k < 4)
     {
@@ -530,7 +552,7 @@ __device__ __forceinline__ void build_ee_poly(int k, const V3 *s, const V3 *v, d
 // Return R_MISS / R_HIT (t written) / R_DEFER (only with defer=true: needs the iterative isolator).
 // ------------------------------------------------------------------------------------------
 // CTCD::vertexFaceCTCD, src/CTCD.cpp:413-508 — vertex s[0] against face (s[1],s[2],s[3])
-template <int MODE> static __device__ __noinline__ int vertex_face(const V3 *s, const V3 *v, double eta, double &t, Pend &P, const double *trec)
+template <int MODE> static CCD_HD __noinline__ int vertex_face(const V3 *s, const V3 *v, double eta, double &t, Pend &P, const double *trec)
 {
     Ivals iv[4];       // e1, e2, e3, coplane
     P.mask = 0;
@@ -589,7 +611,7 @@ template <int MODE> static __device__ __noinline__ int vertex_face(const V3 *s, 
 }
 
 // CTCD::edgeEdgeCTCD, src/CTCD.cpp:259-411 — points (q0,p0,q1,p1) = s[0..3]: edges (q0,p0) and (q1,p1)
-template <int MODE> static __device__ __noinline__ int edge_edge(const V3 *s, const V3 *v, double eta, double &t, Pend &P, const double *trec)
+template <int MODE> static CCD_HD __noinline__ int edge_edge(const V3 *s, const V3 *v, double eta, double &t, Pend &P, const double *trec)
 {
     Ivals cop, par, q[5];      // q[0..3] = a0,a1,b0,b1 ; q[4] = raw coplanarity intervals
     P.mask = 0;
@@ -669,7 +691,7 @@ template <int MODE> static __device__ __noinline__ int edge_edge(const V3 *s, co
 }
 
 // CTCD::vertexEdgeCTCD, src/CTCD.cpp:511-602 — vertex q0 against segment (q1,q2); v* = end - start
-template <int MODE> static __device__ __noinline__ int vertex_edge(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, double &t, Pend &P, const double *trec)
+template <int MODE> static CCD_HD __noinline__ int vertex_edge(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, double &t, Pend &P, const double *trec)
 {
     const double minD = eta * eta;
     const V3 ab = q2s - q1s, ac = q0s - q1s, cb = q2s - q0s;
@@ -729,7 +751,7 @@ template <int MODE> static __device__ __noinline__ int vertex_edge(V3 q0s, V3 q1
 }
 
 // checkInterval with a throw-away list, as CTCD::vertexVertexCTCD uses it (src/CTCD.cpp:645-690)
-__device__ __forceinline__ bool check_once(double t1, double t2, const double *op)
+CCD_FN bool check_once(double t1, double t2, const double *op)
 {
     Ivals iv;
     iv.n = 0;
@@ -738,7 +760,7 @@ __device__ __forceinline__ bool check_once(double t1, double t2, const double *o
 }
 
 // CTCD::vertexVertexCTCD, src/CTCD.cpp:604-692 — closed form, never deferred
-static __device__ __noinline__ int vertex_vertex(V3 q1s, V3 q2s, V3 v1, V3 v2, double eta, double &t)
+static CCD_HD __noinline__ int vertex_vertex(V3 q1s, V3 q2s, V3 v1, V3 v2, double eta, double &t)
 {
     int roots = 0;
     const double min_d = eta * eta;

@@ -11,7 +11,7 @@
 
 namespace ccd {
 
-template <int D> __device__ __forceinline__ void horner2_padded(const double (&p)[D + 1], double x, double &f, double &df)
+template <int D> CCD_FN void horner2_padded(const double (&p)[D + 1], double x, double &f, double &df)
 {
     f = p[0];
     df = 0.0;
@@ -23,7 +23,7 @@ template <int D> __device__ __forceinline__ void horner2_padded(const double (&p
     }
 }
 
-template <int D> __device__ __forceinline__ double horner_padded(const double (&p)[D + 1], double x)
+template <int D> CCD_FN double horner_padded(const double (&p)[D + 1], double x)
 {
     double f = p[0];
 #pragma unroll
@@ -33,7 +33,7 @@ template <int D> __device__ __forceinline__ double horner_padded(const double (&
 }
 
 // same iteration as solve_bracket() on the padded polynomial
-template <int D> __device__ __forceinline__ double solve_bracket_t(const double (&p)[D + 1], double lo, double hi, double flo)
+template <int D> CCD_FN double solve_bracket_t(const double (&p)[D + 1], double lo, double hi, double flo)
 {
     double x = 0.5 * (lo + hi);
     double dxold = hi - lo, dx = dxold;
@@ -71,7 +71,7 @@ template <int D> __device__ __forceinline__ double solve_bracket_t(const double 
 }
 
 // level m of c (degree D) right-aligned in p
-template <int D> __device__ __forceinline__ void deriv_level_padded(const double (&c)[D + 1], int m, double (&p)[D + 1])
+template <int D> CCD_FN void deriv_level_padded(const double (&c)[D + 1], int m, double (&p)[D + 1])
 {
 #pragma unroll
     for (int i = 0; i <= D; i++)
@@ -86,7 +86,7 @@ template <int D> __device__ __forceinline__ void deriv_level_padded(const double
 }
 
 // real roots in [0,1] of c[0] t^D + ... + c[D], c[0] != 0; returns the count, roots ascending in r[]
-template <int D> __device__ __forceinline__ int roots01_t(const double (&c)[D + 1], double (&r)[6])
+template <int D> CCD_FN int roots01_t(const double (&c)[D + 1], double (&r)[6])
 {
     static_assert(D >= 3 && D <= 6, "degree 3..6");
     double b[D + 1], p[D + 1];

@@ -1,0 +1,124 @@
+// Per-stencil structure of the CTCD narrowphase (src/CTCDNarrowPhase.cpp:24-135): numbering of the sub-tests, the
+// swept-box culling of the degenerate sub-tests, and the whole reference-order sequence for one linear segment
+// (stencil_segment_full: used for multi-entry Histories and as the general routine of the single-step pipeline).
+// Host+device: tests/np_emul.cu runs the same code on the CPU.
+#pragma once
+#include "ccd_math.cuh"
+
+namespace ccd {
+
+struct Box { V3 lo, hi; };
+
+CCD_FN Box swept_box(V3 s, V3 e)
+{
+    Box b;
+    b.lo = mk(fmin(s.x, e.x), fmin(s.y, e.y), fmin(s.z, e.z));
+    b.hi = mk(fmax(s.x, e.x), fmax(s.y, e.y), fmax(s.z, e.z));
+    return b;
+}
+CCD_FN Box join(const Box &a, const Box &b)
+{
+    Box r;
+    r.lo = mk(fmin(a.lo.x, b.lo.x), fmin(a.lo.y, b.lo.y), fmin(a.lo.z, b.lo.z));
+    r.hi = mk(fmax(a.hi.x, b.hi.x), fmax(a.hi.y, b.hi.y), fmax(a.hi.z, b.hi.z));
+    return r;
+}
+// true when the boxes stay more than m apart along some axis
+CCD_FN bool apart(const Box &a, const Box &b, double m)
+{
+    return a.hi.x + m < b.lo.x || b.hi.x + m < a.lo.x || a.hi.y + m < b.lo.y || b.hi.y + m < a.lo.y || a.hi.z + m < b.lo.z ||
+           b.hi.z + m < a.lo.z;
+}
+CCD_FN double box_scale(const Box &b)
+{
+    return fmax(fmax(fmax(fabs(b.lo.x), fabs(b.hi.x)), fmax(fabs(b.lo.y), fabs(b.hi.y))), fmax(fabs(b.lo.z), fabs(b.hi.z)));
+}
+
+// ---- per-segment stencil tests --------------------------------------------------------------
+// Sub-tests are numbered in the reference's order: 0 = the VF / EE primitive, 1.. = the vertex-edge tests (3 for a VF
+// stencil: face edges (1,2),(2,3),(3,1), src/CTCDNarrowPhase.cpp:51-59; 4 for an EE stencil: p0|p1 against (q0,q1),
+// q0|q1 against (p0,p1), :99-114), then the vertex-vertex tests (:61-69, :117-132).  stage = sub-test index + 1.
+// a[0..3] start positions of (p,q0,q1,q2) / (p0,p1,q0,q1), v[] = end - start.
+template <bool IS_VF> struct Subs
+{
+    static constexpr int NVE = IS_VF ? 3 : 4;
+    static constexpr int NVV = IS_VF ? 3 : 4;
+    // vertex / edge endpoints of vertex-edge sub-test `sub` (1-based)
+    static CCD_FN void ve(int sub, int &iv, int &i1, int &i2)
+    {
+        if (IS_VF) { iv = 0; i1 = sub; i2 = 1 + (sub % 3); }
+        else { iv = sub - 1; i1 = (sub <= 2) ? 2 : 0; i2 = i1 + 1; }
+    }
+    static CCD_FN void vv(int k, int &i1, int &i2)
+    {
+        if (IS_VF) { i1 = 0; i2 = 1 + k; }
+        else { i1 = k >> 1; i2 = 2 + (k & 1); }
+    }
+};
+
+// the primitive or one vertex-edge test (sub <= NVE)
+template <bool IS_VF, int MODE>
+CCD_FN int eval_sub(int sub, const V3 *a, const V3 *v, double eta, double &t, Pend &P, const double *trec)
+{
+    if (sub == 0)
+        return IS_VF ? vertex_face<MODE>(a, v, eta, t, P, trec) : edge_edge<MODE>(a, v, eta, t, P, trec);
+    int iv, i1, i2;
+    Subs<IS_VF>::ve(sub, iv, i1, i2);
+    return vertex_edge<MODE>(a[iv], a[i1], a[i2], v[iv], v[i1], v[i2], eta, t, P, trec);
+}
+
+// swept boxes of the four vertices and the culling margin of the stencil
+template <bool IS_VF> struct Cull
+{
+    Box bx[4], g0, g1;      // VF: g0 = vertex, g1 = face ; EE: g0 = edge (0,1), g1 = edge (2,3)
+    double m;
+    CCD_FN void init(const V3 *a, const V3 *b, double eta)
+    {
+        for (int i = 0; i < 4; i++) bx[i] = swept_box(a[i], b[i]);
+        if (IS_VF) { g0 = bx[0]; g1 = join(join(bx[1], bx[2]), bx[3]); }
+        else { g0 = join(bx[0], bx[1]); g1 = join(bx[2], bx[3]); }
+        m = eta + 4e-5 * fmax(box_scale(g0), box_scale(g1));
+    }
+    CCD_FN bool stencil_apart() const { return apart(g0, g1, m); }
+    CCD_FN bool ve_apart(int sub) const
+    {
+        int iv, i1, i2;
+        Subs<IS_VF>::ve(sub, iv, i1, i2);
+        return apart(bx[iv], join(bx[i1], bx[i2]), m);
+    }
+    CCD_FN bool vv_apart(int k) const
+    {
+        int i1, i2;
+        Subs<IS_VF>::vv(k, i1, i2);
+        return apart(bx[i1], bx[i2], m);
+    }
+};
+
+// Whole sequence in place (FULL mode): multi-entry History segments and the reference-order semantics in one walk.
+// Returns the stage that hit, 0 for a miss.
+template <bool IS_VF> static CCD_HD __noinline__ int stencil_segment_full(const V3 *a, const V3 *b, double eta, double &t)
+{
+    V3 v[4];
+    for (int i = 0; i < 4; i++) v[i] = b[i] - a[i];
+    Cull<IS_VF> c;
+    c.init(a, b, eta);
+    Pend P;
+    if (!IS_VF && c.stencil_apart()) return 0;      // every EE sub-test is a distance between parts of the two edges
+    if (eval_sub<IS_VF, MODE_FULL>(0, a, v, eta, t, P, nullptr) == R_HIT) return 1;
+    if (IS_VF && c.stencil_apart()) return 0;
+    for (int sub = 1; sub <= Subs<IS_VF>::NVE; sub++)
+    {
+        if (c.ve_apart(sub)) continue;
+        if (eval_sub<IS_VF, MODE_FULL>(sub, a, v, eta, t, P, nullptr) == R_HIT) return sub + 1;
+    }
+    for (int k = 0; k < Subs<IS_VF>::NVV; k++)
+    {
+        if (c.vv_apart(k)) continue;
+        int i1, i2;
+        Subs<IS_VF>::vv(k, i1, i2);
+        if (vertex_vertex(a[i1], a[i2], v[i1], v[i2], eta, t) == R_HIT) return Subs<IS_VF>::NVE + 2 + k;
+    }
+    return 0;
+}
+
+} // namespace ccd

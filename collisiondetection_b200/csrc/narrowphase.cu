@@ -6,14 +6,10 @@
 // vertex-vertex tests, first hit wins; over a multi-entry History the sequence repeats per
 // stitched linear segment (src/History.cpp:98-140).
 //
-// Three kernels keep the warps converged (profiles/: the one-pass version ran with 5.7 of 32 lanes active):
-//   pass 1  every stencil, straight-line work only: coefficient construction, the reference's own quick
-//           rejects, closed-form quadratics and the Bernstein "no root in [0,1]" decision.  A stencil whose
-//           next sub-test needs the iterative root isolator goes on a work list, with one 64-byte task
-//           record per pending polynomial (warp-aggregated allocation);
-//   roots   one thread per pending polynomial: dense warps, every lane inside the isolator;
-//           (the walk goes on past a deferring sub-test, so one round collects everything a stencil needs);
-//   pass 3  the work list only: re-evaluates just the deferred sub-tests, in order, with their roots.
+// The single-step path is a chain of dense kernels connected by queues (see "Single-step pipeline" below): the
+// one-thread-per-stencil walk ran with 5.7 of 32 lanes active, and even the first staged version (one kernel per
+// sub-test kind) stayed at 7-12 lanes because stencils leave at different polynomials and every root solve was an
+// inlined copy (profiles/).  Now every kernel handles ONE polynomial (or one kind of step) for all its lanes.
 // Degenerate sub-tests (and the EE primitive) are skipped when the swept boxes of the two parts stay further
 // apart than eta plus a safety margin: those tests measure true distances (include/CTCD.h:31-79), so the
 // reference cannot report a hit there; the margin (4e-5 of the coordinate scale) is ~1e3 times the distance
@@ -27,127 +23,15 @@
 #endif
 #include "ccd_math.cuh"
 #include "ccd_roots_t.cuh"
+#include "ccd_stencil.cuh"
 #include "ccd_classify.cuh"
-#include "ccd_resume.cuh"
+#include "ccd_solve.cuh"
+#include "ccd_stages.cuh"
 #include <cooperative_groups.h>
 #include <cooperative_groups/scan.h>
 namespace cg = cooperative_groups;
 
 namespace ccd {
-
-struct Box { V3 lo, hi; };
-
-__device__ __forceinline__ Box swept_box(V3 s, V3 e)
-{
-    Box b;
-    b.lo = mk(fmin(s.x, e.x), fmin(s.y, e.y), fmin(s.z, e.z));
-    b.hi = mk(fmax(s.x, e.x), fmax(s.y, e.y), fmax(s.z, e.z));
-    return b;
-}
-__device__ __forceinline__ Box join(const Box &a, const Box &b)
-{
-    Box r;
-    r.lo = mk(fmin(a.lo.x, b.lo.x), fmin(a.lo.y, b.lo.y), fmin(a.lo.z, b.lo.z));
-    r.hi = mk(fmax(a.hi.x, b.hi.x), fmax(a.hi.y, b.hi.y), fmax(a.hi.z, b.hi.z));
-    return r;
-}
-// true when the boxes stay more than m apart along some axis
-__device__ __forceinline__ bool apart(const Box &a, const Box &b, double m)
-{
-    return a.hi.x + m < b.lo.x || b.hi.x + m < a.lo.x || a.hi.y + m < b.lo.y || b.hi.y + m < a.lo.y || a.hi.z + m < b.lo.z ||
-           b.hi.z + m < a.lo.z;
-}
-__device__ __forceinline__ double box_scale(const Box &b)
-{
-    return fmax(fmax(fmax(fabs(b.lo.x), fabs(b.hi.x)), fmax(fabs(b.lo.y), fabs(b.hi.y))), fmax(fabs(b.lo.z), fabs(b.hi.z)));
-}
-
-// ---- per-segment stencil tests --------------------------------------------------------------
-// Sub-tests are numbered in the reference's order: 0 = the VF / EE primitive, 1.. = the vertex-edge tests (3 for a VF
-// stencil: face edges (1,2),(2,3),(3,1), src/CTCDNarrowPhase.cpp:51-59; 4 for an EE stencil: p0|p1 against (q0,q1),
-// q0|q1 against (p0,p1), :99-114), then the vertex-vertex tests (:61-69, :117-132).  stage = sub-test index + 1.
-// a[0..3] start positions of (p,q0,q1,q2) / (p0,p1,q0,q1), v[] = end - start.
-template <bool IS_VF> struct Subs
-{
-    static constexpr int NVE = IS_VF ? 3 : 4;
-    static constexpr int NVV = IS_VF ? 3 : 4;
-    // vertex / edge endpoints of vertex-edge sub-test `sub` (1-based)
-    static __device__ __forceinline__ void ve(int sub, int &iv, int &i1, int &i2)
-    {
-        if (IS_VF) { iv = 0; i1 = sub; i2 = 1 + (sub % 3); }
-        else { iv = sub - 1; i1 = (sub <= 2) ? 2 : 0; i2 = i1 + 1; }
-    }
-    static __device__ __forceinline__ void vv(int k, int &i1, int &i2)
-    {
-        if (IS_VF) { i1 = 0; i2 = 1 + k; }
-        else { i1 = k >> 1; i2 = 2 + (k & 1); }
-    }
-};
-
-// the primitive or one vertex-edge test (sub <= NVE)
-template <bool IS_VF, int MODE>
-__device__ __forceinline__ int eval_sub(int sub, const V3 *a, const V3 *v, double eta, double &t, Pend &P, const double *trec)
-{
-    if (sub == 0)
-        return IS_VF ? vertex_face<MODE>(a, v, eta, t, P, trec) : edge_edge<MODE>(a, v, eta, t, P, trec);
-    int iv, i1, i2;
-    Subs<IS_VF>::ve(sub, iv, i1, i2);
-    return vertex_edge<MODE>(a[iv], a[i1], a[i2], v[iv], v[i1], v[i2], eta, t, P, trec);
-}
-
-// swept boxes of the four vertices and the culling margin of the stencil
-template <bool IS_VF> struct Cull
-{
-    Box bx[4], g0, g1;      // VF: g0 = vertex, g1 = face ; EE: g0 = edge (0,1), g1 = edge (2,3)
-    double m;
-    __device__ __forceinline__ void init(const V3 *a, const V3 *b, double eta)
-    {
-        for (int i = 0; i < 4; i++) bx[i] = swept_box(a[i], b[i]);
-        if (IS_VF) { g0 = bx[0]; g1 = join(join(bx[1], bx[2]), bx[3]); }
-        else { g0 = join(bx[0], bx[1]); g1 = join(bx[2], bx[3]); }
-        m = eta + 4e-5 * fmax(box_scale(g0), box_scale(g1));
-    }
-    __device__ __forceinline__ bool stencil_apart() const { return apart(g0, g1, m); }
-    __device__ __forceinline__ bool ve_apart(int sub) const
-    {
-        int iv, i1, i2;
-        Subs<IS_VF>::ve(sub, iv, i1, i2);
-        return apart(bx[iv], join(bx[i1], bx[i2]), m);
-    }
-    __device__ __forceinline__ bool vv_apart(int k) const
-    {
-        int i1, i2;
-        Subs<IS_VF>::vv(k, i1, i2);
-        return apart(bx[i1], bx[i2], m);
-    }
-};
-
-// Whole sequence in place (FULL mode): multi-entry History segments and the reference-order semantics in one walk.
-// Returns the stage that hit, 0 for a miss.
-template <bool IS_VF> static __device__ __noinline__ int stencil_segment_full(const V3 *a, const V3 *b, double eta, double &t)
-{
-    V3 v[4];
-    for (int i = 0; i < 4; i++) v[i] = b[i] - a[i];
-    Cull<IS_VF> c;
-    c.init(a, b, eta);
-    Pend P;
-    if (!IS_VF && c.stencil_apart()) return 0;      // every EE sub-test is a distance between parts of the two edges
-    if (eval_sub<IS_VF, MODE_FULL>(0, a, v, eta, t, P, nullptr) == R_HIT) return 1;
-    if (IS_VF && c.stencil_apart()) return 0;
-    for (int sub = 1; sub <= Subs<IS_VF>::NVE; sub++)
-    {
-        if (c.ve_apart(sub)) continue;
-        if (eval_sub<IS_VF, MODE_FULL>(sub, a, v, eta, t, P, nullptr) == R_HIT) return sub + 1;
-    }
-    for (int k = 0; k < Subs<IS_VF>::NVV; k++)
-    {
-        if (c.vv_apart(k)) continue;
-        int i1, i2;
-        Subs<IS_VF>::vv(k, i1, i2);
-        if (vertex_vertex(a[i1], a[i2], v[i1], v[i2], eta, t) == R_HIT) return Subs<IS_VF>::NVE + 2 + k;
-    }
-    return 0;
-}
 
 // ---- History::stitchCommonHistory for four vertices over the CSR history (src/History.cpp:98-140)
 struct Stitcher
@@ -273,45 +157,43 @@ __device__ __forceinline__ unsigned long long alloc_task_slots(const NpArgs &A, 
     return base + (unsigned long long)pre;
 }
 
-// One task record per pending polynomial of P (coefficients + reduced degree); returns the first record's index.
-__device__ __forceinline__ int alloc_tasks(const NpArgs &A, const Pend &P)
-{
-    const unsigned long long t0 = alloc_task_slots(A, __popc(P.mask));
-    int j = 0;
-    unsigned mask = P.mask;
-    while (mask)
-    {
-        const int k = __ffs(mask) - 1;
-        mask &= mask - 1;
-        if (t0 + j < A.task_cap)
-        {
-            double *rec = A.tasks + 8 * (t0 + j);
-            const int rd = P.rds[k];
-            for (int c = 0; c <= rd; c++) rec[c] = P.ops[k][c];
-            rec[7] = (double)rd;
-        }
-        j++;
-    }
-    return (int)t0;
-}
 
-// pass 1: every stencil, straight-line work only, as a chain of dense kernels connected by queues in HBM, so that the
-// lanes of a warp do the same kind of work at the same time and every kernel is small:
-//   cull     one thread per stencil: gather the 8 positions, swept-box culling -> the sub-tests that have to be
-//            evaluated at all become items of three queues (primitive / vertex-edge / vertex-vertex);
-//   prim, ve, vv   one thread per queue item: the item ends as miss, hit or deferred (its pending polynomials exported
-//            as task records); 2 bits per sub-test are OR-ed into the stencil's status word;
-//   decide   one thread per stencil: first hit in the reference's order wins if nothing before it is deferred; a stencil
-//            with deferred sub-tests goes on the work list with the later hit (if any) pass 1 already knows.
-// Evaluating every culling survivor instead of stopping at the first hit costs little (hits are ~10 %) and changes no
-// result: the winner is still the first hit in order.
+// ================================================================================================================
+// Single-step pipeline.  Every kernel does one kind of work for all its lanes; kernels are connected by queues in HBM
+// (indices only: positions are re-gathered, they live in L2).
+//   cull      one thread per stencil: swept-box culling -> the sub-tests that have to be evaluated at all become items
+//             of three queues (primitive / vertex-edge / vertex-vertex);
+//   stage<S>  one thread per surviving stencil, ONE polynomial of the primitive per kernel (VF: e1,e2,e3,coplanarity;
+//             EE: distance sextic, a0,a1,b0,b1): most stencils leave at the first or second polynomial, and the
+//             survivors are compacted before the next one, so warps stay full.  The last stage reserves the records of
+//             a surviving stencil and feeds one export queue per polynomial;
+//   export<K> rebuilds polynomial K for the survivors that need its record (all lanes build the same polynomial);
+//   ve, vv    one thread per queued vertex-edge / vertex-vertex test;
+//   decide    one thread per stencil: final when pass 1 settled everything before the first hit, else the stencil goes
+//             on the work list (deferred sub-tests) or to the general routine (rare shapes);
+//   bucket    pending records by reduced degree 3..6;
+//   solve<D>  root isolation + interval rules, one lane per record, lanes refilled from a shared cursor;
+//             two rounds: first the distance polynomials, then — after `window` has finalised every inside polynomial
+//             that keeps one sign on the (short) intervals of its distance polynomial — the few that are left;
+//   combine   work list: interval lists of each deferred sub-test intersected in the reference's order of sub-tests;
+//   general   the few stencils left: the reference's whole sequence in one thread (stencil_segment_full).
+// ================================================================================================================
+enum
+{
+    K_NWORK = 0, K_NTASK = 1, K_NDEG = 2 /* 4 */, K_NQ = 6 /* prim, ve, vv */, K_NGEN = 9, K_NSQ = 10 /* after stage 0..3 */,
+    K_NXQ = 14 /* polynomial 0..4 */, K_CURSOR = 19 /* degree 3..6 */, K_NDEG2 = 23 /* second solve round */, K_CURSOR2 = 27, K_COUNT = 31
+};
+
 struct P1Args
 {
     NpArgs A;
-    unsigned *status;            // per stencil: 2 bits per sub-test (1 hit, 2 deferred)
-    int *sbase;                  // per stencil: first task record of deferred sub-test 0..4
-    int *qprim, *qve, *qvv;      // queues: stencil index | sub-test << 28
-    unsigned long long *nq;      // queue lengths: prim, ve, vv
+    unsigned *status;            // per stencil: 2 bits per sub-test (SC_*)
+    int *sbase;                  // per stencil, per deferred sub-test 0..4: first record | number of records << 28
+    int *qprim, *qve, *qvv;      // queues out of cull: stencil index (| sub-test << 28)
+    int2 *sq[2];                 // stage queues (ping-pong): {stencil, state}
+    int2 *xq[5];                 // export queues per polynomial: {stencil, record slot}
+    int *qgen;                   // stencils for the general routine
+    unsigned long long *ctr;     // counters, K_* above
 };
 
 __device__ __forceinline__ void queue_push(bool want, int value, int *queue, unsigned long long *count)
@@ -323,6 +205,25 @@ __device__ __forceinline__ void queue_push(bool want, int value, int *queue, uns
     if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (want) queue[base + __popc(m & ((1u << lane) - 1))] = value;
+}
+__device__ __forceinline__ void queue_push2(bool want, int2 value, int2 *queue, unsigned long long *count)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (want) queue[base + __popc(m & ((1u << lane) - 1))] = value;
+}
+
+__device__ __forceinline__ void store_record(double *dst, const double (&rec)[8])
+{
+    double2 *d = reinterpret_cast<double2 *>(dst);
+    d[0] = make_double2(rec[0], rec[1]);
+    d[1] = make_double2(rec[2], rec[3]);
+    d[2] = make_double2(rec[4], rec[5]);
+    d[3] = make_double2(rec[6], rec[7]);
 }
 
 template <bool IS_VF> __global__ void __launch_bounds__(256) np_cull_kernel(P1Args Q)
@@ -348,56 +249,105 @@ template <bool IS_VF> __global__ void __launch_bounds__(256) np_cull_kernel(P1Ar
         }
         Q.status[i] = 0u;
     }
-    queue_push((todo & 1u) != 0, (int)i, Q.qprim, Q.nq + 0);
+    queue_push((todo & 1u) != 0, (int)i, Q.qprim, Q.ctr + K_NQ + 0);
 #pragma unroll
     for (int sub = 1; sub <= NVE; sub++)
-        queue_push((todo >> sub) & 1u, (int)i | (sub << 28), Q.qve, Q.nq + 1);
+        queue_push((todo >> sub) & 1u, (int)i | (sub << 28), Q.qve, Q.ctr + K_NQ + 1);
 #pragma unroll
     for (int k = 0; k < NVV; k++)
-        queue_push((todo >> (NVE + 1 + k)) & 1u, (int)i | (k << 28), Q.qvv, Q.nq + 2);
+        queue_push((todo >> (NVE + 1 + k)) & 1u, (int)i | (k << 28), Q.qvv, Q.ctr + K_NQ + 2);
 }
 
-template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_prim_kernel(P1Args Q)
+template <bool IS_VF, int S> __global__ void __launch_bounds__(128, NP_MINB) np_stage_kernel(P1Args Q)
 {
     const NpArgs &A = Q.A;
-    const unsigned long long n = Q.nq[0];
+    constexpr int NST = Prim<IS_VF>::NST;
+    constexpr bool LAST = (S == NST - 1);
+    constexpr int KOWN = Prim<IS_VF>::poly(S);
+    const unsigned long long n = (S == 0) ? Q.ctr[K_NQ] : Q.ctr[K_NSQ + S - 1];
+    const unsigned long long nround = (n + 31ull) & ~31ull;
+    const int2 *in = Q.sq[(S + 1) & 1];
+    int2 *out = Q.sq[S & 1];
+    const int lane = threadIdx.x & 31;
+    for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < nround; it += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        bool alive = false, has_rec = false;
+        unsigned state = 0xff00u;
+        long long i = 0;
+        double rec[8];
+        if (it < n)
+        {
+            if (S == 0) i = Q.qprim[it];
+            else { const int2 e = in[it]; i = e.x; state = (unsigned)e.y; }
+            StencilIn St;
+            load_single<IS_VF>(A, i, St);
+            V3 v[4];
+            for (int k = 0; k < 4; k++) v[k] = St.b[k] - St.a[k];
+            unsigned so = state;
+            alive = stage_item<IS_VF, S, LAST>(St.a, v, St.eta, state, so, rec, has_rec);
+            state = so;
+        }
+        if (!LAST)
+            queue_push2(alive, make_int2((int)i, (int)state), out, Q.ctr + K_NSQ + S);
+        else
+        {
+            const unsigned need = state & 0x1fu;
+            const bool gen = alive && need == 0u, def = alive && need != 0u;
+            if (gen) atomicOr(&Q.status[i], (unsigned)SC_GENERAL);
+            // records of the surviving stencils of this warp: one reservation
+            const int cnt = def ? __popc(need) : 0;
+            int pre = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const int x = __shfl_up_sync(0xffffffffu, pre, o);
+                if (lane >= o) pre += x;
+            }
+            const int total = __shfl_sync(0xffffffffu, pre, 31);
+            pre -= cnt;
+            unsigned long long base = 0;
+            if (total)
+            {
+                if (lane == 0) base = atomicAdd(A.ntask, (unsigned long long)total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+            }
+            const unsigned long long t0 = base + (unsigned long long)pre;
+            const bool fits = t0 + (unsigned long long)cnt <= A.task_cap && t0 + (unsigned long long)cnt < (1ull << 28);
+            if (def)
+            {
+                Q.sbase[5 * i + 0] = (int)((t0 < 0x0fffffffull ? (unsigned)t0 : 0x0fffffffu) | ((unsigned)cnt << 28));
+                atomicOr(&Q.status[i], (unsigned)SC_DEFERRED);
+                if (has_rec && fits) store_record(A.tasks + 8ull * (t0 + __popc(need & ((1u << KOWN) - 1u))), rec);
+            }
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+                if (k != KOWN && k < NST)
+                    queue_push2(def && fits && ((need >> k) & 1u), make_int2((int)i, (int)(t0 + __popc(need & ((1u << k) - 1u)))), Q.xq[k], Q.ctr + K_NXQ + k);
+        }
+    }
+}
+
+template <bool IS_VF, int K> __global__ void __launch_bounds__(128, NP_MINB) np_export_kernel(P1Args Q)
+{
+    const NpArgs &A = Q.A;
+    const unsigned long long n = Q.ctr[K_NXQ + K];
     for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < n; it += (unsigned long long)gridDim.x * blockDim.x)
     {
-        // register-resident classification of the primitive's polynomials (ccd_classify.cuh); only when every list is
-        // already known and non-empty (rare) is the general routine run for the interval combination
-        const long long i = Q.qprim[it];
-        StencilIn S;
-        load_single<IS_VF>(A, i, S);
+        const int2 e = Q.xq[K][it];
+        StencilIn St;
+        load_single<IS_VF>(A, e.x, St);
         V3 v[4];
-        for (int k = 0; k < 4; k++) v[k] = S.b[k] - S.a[k];
-        unsigned pend;
-        if (!classify_primitive<IS_VF>(S.a, v, S.eta, pend))
-            continue;
-        if (pend == 0)
-        {
-            double t = 0.0;
-            Pend P;
-            if (eval_sub<IS_VF, MODE_DEFER>(0, S.a, v, S.eta, t, P, nullptr) == R_HIT) atomicOr(&Q.status[i], 1u);
-            continue;
-        }
-        const unsigned long long t0 = alloc_task_slots(A, __popc(pend));
-        int j = 0;
-        while (pend)
-        {
-            const int k = __ffs(pend) - 1;
-            pend &= pend - 1;
-            if (t0 + j < A.task_cap) export_poly<IS_VF>(k, S.a, v, S.eta, A.tasks + 8 * (t0 + j));
-            j++;
-        }
-        Q.sbase[5 * i + 0] = (int)t0;
-        atomicOr(&Q.status[i], 2u);
+        for (int k = 0; k < 4; k++) v[k] = St.b[k] - St.a[k];
+        double rec[8];
+        export_item<IS_VF, K>(St.a, v, St.eta, rec);
+        store_record(A.tasks + 8ull * (unsigned)e.y, rec);
     }
 }
 
 template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_ve_kernel(P1Args Q)
 {
     const NpArgs &A = Q.A;
-    const unsigned long long n = Q.nq[1];
+    const unsigned long long n = Q.ctr[K_NQ + 1];
     for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < n; it += (unsigned long long)gridDim.x * blockDim.x)
     {
         const int item = Q.qve[it];
@@ -411,36 +361,30 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_ve_kern
         const long long vs = A.vstride;
         const V3 a0 = ldv(A.q0 + vs * idx[iv]), a1 = ldv(A.q0 + vs * idx[i1]), a2 = ldv(A.q0 + vs * idx[i2]);
         const V3 v0 = ldv(A.q1 + vs * idx[iv]) - a0, v1 = ldv(A.q1 + vs * idx[i1]) - a1, v2 = ldv(A.q1 + vs * idx[i2]) - a2;
-        double rec[8];
-        bool want_rec;
-        const int c = classify_ve(a0, a1, a2, v0, v1, v2, eta, rec, want_rec);
-        if (c == VE_MISS)
+        double recs[3][8];
+        int nrec;
+        const int code = ve_item(a0, a1, a2, v0, v1, v2, eta, recs, nrec);
+        if (code == SC_MISS)
             continue;
-        if (c == VE_FULL)
+        if (code == SC_DEFERRED)
         {
-            double t = 0.0;
-            Pend P;
-            if (vertex_edge<MODE_DEFER>(a0, a1, a2, v0, v1, v2, eta, t, P, nullptr) == R_HIT) atomicOr(&Q.status[i], 1u << (2 * sub));
-            continue;
+            const unsigned long long t0 = alloc_task_slots(A, nrec);
+            if (t0 + (unsigned long long)nrec <= A.task_cap && t0 + (unsigned long long)nrec < (1ull << 28))
+            {
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    if (k < nrec) store_record(A.tasks + 8ull * (t0 + k), recs[k]);
+            }
+            Q.sbase[5 * i + sub] = (int)((t0 < 0x0fffffffull ? (unsigned)t0 : 0x0fffffffu) | ((unsigned)nrec << 28));
         }
-        const unsigned long long t0 = alloc_task_slots(A, 1);
-        if (t0 < A.task_cap)
-        {
-            double *out = A.tasks + 8 * t0;
-            const int rd = (int)rec[7];
-            out[0] = rec[0]; out[1] = rec[1]; out[2] = rec[2]; out[3] = rec[3];
-            if (rd == 4) out[4] = rec[4];
-            out[7] = rec[7];
-        }
-        Q.sbase[5 * i + sub] = (int)t0;
-        atomicOr(&Q.status[i], 2u << (2 * sub));
+        atomicOr(&Q.status[i], (unsigned)code << (2 * sub));
     }
 }
 
 template <bool IS_VF> __global__ void __launch_bounds__(256) np_vv_kernel(P1Args Q)
 {
     const NpArgs &A = Q.A;
-    const unsigned long long n = Q.nq[2];
+    const unsigned long long n = Q.ctr[K_NQ + 2];
     constexpr int NVE = Subs<IS_VF>::NVE;
     for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < n; it += (unsigned long long)gridDim.x * blockDim.x)
     {
@@ -456,27 +400,17 @@ template <bool IS_VF> __global__ void __launch_bounds__(256) np_vv_kernel(P1Args
         const V3 a1 = ldv(A.q0 + vs * idx[i1]), a2 = ldv(A.q0 + vs * idx[i2]);
         const V3 v1 = ldv(A.q1 + vs * idx[i1]) - a1, v2 = ldv(A.q1 + vs * idx[i2]) - a2;
         double t = 0.0;
-        if (vertex_vertex(a1, a2, v1, v2, eta, t) == R_HIT) atomicOr(&Q.status[i], 1u << (2 * (NVE + 1 + k)));
+        if (vertex_vertex(a1, a2, v1, v2, eta, t) == R_HIT) atomicOr(&Q.status[i], (unsigned)SC_HIT << (2 * (NVE + 1 + k)));
     }
 }
 
-// the t of a sub-test pass 1 decided as a hit (recomputed: only the first such hit of a stencil is ever needed)
-template <bool IS_VF> static __device__ __noinline__ double decided_toi(const StencilIn &S, int sub)
+// time of impact of vertex-vertex sub-test `sub` (pass 1 only recorded that it hits)
+template <bool IS_VF> __device__ __forceinline__ double vv_toi(const StencilIn &S, int sub)
 {
-    V3 v[4];
-    for (int k = 0; k < 4; k++) v[k] = S.b[k] - S.a[k];
+    int i1, i2;
+    Subs<IS_VF>::vv(sub - Subs<IS_VF>::NVE - 1, i1, i2);
     double t = 0.0;
-    if (sub <= Subs<IS_VF>::NVE)
-    {
-        Pend P;
-        eval_sub<IS_VF, MODE_DEFER>(sub, S.a, v, S.eta, t, P, nullptr);
-    }
-    else
-    {
-        int i1, i2;
-        Subs<IS_VF>::vv(sub - Subs<IS_VF>::NVE - 1, i1, i2);
-        vertex_vertex(S.a[i1], S.a[i2], v[i1], v[i2], S.eta, t);
-    }
+    vertex_vertex(S.a[i1], S.a[i2], S.b[i1] - S.a[i1], S.b[i2] - S.a[i2], S.eta, t);
     return t;
 }
 
@@ -486,6 +420,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_decide_
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     constexpr int NSUB = 1 + Subs<IS_VF>::NVE + Subs<IS_VF>::NVV;
     int stage = 0, meta = 0, nd = 0;
+    bool general = false;
     int base[5] = {0, 0, 0, 0, 0};
     double toi = 0.0;
     if (i < A.n)
@@ -498,26 +433,29 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_decide_
             for (int sub = 0; sub < NSUB; sub++)
             {
                 const unsigned r = (st >> (2 * sub)) & 3u;
-                if (r == 1u)
+                if (r == (unsigned)SC_GENERAL) { general = true; break; }
+                if (r == (unsigned)SC_HIT)
                 {
                     if (nd == 0) stage = sub + 1; else later_hit = sub;
                     break;
                 }
-                if (r == 2u) { base[nd++] = Q.sbase[5 * i + sub]; submask |= 1u << sub; }
+                if (r == (unsigned)SC_DEFERRED) { base[nd++] = Q.sbase[5 * i + sub]; submask |= 1u << sub; }
             }
         }
-        if (nd == 0)
+        if (general) stage = 0;
+        else if (nd == 0)
         {
             if (stage)
             {
                 StencilIn S;
                 load_single<IS_VF>(A, i, S);
-                toi = decided_toi<IS_VF>(S, stage - 1);
+                toi = vv_toi<IS_VF>(S, stage - 1);
             }
             store_result(A, i, stage, toi);
         }
         else { stage = -1; meta = (int)(submask | ((unsigned)later_hit << 8)); }
     }
+    queue_push(general, (int)i, Q.qgen, Q.ctr + K_NGEN);
     // warp-aggregated append to the work list
     const bool deferred = stage < 0;
     const unsigned m = __ballot_sync(0xffffffffu, deferred);
@@ -538,10 +476,10 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_decide_
     reduce_warp(stage > 0, toi, A.earliest_bits, A.nhit);
 }
 
-// Root stage.  Task records are bucketed by reduced degree (3..6) so that each root kernel is specialised for one degree:
-// compile-time array sizes, everything in registers (ccd_roots_t.cuh), dense warps of identical work.
+// pending records by reduced degree (3..6); final records (closed forms) are skipped
+// phase 0: the distance polynomials ("<= 0 wanted": VF / EE sextic, vertex-edge quartic); phase 1: whatever is still pending
 __global__ void __launch_bounds__(256) bucket_tasks_kernel(const double *__restrict__ tasks, const unsigned long long *ntask_ptr,
-                                                           unsigned long long cap, int *__restrict__ lists, unsigned long long *counts)
+                                                           unsigned long long cap, int *__restrict__ lists, unsigned long long *counts, int phase)
 {
     unsigned long long nt = *ntask_ptr;
     if (nt > cap) nt = cap;
@@ -549,7 +487,12 @@ __global__ void __launch_bounds__(256) bucket_tasks_kernel(const double *__restr
     for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < nround;
          j += (unsigned long long)gridDim.x * blockDim.x)
     {
-        const int rd = (j < nt) ? (int)tasks[8 * j + 7] : 0;
+        int rd = 0;
+        if (j < nt)
+        {
+            const unsigned tag = rec_untag(tasks[8 * j + 7]);
+            if (!(tag & REC_FINAL) && (phase == 1 || !(tag & REC_POS))) rd = (int)((tag >> 4) & 7u);
+        }
         const int lane = threadIdx.x & 31;
 #pragma unroll
         for (int d = 3; d <= 6; d++)
@@ -566,99 +509,147 @@ __global__ void __launch_bounds__(256) bucket_tasks_kernel(const double *__restr
     }
 }
 
-// one thread per pending polynomial of degree D; the record's coefficients are replaced by its roots in [0,1]
+// One lane per pending record of degree D: root isolation (RootLane, ccd_solve.cuh) then the interval rules; the record
+// is rewritten as a final one.  All lanes of a warp with a solve pending iterate the ONE Newton loop below together;
+// a lane that has finished its polynomial takes the next record from the shared cursor.
 template <int D>
-__global__ void __launch_bounds__(128) roots_kernel(double *tasks, const int *__restrict__ list, const unsigned long long *count_ptr)
+__global__ void __launch_bounds__(128, 3) solve_kernel(double *tasks, const int *__restrict__ list, const unsigned long long *count_ptr,
+                                                       unsigned long long *cursor)
 {
     const unsigned long long nt = *count_ptr;
-    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nt;
-         w += (unsigned long long)gridDim.x * blockDim.x)
+    const int lane = threadIdx.x & 31;
+    RootLane<D> L;
+    L.done = true;
+    L.solving = false;
+    bool have = false, exhausted = false;
+    double *rec = nullptr;
+    unsigned tag = 0;
+    for (;;)
     {
-        double *rec = tasks + 8ll * list[w];
-        double op[D + 1], roots[6];
+        const unsigned need = __ballot_sync(0xffffffffu, !have && !exhausted);
+        if (need)
+        {
+            unsigned long long base = 0;
+            if (lane == __ffs(need) - 1) base = atomicAdd(cursor, (unsigned long long)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, __ffs(need) - 1);
+            if (!have && !exhausted)
+            {
+                const unsigned long long my = base + __popc(need & ((1u << lane) - 1));
+                if (my < nt)
+                {
+                    rec = tasks + 8ll * list[my];
+                    double c[D + 1];
 #pragma unroll
-        for (int c = 0; c <= D; c++) op[c] = rec[c];
-        const int nr = roots01_t<D>(op, roots);
-#pragma unroll
-        for (int c = 0; c < 6; c++)
-            if (c < nr) rec[c] = roots[c];
-        rec[7] = (double)nr;
+                    for (int k = 0; k <= D; k++) c[k] = rec[k];
+                    tag = rec_untag(rec[7]);
+                    L.begin(c);
+                    have = true;
+                }
+                else
+                    exhausted = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, have))
+            break;
+        if (have) L.advance();
+        while (__any_sync(0xffffffffu, have && L.solving))
+            if (have && L.solving) L.newton_step();
+        if (have && L.done)
+        {
+            double r[6];
+            const int nr = L.result(r);
+            finalize_record<D>(L.c, tag, r, nr, rec);
+            have = false;
+        }
     }
 }
 
-// pass 3: the deferred stencils.  Only the sub-tests that exported polynomials are evaluated again, in order, with
-// their roots read from the task records; the first one that hits wins, else the hit pass 1 found later (if any).
-// GENERAL = false: register-resident finish (ccd_resume.cuh); returns -1 when a sub-test needs the general routine —
-// the stencil is then redone by the GENERAL = true instance in a separate, rarely needed kernel, so that the hot
-// kernel does not carry the general code.
-template <bool IS_VF, bool GENERAL>
-static __device__ __noinline__ int resume_walk(const NpArgs &A, const StencilIn &S, double &t, int meta, const int *base)
+// work list, between the two solve rounds: inside polynomials that keep one sign on every window of the solved distance
+// polynomial are finalised without root isolation (window_item, ccd_stages.cuh)
+template <bool IS_VF> __global__ void __launch_bounds__(128) np_window_kernel(P1Args Q)
 {
-    V3 v[4];
-    for (int i = 0; i < 4; i++) v[i] = S.b[i] - S.a[i];
-    unsigned submask = (unsigned)meta & 0xffu;
-    const int later_hit = (meta >> 8) & 0xff;
-    int j = 0;
-    while (submask)
+    const NpArgs &A = Q.A;
+    const unsigned long long nw = *A.nwork;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += (unsigned long long)gridDim.x * blockDim.x)
     {
-        const int sub = __ffs(submask) - 1;
-        submask &= submask - 1;
-        const double *rec = A.tasks + 8ll * base[j];
-        int r;
-        if (GENERAL)
-        {
-            Pend P;
-            r = (eval_sub<IS_VF, MODE_RESUME>(sub, S.a, v, S.eta, t, P, rec) == R_HIT) ? RS_HIT : RS_MISS;
-        }
-        else if (sub == 0)
-            r = resume_primitive<IS_VF>(S.a, v, S.eta, rec, t);
-        else
-        {
-            int iv, i1, i2;
-            Subs<IS_VF>::ve(sub, iv, i1, i2);
-            r = resume_ve(S.a[iv], S.a[i1], S.a[i2], v[iv], v[i1], v[i2], S.eta, rec, t);
-        }
-        if (r == RS_FALLBACK) return -1;
-        if (r == RS_HIT) return sub + 1;
-        j++;
+        if (!(A.w_meta[w] & 1)) continue;      // primitive not deferred
+        const unsigned b = (unsigned)A.w_base[5 * w];
+        const unsigned long long t0 = b & 0x0fffffffu;
+        const int nrec = (int)(b >> 28);
+        if (t0 + (unsigned long long)nrec > A.task_cap) continue;
+        window_item(A.tasks + 8ull * t0, nrec, IS_VF ? 3 : 4);
     }
-    if (later_hit == 255) return 0;
-    if (!GENERAL) return -1;        // a decided later hit: its t is recomputed by the general routine (rare)
-    t = decided_toi<IS_VF>(S, later_hit);
-    return later_hit + 1;
 }
 
-// work: list of work-list entries to process (nullptr = all nwork entries); fb_list/fb_count: entries to redo generally
-template <bool IS_VF, bool GENERAL>
-__global__ void __launch_bounds__(128, NP_MINB) stencil_resume_kernel(NpArgs A, const int *work, const unsigned long long *work_count,
-                                                                      int *fb_list, unsigned long long *fb_count)
+// work list: the deferred sub-tests of a stencil in the reference's order; first hit wins, else the vertex-vertex hit
+// pass 1 found behind them (if any)
+template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_combine_kernel(P1Args Q)
 {
-    const unsigned long long nw = *work_count;
+    const NpArgs &A = Q.A;
+    const unsigned long long nw = *A.nwork;
     const unsigned long long nround = (nw + 31ull) & ~31ull;
-    for (unsigned long long x = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; x < nround;
-         x += (unsigned long long)gridDim.x * blockDim.x)
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nround;
+         w += (unsigned long long)gridDim.x * blockDim.x)
     {
         int stage = 0;
         double toi = 0.0;
         bool fb = false;
-        unsigned long long w = 0;
-        if (x < nw)
+        long long i = 0;
+        if (w < nw)
         {
-            w = work ? (unsigned long long)work[x] : x;
-            int base[5];
-            bool ok = true;      // records past the capacity were never written: the caller grows the buffer and reruns
-            for (int j = 0; j < 5; j++) { base[j] = A.w_base[5 * w + j]; ok = ok && ((unsigned long long)base[j] + 5ull <= A.task_cap); }
-            if (ok)
+            i = A.w_stencil[w];
+            const int meta = A.w_meta[w];
+            StencilIn S;
+            load_single<IS_VF>(A, i, S);
+            V3 v[4];
+            for (int k = 0; k < 4; k++) v[k] = S.b[k] - S.a[k];
+            unsigned submask = (unsigned)meta & 0xffu;
+            const int later_hit = (meta >> 8) & 0xff;
+            int j = 0;
+            bool settled = false;
+            while (submask)
             {
-                const long long i = A.w_stencil[w];
-                StencilIn S;
-                load_single<IS_VF>(A, i, S);
-                stage = resume_walk<IS_VF, GENERAL>(A, S, toi, A.w_meta[w], base);
-                if (stage >= 0) store_result(A, i, stage, toi);
-                else { fb = true; stage = 0; }
+                const int sub = __ffs(submask) - 1;
+                submask &= submask - 1;
+                const unsigned b = (unsigned)A.w_base[5 * w + j];
+                j++;
+                const unsigned long long t0 = b & 0x0fffffffu;
+                const int nrec = (int)(b >> 28);
+                if (t0 + (unsigned long long)nrec > A.task_cap) { settled = true; break; }      // never written: the caller grows the buffer and reruns
+                const int r = combine_records(A.tasks + 8ull * t0, nrec, !IS_VF && sub == 0, S.a, v, toi);
+                if (r == RS_FALLBACK) { fb = true; settled = true; break; }
+                if (r == RS_HIT) { stage = sub + 1; settled = true; break; }
             }
+            if (!settled && later_hit != 255)
+            {
+                stage = later_hit + 1;
+                toi = vv_toi<IS_VF>(S, later_hit);
+            }
+            if (!fb) store_result(A, i, stage, toi);
+            else stage = 0;
         }
-        if (!GENERAL) queue_push(fb, (int)w, fb_list, fb_count);
+        queue_push(fb, (int)i, Q.qgen, Q.ctr + K_NGEN);
+        reduce_warp(stage > 0, toi, A.earliest_bits, A.nhit);
+    }
+}
+
+template <bool IS_VF> __global__ void __launch_bounds__(128) np_general_kernel(P1Args Q)
+{
+    const NpArgs &A = Q.A;
+    const unsigned long long n = Q.ctr[K_NGEN];
+    const unsigned long long nround = (n + 31ull) & ~31ull;
+    for (unsigned long long x = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; x < nround; x += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        int stage = 0;
+        double toi = 0.0;
+        if (x < n)
+        {
+            const long long i = Q.qgen[x];
+            StencilIn S;
+            load_single<IS_VF>(A, i, S);
+            stage = stencil_segment_full<IS_VF>(S.a, S.b, S.eta, toi);
+            store_result(A, i, stage, toi);
+        }
         reduce_warp(stage > 0, toi, A.earliest_bits, A.nhit);
     }
 }
@@ -732,70 +723,80 @@ using namespace ccd;
 
 static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
-// Buffers: work list {w_stencil: n ints, w_meta: n ints, w_base: 5n ints}, tasks (task_cap records of 8 doubles),
-// tlists (4 x task_cap ints: task indices by degree), pass-1 scratch {status: n u32, sbase: 5n ints, queues: 9n ints},
-// counters ctr[0] = work-list entries, ctr[1] = task records, ctr[2..5] = tasks of degree 3..6, ctr[6..8] = queue
-// lengths, ctr[9] = stencils for the general resume kernel (all zeroed here).  Returns the number of kernels launched.
-// If ctr[1] ends above task_cap - 5 the caller must grow the task buffer and call again.
+template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Args &Q, long long n, int *tlists)
+{
+    const NpArgs &A = Q.A;
+    const int B = 128;
+    const unsigned gq = 148 * 16;
+    np_cull_kernel<IS_VF><<<grid_for(n, 256), 256, 0, st>>>(Q);
+    np_stage_kernel<IS_VF, 0><<<gq, B, 0, st>>>(Q);
+    np_stage_kernel<IS_VF, 1><<<gq, B, 0, st>>>(Q);
+    np_stage_kernel<IS_VF, 2><<<gq, B, 0, st>>>(Q);
+    np_stage_kernel<IS_VF, 3><<<gq, B, 0, st>>>(Q);
+    int nl = 5;
+    if (!IS_VF)
+    {
+        np_stage_kernel<false, 4><<<gq, B, 0, st>>>(Q);
+        np_export_kernel<false, 4><<<gq, B, 0, st>>>(Q);
+        nl += 2;
+    }
+    np_export_kernel<IS_VF, 0><<<gq, B, 0, st>>>(Q);
+    np_export_kernel<IS_VF, 1><<<gq, B, 0, st>>>(Q);
+    np_export_kernel<IS_VF, 2><<<gq, B, 0, st>>>(Q);
+    np_ve_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
+    np_vv_kernel<IS_VF><<<gq, 256, 0, st>>>(Q);
+    np_decide_kernel<IS_VF><<<grid_for(n, B), B, 0, st>>>(Q);
+    const unsigned gs = 148 * 3;
+    for (int phase = 0; phase < 2; phase++)
+    {
+        unsigned long long *nd = Q.ctr + (phase ? K_NDEG2 : K_NDEG), *cu = Q.ctr + (phase ? K_CURSOR2 : K_CURSOR);
+        bucket_tasks_kernel<<<148 * 4, 256, 0, st>>>(A.tasks, A.ntask, A.task_cap, tlists, nd, phase);
+        solve_kernel<3><<<gs, B, 0, st>>>(A.tasks, tlists + 0 * A.task_cap, nd + 0, cu + 0);
+        solve_kernel<4><<<gs, B, 0, st>>>(A.tasks, tlists + 1 * A.task_cap, nd + 1, cu + 1);
+        solve_kernel<5><<<gs, B, 0, st>>>(A.tasks, tlists + 2 * A.task_cap, nd + 2, cu + 2);
+        solve_kernel<6><<<gs, B, 0, st>>>(A.tasks, tlists + 3 * A.task_cap, nd + 3, cu + 3);
+        if (phase == 0) np_window_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
+    }
+    np_combine_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
+    np_general_kernel<IS_VF><<<148 * 2, B, 0, st>>>(Q);
+    return nl + 3 + 3 + 2 * 5 + 1 + 2;
+}
+
+// Scratch (sizes in elements, n = number of stencils): work list {w_stencil: n ints, w_meta: n ints, w_base: 5n ints},
+// tasks (task_cap records of 8 doubles, task_cap < 2^28), tlists (4 x task_cap ints: pending records by degree),
+// status (n u32), sbase (5n ints), queues (9n ints: primitive / vertex-edge / vertex-vertex items), sq (2 x n int2: stage
+// queues), xq (5 x n int2: export queues), ctr (CCD_NP_COUNTERS counters, zeroed here; ctr[0] = work-list entries,
+// ctr[1] = records).  Returns the number of kernels launched.  If ctr[1] ends above task_cap the caller must grow the
+// record buffer and call again.
 int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, double eta_all,
                      const double *q0, const double *q1, int vstride, const long long *hoff, const double *htime, const double *hpos,
                      unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits,
                      unsigned long long *nhit, int *w_stencil, int *w_meta, int *w_base, double *tasks, int *tlists,
-                     unsigned long long task_cap, unsigned *status, int *sbase, int *queues, unsigned long long *ctr)
+                     unsigned long long task_cap, unsigned *status, int *sbase, int *queues, int *sq, int *xq, unsigned long long *ctr)
 {
+    static_assert(K_COUNT <= CCD_NP_COUNTERS, "counter block too small");
     if (n <= 0) return 0;
     NpArgs A;
     A.n = n; A.stencils = stencils; A.eta_arr = eta_arr; A.eta_all = eta_all; A.q0 = q0; A.q1 = q1; A.vstride = vstride;
     A.hoff = hoff; A.htime = htime; A.hpos = hpos; A.hit = hit; A.toi = toi; A.stage = stage;
     A.earliest_bits = earliest_bits; A.nhit = nhit;
-    A.w_stencil = w_stencil; A.w_meta = w_meta; A.w_base = w_base; A.nwork = ctr + 0;
-    A.tasks = tasks; A.ntask = ctr + 1; A.task_cap = task_cap;
-    const int B = 128;
+    A.w_stencil = w_stencil; A.w_meta = w_meta; A.w_base = w_base; A.nwork = ctr + K_NWORK;
+    A.tasks = tasks; A.ntask = ctr + K_NTASK; A.task_cap = task_cap;
     if (q0 == nullptr)
     {
-        if (is_vf) stencil_history_kernel<true><<<grid_for(n, B), B, 0, st>>>(A);
-        else stencil_history_kernel<false><<<grid_for(n, B), B, 0, st>>>(A);
+        if (is_vf) stencil_history_kernel<true><<<grid_for(n, 128), 128, 0, st>>>(A);
+        else stencil_history_kernel<false><<<grid_for(n, 128), 128, 0, st>>>(A);
         return 1;
     }
-    cudaMemsetAsync(ctr, 0, 10 * sizeof(unsigned long long), st);
-    const unsigned g2 = (unsigned)min((long long)148 * 32, (long long)grid_for(n, B));
+    cudaMemsetAsync(ctr, 0, CCD_NP_COUNTERS * sizeof(unsigned long long), st);
     P1Args Q;
     Q.A = A; Q.status = status; Q.sbase = sbase;
-    Q.qprim = queues; Q.qve = queues + n; Q.qvv = queues + 5 * n; Q.nq = ctr + 6;
-    const unsigned gq = 148 * 16;
-    if (is_vf)
-    {
-        np_cull_kernel<true><<<grid_for(n, 256), 256, 0, st>>>(Q);
-        np_prim_kernel<true><<<gq, B, 0, st>>>(Q);
-        np_ve_kernel<true><<<gq, B, 0, st>>>(Q);
-        np_vv_kernel<true><<<gq, 256, 0, st>>>(Q);
-        np_decide_kernel<true><<<grid_for(n, B), B, 0, st>>>(Q);
-    }
-    else
-    {
-        np_cull_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(Q);
-        np_prim_kernel<false><<<gq, B, 0, st>>>(Q);
-        np_ve_kernel<false><<<gq, B, 0, st>>>(Q);
-        np_vv_kernel<false><<<gq, 256, 0, st>>>(Q);
-        np_decide_kernel<false><<<grid_for(n, B), B, 0, st>>>(Q);
-    }
-    bucket_tasks_kernel<<<148 * 4, 256, 0, st>>>(tasks, ctr + 1, task_cap, tlists, ctr + 2);
-    roots_kernel<3><<<g2, B, 0, st>>>(tasks, tlists + 0 * task_cap, ctr + 2);
-    roots_kernel<4><<<g2, B, 0, st>>>(tasks, tlists + 1 * task_cap, ctr + 3);
-    roots_kernel<5><<<g2, B, 0, st>>>(tasks, tlists + 2 * task_cap, ctr + 4);
-    roots_kernel<6><<<g2, B, 0, st>>>(tasks, tlists + 3 * task_cap, ctr + 5);
-    // the queues of pass 1 are free again: their buffer holds the (short) list of stencils for the general routine
-    if (is_vf)
-    {
-        stencil_resume_kernel<true, false><<<g2, B, 0, st>>>(A, nullptr, ctr + 0, queues, ctr + 9);
-        stencil_resume_kernel<true, true><<<148 * 2, B, 0, st>>>(A, queues, ctr + 9, nullptr, nullptr);
-    }
-    else
-    {
-        stencil_resume_kernel<false, false><<<g2, B, 0, st>>>(A, nullptr, ctr + 0, queues, ctr + 9);
-        stencil_resume_kernel<false, true><<<148 * 2, B, 0, st>>>(A, queues, ctr + 9, nullptr, nullptr);
-    }
-    return 12;
+    Q.qprim = queues; Q.qve = queues + n; Q.qvv = queues + 5 * n;
+    Q.sq[0] = reinterpret_cast<int2 *>(sq); Q.sq[1] = reinterpret_cast<int2 *>(sq) + n;
+    for (int k = 0; k < 5; k++) Q.xq[k] = reinterpret_cast<int2 *>(xq) + (size_t)k * n;
+    Q.qgen = queues;      // the primitive queue is consumed by stage 0 long before anything goes to the general routine
+    Q.ctr = ctr;
+    return is_vf ? launch_single_step<true>(st, Q, n, tlists) : launch_single_step<false>(st, Q, n, tlists);
 }
 
 void ccdk_prim_batch(cudaStream_t st, int kind, long long n, const double *pts, const double *eta, unsigned char *hit, double *t)
