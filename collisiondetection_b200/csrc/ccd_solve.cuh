@@ -131,7 +131,7 @@ template <int D> struct RootLane
     double brk_lo, f_lo, x_hi, f_hi;
     double lo, hi, x, dx, dxold;      // the solve in flight
     int ncur, nr, m, m0, i, nb, it;
-    bool one, plain, last, lo_neg, solving, done;
+    bool one, plain, last, lo_neg, solving, done, got_root;      // got_root: x holds a converged root not yet recorded
 
     CCD_FN double cur_at(int j) const
     {
@@ -189,6 +189,7 @@ template <int D> struct RootLane
         one = false;
         solving = false;
         done = false;
+        got_root = false;
         for (m0 = D; m0 >= 2; m0--)
         {
             if (m0 < D)
@@ -251,6 +252,13 @@ template <int D> struct RootLane
     // until a solve is pending or the polynomial is finished
     CCD_FN void advance()
     {
+        if (got_root)
+        {
+            // the solve that just converged (recorded here, outside the Newton loop, so that loop stays small)
+            if (nr == 0 || prev != x) push_out(x);
+            next_piece();
+            got_root = false;
+        }
         while (!solving && !done)
         {
             if (i + 1 < nb)
@@ -299,41 +307,40 @@ template <int D> struct RootLane
         }
     }
 
-    CCD_FN void finish_solve(double root)
-    {
-        if (nr == 0 || prev != root) push_out(root);
-        next_piece();
-        solving = false;
-    }
-
-    // one iteration of solve_bracket_t
+    // one iteration of solve_bracket_t (same operations in the same order; the exits are folded into one flag)
     CCD_FN void newton_step()
     {
         double f, df;
         horner2_padded<D>(p, x, f, df);
-        if (f == 0.0) { finish_solve(x); return; }
-        if ((f < 0.0) == lo_neg)
-            lo = x;
-        else
-            hi = x;
-        const double step = f / df;
-        double xn = x - step;
-        bool bisect = !(xn > lo && xn < hi);
-        if (!bisect && fabs(2.0 * f) > fabs(dxold * df))
-            bisect = true;
-        dxold = dx;
-        if (bisect)
+        bool conv = (f == 0.0);
+        if (!conv)
         {
-            dx = 0.5 * (hi - lo);
-            xn = lo + dx;
-            if (!(xn > lo && xn < hi)) { finish_solve(xn); return; }
+            if ((f < 0.0) == lo_neg)
+                lo = x;
+            else
+                hi = x;
+            const double step = f / df;
+            double xn = x - step;
+            const bool bisect = !(xn > lo && xn < hi) || fabs(2.0 * f) > fabs(dxold * df);
+            dxold = dx;
+            if (bisect)
+            {
+                dx = 0.5 * (hi - lo);
+                xn = lo + dx;
+                conv = !(xn > lo && xn < hi);
+            }
+            else
+                dx = step;
+            if (!conv) conv = fabs(xn - x) <= 8.9e-16 * fabs(xn);
+            x = xn;
+            it++;
+            if (it == 128) conv = true;
         }
-        else
-            dx = step;
-        if (fabs(xn - x) <= 8.9e-16 * fabs(xn)) { finish_solve(xn); return; }
-        x = xn;
-        it++;
-        if (it == 128) finish_solve(x);
+        if (conv)
+        {
+            solving = false;
+            got_root = true;
+        }
     }
 
     // roots in [0,1] (ascending) once done

@@ -512,8 +512,9 @@ __global__ void __launch_bounds__(256) bucket_tasks_kernel(const double *__restr
 // One lane per pending record of degree D: root isolation (RootLane, ccd_solve.cuh) then the interval rules; the record
 // is rewritten as a final one.  All lanes of a warp with a solve pending iterate the ONE Newton loop below together;
 // a lane that has finished its polynomial takes the next record from the shared cursor.
+#define SOLVE_MINB(D) ((D) <= 4 ? 4 : 3)
 template <int D>
-__global__ void __launch_bounds__(128, 3) solve_kernel(double *tasks, const int *__restrict__ list, const unsigned long long *count_ptr,
+__global__ void __launch_bounds__(128, SOLVE_MINB(D)) solve_kernel(double *tasks, const int *__restrict__ list, const unsigned long long *count_ptr,
                                                        unsigned long long *cursor)
 {
     const unsigned long long nt = *count_ptr;
@@ -551,15 +552,26 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(double *tasks, const int 
         }
         if (!__any_sync(0xffffffffu, have))
             break;
-        if (have) L.advance();
-        while (__any_sync(0xffffffffu, have && L.solving))
-            if (have && L.solving) L.newton_step();
+        if (have && !L.solving) L.advance();
         if (have && L.done)
         {
             double r[6];
             const int nr = L.result(r);
             finalize_record<D>(L.c, tag, r, nr, rec);
             have = false;
+        }
+        // Newton rounds for the lanes with a solve in flight.  Iteration counts have a long tail (near-double roots are
+        // the rule for the distance sextics), so the round ends as soon as a quarter of its lanes have converged: those
+        // go back to advance() / take new records while the slow solves simply continue in the next round.
+        unsigned ms = __ballot_sync(0xffffffffu, have && L.solving);
+        if (ms)
+        {
+            const int thresh = max(1, (__popc(ms) * 3) >> 2);
+            do
+            {
+                if (have && L.solving) L.newton_step();
+                ms = __ballot_sync(0xffffffffu, have && L.solving);
+            } while (__popc(ms) >= thresh);
         }
     }
 }
@@ -746,15 +758,14 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
     np_ve_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
     np_vv_kernel<IS_VF><<<gq, 256, 0, st>>>(Q);
     np_decide_kernel<IS_VF><<<grid_for(n, B), B, 0, st>>>(Q);
-    const unsigned gs = 148 * 3;
     for (int phase = 0; phase < 2; phase++)
     {
         unsigned long long *nd = Q.ctr + (phase ? K_NDEG2 : K_NDEG), *cu = Q.ctr + (phase ? K_CURSOR2 : K_CURSOR);
         bucket_tasks_kernel<<<148 * 4, 256, 0, st>>>(A.tasks, A.ntask, A.task_cap, tlists, nd, phase);
-        solve_kernel<3><<<gs, B, 0, st>>>(A.tasks, tlists + 0 * A.task_cap, nd + 0, cu + 0);
-        solve_kernel<4><<<gs, B, 0, st>>>(A.tasks, tlists + 1 * A.task_cap, nd + 1, cu + 1);
-        solve_kernel<5><<<gs, B, 0, st>>>(A.tasks, tlists + 2 * A.task_cap, nd + 2, cu + 2);
-        solve_kernel<6><<<gs, B, 0, st>>>(A.tasks, tlists + 3 * A.task_cap, nd + 3, cu + 3);
+        solve_kernel<3><<<148 * SOLVE_MINB(3), B, 0, st>>>(A.tasks, tlists + 0 * A.task_cap, nd + 0, cu + 0);
+        solve_kernel<4><<<148 * SOLVE_MINB(4), B, 0, st>>>(A.tasks, tlists + 1 * A.task_cap, nd + 1, cu + 1);
+        solve_kernel<5><<<148 * SOLVE_MINB(5), B, 0, st>>>(A.tasks, tlists + 2 * A.task_cap, nd + 2, cu + 2);
+        solve_kernel<6><<<148 * SOLVE_MINB(6), B, 0, st>>>(A.tasks, tlists + 3 * A.task_cap, nd + 3, cu + 3);
         if (phase == 0) np_window_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
     }
     np_combine_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
