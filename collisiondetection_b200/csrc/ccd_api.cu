@@ -483,8 +483,8 @@ static int narrowphase_device(ccd_context *c, long long nvf, const int *d_vf, co
         // task records: one per polynomial that needs the root isolator; grown on demand (count known after pass 1)
         if (c->taskCapVf < (size_t)nvf / 2 + 1024) c->taskCapVf = (size_t)nvf / 2 + 1024;
         if (c->taskCapEe < (size_t)nee + 1024) c->taskCapEe = (size_t)nee + 1024;
-        CKR(ensure(c, c->tasksVf, 64 * c->taskCapVf));
-        CKR(ensure(c, c->tasksEe, 64 * c->taskCapEe));
+        CKR(ensure(c, c->tasksVf, 128 * c->taskCapVf));
+        CKR(ensure(c, c->tasksEe, 128 * c->taskCapEe));
         CKR(ensure(c, c->tlistVf, sizeof(int) * 4 * c->taskCapVf));
         CKR(ensure(c, c->tlistEe, sizeof(int) * 4 * c->taskCapEe));
         unsigned long long init[4] = {0xFFFFFFFFFFFFFFFFull, 0ull, 0xFFFFFFFFFFFFFFFFull, 0ull};

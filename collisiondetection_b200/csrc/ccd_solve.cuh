@@ -13,7 +13,9 @@
 
 namespace ccd {
 
-// ---- task / interval records (8 doubles = 64 bytes) -----------------------------------------------------------
+// ---- task / interval records (REC_STRIDE doubles = 128 bytes; the first 8 are "the record") -------------------------
+// scratch of a pending record (second half): after `prepare` d[8], d[9] = roots of the quadratic level, d[10] = packed
+// start state; after `solve` d[8..13] = roots in [0,1], d[14] = their number
 // pending: d[0..rd] = normalised coefficients of the reduced polynomial (descending), d[7] = tag
 // final:   d[0] = number of intervals n (<= 3), d[1+2j], d[2+2j] = [l_j, u_j] (closed, clamped to [0,1], in the
 //          reference's order), d[7] = tag | REC_FINAL (| REC_BAD when n > 3 or a NaN was seen: the stencil is then
@@ -21,6 +23,7 @@ namespace ccd {
 // tag bits: 0-2 polynomial index inside its sub-test, 3 REC_POS (intervals where the polynomial is >= 0, else <= 0),
 //           4-6 reduced degree, 8 REC_FINAL, 9 REC_BAD
 enum { REC_POS = 1 << 3, REC_FINAL = 1 << 8, REC_BAD = 1 << 9 };
+enum { REC_STRIDE = 16 };
 CCD_FN double rec_tag(unsigned t) { return (double)t; }
 CCD_FN unsigned rec_untag(double d) { return (unsigned)d; }
 CCD_FN unsigned make_tag(int k, bool pos, int rd) { return (unsigned)k | (pos ? (unsigned)REC_POS : 0u) | ((unsigned)rd << 4); }
@@ -168,9 +171,8 @@ template <int D> struct RootLane
         f_lo = f_hi;
     }
 
-    // Bernstein sign variations down the derivative chain (roots01_t, first half); leaves the machine at the first
-    // level to climb, or done with no root
-    CCD_FN void begin(const double (&coef)[D + 1])
+    // Bernstein sign variations down the derivative chain (roots01_t, first half): finds the first level to climb
+    CCD_FN void prepare(const double (&coef)[D + 1])
     {
         double b[D + 1];
 #pragma unroll
@@ -244,9 +246,42 @@ template <int D> struct RootLane
                 break;
             }
         }
+    }
+    // first level to climb after prepare() / load_start()
+    CCD_FN void start()
+    {
+        solving = false;
+        done = false;
+        got_root = false;
         m = one ? m0 : m0 + 1;
         if (m > D) { done = true; return; }
         setup_level();
+    }
+    CCD_FN void begin(const double (&coef)[D + 1])
+    {
+        prepare(coef);
+        start();
+    }
+    // the outcome of prepare() in three doubles, and back
+    CCD_FN void save_start(double *aux) const
+    {
+        aux[0] = cur[0];
+        aux[1] = cur[1];
+        aux[2] = (double)(m0 | (one ? 16 : 0) | (ncur << 5));
+    }
+    CCD_FN void load_start(const double (&coef)[D + 1], const double *aux)
+    {
+#pragma unroll
+        for (int k = 0; k <= D; k++) c[k] = coef[k];
+#pragma unroll
+        for (int k = 0; k < D; k++) { cur[k] = 0.0; out[k] = 0.0; }
+        cur[0] = aux[0];
+        cur[1] = aux[1];
+        const int pk = (int)aux[2];
+        m0 = pk & 15;
+        one = (pk & 16) != 0;
+        ncur = pk >> 5;
+        start();
     }
 
     // until a solve is pending or the polynomial is finished

@@ -376,7 +376,7 @@ CCD_FN int combine_records(const double *rec, int nrec, bool ee_prim, const V3 *
     {
         Ivl3 iv;
         unsigned tag;
-        read_final_record(rec + 8 * j, iv, tag);
+        read_final_record(rec + REC_STRIDE * j, iv, tag);
         if (iv.bad) return RS_FALLBACK;
         const bool sext = ee_prim && (tag & 7u) == 4u;
         saw_sextic = saw_sextic || sext;
@@ -480,12 +480,12 @@ CCD_FN void window_item(double *rec, int nrec, int KD)
     if (nrec < 2) return;
     Ivl3 W;
     unsigned wtag;
-    read_final_record(rec + 8 * (nrec - 1), W, wtag);
+    read_final_record(rec + REC_STRIDE * (nrec - 1), W, wtag);
     if (W.bad || (int)(wtag & 7u) != KD) return;
     bool alive[3] = {W.n > 0, W.n > 1, W.n > 2};
     for (int j = 0; j < nrec - 1; j++)
     {
-        double *r = rec + 8 * j;
+        double *r = rec + REC_STRIDE * j;
         const unsigned tag = rec_untag(r[7]);
         if (tag & REC_FINAL) continue;
         const int rd = (int)((tag >> 4) & 7u);

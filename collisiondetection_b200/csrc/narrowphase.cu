@@ -27,6 +27,8 @@
 #include "ccd_classify.cuh"
 #include "ccd_solve.cuh"
 #include "ccd_stages.cuh"
+#include <stdio.h>
+#include <stdlib.h>
 #include <cooperative_groups.h>
 #include <cooperative_groups/scan.h>
 namespace cg = cooperative_groups;
@@ -317,7 +319,7 @@ template <bool IS_VF, int S> __global__ void __launch_bounds__(128, NP_MINB) np_
             {
                 Q.sbase[5 * i + 0] = (int)((t0 < 0x0fffffffull ? (unsigned)t0 : 0x0fffffffu) | ((unsigned)cnt << 28));
                 atomicOr(&Q.status[i], (unsigned)SC_DEFERRED);
-                if (has_rec && fits) store_record(A.tasks + 8ull * (t0 + __popc(need & ((1u << KOWN) - 1u))), rec);
+                if (has_rec && fits) store_record(A.tasks + (unsigned long long)REC_STRIDE * (t0 + __popc(need & ((1u << KOWN) - 1u))), rec);
             }
 #pragma unroll
             for (int k = 0; k < 5; k++)
@@ -340,7 +342,7 @@ template <bool IS_VF, int K> __global__ void __launch_bounds__(128, NP_MINB) np_
         for (int k = 0; k < 4; k++) v[k] = St.b[k] - St.a[k];
         double rec[8];
         export_item<IS_VF, K>(St.a, v, St.eta, rec);
-        store_record(A.tasks + 8ull * (unsigned)e.y, rec);
+        store_record(A.tasks + (unsigned long long)REC_STRIDE * (unsigned)e.y, rec);
     }
 }
 
@@ -373,7 +375,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_ve_kern
             {
 #pragma unroll
                 for (int k = 0; k < 3; k++)
-                    if (k < nrec) store_record(A.tasks + 8ull * (t0 + k), recs[k]);
+                    if (k < nrec) store_record(A.tasks + (unsigned long long)REC_STRIDE * (t0 + k), recs[k]);
             }
             Q.sbase[5 * i + sub] = (int)((t0 < 0x0fffffffull ? (unsigned)t0 : 0x0fffffffu) | ((unsigned)nrec << 28));
         }
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(256) bucket_tasks_kernel(const double *__restr
         int rd = 0;
         if (j < nt)
         {
-            const unsigned tag = rec_untag(tasks[8 * j + 7]);
+            const unsigned tag = rec_untag(tasks[REC_STRIDE * j + 7]);
             if (!(tag & REC_FINAL) && (phase == 1 || !(tag & REC_POS))) rd = (int)((tag >> 4) & 7u);
         }
         const int lane = threadIdx.x & 31;
@@ -509,22 +511,40 @@ __global__ void __launch_bounds__(256) bucket_tasks_kernel(const double *__restr
     }
 }
 
-// One lane per pending record of degree D: root isolation (RootLane, ccd_solve.cuh) then the interval rules; the record
-// is rewritten as a final one.  All lanes of a warp with a solve pending iterate the ONE Newton loop below together;
-// a lane that has finished its polynomial takes the next record from the shared cursor.
+// The root isolator runs as three kernels per degree so that each of them is uniform work:
+//   prepare<D>   one lane per pending record: Bernstein sign variations down the derivative chain (RootLane::prepare);
+//   solve<D>     the climb: all lanes of a warp with a solve in flight iterate ONE Newton loop together, lanes walk their
+//                pieces / levels in between, and a lane that has finished its polynomial takes the next record from
+//                the shared cursor; roots go to the record's scratch half;
+//   finalize<D>  one lane per record: the interval rules (checkInterval midpoints), record rewritten as a final one.
+template <int D> __global__ void __launch_bounds__(128) prepare_kernel(double *tasks, const int *__restrict__ list, const unsigned long long *count_ptr)
+{
+    const unsigned long long nt = *count_ptr;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nt; w += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        double *rec = tasks + (long long)REC_STRIDE * list[w];
+        double c[D + 1];
+#pragma unroll
+        for (int k = 0; k <= D; k++) c[k] = rec[k];
+        RootLane<D> L;
+        L.prepare(c);
+        L.save_start(rec + 8);
+    }
+}
+
 #define SOLVE_MINB(D) ((D) <= 4 ? 4 : 3)
 template <int D>
 __global__ void __launch_bounds__(128, SOLVE_MINB(D)) solve_kernel(double *tasks, const int *__restrict__ list, const unsigned long long *count_ptr,
-                                                       unsigned long long *cursor)
+                                                                   unsigned long long *cursor)
 {
     const unsigned long long nt = *count_ptr;
     const int lane = threadIdx.x & 31;
     RootLane<D> L;
     L.done = true;
     L.solving = false;
+    L.got_root = false;
     bool have = false, exhausted = false;
     double *rec = nullptr;
-    unsigned tag = 0;
     for (;;)
     {
         const unsigned need = __ballot_sync(0xffffffffu, !have && !exhausted);
@@ -538,12 +558,12 @@ __global__ void __launch_bounds__(128, SOLVE_MINB(D)) solve_kernel(double *tasks
                 const unsigned long long my = base + __popc(need & ((1u << lane) - 1));
                 if (my < nt)
                 {
-                    rec = tasks + 8ll * list[my];
+                    rec = tasks + (long long)REC_STRIDE * list[my];
                     double c[D + 1];
 #pragma unroll
                     for (int k = 0; k <= D; k++) c[k] = rec[k];
-                    tag = rec_untag(rec[7]);
-                    L.begin(c);
+                    const double aux[3] = {rec[8], rec[9], rec[10]};
+                    L.load_start(c, aux);
                     have = true;
                 }
                 else
@@ -557,22 +577,39 @@ __global__ void __launch_bounds__(128, SOLVE_MINB(D)) solve_kernel(double *tasks
         {
             double r[6];
             const int nr = L.result(r);
-            finalize_record<D>(L.c, tag, r, nr, rec);
+#pragma unroll
+            for (int k = 0; k < 6; k++) rec[8 + k] = r[k];
+            rec[14] = (double)nr;
             have = false;
         }
         // Newton rounds for the lanes with a solve in flight.  Iteration counts have a long tail (near-double roots are
-        // the rule for the distance sextics), so the round ends as soon as a quarter of its lanes have converged: those
-        // go back to advance() / take new records while the slow solves simply continue in the next round.
+        // the rule for the distance sextics), so the round ends as soon as half of its lanes have converged: those go
+        // back to advance() / take new records while the slow solves simply continue in the next round.
         unsigned ms = __ballot_sync(0xffffffffu, have && L.solving);
         if (ms)
         {
-            const int thresh = max(1, (__popc(ms) * 3) >> 2);
+            const int thresh = max(1, __popc(ms) >> 1);
             do
             {
                 if (have && L.solving) L.newton_step();
                 ms = __ballot_sync(0xffffffffu, have && L.solving);
             } while (__popc(ms) >= thresh);
         }
+    }
+}
+
+template <int D> __global__ void __launch_bounds__(128) finalize_kernel(double *tasks, const int *__restrict__ list, const unsigned long long *count_ptr)
+{
+    const unsigned long long nt = *count_ptr;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nt; w += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        double *rec = tasks + (long long)REC_STRIDE * list[w];
+        double c[D + 1], r[6];
+#pragma unroll
+        for (int k = 0; k <= D; k++) c[k] = rec[k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) r[k] = rec[8 + k];
+        finalize_record<D>(c, rec_untag(rec[7]), r, (int)rec[14], rec);
     }
 }
 
@@ -589,7 +626,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(128) np_window_kernel(P1
         const unsigned long long t0 = b & 0x0fffffffu;
         const int nrec = (int)(b >> 28);
         if (t0 + (unsigned long long)nrec > A.task_cap) continue;
-        window_item(A.tasks + 8ull * t0, nrec, IS_VF ? 3 : 4);
+        window_item(A.tasks + (unsigned long long)REC_STRIDE * t0, nrec, IS_VF ? 3 : 4);
     }
 }
 
@@ -628,7 +665,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_combine
                 const unsigned long long t0 = b & 0x0fffffffu;
                 const int nrec = (int)(b >> 28);
                 if (t0 + (unsigned long long)nrec > A.task_cap) { settled = true; break; }      // never written: the caller grows the buffer and reruns
-                const int r = combine_records(A.tasks + 8ull * t0, nrec, !IS_VF && sub == 0, S.a, v, toi);
+                const int r = combine_records(A.tasks + (unsigned long long)REC_STRIDE * t0, nrec, !IS_VF && sub == 0, S.a, v, toi);
                 if (r == RS_FALLBACK) { fb = true; settled = true; break; }
                 if (r == RS_HIT) { stage = sub + 1; settled = true; break; }
             }
@@ -735,12 +772,58 @@ using namespace ccd;
 
 static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
+// Diagnostics: CCD_NP_TRACE=1 prints the device time of each kernel group of the single-step pipeline to stderr
+// (CUDA events on the launching stream; adds a synchronisation per call, so never set it for measurements of the step).
+struct NpTrace
+{
+    bool on = false;
+    int n = 0;
+    cudaEvent_t ev[40];
+    const char *name[40];
+    NpTrace()
+    {
+        const char *e = getenv("CCD_NP_TRACE");
+        on = e && e[0] == '1';
+        if (on) for (int i = 0; i < 40; i++) cudaEventCreate(&ev[i]);
+    }
+    void mark(cudaStream_t st, const char *what)
+    {
+        if (!on || n >= 40) return;
+        name[n] = what;
+        cudaEventRecord(ev[n++], st);
+    }
+    void flush(const char *title)
+    {
+        if (!on || n == 0) return;
+        cudaEventSynchronize(ev[n - 1]);
+        fprintf(stderr, "[np trace %s]", title);
+        for (int i = 1; i < n; i++)
+        {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            fprintf(stderr, " %s %.3f", name[i], ms);
+        }
+        fprintf(stderr, "\n");
+        n = 0;
+    }
+};
+static NpTrace g_trace;
+
+template <int D> static void launch_solve(cudaStream_t st, double *tasks, const int *list, const unsigned long long *count, unsigned long long *cursor)
+{
+    prepare_kernel<D><<<148 * 8, 128, 0, st>>>(tasks, list, count);
+    solve_kernel<D><<<148 * SOLVE_MINB(D), 128, 0, st>>>(tasks, list, count, cursor);
+    finalize_kernel<D><<<148 * 8, 128, 0, st>>>(tasks, list, count);
+}
+
 template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Args &Q, long long n, int *tlists)
 {
     const NpArgs &A = Q.A;
     const int B = 128;
     const unsigned gq = 148 * 16;
+    g_trace.mark(st, "start");
     np_cull_kernel<IS_VF><<<grid_for(n, 256), 256, 0, st>>>(Q);
+    g_trace.mark(st, "cull");
     np_stage_kernel<IS_VF, 0><<<gq, B, 0, st>>>(Q);
     np_stage_kernel<IS_VF, 1><<<gq, B, 0, st>>>(Q);
     np_stage_kernel<IS_VF, 2><<<gq, B, 0, st>>>(Q);
@@ -752,29 +835,41 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
         np_export_kernel<false, 4><<<gq, B, 0, st>>>(Q);
         nl += 2;
     }
+    g_trace.mark(st, "stages");
     np_export_kernel<IS_VF, 0><<<gq, B, 0, st>>>(Q);
     np_export_kernel<IS_VF, 1><<<gq, B, 0, st>>>(Q);
     np_export_kernel<IS_VF, 2><<<gq, B, 0, st>>>(Q);
+    g_trace.mark(st, "export");
     np_ve_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
+    g_trace.mark(st, "ve");
     np_vv_kernel<IS_VF><<<gq, 256, 0, st>>>(Q);
     np_decide_kernel<IS_VF><<<grid_for(n, B), B, 0, st>>>(Q);
+    g_trace.mark(st, "vv+decide");
     for (int phase = 0; phase < 2; phase++)
     {
         unsigned long long *nd = Q.ctr + (phase ? K_NDEG2 : K_NDEG), *cu = Q.ctr + (phase ? K_CURSOR2 : K_CURSOR);
         bucket_tasks_kernel<<<148 * 4, 256, 0, st>>>(A.tasks, A.ntask, A.task_cap, tlists, nd, phase);
-        solve_kernel<3><<<148 * SOLVE_MINB(3), B, 0, st>>>(A.tasks, tlists + 0 * A.task_cap, nd + 0, cu + 0);
-        solve_kernel<4><<<148 * SOLVE_MINB(4), B, 0, st>>>(A.tasks, tlists + 1 * A.task_cap, nd + 1, cu + 1);
-        solve_kernel<5><<<148 * SOLVE_MINB(5), B, 0, st>>>(A.tasks, tlists + 2 * A.task_cap, nd + 2, cu + 2);
-        solve_kernel<6><<<148 * SOLVE_MINB(6), B, 0, st>>>(A.tasks, tlists + 3 * A.task_cap, nd + 3, cu + 3);
-        if (phase == 0) np_window_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
+        g_trace.mark(st, "bucket");
+        launch_solve<3>(st, A.tasks, tlists + 0 * A.task_cap, nd + 0, cu + 0);
+        g_trace.mark(st, "solve3");
+        launch_solve<4>(st, A.tasks, tlists + 1 * A.task_cap, nd + 1, cu + 1);
+        g_trace.mark(st, "solve4");
+        launch_solve<5>(st, A.tasks, tlists + 2 * A.task_cap, nd + 2, cu + 2);
+        g_trace.mark(st, "solve5");
+        launch_solve<6>(st, A.tasks, tlists + 3 * A.task_cap, nd + 3, cu + 3);
+        g_trace.mark(st, "solve6");
+        if (phase == 0) { np_window_kernel<IS_VF><<<gq, B, 0, st>>>(Q); g_trace.mark(st, "window"); }
     }
     np_combine_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
+    g_trace.mark(st, "combine");
     np_general_kernel<IS_VF><<<148 * 2, B, 0, st>>>(Q);
-    return nl + 3 + 3 + 2 * 5 + 1 + 2;
+    g_trace.mark(st, "general");
+    g_trace.flush(IS_VF ? "VF" : "EE");
+    return nl + 3 + 3 + 2 * 13 + 1 + 2;
 }
 
 // Scratch (sizes in elements, n = number of stencils): work list {w_stencil: n ints, w_meta: n ints, w_base: 5n ints},
-// tasks (task_cap records of 8 doubles, task_cap < 2^28), tlists (4 x task_cap ints: pending records by degree),
+// tasks (task_cap records of REC_STRIDE doubles, task_cap < 2^28), tlists (4 x task_cap ints: pending records by degree),
 // status (n u32), sbase (5n ints), queues (9n ints: primitive / vertex-edge / vertex-vertex items), sq (2 x n int2: stage
 // queues), xq (5 x n int2: export queues), ctr (CCD_NP_COUNTERS counters, zeroed here; ctr[0] = work-list entries,
 // ctr[1] = records).  Returns the number of kernels launched.  If ctr[1] ends above task_cap the caller must grow the

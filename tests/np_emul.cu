@@ -19,15 +19,27 @@ using namespace ccd;
 
 namespace {
 
-struct Rec { double d[8]; };
+struct Rec { double d[REC_STRIDE]; };
 
 template <int D> void solve_one(Rec &r)
 {
     double c[D + 1];
     for (int k = 0; k <= D; k++) c[k] = r.d[k];
     const unsigned tag = rec_untag(r.d[7]);
+    // prepare -> (start state through the record's scratch half, as the kernels pass it) -> climb -> finalize
+    RootLane<D> P;
+    P.prepare(c);
+    P.save_start(r.d + 8);
+    RootLane<D> L;
+    const double aux[3] = {r.d[8], r.d[9], r.d[10]};
+    L.load_start(c, aux);
+    while (!L.done)
+    {
+        L.advance();
+        while (L.solving) L.newton_step();
+    }
     double roots[6];
-    const int nr = roots01_lane<D>(c, roots);
+    const int nr = L.result(roots);
     finalize_record<D>(c, tag, roots, nr, r.d);
 }
 
@@ -51,13 +63,13 @@ template <bool IS_VF, int S> bool run_stage(const V3 *a, const V3 *v, double eta
 {
     unsigned so = state;
     bool alive;
-    if (S == Prim<IS_VF>::NST - 1) alive = stage_item<IS_VF, S, true>(a, v, eta, state, so, own.d, has);
+    if (S == Prim<IS_VF>::NST - 1) { double d8[8]; alive = stage_item<IS_VF, S, true>(a, v, eta, state, so, d8, has); memset(own.d, 0, sizeof(own.d)); memcpy(own.d, d8, sizeof(d8)); }
     else { double dummy[8]; bool h; alive = stage_item<IS_VF, S, false>(a, v, eta, state, so, dummy, h); }
     state = so;
     return alive;
 }
 
-template <bool IS_VF, int K> void run_export(const V3 *a, const V3 *v, double eta, Rec &r) { export_item<IS_VF, K>(a, v, eta, r.d); }
+template <bool IS_VF, int K> void run_export(const V3 *a, const V3 *v, double eta, Rec &r) { { double d8[8]; export_item<IS_VF, K>(a, v, eta, d8); memset(r.d, 0, sizeof(r.d)); memcpy(r.d, d8, sizeof(d8)); } }
 
 // returns the status code of the primitive and appends its records
 template <bool IS_VF> int primitive(const V3 *a, const V3 *v, double eta, std::vector<Rec> &recs, int &nrec)
@@ -144,7 +156,7 @@ void run(long long n, const int *stencils, const double *q0, const double *q1, i
                 {
                     first[sub] = (int)recs.size();
                     cnt[sub] = nrec;
-                    for (int k = 0; k < nrec; k++) { Rec r; memcpy(r.d, r3[k], sizeof(r.d)); recs.push_back(r); }
+                    for (int k = 0; k < nrec; k++) { Rec r; memset(r.d, 0, sizeof(r.d)); memcpy(r.d, r3[k], 8 * sizeof(double)); recs.push_back(r); }
                     stats[2]++;
                 }
             }
