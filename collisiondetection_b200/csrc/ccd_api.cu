@@ -44,7 +44,7 @@ struct ccd_context
     // emission
     DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut, shardBounds;
     // narrowphase
-    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, work2Vf, work2Ee, work2TaskVf, work2TaskEe, work2SubVf, work2SubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, selTmp, selA, selB, selC, selD, selCount;
+    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, work2Vf, work2Ee, work2TaskVf, work2TaskEe, work2SubVf, work2SubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, qpack, selTmp, selA, selB, selC, selD, selCount;
     // pinned host scratch
     unsigned long long *h_counters = nullptr; // C_TOTAL entries
     // pinned host buffers for the hit lists returned by ccd_step (valid until the next call on the context)
@@ -215,7 +215,7 @@ void ccd_destroy(ccd_context *c)
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->shardBounds, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->work2Vf, &c->work2Ee, &c->work2TaskVf, &c->work2TaskEe, &c->work2SubVf, &c->work2SubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->work2Vf, &c->work2Ee, &c->work2TaskVf, &c->work2TaskEe, &c->work2SubVf, &c->work2SubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->qpack, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
     for (DBuf *b : all)
         if (b->p)
             cudaFree(b->p);
@@ -451,7 +451,7 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
 }
 
 // Narrowphase over device-resident stencils; results left in c->vfHit/... ; summary via counters.
-static int narrowphase_device(ccd_context *c, long long nvf, const int *d_vf, const double *d_vf_eta, long long nee, const int *d_ee,
+static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d_vf, const double *d_vf_eta, long long nee, const int *d_ee,
                               const double *d_ee_eta, double eta_all, const double *d_q0, const double *d_q1, int vstride, const long long *d_hoff,
                               const double *d_htime, const double *d_hpos, ccd_np_summary *sum)
 {
@@ -477,6 +477,15 @@ static int narrowphase_device(ccd_context *c, long long nvf, const int *d_vf, co
         CKR(ensure(c, c->p1Sq, sizeof(int) * 4 * nmax));
         CKR(ensure(c, c->p1Xq, sizeof(int) * 10 * nmax));
     }
+    if (d_q0)
+    {
+        CKR(ensure(c, c->qpack, sizeof(double) * 8 * ((size_t)V + 1)));
+        ccdk_pack_positions(c->st, V, d_q0, d_q1, vstride, P<double>(c->qpack));
+        d_q0 = P<double>(c->qpack);
+        d_q1 = d_q0 + 4;
+        vstride = 8;
+        c->launches += 1;
+    }
     int nl = 0;
     for (int attempt = 0; attempt < 4; attempt++)
     {
@@ -485,8 +494,8 @@ static int narrowphase_device(ccd_context *c, long long nvf, const int *d_vf, co
         if (c->taskCapEe < (size_t)nee + 1024) c->taskCapEe = (size_t)nee + 1024;
         CKR(ensure(c, c->tasksVf, 128 * c->taskCapVf));
         CKR(ensure(c, c->tasksEe, 128 * c->taskCapEe));
-        CKR(ensure(c, c->tlistVf, sizeof(int) * 4 * c->taskCapVf));
-        CKR(ensure(c, c->tlistEe, sizeof(int) * 4 * c->taskCapEe));
+        CKR(ensure(c, c->tlistVf, sizeof(int) * 5 * c->taskCapVf));
+        CKR(ensure(c, c->tlistEe, sizeof(int) * 5 * c->taskCapEe));
         unsigned long long init[4] = {0xFFFFFFFFFFFFFFFFull, 0ull, 0xFFFFFFFFFFFFFFFFull, 0ull};
         memcpy(c->h_counters + 8, init, sizeof(init));
         CK(cudaMemcpyAsync(ctr + C_EARLY_VF, c->h_counters + 8, sizeof(init), cudaMemcpyHostToDevice, c->st));
@@ -625,7 +634,7 @@ int ccd_narrowphase(ccd_context *c, int V, const int64_t *hoff, const double *ht
     ccd_np_summary s;
     // two entries per vertex = one linear segment: read q0/q1 straight out of hpos (stride 6)
     const bool single = history_is_single_step(V, hoff);
-    CKR(narrowphase_device(c, nvf, P<int>(c->vf_in), P<double>(c->vf_eta), nee, P<int>(c->ee_in), P<double>(c->ee_eta), 0.0,
+    CKR(narrowphase_device(c, V, nvf, P<int>(c->vf_in), P<double>(c->vf_eta), nee, P<int>(c->ee_in), P<double>(c->ee_eta), 0.0,
                            single ? P<double>(c->hpos) : nullptr, single ? P<double>(c->hpos) + 3 : nullptr, 6, P<long long>(c->hoff),
                            P<double>(c->htime), P<double>(c->hpos), &s));
     if (nvf > 0)
@@ -659,7 +668,7 @@ int ccd_step_device(ccd_context *c, int kind, int V, int F, const int32_t *d_fac
     CKR(broadphase_device(c, kind, V, F, d_faces, d_q0, d_q1, nullptr, nullptr, outerEta, d_fixedMask, shard_rank, shard_world, &r));
     CK(cudaEventRecord(c->ev[1], c->st));
     ccd_np_summary s;
-    CKR(narrowphase_device(c, r.nvf, P<int>(c->vfOut), nullptr, r.nee, P<int>(c->eeOut), nullptr, eta, d_q0, d_q1, 3, nullptr, nullptr, nullptr, &s));
+    CKR(narrowphase_device(c, V, r.nvf, P<int>(c->vfOut), nullptr, r.nee, P<int>(c->eeOut), nullptr, eta, d_q0, d_q1, 3, nullptr, nullptr, nullptr, &s));
     CK(cudaEventRecord(c->ev[2], c->st));
     CK(cudaEventSynchronize(c->ev[2]));
     cudaEventElapsedTime(&out->ms_broadphase, c->ev[0], c->ev[1]);

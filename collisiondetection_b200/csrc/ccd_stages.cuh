@@ -157,112 +157,6 @@ template <bool IS_VF, int K> CCD_FN void export_item(const V3 *a, const V3 *v, d
     }
 }
 
-// CTCD::vertexEdgeCTCD (src/CTCD.cpp:511-602), vertex q0 against segment (q1,q2); v* = end - start.
-// Returns SC_MISS, SC_DEFERRED (nrec records in recs: polynomial 0,1 = the two inside quadratics, 2 = the distance
-// quartic; whole-[0,1] lists have no record) or SC_GENERAL (nothing constrains the test: left to the general routine).
-CCD_FN int ve_item(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, double (&recs)[3][8], int &nrec)
-{
-    const double minD = eta * eta;
-    const V3 ab = q2s - q1s, ac = q0s - q1s, cb = q2s - q0s;
-    const V3 vab = v2 - v1, vac = v0 - v1, vcb = v2 - v0;
-    nrec = 0;
-    unsigned occ = 0xffu;
-    int rd;
-    {
-        double op[3];
-        op[2] = dot(ab, ac);
-        op[1] = dot(ac, vab) + dot(ab, vac);
-        op[0] = dot(vab, vac);
-        if (classify_poly<2>(op, true, rd) == PC_EMPTY) return SC_MISS;
-        if (rd >= 1)
-        {
-            Ivl3 o;
-            lowdeg_intervals<2>(op, rd, true, o);
-            if (!ivl_is_whole(o))
-            {
-                occ &= ivl_mask(o);
-                write_final_record(recs[nrec], o, make_tag(0, true, rd));
-                nrec++;
-            }
-        }
-    }
-    {
-        double op[3];
-        op[2] = dot(ab, cb);
-        op[1] = dot(cb, vab) + dot(ab, vcb);
-        op[0] = dot(vab, vcb);
-        if (classify_poly<2>(op, true, rd) == PC_EMPTY) return SC_MISS;
-        if (rd >= 1)
-        {
-            Ivl3 o;
-            lowdeg_intervals<2>(op, rd, true, o);
-            if (!ivl_is_whole(o))
-            {
-                occ &= ivl_mask(o);
-                if (!occ) return SC_MISS;
-                if (nrec == 0) write_final_record(recs[0], o, make_tag(1, true, rd));
-                else write_final_record(recs[1], o, make_tag(1, true, rd));
-                nrec++;
-            }
-        }
-    }
-    double op[5];
-    {
-        double A = dot(ab, ab);
-        double B = 2 * dot(ab, vab);
-        double C = dot(vab, vab);
-        double D = dot(ac, ac);
-        double E = 2 * dot(ac, vac);
-        double F = dot(vac, vac);
-        double G = dot(ac, ab);
-        double H = dot(vab, ac) + dot(vac, ab);
-        double I = dot(vab, vac);
-        op[4] = A * D - G * G - minD * A;
-        op[3] = B * D + A * E - 2 * G * H - minD * B;
-        op[2] = B * E + A * F + C * D - H * H - 2 * G * I - minD * C;
-        op[1] = B * F + C * E - 2 * H * I;
-        op[0] = C * F - I * I;
-    }
-    const int r = classify_poly<4>(op, false, rd);
-    if (r == PC_EMPTY) return SC_MISS;
-    if (r == PC_PENDING)
-    {
-        occ &= dyadic_mask_reduced<4>(op, rd, false);
-        if (!occ) return SC_MISS;
-        double rec[8];
-        pending_record<4>(op, rd, make_tag(2, false, rd), rec);
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-            if (k == nrec)
-            {
-#pragma unroll
-                for (int c = 0; c < 8; c++) recs[k][c] = rec[c];
-            }
-        nrec++;
-    }
-    else if (rd == 1 || rd == 2)
-    {
-        Ivl3 o;
-        lowdeg_intervals<4>(op, rd, false, o);
-        if (!ivl_is_whole(o))
-        {
-            occ &= ivl_mask(o);
-            if (!occ) return SC_MISS;
-            double rec[8];
-            write_final_record(rec, o, make_tag(2, false, rd));
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-                if (k == nrec)
-                {
-#pragma unroll
-                    for (int c = 0; c < 8; c++) recs[k][c] = rec[c];
-                }
-            nrec++;
-        }
-    }
-    return nrec ? SC_DEFERRED : SC_GENERAL;
-}
-
 // ---- interval combination ------------------------------------------------------------------------------------
 // The reference tests every combination of one interval per list for pairwise overlap and takes the smallest "largest
 // lower end" (src/CTCD.cpp:352-410, :477-507).  For closed intervals on a line that is exactly: hit iff the
@@ -404,17 +298,9 @@ CCD_FN int combine_records(const double *rec, int nrec, bool ee_prim, const V3 *
 // record is finalised with the windows on which it is satisfied AS ITS INTERVALS: intersecting with them keeps exactly
 // those windows, bit for bit, which is all the exact interval list of q could do to them (it covers a window where q > 0
 // and misses a window where q < 0).  Only polynomials with a sign change near a window still go to the root isolator.
-template <int RD> CCD_FN int window_class(const double (&c)[RD + 1], bool pos, double wl, double wu)
+// Bernstein coefficients b on some interval -> on its sub-interval [wl, wu] (in the interval's own [0,1] parameter)
+template <int RD> CCD_FN void bernstein_restrict(double (&b)[RD + 1], double wl, double wu)
 {
-    double b[RD + 1];
-#pragma unroll
-    for (int i = 0; i <= RD; i++)
-        b[i] = c[RD - i] * rbinom(RD, i);
-#pragma unroll
-    for (int k = 1; k <= RD; k++)
-#pragma unroll
-        for (int i = RD; i >= k; i--)
-            b[i] = b[i] + b[i - 1];
     // keep [wl, 1]: after step k, b[0..RD-k] are the level-k points; the right part collects the last point of each level
     {
         double r[RD + 1];
@@ -446,6 +332,26 @@ template <int RD> CCD_FN int window_class(const double (&c)[RD + 1], bool pos, d
 #pragma unroll
         for (int i = 0; i <= RD; i++) b[i] = l[i];
     }
+}
+
+// Bernstein coefficients of c (degree RD, descending power coefficients) on the window [wl, wu] of [0,1]
+template <int RD> CCD_FN void window_bernstein(const double (&c)[RD + 1], double wl, double wu, double (&b)[RD + 1])
+{
+#pragma unroll
+    for (int i = 0; i <= RD; i++)
+        b[i] = c[RD - i] * rbinom(RD, i);
+#pragma unroll
+    for (int k = 1; k <= RD; k++)
+#pragma unroll
+        for (int i = RD; i >= k; i--)
+            b[i] = b[i] + b[i - 1];
+    bernstein_restrict<RD>(b, wl, wu);
+}
+
+template <int RD> CCD_FN int window_class(const double (&c)[RD + 1], bool pos, double wl, double wu)
+{
+    double b[RD + 1];
+    window_bernstein<RD>(c, wl, wu, b);
     bool allp = true, alln = true;
 #pragma unroll
     for (int i = 0; i <= RD; i++)
@@ -456,6 +362,26 @@ template <int RD> CCD_FN int window_class(const double (&c)[RD + 1], bool pos, d
     if (pos ? allp : alln) return 1;       // satisfied on the whole window
     if (pos ? alln : allp) return -1;      // violated on the whole window
     return 0;                              // mixed / too close to call
+}
+
+// true when c cannot be satisfied anywhere on [wl, wu]: the Bernstein hull has the wrong sign by more than 1e-12 on every
+// 64th of the window (three dyadic levels, then three more inside each eighth that is still possible)
+template <int RD> CCD_FN bool window_excluded(const double (&c)[RD + 1], bool pos, double wl, double wu)
+{
+    double b[RD + 1];
+    window_bernstein<RD>(c, wl, wu, b);
+    unsigned m = dyadic_sub<RD, 3>(b, pos);
+    while (m)
+    {
+        const int k = ccd_ffs(m) - 1;
+        m &= m - 1;
+        double bb[RD + 1];
+#pragma unroll
+        for (int i = 0; i <= RD; i++) bb[i] = b[i];
+        bernstein_restrict<RD>(bb, 0.125 * (double)k, 0.125 * (double)(k + 1));
+        if (dyadic_sub<RD, 3>(bb, pos)) return false;
+    }
+    return true;
 }
 
 CCD_FN int window_class_rd(const double *rec, int rd, bool pos, double wl, double wu)
@@ -513,6 +439,165 @@ CCD_FN void window_item(double *rec, int nrec, int KD)
         }
         if (!mixed) write_final_record(r, o, tag);
     }
+}
+
+// CTCD::vertexEdgeCTCD (src/CTCD.cpp:511-602), vertex q0 against segment (q1,q2); v* = end - start.
+// Returns SC_MISS, SC_DEFERRED (nrec records in recs: polynomial 0,1 = the two inside quadratics, 2 = the distance
+// quartic; whole-[0,1] lists have no record) or SC_GENERAL (nothing constrains the test: left to the general routine).
+CCD_FN int ve_item(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, double (&recs)[3][8], int &nrec)
+{
+    const double minD = eta * eta;
+    const V3 ab = q2s - q1s, ac = q0s - q1s, cb = q2s - q0s;
+    const V3 vab = v2 - v1, vac = v0 - v1, vcb = v2 - v0;
+    nrec = 0;
+    unsigned occ = 0xffu;
+    int rd;
+    {
+        double op[3];
+        op[2] = dot(ab, ac);
+        op[1] = dot(ac, vab) + dot(ab, vac);
+        op[0] = dot(vab, vac);
+        if (classify_poly<2>(op, true, rd) == PC_EMPTY) return SC_MISS;
+        if (rd >= 1)
+        {
+            Ivl3 o;
+            lowdeg_intervals<2>(op, rd, true, o);
+            if (!ivl_is_whole(o))
+            {
+                occ &= ivl_mask(o);
+                write_final_record(recs[nrec], o, make_tag(0, true, rd));
+                nrec++;
+            }
+        }
+    }
+    {
+        double op[3];
+        op[2] = dot(ab, cb);
+        op[1] = dot(cb, vab) + dot(ab, vcb);
+        op[0] = dot(vab, vcb);
+        if (classify_poly<2>(op, true, rd) == PC_EMPTY) return SC_MISS;
+        if (rd >= 1)
+        {
+            Ivl3 o;
+            lowdeg_intervals<2>(op, rd, true, o);
+            if (!ivl_is_whole(o))
+            {
+                occ &= ivl_mask(o);
+                if (!occ) return SC_MISS;
+                if (nrec == 0) write_final_record(recs[0], o, make_tag(1, true, rd));
+                else write_final_record(recs[1], o, make_tag(1, true, rd));
+                nrec++;
+            }
+        }
+    }
+    double op[5];
+    {
+        double A = dot(ab, ab);
+        double B = 2 * dot(ab, vab);
+        double C = dot(vab, vab);
+        double D = dot(ac, ac);
+        double E = 2 * dot(ac, vac);
+        double F = dot(vac, vac);
+        double G = dot(ac, ab);
+        double H = dot(vab, ac) + dot(vac, ab);
+        double I = dot(vab, vac);
+        op[4] = A * D - G * G - minD * A;
+        op[3] = B * D + A * E - 2 * G * H - minD * B;
+        op[2] = B * E + A * F + C * D - H * H - 2 * G * I - minD * C;
+        op[1] = B * F + C * E - 2 * H * I;
+        op[0] = C * F - I * I;
+    }
+    const int r = classify_poly<4>(op, false, rd);
+    if (r == PC_EMPTY) return SC_MISS;
+    if (r == PC_PENDING)
+    {
+        occ &= dyadic_mask_reduced<4>(op, rd, false);
+        if (!occ) return SC_MISS;
+        double rec[8];
+        pending_record<4>(op, rd, make_tag(2, false, rd), rec);
+        rec[5] = (double)nrec;      // sibling records (the inside quadratics) right before this one: see ve_refine_item
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (k == nrec)
+            {
+#pragma unroll
+                for (int c = 0; c < 8; c++) recs[k][c] = rec[c];
+            }
+        nrec++;
+    }
+    else if (rd == 1 || rd == 2)
+    {
+        Ivl3 o;
+        lowdeg_intervals<4>(op, rd, false, o);
+        if (!ivl_is_whole(o))
+        {
+            occ &= ivl_mask(o);
+            if (!occ) return SC_MISS;
+            double rec[8];
+            write_final_record(rec, o, make_tag(2, false, rd));
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                if (k == nrec)
+                {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) recs[k][c] = rec[c];
+                }
+            nrec++;
+        }
+    }
+    return nrec ? SC_DEFERRED : SC_GENERAL;
+}
+
+// A pending vertex-edge distance quartic (record `rec`, its sub-test's inside-quadratic records right before it).  The
+// quartic dips wherever the vertex sweeps over the edge's LINE, usually without coming within eta of it, and on [0,1] its
+// Bernstein hull is rarely conclusive.  Only the times at which the vertex projects inside the segment count ([0,1]
+// narrowed by the quadratics' intervals), and on those windows the hull, refined down to 64ths, usually proves "further
+// than eta": the record is then finalised with no interval and no root is isolated.  Returns true in that case.
+CCD_FN bool ve_refine_item(double *rec)
+{
+    const unsigned tag = rec_untag(rec[7]);
+    const int rd = (int)((tag >> 4) & 7u);
+    const int nsib = (int)rec[5];
+    if ((tag & (REC_FINAL | REC_POS)) || (rd != 3 && rd != 4) || nsib < 0 || nsib > 2) return false;
+    RunSet R;
+    runset_full(R);
+    const V3 z = mk(0, 0, 0);
+    for (int s = nsib; s >= 1; s--)
+    {
+        Ivl3 o;
+        unsigned t;
+        read_final_record(rec - REC_STRIDE * s, o, t);
+        if (o.bad) return false;
+        narrow_ivl(R, o, false, z, z, z, z);
+    }
+    if (R.bad) return false;
+    bool excluded = true;
+    for (int j = 0; j < RCAP && excluded; j++)
+        if (j < R.n)
+        {
+            double lj = R.l[0], uj = R.u[0];
+#pragma unroll
+            for (int k = 1; k < RCAP; k++)
+                if (k == j) { lj = R.l[k]; uj = R.u[k]; }
+            if (rd == 4)
+            {
+                const double c4[5] = {rec[0], rec[1], rec[2], rec[3], rec[4]};
+                excluded = window_excluded<4>(c4, false, lj, uj);
+            }
+            else
+            {
+                const double c3[4] = {rec[0], rec[1], rec[2], rec[3]};
+                excluded = window_excluded<3>(c3, false, lj, uj);
+            }
+        }
+    if (!excluded) return false;
+    Ivl3 none;
+    none.n = 0;
+    none.bad = false;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { none.l[k] = 0.0; none.u[k] = 0.0; }
+    write_final_record(rec, none, tag);
+    return true;
 }
 
 // turn a pending record into a final one: isolate the roots of its polynomial, apply the interval rules

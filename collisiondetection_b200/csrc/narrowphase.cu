@@ -131,13 +131,38 @@ struct StencilIn
     double eta;
 };
 
+// Single-step positions are packed per vertex as {x0,y0,z0,-,x1,y1,z1,-} (64 bytes, pack_positions_kernel): the start
+// and end position of a vertex come from one aligned 64-byte chunk with four 16-byte loads, instead of six 8-byte loads
+// from two arrays whose 24-byte elements straddle sectors.
+__device__ __forceinline__ void ldpair(const double *qpack, int idx, V3 &a, V3 &b)
+{
+    const double2 *p = reinterpret_cast<const double2 *>(qpack + 8ll * idx);
+    const double2 p0 = __ldg(p), p1 = __ldg(p + 1), p2 = __ldg(p + 2), p3 = __ldg(p + 3);
+    a = mk(p0.x, p0.y, p1.x);
+    b = mk(p2.x, p2.y, p3.x);
+}
+
 template <bool IS_VF> __device__ __forceinline__ void load_single(const NpArgs &A, long long i, StencilIn &S)
 {
     const int4 s = reinterpret_cast<const int4 *>(A.stencils)[i];
     S.eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
-    const long long vs = A.vstride;
-    S.a[0] = ldv(A.q0 + vs * s.x); S.a[1] = ldv(A.q0 + vs * s.y); S.a[2] = ldv(A.q0 + vs * s.z); S.a[3] = ldv(A.q0 + vs * s.w);
-    S.b[0] = ldv(A.q1 + vs * s.x); S.b[1] = ldv(A.q1 + vs * s.y); S.b[2] = ldv(A.q1 + vs * s.z); S.b[3] = ldv(A.q1 + vs * s.w);
+    ldpair(A.q0, s.x, S.a[0], S.b[0]);
+    ldpair(A.q0, s.y, S.a[1], S.b[1]);
+    ldpair(A.q0, s.z, S.a[2], S.b[2]);
+    ldpair(A.q0, s.w, S.a[3], S.b[3]);
+}
+
+__global__ void __launch_bounds__(256) pack_positions_kernel(int V, const double *__restrict__ q0, const double *__restrict__ q1, int vstride,
+                                                             double *__restrict__ qpack)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const double *a = q0 + (long long)vstride * v, *b = q1 + (long long)vstride * v;
+    double2 *o = reinterpret_cast<double2 *>(qpack + 8ll * v);
+    o[0] = make_double2(a[0], a[1]);
+    o[1] = make_double2(a[2], 0.0);
+    o[2] = make_double2(b[0], b[1]);
+    o[3] = make_double2(b[2], 0.0);
 }
 
 __device__ __forceinline__ void store_result(const NpArgs &A, long long i, int stage, double toi)
@@ -183,7 +208,7 @@ __device__ __forceinline__ unsigned long long alloc_task_slots(const NpArgs &A, 
 enum
 {
     K_NWORK = 0, K_NTASK = 1, K_NDEG = 2 /* 4 */, K_NQ = 6 /* prim, ve, vv */, K_NGEN = 9, K_NSQ = 10 /* after stage 0..3 */,
-    K_NXQ = 14 /* polynomial 0..4 */, K_CURSOR = 19 /* degree 3..6 */, K_NDEG2 = 23 /* second solve round */, K_CURSOR2 = 27, K_COUNT = 31
+    K_NXQ = 14 /* polynomial 0..4 */, K_CURSOR = 19 /* degree 3..6 */, K_NDEG2 = 23 /* second solve round */, K_CURSOR2 = 27, K_NREF = 31 /* vertex-edge quartics left after ve_refine */, K_COUNT = 32
 };
 
 struct P1Args
@@ -360,9 +385,11 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_ve_kern
         const int4 s4 = reinterpret_cast<const int4 *>(A.stencils)[i];
         const int idx[4] = {s4.x, s4.y, s4.z, s4.w};
         const double eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
-        const long long vs = A.vstride;
-        const V3 a0 = ldv(A.q0 + vs * idx[iv]), a1 = ldv(A.q0 + vs * idx[i1]), a2 = ldv(A.q0 + vs * idx[i2]);
-        const V3 v0 = ldv(A.q1 + vs * idx[iv]) - a0, v1 = ldv(A.q1 + vs * idx[i1]) - a1, v2 = ldv(A.q1 + vs * idx[i2]) - a2;
+        V3 a0, a1, a2, b0, b1, b2;
+        ldpair(A.q0, idx[iv], a0, b0);
+        ldpair(A.q0, idx[i1], a1, b1);
+        ldpair(A.q0, idx[i2], a2, b2);
+        const V3 v0 = b0 - a0, v1 = b1 - a1, v2 = b2 - a2;
         double recs[3][8];
         int nrec;
         const int code = ve_item(a0, a1, a2, v0, v1, v2, eta, recs, nrec);
@@ -398,9 +425,10 @@ template <bool IS_VF> __global__ void __launch_bounds__(256) np_vv_kernel(P1Args
         const int4 s4 = reinterpret_cast<const int4 *>(A.stencils)[i];
         const int idx[4] = {s4.x, s4.y, s4.z, s4.w};
         const double eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
-        const long long vs = A.vstride;
-        const V3 a1 = ldv(A.q0 + vs * idx[i1]), a2 = ldv(A.q0 + vs * idx[i2]);
-        const V3 v1 = ldv(A.q1 + vs * idx[i1]) - a1, v2 = ldv(A.q1 + vs * idx[i2]) - a2;
+        V3 a1, a2, b1, b2;
+        ldpair(A.q0, idx[i1], a1, b1);
+        ldpair(A.q0, idx[i2], a2, b2);
+        const V3 v1 = b1 - a1, v2 = b2 - a2;
         double t = 0.0;
         if (vertex_vertex(a1, a2, v1, v2, eta, t) == R_HIT) atomicOr(&Q.status[i], (unsigned)SC_HIT << (2 * (NVE + 1 + k)));
     }
@@ -529,6 +557,34 @@ template <int D> __global__ void __launch_bounds__(128) prepare_kernel(double *t
         RootLane<D> L;
         L.prepare(c);
         L.save_start(rec + 8);
+    }
+}
+
+// first-round degree-3 / degree-4 lists (= the vertex-edge distance quartics): ve_refine_item settles most of them without
+// the root isolator; the rest are compacted into `out`
+__global__ void __launch_bounds__(128) ve_refine_kernel(double *tasks, const int *__restrict__ list, const unsigned long long *count_ptr,
+                                                        int *__restrict__ out, unsigned long long *out_count)
+{
+    const unsigned long long nt = *count_ptr;
+    const unsigned long long nround = (nt + 31ull) & ~31ull;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nround; w += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        bool keep = false;
+        int j = 0;
+        if (w < nt)
+        {
+            j = list[w];
+            keep = !ve_refine_item(tasks + (long long)REC_STRIDE * j);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m)
+        {
+            const int lane = threadIdx.x & 31;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(out_count, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) out[base + __popc(m & ((1u << lane) - 1))] = j;
+        }
     }
 }
 
@@ -792,10 +848,18 @@ struct NpTrace
         name[n] = what;
         cudaEventRecord(ev[n++], st);
     }
-    void flush(const char *title)
+    void flush(const char *title, const unsigned long long *ctr = nullptr, long long nst = 0)
     {
         if (!on || n == 0) return;
         cudaEventSynchronize(ev[n - 1]);
+        if (ctr)
+        {
+            unsigned long long h[CCD_NP_COUNTERS];
+            cudaMemcpy(h, ctr, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[np counts %s] stencils %lld", title, nst);
+            for (int i = 0; i < CCD_NP_COUNTERS; i++) fprintf(stderr, " %llu", h[i]);
+            fprintf(stderr, "\n");
+        }
         fprintf(stderr, "[np trace %s]", title);
         for (int i = 1; i < n; i++)
         {
@@ -852,7 +916,14 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
         g_trace.mark(st, "bucket");
         launch_solve<3>(st, A.tasks, tlists + 0 * A.task_cap, nd + 0, cu + 0);
         g_trace.mark(st, "solve3");
-        launch_solve<4>(st, A.tasks, tlists + 1 * A.task_cap, nd + 1, cu + 1);
+        if (phase == 0)
+        {
+            ve_refine_kernel<<<148 * 8, 128, 0, st>>>(A.tasks, tlists + 1 * A.task_cap, nd + 1, tlists + 4 * A.task_cap, Q.ctr + K_NREF);
+            g_trace.mark(st, "ve_refine");
+            launch_solve<4>(st, A.tasks, tlists + 4 * A.task_cap, Q.ctr + K_NREF, cu + 1);
+        }
+        else
+            launch_solve<4>(st, A.tasks, tlists + 1 * A.task_cap, nd + 1, cu + 1);
         g_trace.mark(st, "solve4");
         launch_solve<5>(st, A.tasks, tlists + 2 * A.task_cap, nd + 2, cu + 2);
         g_trace.mark(st, "solve5");
@@ -864,12 +935,13 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
     g_trace.mark(st, "combine");
     np_general_kernel<IS_VF><<<148 * 2, B, 0, st>>>(Q);
     g_trace.mark(st, "general");
-    g_trace.flush(IS_VF ? "VF" : "EE");
-    return nl + 3 + 3 + 2 * 13 + 1 + 2;
+    g_trace.flush(IS_VF ? "VF" : "EE", Q.ctr, n);
+    return nl + 3 + 3 + 2 * 13 + 1 + 1 + 2;
 }
 
+// Single step: q0 = positions packed by ccdk_pack_positions (q1, vstride unused); multi-entry History: q0 == nullptr.
 // Scratch (sizes in elements, n = number of stencils): work list {w_stencil: n ints, w_meta: n ints, w_base: 5n ints},
-// tasks (task_cap records of REC_STRIDE doubles, task_cap < 2^28), tlists (4 x task_cap ints: pending records by degree),
+// tasks (task_cap records of REC_STRIDE doubles, task_cap < 2^28), tlists (5 x task_cap ints: pending records by degree + refined list),
 // status (n u32), sbase (5n ints), queues (9n ints: primitive / vertex-edge / vertex-vertex items), sq (2 x n int2: stage
 // queues), xq (5 x n int2: export queues), ctr (CCD_NP_COUNTERS counters, zeroed here; ctr[0] = work-list entries,
 // ctr[1] = records).  Returns the number of kernels launched.  If ctr[1] ends above task_cap the caller must grow the
@@ -903,6 +975,11 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
     Q.qgen = queues;      // the primitive queue is consumed by stage 0 long before anything goes to the general routine
     Q.ctr = ctr;
     return is_vf ? launch_single_step<true>(st, Q, n, tlists) : launch_single_step<false>(st, Q, n, tlists);
+}
+
+void ccdk_pack_positions(cudaStream_t st, int V, const double *q0, const double *q1, int vstride, double *qpack)
+{
+    if (V > 0) pack_positions_kernel<<<grid_for(V, 256), 256, 0, st>>>(V, q0, q1, vstride, qpack);
 }
 
 void ccdk_prim_batch(cudaStream_t st, int kind, long long n, const double *pts, const double *eta, unsigned char *hit, double *t)

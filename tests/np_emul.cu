@@ -195,6 +195,7 @@ void run(long long n, const int *stencils, const double *q0, const double *q1, i
         }
         else if (!general)
         {
+            for (size_t k = 0; k < recs.size(); k++) ve_refine_item(recs[k].d);      // no-op for anything but pending VE quartics
             solve_records(recs, stats, 0);
             if (code[0] == SC_DEFERRED) window_item(recs[first[0]].d, cnt[0], IS_VF ? 3 : 4);
             solve_records(recs, stats, 1);
