@@ -149,7 +149,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    config = dict(workload=args.workload, kind="KDOP-13", sharding="vertex/edge ranges over %d rank(s), replicated LBVH" % world,
+    config = dict(workload=args.workload, kind="KDOP-13", sharding="vertex/edge ownership ranges over %d rank(s), rebalanced every step from the previous step's load profile; replicated LBVH, sharded traversal / emission / narrowphase" % world,
                   l2="working set (inputs 144 MB at cloth1415 + GBs of intermediates) exceeds the 126 MB L2; nothing is reused across steps")
 
     if args.impl == "reference":
@@ -186,9 +186,10 @@ def main():
 
     def step_dev():
         r = ctx.step_device(api.KDOP, V, F, d_f.data_ptr(), d_q0.data_ptr(), d_q1.data_ptr(), wl["outer_eta"], wl["eta"], 0, rank, world)
-        # the path's only exchange: earliest TOI (min) and hit / stencil counts (sum) — one fused all-reduce
-        summary["toi"], summary["hits"], summary["stencils"] = D.reduce_step_summary(
-            r.earliest_toi, r.n_vf_hits + r.n_ee_hits, r.n_vf_candidates + r.n_ee_candidates, device="cuda")
+        # the path's only exchange: earliest TOI, hit / stencil counts and the load profile that balances the next
+        # step's ownership ranges — one small all-gather
+        summary["toi"], summary["hits"], summary["stencils"] = D.exchange_step(
+            ctx, r.earliest_toi, r.n_vf_hits + r.n_ee_hits, r.n_vf_candidates + r.n_ee_candidates, device="cuda")
         return r
 
     def barrier():

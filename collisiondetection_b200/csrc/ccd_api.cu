@@ -51,10 +51,16 @@ struct ccd_context
     void *h_res[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t h_res_cap[4] = {0, 0, 0, 0};
     size_t candCap = 0, pairCap = 0, taskCapVf = 0, taskCapEe = 0;
+    // sharding: ownership ranges chosen by the caller (ccd_set_shard_partition), load profile of the last sharded step
+    std::vector<int> partV, partE;
+    DBuf qlist, hist;
+    unsigned long long *h_hist = nullptr;      // pinned, 2 * CCD_SHARD_BUCKETS
+    int histV = 0, histE = 0;
+    bool hist_valid = false;
 };
 
 // device counters layout (unsigned long long each)
-enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NP_VF = 16 /* CCD_NP_COUNTERS counters per run: work-list entries, records, ... (narrowphase.cu K_*) */, C_NP_EE = 16 + CCD_NP_COUNTERS, C_TOTAL = 16 + 2 * CCD_NP_COUNTERS };
+enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NQUERY = 7, C_NP_VF = 16 /* CCD_NP_COUNTERS counters per run: work-list entries, records, ... (narrowphase.cu K_*) */, C_NP_EE = 16 + CCD_NP_COUNTERS, C_TOTAL = 16 + 2 * CCD_NP_COUNTERS };
 enum { C_NWORK_VF = C_NP_VF, C_NTASK_VF = C_NP_VF + 1, C_NWORK_EE = C_NP_EE, C_NTASK_EE = C_NP_EE + 1 };
 
 #define CK(call)                                                                                      \
@@ -136,11 +142,14 @@ void ccdk_build_tree(cudaStream_t st, int F, const float *faabb, unsigned *bound
 void ccdk_traverse(cudaStream_t st, int kind, int F, int qbegin, int qend, const int *qlist, bool all, const unsigned *sortedFace,
                    const float *faabb, const int *faces, const float *fkdop, const void *nodes, void *cand, unsigned long long cap,
                    unsigned long long *count);
-void ccdk_exact_pairs(cudaStream_t st, int kind, const unsigned long long *ncand, unsigned long long cap, const void *cand,
+void ccdk_shard_queries(cudaStream_t st, int F, const unsigned *sortedFace, const int *faces, const int *faceEdge, int v0, int v1, int e0, int e1,
+                        int *qlist, unsigned long long *count);
+void ccdk_shard_hist(cudaStream_t st, const int *counts, int begin, int end, int n, int nb, unsigned long long *hist);
+void ccdk_exact_pairs(cudaStream_t st, int kind, bool both, const unsigned long long *ncand, unsigned long long cap, const void *cand,
                       const unsigned *sortedFace, const int *faces, const double *boxes, int *pairL, int *pairR, unsigned long long pcap,
                       unsigned long long *npairs, int *deg);
 void ccdk_adjacency_fill(cudaStream_t st, const unsigned long long *npairs, const int *pairL, const int *pairR, const long long *adjOff,
-                         int *cursor, int *adj);
+                         int *cursor, int *adj, bool both);
 void ccdk_topology_edges(cudaStream_t st, int F, const int *faces, unsigned long long *keys_in, unsigned long long *keys_sorted,
                          unsigned *vals_in, unsigned *vals_sorted, void *temp, size_t temp_bytes, int *flags, int *ids, void *edgeVerts,
                          int *edgeStart, int *faceEdge, int *heFace);
@@ -191,6 +200,7 @@ int ccd_create(ccd_context **out, int device)
     for (int i = 0; i <= CCD_N_STAGES; i++)
         cudaEventCreate(&c->sev[i]);
     cudaMallocHost((void **)&c->h_counters, sizeof(unsigned long long) * C_TOTAL);
+    cudaMallocHost((void **)&c->h_hist, sizeof(unsigned long long) * 2 * CCD_SHARD_BUCKETS);
     double ax[13][3];
     kdop_axes(ax);
     ccdk_set_axes(ax);
@@ -215,12 +225,14 @@ void ccd_destroy(ccd_context *c)
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->shardBounds, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->work2Vf, &c->work2Ee, &c->work2TaskVf, &c->work2TaskEe, &c->work2SubVf, &c->work2SubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->qpack, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->work2Vf, &c->work2Ee, &c->work2TaskVf, &c->work2TaskEe, &c->work2SubVf, &c->work2SubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->qpack, &c->qlist, &c->hist, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
     for (DBuf *b : all)
         if (b->p)
             cudaFree(b->p);
     if (c->h_counters)
         cudaFreeHost(c->h_counters);
+    if (c->h_hist)
+        cudaFreeHost(c->h_hist);
     for (int i = 0; i < 4; i++)
         if (c->h_res[i])
             cudaFreeHost(c->h_res[i]);
@@ -360,6 +372,28 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     const unsigned *sortedFace = P<unsigned>(c->valsB);
     cudaEventRecord(c->sev[ST_TRAVERSE_EXACT], c->st);
 
+    // Ownership of a shard: vertices [v0,v1) for VF stencils, unique edges [e0,e1) for EE stencils.  With one rank the
+    // ranges are everything and the traversal visits unordered pairs once; with several ranks the ranges come from the
+    // caller (ccd_set_shard_partition, balanced on the previous step's load profile; equal index split until then) and
+    // the rank traverses, tests and counts only for the faces its own emission reads.
+    const bool sharded = shard_world > 1;
+    const int E = c->nEdges;
+    int v0 = 0, v1 = V, e0 = 0, e1 = E;
+    if (sharded)
+    {
+        if ((int)c->partV.size() == shard_world + 1 && (int)c->partE.size() == shard_world + 1 && c->partV[shard_world] == V && c->partE[shard_world] == E)
+        {
+            v0 = c->partV[shard_rank]; v1 = c->partV[shard_rank + 1];
+            e0 = c->partE[shard_rank]; e1 = c->partE[shard_rank + 1];
+        }
+        else
+        {
+            v0 = (int)(((long long)V * shard_rank) / shard_world); v1 = (int)(((long long)V * (shard_rank + 1)) / shard_world);
+            e0 = (int)(((long long)E * shard_rank) / shard_world); e1 = (int)(((long long)E * (shard_rank + 1)) / shard_world);
+        }
+        CKR(ensure(c, c->qlist, sizeof(int) * (size_t)(F + 32)));
+    }
+    int nquery = F;
     for (int attempt = 0; attempt < 8; attempt++)
     {
         CKR(ensure(c, c->cand, sizeof(int) * 2 * c->candCap));
@@ -367,9 +401,23 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         CKR(ensure(c, c->pairR, sizeof(int) * c->pairCap));
         CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 2, c->st));
         CK(cudaMemsetAsync(c->deg.p, 0, sizeof(int) * (size_t)(F + 2), c->st));
-        ccdk_traverse(c->st, kind, F, 0, F, nullptr, false, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p, c->cand.p,
-                      c->candCap, ctr + C_NCAND);
-        ccdk_exact_pairs(c->st, kind, ctr + C_NCAND, c->candCap, c->cand.p, sortedFace, d_faces, P<double>(c->boxes), P<int>(c->pairL),
+        if (sharded)
+        {
+            if (attempt == 0)
+            {
+                CK(cudaMemsetAsync(ctr + C_NQUERY, 0, sizeof(unsigned long long), c->st));
+                ccdk_shard_queries(c->st, F, sortedFace, d_faces, P<int>(c->faceEdge), v0, v1, e0, e1, P<int>(c->qlist), ctr + C_NQUERY);
+                CKR(sync_counters(c));
+                nquery = (int)c->h_counters[C_NQUERY];
+                c->launches += 1;
+            }
+            ccdk_traverse(c->st, kind, F, 0, nquery, P<int>(c->qlist), true, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p,
+                          c->cand.p, c->candCap, ctr + C_NCAND);
+        }
+        else
+            ccdk_traverse(c->st, kind, F, 0, F, nullptr, false, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p, c->cand.p,
+                          c->candCap, ctr + C_NCAND);
+        ccdk_exact_pairs(c->st, kind, !sharded, ctr + C_NCAND, c->candCap, c->cand.p, sortedFace, d_faces, P<double>(c->boxes), P<int>(c->pairL),
                          P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg));
         c->launches += 2;
         CKR(sync_counters(c));
@@ -405,35 +453,38 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, F + 1, P<int>(c->deg), P<long long>(c->adjOff));
     CKR(ensure(c, c->adj, sizeof(int) * (size_t)(2 * res->npairs + 1)));
     CK(cudaMemsetAsync(c->cursor.p, 0, sizeof(int) * (size_t)(F + 2), c->st));
-    ccdk_adjacency_fill(c->st, ctr + C_NPAIRS, P<int>(c->pairL), P<int>(c->pairR), P<long long>(c->adjOff), P<int>(c->cursor), P<int>(c->adj));
+    ccdk_adjacency_fill(c->st, ctr + C_NPAIRS, P<int>(c->pairL), P<int>(c->pairR), P<long long>(c->adjOff), P<int>(c->cursor), P<int>(c->adj), !sharded);
     c->launches += 3;
 
-    // Stencil counts for every vertex / unique edge (replicated on all ranks), then ownership ranges balanced by the
-    // number of stencils: rank r owns the items whose first stencil falls in [T*r/W, T*(r+1)/W).
-    const int E = c->nEdges;
+    // Stencil counts of the owned vertices / unique edges, scanned into write offsets (relative to the range start)
     CKR(ensure(c, c->vfCounts, sizeof(int) * (size_t)(V + 2)));
     CKR(ensure(c, c->vfOffsets, sizeof(long long) * (size_t)(V + 2)));
     CKR(ensure(c, c->eeCounts, sizeof(int) * (size_t)(E + 2)));
     CKR(ensure(c, c->eeOffsets, sizeof(long long) * (size_t)(E + 2)));
-    CKR(ensure(c, c->shardBounds, 64));
     cudaEventRecord(c->sev[ST_EMIT_COUNT], c->st);
-    ccdk_vf_emit(c->st, true, 0, V, d_faces, P<long long>(c->starOff), P<int>(c->star), P<long long>(c->adjOff), P<int>(c->adj),
+    ccdk_vf_emit(c->st, true, v0, v1, d_faces, P<long long>(c->starOff), P<int>(c->star), P<long long>(c->adjOff), P<int>(c->adj),
                  P<int>(c->faceRank), P<int>(c->rankFace), d_fixed, P<int>(c->vfCounts), nullptr, nullptr);
-    ccdk_ee_emit(c->st, true, 0, E, P<int>(c->edgeStart), P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceEdge),
+    ccdk_ee_emit(c->st, true, e0, e1, P<int>(c->edgeStart), P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceEdge),
                  c->edgeVerts.p, d_fixed, P<int>(c->eeCounts), nullptr, nullptr);
-    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, V + 1, P<int>(c->vfCounts), P<long long>(c->vfOffsets));
-    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, E + 1, P<int>(c->eeCounts), P<long long>(c->eeOffsets));
-    ccdk_shard_bounds(c->st, P<long long>(c->vfOffsets), V, shard_rank, shard_world, P<int>(c->shardBounds));
-    ccdk_shard_bounds(c->st, P<long long>(c->eeOffsets), E, shard_rank, shard_world, P<int>(c->shardBounds) + 2);
-    c->launches += 8;
-    int bounds[4] = {0, 0, 0, 0};
-    CK(cudaMemcpyAsync(bounds, c->shardBounds.p, sizeof(bounds), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
-    const int v0 = bounds[0], v1 = bounds[1], e0 = bounds[2], e1 = bounds[3];
+    // the scan reads one element past the range (never added to anything it outputs)
+    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, v1 - v0 + 1, P<int>(c->vfCounts) + v0, P<long long>(c->vfOffsets) + v0);
+    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, e1 - e0 + 1, P<int>(c->eeCounts) + e0, P<long long>(c->eeOffsets) + e0);
+    c->launches += 4;
+    c->hist_valid = false;
+    if (sharded)
+    {
+        CKR(ensure(c, c->hist, sizeof(unsigned long long) * 2 * CCD_SHARD_BUCKETS));
+        CK(cudaMemsetAsync(c->hist.p, 0, sizeof(unsigned long long) * 2 * CCD_SHARD_BUCKETS, c->st));
+        ccdk_shard_hist(c->st, P<int>(c->vfCounts), v0, v1, V, CCD_SHARD_BUCKETS, P<unsigned long long>(c->hist));
+        ccdk_shard_hist(c->st, P<int>(c->eeCounts), e0, e1, E > 0 ? E : 1, CCD_SHARD_BUCKETS, P<unsigned long long>(c->hist) + CCD_SHARD_BUCKETS);
+        CK(cudaMemcpyAsync(c->h_hist, c->hist.p, sizeof(unsigned long long) * 2 * CCD_SHARD_BUCKETS, cudaMemcpyDeviceToHost, c->st));
+        c->histV = V;
+        c->histE = E;
+        c->hist_valid = true;
+        c->launches += 2;
+    }
     long long range[4] = {0, 0, 0, 0};
-    CK(cudaMemcpyAsync(&range[0], P<long long>(c->vfOffsets) + v0, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(&range[1], P<long long>(c->vfOffsets) + v1, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaMemcpyAsync(&range[2], P<long long>(c->eeOffsets) + e0, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(&range[3], P<long long>(c->eeOffsets) + e1, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     res->nvf = range[1] - range[0];
@@ -778,6 +829,37 @@ void ccd_step_result_free(ccd_step_result *r)
     // the arrays live in pinned buffers owned by the context: nothing to release, just forget them
     r->vf_hits = r->ee_hits = nullptr;
     r->vf_hit_toi = r->ee_hit_toi = nullptr;
+}
+
+int ccd_set_shard_partition(ccd_context *c, int world, const int32_t *vbounds, const int32_t *ebounds)
+{
+    if (!c || world < 1 || !vbounds || !ebounds || vbounds[0] != 0 || ebounds[0] != 0)
+        return CCD_ERR_ARG;
+    for (int r = 0; r < world; r++)
+        if (vbounds[r + 1] < vbounds[r] || ebounds[r + 1] < ebounds[r])
+            return CCD_ERR_ARG;
+    c->partV.assign(vbounds, vbounds + world + 1);
+    c->partE.assign(ebounds, ebounds + world + 1);
+    return CCD_OK;
+}
+
+int ccd_shard_histogram(ccd_context *c, int64_t *vf_hist, int64_t *ee_hist, int32_t *n_vertices, int32_t *n_edges)
+{
+    if (!c || !vf_hist || !ee_hist)
+        return CCD_ERR_ARG;
+    if (!c->hist_valid)
+    {
+        c->err = "ccd_shard_histogram: the last step on this context was not sharded";
+        return CCD_ERR_ARG;
+    }
+    for (int i = 0; i < CCD_SHARD_BUCKETS; i++)
+    {
+        vf_hist[i] = (int64_t)c->h_hist[i];
+        ee_hist[i] = (int64_t)c->h_hist[CCD_SHARD_BUCKETS + i];
+    }
+    if (n_vertices) *n_vertices = c->histV;
+    if (n_edges) *n_edges = c->histE;
+    return CCD_OK;
 }
 
 int ccd_stage_times(ccd_context *c, float *ms, int n)

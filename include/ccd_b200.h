@@ -101,11 +101,13 @@ int ccd_step_shard(ccd_context *ctx, int kind, int V, int F, const int32_t *face
                    ccd_step_result *out);
 
 /* Device-resident variant: inputs already in HBM, results stay in HBM (pointers valid until the next
- * call on this context).  shard_rank / shard_world partition the step across GPUs of one job: every
- * rank builds the (replicated) tree and counts the stencils of every vertex / unique edge; rank r then owns
- * a contiguous range of vertices (VF stencils) and of unique edges (EE stencils) chosen so that every rank
- * gets the same number of stencils.  world = 1 means the whole step.  The concatenation over ranks of the
- * stencil lists equals the single-GPU lists exactly. */
+ * call on this context).  shard_rank / shard_world partition the step across GPUs of one job: rank r owns a
+ * contiguous range of vertices (its VF stencils) and of unique edges (its EE stencils).  Every rank builds the
+ * (replicated) LBVH, but traverses it, tests face pairs and counts stencils only for the faces its own ranges
+ * touch.  The ranges are an equal index split until the caller installs better ones with
+ * ccd_set_shard_partition — normally computed from the load profiles of the previous step
+ * (ccd_shard_histogram, summed over ranks).  Whatever the ranges, the concatenation over ranks of the
+ * stencil lists equals the single-GPU lists exactly.  world = 1 means the whole step. */
 typedef struct
 {
     int64_t n_vf_candidates, n_ee_candidates;
@@ -127,6 +129,16 @@ typedef struct
 int ccd_step_device(ccd_context *ctx, int kind, int V, int F, const int32_t *d_faces, const double *d_q0,
                     const double *d_q1, double outerEta, double eta, const uint8_t *d_fixedMask, int shard_rank,
                     int shard_world, ccd_device_result *out);
+
+/* Ownership ranges for sharded steps on this context: vbounds / ebounds have world+1 ascending entries,
+ * vbounds[0] = ebounds[0] = 0, vbounds[world] = V, ebounds[world] = number of unique edges (returned by
+ * ccd_shard_histogram).  Ignored (equal split) when they do not match the mesh of a later call. */
+int ccd_set_shard_partition(ccd_context *ctx, int world, const int32_t *vbounds, const int32_t *ebounds);
+/* Load profile of the last sharded step on this context: stencils owned by this rank per bucket, CCD_SHARD_BUCKETS
+ * equal-width buckets over the vertex ids (vf_hist) and over the unique-edge ids (ee_hist); item i falls in bucket
+ * i * CCD_SHARD_BUCKETS / n.  Summing over ranks gives the whole step's profile.  n_vertices / n_edges: the id ranges. */
+#define CCD_SHARD_BUCKETS 1024
+int ccd_shard_histogram(ccd_context *ctx, int64_t *vf_hist, int64_t *ee_hist, int32_t *n_vertices, int32_t *n_edges);
 
 /* Utilities for bindings that hold device results: copy `bytes` from a device pointer of this context to host
  * memory, and a measured FP64 roofline denominator (dependent-free DFMA streams on every SM) in TFLOP/s. */

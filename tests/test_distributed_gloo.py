@@ -73,3 +73,70 @@ def test_shard_ranges_partition():
             assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in ranges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_balanced_bounds():
+    from collisiondetection_b200.distributed import balanced_bounds
+    rng = np.random.default_rng(3)
+    for n_items in (5, 1000, 2002225):
+        for world in (1, 2, 3, 8):
+            nb = 1024
+            bucket = (np.arange(n_items, dtype=np.int64) * nb) // n_items
+            load = rng.integers(0, 20, size=n_items) * (np.arange(n_items) > n_items // 3)      # one third of the ids idle
+            hist = np.bincount(bucket, weights=load, minlength=nb)
+            b = balanced_bounds(hist, n_items, world)
+            assert b[0] == 0 and b[-1] == n_items and np.all(np.diff(b) >= 0) and len(b) == world + 1
+            if n_items >= 1000:
+                per = np.array([load[b[r]:b[r + 1]].sum() for r in range(world)], dtype=np.float64)
+                assert per.max() <= 1.05 * per.mean() + 40, (n_items, world, per)
+    # empty profile: equal index split
+    assert list(balanced_bounds(np.zeros(16), 100, 4)) == [0, 25, 50, 75, 100]
+
+
+class _FakeCtx(object):
+    """Stands in for api.Context in the CPU test of the exchange: a fixed load profile per rank, records the partition."""
+    SHARD_BUCKETS = 1024
+
+    def __init__(self, rank, world, nv, ne):
+        self.rank, self.world, self.nv, self.ne = rank, world, nv, ne
+        self.partition = None
+
+    def shard_histogram(self):
+        vf = np.zeros(self.SHARD_BUCKETS, np.int64)
+        ee = np.zeros(self.SHARD_BUCKETS, np.int64)
+        lo, hi = (self.SHARD_BUCKETS * self.rank) // self.world, (self.SHARD_BUCKETS * (self.rank + 1)) // self.world
+        vf[lo:hi] = 10 * (self.rank + 1)      # later ranks are heavier
+        ee[lo:hi] = 7
+        return vf, ee, self.nv, self.ne
+
+    def set_shard_partition(self, vb, eb):
+        self.partition = (list(map(int, vb)), list(map(int, eb)))
+
+
+def _exchange_worker(rank, world, port_no, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from collisiondetection_b200 import distributed as D
+    ctx = _FakeCtx(rank, world, 100000, 300000)
+    toi, nh, ns = D.exchange_step(ctx, 0.25 + 0.1 * rank if rank else float("inf"), 10 + rank, 1000 * (rank + 1))
+    results[rank] = (toi, nh, ns, ctx.partition)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_step_gathers_and_rebalances(world):
+    mgr = mp.get_context("spawn").Manager()
+    results = mgr.dict()
+    mp.spawn(_exchange_worker, args=(world, 29650 + world, results), nprocs=world, join=True)
+    parts = {results[r][3] and (tuple(results[r][3][0]), tuple(results[r][3][1])) for r in range(world)}
+    assert len(parts) == 1, "ranks derived different partitions"
+    vb, eb = results[0][3]
+    assert vb[0] == 0 and vb[-1] == 100000 and eb[-1] == 300000
+    # heavier late ranks -> their vertex ranges shrink; the uniform edge profile stays an equal split
+    assert vb[1] > 100000 // world
+    assert abs(eb[1] - 300000 // world) <= 300000 // 1024 + 1
+    for r in range(world):
+        toi, nh, ns, _ = results[r]
+        assert toi == (0.35 if world > 1 else float("inf"))
+        assert nh == sum(10 + k for k in range(world)) and ns == sum(1000 * (k + 1) for k in range(world))

@@ -253,6 +253,26 @@ def test_cloth_sharded_union_equals_whole(ctx):
         assert np.array_equal(np.concatenate([p[4] for p in parts]), whole[4])
         assert sum(p[0] for p in parts) == whole[0] and sum(p[1] for p in parts) == whole[1]
         assert min(p[2] for p in parts) == whole[2]
+    # rebalanced ownership (what distributed.exchange_step installs every step): same union, loads within a few per cent
+    from collisiondetection_b200.distributed import balanced_bounds
+    world = 4
+    hv = np.zeros(ctx.SHARD_BUCKETS, np.int64)
+    he = np.zeros(ctx.SHARD_BUCKETS, np.int64)
+    for r in range(world):
+        run(r, world)
+        a, b, nv, ne = ctx.shard_histogram()
+        hv += a
+        he += b
+    assert hv.sum() == len(whole[3]) and he.sum() == len(whole[4]) and nv == V
+    ctx.set_shard_partition(balanced_bounds(hv, nv, world), balanced_bounds(he, ne, world))
+    parts = [run(r, world) for r in range(world)]
+    assert np.array_equal(np.concatenate([p[3] for p in parts]), whole[3])
+    assert np.array_equal(np.concatenate([p[4] for p in parts]), whole[4])
+    loads = [len(p[3]) + len(p[4]) for p in parts]
+    assert max(loads) <= 1.1 * (sum(loads) / world), loads
+    ctx.set_shard_partition([0, V], [0, ne])      # a partition for another world size is ignored (equal split)
+    parts = [run(r, 2) for r in range(2)]
+    assert np.array_equal(np.concatenate([p[3] for p in parts]), whole[3])
 
 
 @pytest.mark.slow
