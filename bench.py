@@ -218,6 +218,15 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
+    # per-stage device times of every rank (diagnostics: the step is as slow as its slowest rank)
+    stage_names = sorted(stage_sum)
+    st_local = torch.tensor([stage_sum[k] / args.steps for k in stage_names] + [float(r.n_vf_candidates + r.n_ee_candidates)], dtype=torch.float64, device="cuda")
+    st_all = [torch.zeros_like(st_local) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(st_all, st_local)
+    else:
+        st_all = [st_local]
+    st_all = torch.stack(st_all).cpu().numpy()
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -282,7 +291,8 @@ def main():
                e2e=dict(value=n_stencils / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
                gpu_launches=int(launches) * args.steps,
                roofline=roof,
-               stages_ms=stages, kernel_ms_per_step=kern_ms / args.steps,
+               stages_ms=stages, stages_ms_max_over_ranks={k: float(st_all[:, i].max()) for i, k in enumerate(stage_names)},
+               stencils_per_rank=[int(x) for x in st_all[:, -1]], kernel_ms_per_step=kern_ms / args.steps,
                counts=dict(vertices=V, faces=F, stencils=n_stencils, vf_rank0=int(nvf), ee_rank0=int(nee), hits=n_hits,
                            face_pairs_rank0=int(r.n_face_pairs), tree_candidates_rank0=int(r.n_tree_candidates), vf_deferred_rank0=int(r.n_vf_deferred), ee_deferred_rank0=int(r.n_ee_deferred),
                            stencils_per_face=n_stencils / float(F)),

@@ -51,7 +51,7 @@ EXPORTS = [
     "ccd_broadphase_step", "ccd_narrowphase", "ccd_step", "ccd_step_result_free", "ccd_step_device", "ccd_vf_batch",
     "ccd_ee_batch", "ccd_ve_batch", "ccd_vv_batch", "ccd_find_intervals_batch", "ccd_dist_vf_batch",
     "ccd_dist_ee_batch", "ccd_dist_plane_lt_batch", "ccd_dist_line_lt_batch", "ccd_mesh_self_distance",
-    "ccd_memcpy_d2h", "ccd_fp64_peak", "ccd_stage_times", "ccd_step_shard", "ccd_set_shard_partition", "ccd_shard_histogram",
+    "ccd_memcpy_d2h", "ccd_fp64_peak", "ccd_stage_times", "ccd_step_shard", "ccd_set_shard_partition", "ccd_shard_histogram", "ccd_shard_edge_bounds",
 ]
 
 _LIB = None
@@ -234,6 +234,14 @@ class Context(object):
         self._check(self.lib.ccd_shard_histogram(self.h, vf.ctypes.data_as(C.c_void_p), ee.ctypes.data_as(C.c_void_p), C.byref(nv), C.byref(ne)),
                     "ccd_shard_histogram")
         return vf, ee, nv.value, ne.value
+
+    def shard_edge_bounds(self, vbounds):
+        """Unique-edge bounds that go with vertex bounds (ccd_shard_edge_bounds)."""
+        vb = np.ascontiguousarray(vbounds, dtype=np.int32)
+        eb = np.zeros(len(vb), np.int32)
+        self._check(self.lib.ccd_shard_edge_bounds(self.h, C.c_int(len(vb) - 1), vb.ctypes.data_as(C.c_void_p), eb.ctypes.data_as(C.c_void_p)),
+                    "ccd_shard_edge_bounds")
+        return eb
 
     def set_shard_partition(self, vbounds, ebounds):
         """Ownership ranges of the next sharded steps (ccd_set_shard_partition): world+1 ascending bounds each."""

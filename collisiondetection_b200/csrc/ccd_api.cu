@@ -53,7 +53,7 @@ struct ccd_context
     size_t candCap = 0, pairCap = 0, taskCapVf = 0, taskCapEe = 0;
     // sharding: ownership ranges chosen by the caller (ccd_set_shard_partition), load profile of the last sharded step
     std::vector<int> partV, partE;
-    DBuf qlist, hist;
+    DBuf qlist, hist, vactive, eactive, vertEdgeStart;
     unsigned long long *h_hist = nullptr;      // pinned, 2 * CCD_SHARD_BUCKETS
     int histV = 0, histE = 0;
     bool hist_valid = false;
@@ -144,10 +144,11 @@ void ccdk_traverse(cudaStream_t st, int kind, int F, int qbegin, int qend, const
                    unsigned long long *count);
 void ccdk_shard_queries(cudaStream_t st, int F, const unsigned *sortedFace, const int *faces, const int *faceEdge, int v0, int v1, int e0, int e1,
                         int *qlist, unsigned long long *count);
-void ccdk_shard_hist(cudaStream_t st, const int *counts, int begin, int end, int n, int nb, unsigned long long *hist);
+void ccdk_shard_hist(cudaStream_t st, const int *counts, const void *edgeVerts, int begin, int end, int n, int nb, unsigned long long *hist);
+void ccdk_vert_edge_start(cudaStream_t st, int V, int E, const void *edgeVerts, int *out);
 void ccdk_exact_pairs(cudaStream_t st, int kind, bool both, const unsigned long long *ncand, unsigned long long cap, const void *cand,
                       const unsigned *sortedFace, const int *faces, const double *boxes, int *pairL, int *pairR, unsigned long long pcap,
-                      unsigned long long *npairs, int *deg);
+                      unsigned long long *npairs, int *deg, const int *faceEdge, unsigned char *vactive, unsigned char *eactive);
 void ccdk_adjacency_fill(cudaStream_t st, const unsigned long long *npairs, const int *pairL, const int *pairR, const long long *adjOff,
                          int *cursor, int *adj, bool both);
 void ccdk_topology_edges(cudaStream_t st, int F, const int *faces, unsigned long long *keys_in, unsigned long long *keys_sorted,
@@ -160,10 +161,10 @@ void ccdk_topology_star(cudaStream_t st, int V, int F, const int *faces, int *vd
                         size_t temp_bytes);
 void ccdk_vf_emit(cudaStream_t st, bool count, int vbegin, int vend, const int *faces, const long long *starOff, const int *star,
                   const long long *adjOff, const int *adj, const int *faceRank, const int *rankFace, const unsigned char *fixed,
-                  int *counts, const long long *offsets, int *out);
+                  int *counts, const long long *offsets, int *out, const unsigned char *active);
 void ccdk_ee_emit(cudaStream_t st, bool count, int ebegin, int eend, const int *edgeStart, const int *heFace, const long long *adjOff,
                   const int *adj, const int *faceEdge, const void *edgeVerts, const unsigned char *fixed, int *counts,
-                  const long long *offsets, int *out);
+                  const long long *offsets, int *out, const unsigned char *active);
 void ccdk_hash_ints(cudaStream_t st, long long n, const int *d, unsigned long long *out);
 void ccdk_shard_bounds(cudaStream_t st, const long long *offsets, int n, int rank, int world, int *out);
 void ccdk_dist_batch(cudaStream_t st, int which, long long n, const double *pts, const double *eta, double *vec, double *bary, unsigned char *flag);
@@ -225,7 +226,7 @@ void ccd_destroy(ccd_context *c)
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->shardBounds, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->work2Vf, &c->work2Ee, &c->work2TaskVf, &c->work2TaskEe, &c->work2SubVf, &c->work2SubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->qpack, &c->qlist, &c->hist, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->work2Vf, &c->work2Ee, &c->work2TaskVf, &c->work2TaskEe, &c->work2SubVf, &c->work2SubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->qpack, &c->qlist, &c->hist, &c->vactive, &c->eactive, &c->vertEdgeStart, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
     for (DBuf *b : all)
         if (b->p)
             cudaFree(b->p);
@@ -313,7 +314,9 @@ static int ensure_topology(ccd_context *c, int V, int F, const int *d_faces)
     }
     ccdk_topology_star(c->st, V, F, d_faces, P<int>(c->vdeg), P<long long>(c->starOff), P<int>(c->starCur), P<int>(c->star), c->temp.p,
                        c->temp.cap);
-    c->launches += 4;
+    CKR(ensure(c, c->vertEdgeStart, sizeof(int) * (size_t)(V + 2)));
+    ccdk_vert_edge_start(c->st, V, c->nEdges, c->edgeVerts.p, P<int>(c->vertEdgeStart));
+    c->launches += 5;
     CK(cudaGetLastError());
     c->topoF = F;
     c->topoV = V;
@@ -401,6 +404,10 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         CKR(ensure(c, c->pairR, sizeof(int) * c->pairCap));
         CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 2, c->st));
         CK(cudaMemsetAsync(c->deg.p, 0, sizeof(int) * (size_t)(F + 2), c->st));
+        CKR(ensure(c, c->vactive, (size_t)V + 16));
+        CKR(ensure(c, c->eactive, (size_t)E + 16));
+        CK(cudaMemsetAsync(c->vactive.p, 0, (size_t)V + 16, c->st));
+        CK(cudaMemsetAsync(c->eactive.p, 0, (size_t)E + 16, c->st));
         if (sharded)
         {
             if (attempt == 0)
@@ -418,7 +425,7 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
             ccdk_traverse(c->st, kind, F, 0, F, nullptr, false, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p, c->cand.p,
                           c->candCap, ctr + C_NCAND);
         ccdk_exact_pairs(c->st, kind, !sharded, ctr + C_NCAND, c->candCap, c->cand.p, sortedFace, d_faces, P<double>(c->boxes), P<int>(c->pairL),
-                         P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg));
+                         P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg), P<int>(c->faceEdge), P<unsigned char>(c->vactive), P<unsigned char>(c->eactive));
         c->launches += 2;
         CKR(sync_counters(c));
         unsigned long long ncand = c->h_counters[C_NCAND], npairs = c->h_counters[C_NPAIRS];
@@ -463,9 +470,9 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     CKR(ensure(c, c->eeOffsets, sizeof(long long) * (size_t)(E + 2)));
     cudaEventRecord(c->sev[ST_EMIT_COUNT], c->st);
     ccdk_vf_emit(c->st, true, v0, v1, d_faces, P<long long>(c->starOff), P<int>(c->star), P<long long>(c->adjOff), P<int>(c->adj),
-                 P<int>(c->faceRank), P<int>(c->rankFace), d_fixed, P<int>(c->vfCounts), nullptr, nullptr);
+                 P<int>(c->faceRank), P<int>(c->rankFace), d_fixed, P<int>(c->vfCounts), nullptr, nullptr, P<unsigned char>(c->vactive));
     ccdk_ee_emit(c->st, true, e0, e1, P<int>(c->edgeStart), P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceEdge),
-                 c->edgeVerts.p, d_fixed, P<int>(c->eeCounts), nullptr, nullptr);
+                 c->edgeVerts.p, d_fixed, P<int>(c->eeCounts), nullptr, nullptr, P<unsigned char>(c->eactive));
     // the scan reads one element past the range (never added to anything it outputs)
     ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, v1 - v0 + 1, P<int>(c->vfCounts) + v0, P<long long>(c->vfOffsets) + v0);
     ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, e1 - e0 + 1, P<int>(c->eeCounts) + e0, P<long long>(c->eeOffsets) + e0);
@@ -475,8 +482,8 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     {
         CKR(ensure(c, c->hist, sizeof(unsigned long long) * 2 * CCD_SHARD_BUCKETS));
         CK(cudaMemsetAsync(c->hist.p, 0, sizeof(unsigned long long) * 2 * CCD_SHARD_BUCKETS, c->st));
-        ccdk_shard_hist(c->st, P<int>(c->vfCounts), v0, v1, V, CCD_SHARD_BUCKETS, P<unsigned long long>(c->hist));
-        ccdk_shard_hist(c->st, P<int>(c->eeCounts), e0, e1, E > 0 ? E : 1, CCD_SHARD_BUCKETS, P<unsigned long long>(c->hist) + CCD_SHARD_BUCKETS);
+        ccdk_shard_hist(c->st, P<int>(c->vfCounts), nullptr, v0, v1, V, CCD_SHARD_BUCKETS, P<unsigned long long>(c->hist));
+        ccdk_shard_hist(c->st, P<int>(c->eeCounts), c->edgeVerts.p, e0, e1, V, CCD_SHARD_BUCKETS, P<unsigned long long>(c->hist) + CCD_SHARD_BUCKETS);
         CK(cudaMemcpyAsync(c->h_hist, c->hist.p, sizeof(unsigned long long) * 2 * CCD_SHARD_BUCKETS, cudaMemcpyDeviceToHost, c->st));
         c->histV = V;
         c->histE = E;
@@ -493,9 +500,9 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     CKR(ensure(c, c->eeOut, sizeof(int) * 4 * (size_t)(res->nee + 1)));
     cudaEventRecord(c->sev[ST_EMIT_WRITE], c->st);
     ccdk_vf_emit(c->st, false, v0, v1, d_faces, P<long long>(c->starOff), P<int>(c->star), P<long long>(c->adjOff), P<int>(c->adj),
-                 P<int>(c->faceRank), P<int>(c->rankFace), d_fixed, nullptr, P<long long>(c->vfOffsets), P<int>(c->vfOut));
+                 P<int>(c->faceRank), P<int>(c->rankFace), d_fixed, nullptr, P<long long>(c->vfOffsets), P<int>(c->vfOut), P<unsigned char>(c->vactive));
     ccdk_ee_emit(c->st, false, e0, e1, P<int>(c->edgeStart), P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceEdge),
-                 c->edgeVerts.p, d_fixed, nullptr, P<long long>(c->eeOffsets), P<int>(c->eeOut));
+                 c->edgeVerts.p, d_fixed, nullptr, P<long long>(c->eeOffsets), P<int>(c->eeOut), P<unsigned char>(c->eactive));
     c->launches += 2;
     CK(cudaGetLastError());
     return CCD_OK;
@@ -840,6 +847,26 @@ int ccd_set_shard_partition(ccd_context *c, int world, const int32_t *vbounds, c
             return CCD_ERR_ARG;
     c->partV.assign(vbounds, vbounds + world + 1);
     c->partE.assign(ebounds, ebounds + world + 1);
+    return CCD_OK;
+}
+
+int ccd_shard_edge_bounds(ccd_context *c, int world, const int32_t *vbounds, int32_t *ebounds)
+{
+    if (!c || world < 1 || !vbounds || !ebounds)
+        return CCD_ERR_ARG;
+    if (c->topoV < 0 || !c->vertEdgeStart.p)
+    {
+        c->err = "ccd_shard_edge_bounds: no mesh topology on this context yet (run a step first)";
+        return CCD_ERR_ARG;
+    }
+    CK(cudaSetDevice(c->device));
+    for (int r = 0; r <= world; r++)
+    {
+        if (vbounds[r] < 0 || vbounds[r] > c->topoV)
+            return CCD_ERR_ARG;
+        CK(cudaMemcpyAsync(&ebounds[r], P<int>(c->vertEdgeStart) + vbounds[r], sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    }
+    CK(cudaStreamSynchronize(c->st));
     return CCD_OK;
 }
 

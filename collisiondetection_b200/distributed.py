@@ -12,6 +12,11 @@ import torch
 import torch.distributed as dist
 
 
+# cost of owning a vertex (box tests and LBVH traversal for the ~2 faces around it, both directions) in units of the
+# cost of one stencil (emission + narrowphase); measured on B200 at the 4M-triangle cloth: ~3.5 ns vs ~0.9 ns
+VERTEX_WEIGHT = 4.0
+
+
 def shard_range(n, rank, world):
     """Contiguous range [begin, end) of rank `rank` over n equally weighted items."""
     return (n * rank) // world, (n * (rank + 1)) // world
@@ -93,7 +98,11 @@ def exchange_step(ctx, earliest_toi, n_hits, n_stencils, device="cpu", group=Non
     dist.all_gather_into_tensor(recv, send, group=group)
     allr = recv.cpu().numpy().reshape(world, -1)
     if rebalance:
-        ctx.set_shard_partition(balanced_bounds(allr[:, 3:3 + nb].sum(axis=0), nv, world),
-                                balanced_bounds(allr[:, 3 + nb:].sum(axis=0), ne, world))
+        # cost model of a vertex range: its stencils (emission + narrowphase) plus, per vertex, the traversal of the faces
+        # around it; both profiles are over vertex ids, and the edge range follows the vertex range (shard_edge_bounds)
+        items = np.diff([-(-(b * nv) // nb) for b in range(nb + 1)]).astype(np.float64)
+        load = allr[:, 3:3 + nb].sum(axis=0) + allr[:, 3 + nb:].sum(axis=0) + VERTEX_WEIGHT * items
+        vb = balanced_bounds(load, nv, world)
+        ctx.set_shard_partition(vb, ctx.shard_edge_bounds(vb))
     toi = allr[:, 0].min()
     return (float(toi) if np.isfinite(toi) else float("inf")), int(allr[:, 1].sum()), int(allr[:, 2].sum())

@@ -134,9 +134,14 @@ int ccd_step_device(ccd_context *ctx, int kind, int V, int F, const int32_t *d_f
  * vbounds[0] = ebounds[0] = 0, vbounds[world] = V, ebounds[world] = number of unique edges (returned by
  * ccd_shard_histogram).  Ignored (equal split) when they do not match the mesh of a later call. */
 int ccd_set_shard_partition(ccd_context *ctx, int world, const int32_t *vbounds, const int32_t *ebounds);
-/* Load profile of the last sharded step on this context: stencils owned by this rank per bucket, CCD_SHARD_BUCKETS
- * equal-width buckets over the vertex ids (vf_hist) and over the unique-edge ids (ee_hist); item i falls in bucket
- * i * CCD_SHARD_BUCKETS / n.  Summing over ranks gives the whole step's profile.  n_vertices / n_edges: the id ranges. */
+/* Edge bounds that go with vertex bounds: ebounds[r] = first unique edge (ids are in lexicographic (min,max) order)
+ * whose smaller vertex is >= vbounds[r].  With these a rank's edges only touch faces of its own vertices, so the
+ * set of faces it has to traverse for is as small as it can be. */
+int ccd_shard_edge_bounds(ccd_context *ctx, int world, const int32_t *vbounds, int32_t *ebounds);
+/* Load profile of the last sharded step on this context: stencils owned by this rank per bucket of vertex ids,
+ * CCD_SHARD_BUCKETS equal-width buckets (vertex v falls in bucket v * CCD_SHARD_BUCKETS / n_vertices): vf_hist counts
+ * VF stencils by their vertex, ee_hist EE stencils by the smaller vertex of their first edge.  Summing over ranks
+ * gives the whole step's profile.  n_vertices / n_edges: the id ranges. */
 #define CCD_SHARD_BUCKETS 1024
 int ccd_shard_histogram(ccd_context *ctx, int64_t *vf_hist, int64_t *ee_hist, int32_t *n_vertices, int32_t *n_edges);
 

@@ -264,7 +264,8 @@ def test_cloth_sharded_union_equals_whole(ctx):
         hv += a
         he += b
     assert hv.sum() == len(whole[3]) and he.sum() == len(whole[4]) and nv == V
-    ctx.set_shard_partition(balanced_bounds(hv, nv, world), balanced_bounds(he, ne, world))
+    vb = balanced_bounds(hv + he, nv, world)
+    ctx.set_shard_partition(vb, ctx.shard_edge_bounds(vb))
     parts = [run(r, world) for r in range(world)]
     assert np.array_equal(np.concatenate([p[3] for p in parts]), whole[3])
     assert np.array_equal(np.concatenate([p[4] for p in parts]), whole[4])
