@@ -53,14 +53,14 @@ struct ccd_context
     size_t candCap = 0, pairCap = 0, taskCapVf = 0, taskCapEe = 0;
     // sharding: ownership ranges chosen by the caller (ccd_set_shard_partition), load profile of the last sharded step
     std::vector<int> partV, partE;
-    DBuf qlist, hist, vactive, eactive, vertEdgeStart;
+    DBuf qlist, hist, vactive, eactive, vertEdgeStart, alistV, alistE, kstartV, kstartE, keysV, keysE;
     unsigned long long *h_hist = nullptr;      // pinned, 2 * CCD_SHARD_BUCKETS
     int histV = 0, histE = 0;
     bool hist_valid = false;
 };
 
 // device counters layout (unsigned long long each)
-enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NQUERY = 7, C_NP_VF = 16 /* CCD_NP_COUNTERS counters per run: work-list entries, records, ... (narrowphase.cu K_*) */, C_NP_EE = 16 + CCD_NP_COUNTERS, C_TOTAL = 16 + 2 * CCD_NP_COUNTERS };
+enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NQUERY = 7, C_NA_VF = 8, C_NA_EE = 9, C_KCUR_VF = 10, C_KCUR_EE = 11, C_NP_VF = 16 /* CCD_NP_COUNTERS counters per run: work-list entries, records, ... (narrowphase.cu K_*) */, C_NP_EE = 16 + CCD_NP_COUNTERS, C_TOTAL = 16 + 2 * CCD_NP_COUNTERS };
 enum { C_NWORK_VF = C_NP_VF, C_NTASK_VF = C_NP_VF + 1, C_NWORK_EE = C_NP_EE, C_NTASK_EE = C_NP_EE + 1 };
 
 #define CK(call)                                                                                      \
@@ -159,13 +159,16 @@ void ccdk_topology_faceranks(cudaStream_t st, int F, const int *faces, unsigned 
                              int *faceRank, int *rankFace);
 void ccdk_topology_star(cudaStream_t st, int V, int F, const int *faces, int *vdeg, long long *starOff, int *cursor, int *star, void *temp,
                         size_t temp_bytes);
-void ccdk_vf_emit(cudaStream_t st, bool count, int vbegin, int vend, const int *faces, const long long *starOff, const int *star,
-                  const long long *adjOff, const int *adj, const int *faceRank, const int *rankFace, const unsigned char *fixed,
-                  int *counts, const long long *offsets, int *out, const unsigned char *active);
-void ccdk_ee_emit(cudaStream_t st, bool count, int ebegin, int eend, const int *edgeStart, const int *heFace, const long long *adjOff,
-                  const int *adj, const int *faceEdge, const void *edgeVerts, const unsigned char *fixed, int *counts,
-                  const long long *offsets, int *out, const unsigned char *active);
 void ccdk_hash_ints(cudaStream_t st, long long n, const int *d, unsigned long long *out);
+void ccdk_active_list(cudaStream_t st, int begin, int end, const unsigned char *active, int *counts, int *alist, unsigned long long *na);
+void ccdk_emit_sort(cudaStream_t st, bool is_vf, const int *alist, const unsigned long long *na, const int *faces, const long long *starOff,
+                    const int *star, const int *edgeStart, const int *heFace, const long long *adjOff, const int *adj, const int *faceRank,
+                    const int *rankFace, const int *faceEdge, const void *edgeVerts, const unsigned char *fixed, int *counts, long long *kstart,
+                    int *keys_out, unsigned long long *kcursor);
+void ccdk_emit_write(cudaStream_t st, bool is_vf, const int *alist, const unsigned long long *na, int begin, const int *faces, const long long *starOff,
+                     const int *star, const int *edgeStart, const int *heFace, const long long *adjOff, const int *adj, const int *faceRank,
+                     const int *rankFace, const int *faceEdge, const void *edgeVerts, const unsigned char *fixed, const int *counts,
+                     const long long *kstart, const int *keys_in, const long long *offsets, int *out);
 void ccdk_shard_bounds(cudaStream_t st, const long long *offsets, int n, int rank, int world, int *out);
 void ccdk_dist_batch(cudaStream_t st, int which, long long n, const double *pts, const double *eta, double *vec, double *bary, unsigned char *flag);
 void ccdk_vertex_min_dist2(cudaStream_t st, int V, int F, const double *verts, const int *faces, unsigned long long *out_bits);
@@ -226,7 +229,7 @@ void ccd_destroy(ccd_context *c)
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->shardBounds, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->work2Vf, &c->work2Ee, &c->work2TaskVf, &c->work2TaskEe, &c->work2SubVf, &c->work2SubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->qpack, &c->qlist, &c->hist, &c->vactive, &c->eactive, &c->vertEdgeStart, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->work2Vf, &c->work2Ee, &c->work2TaskVf, &c->work2TaskEe, &c->work2SubVf, &c->work2SubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->qpack, &c->qlist, &c->hist, &c->vactive, &c->eactive, &c->vertEdgeStart, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
     for (DBuf *b : all)
         if (b->p)
             cudaFree(b->p);
@@ -469,10 +472,26 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     CKR(ensure(c, c->eeCounts, sizeof(int) * (size_t)(E + 2)));
     CKR(ensure(c, c->eeOffsets, sizeof(long long) * (size_t)(E + 2)));
     cudaEventRecord(c->sev[ST_EMIT_COUNT], c->st);
-    ccdk_vf_emit(c->st, true, v0, v1, d_faces, P<long long>(c->starOff), P<int>(c->star), P<long long>(c->adjOff), P<int>(c->adj),
-                 P<int>(c->faceRank), P<int>(c->rankFace), d_fixed, P<int>(c->vfCounts), nullptr, nullptr, P<unsigned char>(c->vactive));
-    ccdk_ee_emit(c->st, true, e0, e1, P<int>(c->edgeStart), P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceEdge),
-                 c->edgeVerts.p, d_fixed, P<int>(c->eeCounts), nullptr, nullptr, P<unsigned char>(c->eactive));
+    {
+        // warp-cooperative emission (broadphase.cu section 6b): active items -> unique sorted keys + counts
+        const size_t ordered = (size_t)res->npairs * (sharded ? 1 : 2);      // (face, neighbour) entries in the adjacency lists
+        CKR(ensure(c, c->alistV, sizeof(int) * (size_t)(v1 - v0 + 32)));
+        CKR(ensure(c, c->alistE, sizeof(int) * (size_t)(e1 - e0 + 32)));
+        CKR(ensure(c, c->kstartV, sizeof(long long) * (size_t)(V + 2)));
+        CKR(ensure(c, c->kstartE, sizeof(long long) * (size_t)(E + 2)));
+        CKR(ensure(c, c->keysV, sizeof(int) * (3 * ordered + 64)));      // every adjacency entry is seen by the face's 3 vertices
+        CKR(ensure(c, c->keysE, sizeof(int) * (9 * ordered + 64)));      // ... and by its 3 edges, each against the neighbour's 3 edges
+        CK(cudaMemsetAsync(ctr + C_NA_VF, 0, sizeof(unsigned long long) * 4, c->st));
+        ccdk_active_list(c->st, v0, v1, P<unsigned char>(c->vactive), P<int>(c->vfCounts), P<int>(c->alistV), ctr + C_NA_VF);
+        ccdk_active_list(c->st, e0, e1, P<unsigned char>(c->eactive), P<int>(c->eeCounts), P<int>(c->alistE), ctr + C_NA_EE);
+        ccdk_emit_sort(c->st, true, P<int>(c->alistV), ctr + C_NA_VF, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
+                       P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceRank), P<int>(c->rankFace), P<int>(c->faceEdge),
+                       c->edgeVerts.p, d_fixed, P<int>(c->vfCounts), P<long long>(c->kstartV), P<int>(c->keysV), ctr + C_KCUR_VF);
+        ccdk_emit_sort(c->st, false, P<int>(c->alistE), ctr + C_NA_EE, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
+                       P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceRank), P<int>(c->rankFace), P<int>(c->faceEdge),
+                       c->edgeVerts.p, d_fixed, P<int>(c->eeCounts), P<long long>(c->kstartE), P<int>(c->keysE), ctr + C_KCUR_EE);
+        c->launches += 2;
+    }
     // the scan reads one element past the range (never added to anything it outputs)
     ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, v1 - v0 + 1, P<int>(c->vfCounts) + v0, P<long long>(c->vfOffsets) + v0);
     ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, e1 - e0 + 1, P<int>(c->eeCounts) + e0, P<long long>(c->eeOffsets) + e0);
@@ -499,10 +518,12 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     CKR(ensure(c, c->vfOut, sizeof(int) * 4 * (size_t)(res->nvf + 1)));
     CKR(ensure(c, c->eeOut, sizeof(int) * 4 * (size_t)(res->nee + 1)));
     cudaEventRecord(c->sev[ST_EMIT_WRITE], c->st);
-    ccdk_vf_emit(c->st, false, v0, v1, d_faces, P<long long>(c->starOff), P<int>(c->star), P<long long>(c->adjOff), P<int>(c->adj),
-                 P<int>(c->faceRank), P<int>(c->rankFace), d_fixed, nullptr, P<long long>(c->vfOffsets), P<int>(c->vfOut), P<unsigned char>(c->vactive));
-    ccdk_ee_emit(c->st, false, e0, e1, P<int>(c->edgeStart), P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceEdge),
-                 c->edgeVerts.p, d_fixed, nullptr, P<long long>(c->eeOffsets), P<int>(c->eeOut), P<unsigned char>(c->eactive));
+    ccdk_emit_write(c->st, true, P<int>(c->alistV), ctr + C_NA_VF, v0, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
+                    P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceRank), P<int>(c->rankFace), P<int>(c->faceEdge),
+                    c->edgeVerts.p, d_fixed, P<int>(c->vfCounts), P<long long>(c->kstartV), P<int>(c->keysV), P<long long>(c->vfOffsets), P<int>(c->vfOut));
+    ccdk_emit_write(c->st, false, P<int>(c->alistE), ctr + C_NA_EE, e0, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
+                    P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceRank), P<int>(c->rankFace), P<int>(c->faceEdge),
+                    c->edgeVerts.p, d_fixed, P<int>(c->eeCounts), P<long long>(c->kstartE), P<int>(c->keysE), P<long long>(c->eeOffsets), P<int>(c->eeOut));
     c->launches += 2;
     CK(cudaGetLastError());
     return CCD_OK;
