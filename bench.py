@@ -189,7 +189,7 @@ def main():
         # the path's only exchange: earliest TOI, hit / stencil counts and the load profile that balances the next
         # step's ownership ranges — one small all-gather
         summary["toi"], summary["hits"], summary["stencils"] = D.exchange_step(
-            ctx, r.earliest_toi, r.n_vf_hits + r.n_ee_hits, r.n_vf_candidates + r.n_ee_candidates, device="cuda")
+            ctx, r.earliest_toi, r.n_vf_hits + r.n_ee_hits, r.n_vf_candidates, r.n_ee_candidates, device="cuda")
         return r
 
     def barrier():
@@ -292,7 +292,7 @@ def main():
                gpu_launches=int(launches) * args.steps,
                roofline=roof,
                stages_ms=stages, stages_ms_max_over_ranks={k: float(st_all[:, i].max()) for i, k in enumerate(stage_names)},
-               stencils_per_rank=[int(x) for x in st_all[:, -1]], kernel_ms_per_step=kern_ms / args.steps,
+               stencils_per_rank=[int(x) for x in st_all[:, -1]], stages_ms_per_rank={k: [round(float(x), 3) for x in st_all[:, i]] for i, k in enumerate(stage_names)}, kernel_ms_per_step=kern_ms / args.steps,
                counts=dict(vertices=V, faces=F, stencils=n_stencils, vf_rank0=int(nvf), ee_rank0=int(nee), hits=n_hits,
                            face_pairs_rank0=int(r.n_face_pairs), tree_candidates_rank0=int(r.n_tree_candidates), vf_deferred_rank0=int(r.n_vf_deferred), ee_deferred_rank0=int(r.n_ee_deferred),
                            stencils_per_face=n_stencils / float(F)),

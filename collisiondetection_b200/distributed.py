@@ -12,8 +12,8 @@ import torch
 import torch.distributed as dist
 
 
-# cost of owning a vertex (box tests and LBVH traversal for the ~2 faces around it, both directions) in units of the
-# cost of one stencil (emission + narrowphase); measured on B200 at the 4M-triangle cloth: ~3.5 ns vs ~0.9 ns
+# fallback cost model when no stage times are available: cost of owning a vertex (box tests and LBVH traversal for the
+# ~2 faces around it) in units of the cost of one stencil (emission + narrowphase)
 VERTEX_WEIGHT = 4.0
 
 
@@ -78,31 +78,50 @@ def balanced_bounds(hist, n_items, world):
     return bounds.astype(np.int32)
 
 
-def exchange_step(ctx, earliest_toi, n_hits, n_stencils, device="cpu", group=None, rebalance=True):
-    """The step's only exchange: ONE all-gather of [toi, hits, stencils, vf load profile, ee load profile] per rank.
+def exchange_step(ctx, earliest_toi, n_hits, n_vf, n_ee=0, device="cpu", group=None, rebalance=True, stage_ms=None):
+    """The step's only exchange: ONE all-gather of a small vector per rank — earliest TOI, hit / stencil counts, the rank's
+    measured stage times and its load profile (stencils per bucket of vertex ids).
 
     Returns the global (earliest TOI, hits, stencils).  With `rebalance`, every rank also installs the ownership ranges
-    balanced on the summed load profile for its next step (ccd_set_shard_partition)."""
+    for its next step (ccd_set_shard_partition), balanced on the summed profile under a cost model whose three
+    coefficients are re-measured every step from the gathered times: cost of a rank = a * vertices owned (box tests and
+    LBVH traversal around them) + b * VF stencils + c * EE stencils (emission + narrowphase).
+    `stage_ms`: this rank's ccd_stage_times() of the step (taken from ctx when omitted)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return float(earliest_toi), int(n_hits), int(n_stencils)
-    world = dist.get_world_size(group)
+        return float(earliest_toi), int(n_hits), int(n_vf + n_ee)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
     vf_hist, ee_hist, nv, ne = ctx.shard_histogram()
     nb = len(vf_hist)
-    mine = np.empty(3 + 2 * nb, dtype=np.float64)      # counts up to 2^53 are exact in float64
-    mine[0] = earliest_toi if np.isfinite(earliest_toi) else np.inf
-    mine[1], mine[2] = float(n_hits), float(n_stencils)
-    mine[3:3 + nb] = vf_hist
-    mine[3 + nb:] = ee_hist
+    if stage_ms is None:
+        stage_ms = ctx.stage_times()
+    t_item = stage_ms.get("traverse_exact", 0.0) + stage_ms.get("adjacency", 0.0)
+    t_emit = stage_ms.get("emit_count", 0.0) + stage_ms.get("emit_write", 0.0)
+    part = getattr(ctx, "shard_partition", None)
+    owned = float(part[0][rank + 1] - part[0][rank]) if part is not None and len(part[0]) == world + 1 else float(nv) / world
+    head = [earliest_toi if np.isfinite(earliest_toi) else np.inf, float(n_hits), float(n_vf), float(n_ee), owned, t_item, t_emit,
+            stage_ms.get("np_vf", 0.0), stage_ms.get("np_ee", 0.0)]
+    nh = len(head)
+    mine = np.empty(nh + 2 * nb, dtype=np.float64)      # counts up to 2^53 are exact in float64
+    mine[:nh] = head
+    mine[nh:nh + nb] = vf_hist
+    mine[nh + nb:] = ee_hist
     send = torch.from_numpy(mine).to(device)
     recv = torch.empty(world * len(mine), dtype=torch.float64, device=device)
     dist.all_gather_into_tensor(recv, send, group=group)
     allr = recv.cpu().numpy().reshape(world, -1)
     if rebalance:
-        # cost model of a vertex range: its stencils (emission + narrowphase) plus, per vertex, the traversal of the faces
-        # around it; both profiles are over vertex ids, and the edge range follows the vertex range (shard_edge_bounds)
-        items = np.diff([-(-(b * nv) // nb) for b in range(nb + 1)]).astype(np.float64)
-        load = allr[:, 3:3 + nb].sum(axis=0) + allr[:, 3 + nb:].sum(axis=0) + VERTEX_WEIGHT * items
+        tot_vf, tot_ee, tot_owned = allr[:, 2].sum(), allr[:, 3].sum(), allr[:, 4].sum()
+        emit_per_stencil = allr[:, 6].sum() / max(tot_vf + tot_ee, 1.0)
+        a = allr[:, 5].sum() / max(tot_owned, 1.0)
+        b = allr[:, 7].sum() / max(tot_vf, 1.0) + emit_per_stencil
+        c = allr[:, 8].sum() / max(tot_ee, 1.0) + emit_per_stencil
+        if not (a > 0 and b > 0 and c > 0):      # no timings (CPU tests): the fixed model
+            a, b, c = VERTEX_WEIGHT, 1.0, 1.0
+        items = np.diff([-(-(k * nv) // nb) for k in range(nb + 1)]).astype(np.float64)
+        load = b * allr[:, nh:nh + nb].sum(axis=0) + c * allr[:, nh + nb:].sum(axis=0) + a * items
         vb = balanced_bounds(load, nv, world)
-        ctx.set_shard_partition(vb, ctx.shard_edge_bounds(vb))
+        eb = ctx.shard_edge_bounds(vb)
+        ctx.set_shard_partition(vb, eb)
+        ctx.shard_partition = (list(map(int, vb)), list(map(int, eb)))
     toi = allr[:, 0].min()
-    return (float(toi) if np.isfinite(toi) else float("inf")), int(allr[:, 1].sum()), int(allr[:, 2].sum())
+    return (float(toi) if np.isfinite(toi) else float("inf")), int(allr[:, 1].sum()), int(allr[:, 2].sum() + allr[:, 3].sum())

@@ -122,7 +122,7 @@ def _exchange_worker(rank, world, port_no, results):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from collisiondetection_b200 import distributed as D
     ctx = _FakeCtx(rank, world, 100000, 300000)
-    toi, nh, ns = D.exchange_step(ctx, 0.25 + 0.1 * rank if rank else float("inf"), 10 + rank, 1000 * (rank + 1))
+    toi, nh, ns = D.exchange_step(ctx, 0.25 + 0.1 * rank if rank else float("inf"), 10 + rank, 600 * (rank + 1), 400 * (rank + 1), stage_ms={})
     results[rank] = (toi, nh, ns, ctx.partition)
     dist.destroy_process_group()
 
