@@ -556,10 +556,12 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         CKR(ensure(c, c->p1Sq, sizeof(int) * 4 * nmax));
         CKR(ensure(c, c->p1Xq, sizeof(int) * 10 * nmax));
     }
+    const float *d_vbox = nullptr;
     if (d_q0)
     {
-        CKR(ensure(c, c->qpack, sizeof(double) * 8 * ((size_t)V + 1)));
-        ccdk_pack_positions(c->st, V, d_q0, d_q1, vstride, P<double>(c->qpack));
+        CKR(ensure(c, c->qpack, (sizeof(double) * 8 + sizeof(float) * 8) * ((size_t)V + 1)));
+        d_vbox = reinterpret_cast<const float *>(P<double>(c->qpack) + 8 * ((size_t)V + 1));
+        ccdk_pack_positions(c->st, V, d_q0, d_q1, vstride, P<double>(c->qpack), const_cast<float *>(d_vbox));
         d_q0 = P<double>(c->qpack);
         d_q1 = d_q0 + 4;
         vstride = 8;
@@ -579,12 +581,12 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         memcpy(c->h_counters + 8, init, sizeof(init));
         CK(cudaMemcpyAsync(ctr + C_EARLY_VF, c->h_counters + 8, sizeof(init), cudaMemcpyHostToDevice, c->st));
         cudaEventRecord(c->sev[ST_NP_VF], c->st);
-        nl += ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
+        nl += ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
                                P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF, P<int>(c->workVf),
                                P<int>(c->workTaskVf), P<int>(c->workSubVf), P<double>(c->tasksVf), P<int>(c->tlistVf), c->taskCapVf, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
                                P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_VF);
         cudaEventRecord(c->sev[ST_NP_EE], c->st);
-        nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all, d_q0, d_q1, vstride, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
+        nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
                                P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE, P<int>(c->workEe),
                                P<int>(c->workTaskEe), P<int>(c->workSubEe), P<double>(c->tasksEe), P<int>(c->tlistEe), c->taskCapEe, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
                                P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_EE);

@@ -108,6 +108,7 @@ struct NpArgs
     double eta_all;
     const double *q0, *q1;
     int vstride;
+    const float *vbox;          // single step: per-vertex float swept boxes {lo.xyz, hi.xyz, -, -} (pack_positions_kernel)
     const long long *hoff;
     const double *htime, *hpos;
     unsigned char *hit;
@@ -153,7 +154,7 @@ template <bool IS_VF> __device__ __forceinline__ void load_single(const NpArgs &
 }
 
 __global__ void __launch_bounds__(256) pack_positions_kernel(int V, const double *__restrict__ q0, const double *__restrict__ q1, int vstride,
-                                                             double *__restrict__ qpack)
+                                                             double *__restrict__ qpack, float *__restrict__ vbox)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
@@ -163,6 +164,10 @@ __global__ void __launch_bounds__(256) pack_positions_kernel(int V, const double
     o[1] = make_double2(a[2], 0.0);
     o[2] = make_double2(b[0], b[1]);
     o[3] = make_double2(b[2], 0.0);
+    const BoxF bx = swept_box_f(mk(a[0], a[1], a[2]), mk(b[0], b[1], b[2]));
+    float4 *f = reinterpret_cast<float4 *>(vbox + 8ll * v);
+    f[0] = make_float4(bx.lo[0], bx.lo[1], bx.lo[2], bx.hi[0]);
+    f[1] = make_float4(bx.hi[1], bx.hi[2], 0.f, 0.f);
 }
 
 __device__ __forceinline__ void store_result(const NpArgs &A, long long i, int stage, double toi)
@@ -253,6 +258,17 @@ __device__ __forceinline__ void store_record(double *dst, const double (&rec)[8]
     d[3] = make_double2(rec[6], rec[7]);
 }
 
+__device__ __forceinline__ BoxF ldbox(const float *vbox, int idx)
+{
+    const float4 *p = reinterpret_cast<const float4 *>(vbox + 8ll * idx);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    BoxF r;
+    r.lo[0] = a.x; r.lo[1] = a.y; r.lo[2] = a.z;
+    r.hi[0] = a.w; r.hi[1] = b.x; r.hi[2] = b.y;
+    return r;
+}
+
+// one thread per stencil, float swept boxes only (CullF): which sub-tests have to be evaluated at all
 template <bool IS_VF> __global__ void __launch_bounds__(256) np_cull_kernel(P1Args Q)
 {
     const NpArgs &A = Q.A;
@@ -261,28 +277,58 @@ template <bool IS_VF> __global__ void __launch_bounds__(256) np_cull_kernel(P1Ar
     unsigned todo = 0;
     if (i < A.n)
     {
-        StencilIn S;
-        load_single<IS_VF>(A, i, S);
-        Cull<IS_VF> c;
-        c.init(S.a, S.b, S.eta);
-        const bool far = c.stencil_apart();
-        if (IS_VF || !far) todo = 1u;
-        if (!far)
-        {
-            for (int sub = 1; sub <= NVE; sub++)
-                if (!c.ve_apart(sub)) todo |= 1u << sub;
-            for (int k = 0; k < NVV; k++)
-                if (!c.vv_apart(k)) todo |= 1u << (NVE + 1 + k);
-        }
+        const int4 s = reinterpret_cast<const int4 *>(A.stencils)[i];
+        CullF<IS_VF> c;
+        c.bx[0] = ldbox(A.vbox, s.x);
+        c.bx[1] = ldbox(A.vbox, s.y);
+        c.bx[2] = ldbox(A.vbox, s.z);
+        c.bx[3] = ldbox(A.vbox, s.w);
+        c.init(A.eta_arr ? A.eta_arr[i] : A.eta_all);
+        todo = c.todo();
         Q.status[i] = 0u;
     }
-    queue_push((todo & 1u) != 0, (int)i, Q.qprim, Q.ctr + K_NQ + 0);
+    // Queue appends with ONE atomic per block and queue: every warp of the grid appending to the same three counters
+    // with its own atomic (and waiting for the returned base) was what this kernel spent its time on.
+    __shared__ unsigned s_warp[3][8];
+    __shared__ unsigned long long s_base[3];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned ve_bits = (todo >> 1) & ((1u << NVE) - 1u), vv_bits = (todo >> (NVE + 1)) & ((1u << NVV) - 1u);
+    unsigned c[3] = {IS_VF ? 0u : (todo & 1u), (unsigned)__popc(ve_bits), (unsigned)__popc(vv_bits)};      // VF: every stencil runs its primitive
+    unsigned pre[3];
 #pragma unroll
-    for (int sub = 1; sub <= NVE; sub++)
-        queue_push((todo >> sub) & 1u, (int)i | (sub << 28), Q.qve, Q.ctr + K_NQ + 1);
+    for (int q = 0; q < 3; q++)
+    {
+        unsigned incl = c[q];
 #pragma unroll
-    for (int k = 0; k < NVV; k++)
-        queue_push((todo >> (NVE + 1 + k)) & 1u, (int)i | (k << 28), Q.qvv, Q.ctr + K_NQ + 2);
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        pre[q] = incl - c[q];
+        if (lane == 31) s_warp[q][wib] = incl;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3)
+    {
+        unsigned tot = 0;
+        for (int w = 0; w < 8; w++) { const unsigned x = s_warp[threadIdx.x][w]; s_warp[threadIdx.x][w] = tot; tot += x; }
+        s_base[threadIdx.x] = tot ? atomicAdd(Q.ctr + K_NQ + threadIdx.x, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (c[0]) Q.qprim[s_base[0] + s_warp[0][wib] + pre[0]] = (int)i;
+    {
+        unsigned long long o = s_base[1] + s_warp[1][wib] + pre[1];
+#pragma unroll
+        for (int sub = 1; sub <= NVE; sub++)
+            if ((todo >> sub) & 1u) Q.qve[o++] = (int)i | (sub << 28);
+    }
+    {
+        unsigned long long o = s_base[2] + s_warp[2][wib] + pre[2];
+#pragma unroll
+        for (int k = 0; k < NVV; k++)
+            if ((todo >> (NVE + 1 + k)) & 1u) Q.qvv[o++] = (int)i | (k << 28);
+    }
 }
 
 template <bool IS_VF, int S> __global__ void __launch_bounds__(128, NP_MINB) np_stage_kernel(P1Args Q)
@@ -291,7 +337,7 @@ template <bool IS_VF, int S> __global__ void __launch_bounds__(128, NP_MINB) np_
     constexpr int NST = Prim<IS_VF>::NST;
     constexpr bool LAST = (S == NST - 1);
     constexpr int KOWN = Prim<IS_VF>::poly(S);
-    const unsigned long long n = (S == 0) ? Q.ctr[K_NQ] : Q.ctr[K_NSQ + S - 1];
+    const unsigned long long n = (S == 0) ? (IS_VF ? (unsigned long long)A.n : Q.ctr[K_NQ]) : Q.ctr[K_NSQ + S - 1];
     const unsigned long long nround = (n + 31ull) & ~31ull;
     const int2 *in = Q.sq[(S + 1) & 1];
     int2 *out = Q.sq[S & 1];
@@ -304,7 +350,7 @@ template <bool IS_VF, int S> __global__ void __launch_bounds__(128, NP_MINB) np_
         double rec[8];
         if (it < n)
         {
-            if (S == 0) i = Q.qprim[it];
+            if (S == 0) i = IS_VF ? (long long)it : (long long)Q.qprim[it];
             else { const int2 e = in[it]; i = e.x; state = (unsigned)e.y; }
             StencilIn St;
             load_single<IS_VF>(A, i, St);
@@ -889,6 +935,7 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
     np_cull_kernel<IS_VF><<<grid_for(n, 256), 256, 0, st>>>(Q);
     g_trace.mark(st, "cull");
     np_stage_kernel<IS_VF, 0><<<gq, B, 0, st>>>(Q);
+    g_trace.mark(st, "stage0");
     np_stage_kernel<IS_VF, 1><<<gq, B, 0, st>>>(Q);
     np_stage_kernel<IS_VF, 2><<<gq, B, 0, st>>>(Q);
     np_stage_kernel<IS_VF, 3><<<gq, B, 0, st>>>(Q);
@@ -947,7 +994,7 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
 // ctr[1] = records).  Returns the number of kernels launched.  If ctr[1] ends above task_cap the caller must grow the
 // record buffer and call again.
 int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, double eta_all,
-                     const double *q0, const double *q1, int vstride, const long long *hoff, const double *htime, const double *hpos,
+                     const double *q0, const double *q1, int vstride, const float *vbox, const long long *hoff, const double *htime, const double *hpos,
                      unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits,
                      unsigned long long *nhit, int *w_stencil, int *w_meta, int *w_base, double *tasks, int *tlists,
                      unsigned long long task_cap, unsigned *status, int *sbase, int *queues, int *sq, int *xq, unsigned long long *ctr)
@@ -955,7 +1002,7 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
     static_assert(K_COUNT <= CCD_NP_COUNTERS, "counter block too small");
     if (n <= 0) return 0;
     NpArgs A;
-    A.n = n; A.stencils = stencils; A.eta_arr = eta_arr; A.eta_all = eta_all; A.q0 = q0; A.q1 = q1; A.vstride = vstride;
+    A.n = n; A.stencils = stencils; A.eta_arr = eta_arr; A.eta_all = eta_all; A.q0 = q0; A.q1 = q1; A.vstride = vstride; A.vbox = vbox;
     A.hoff = hoff; A.htime = htime; A.hpos = hpos; A.hit = hit; A.toi = toi; A.stage = stage;
     A.earliest_bits = earliest_bits; A.nhit = nhit;
     A.w_stencil = w_stencil; A.w_meta = w_meta; A.w_base = w_base; A.nwork = ctr + K_NWORK;
@@ -977,9 +1024,9 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
     return is_vf ? launch_single_step<true>(st, Q, n, tlists) : launch_single_step<false>(st, Q, n, tlists);
 }
 
-void ccdk_pack_positions(cudaStream_t st, int V, const double *q0, const double *q1, int vstride, double *qpack)
+void ccdk_pack_positions(cudaStream_t st, int V, const double *q0, const double *q1, int vstride, double *qpack, float *vbox)
 {
-    if (V > 0) pack_positions_kernel<<<grid_for(V, 256), 256, 0, st>>>(V, q0, q1, vstride, qpack);
+    if (V > 0) pack_positions_kernel<<<grid_for(V, 256), 256, 0, st>>>(V, q0, q1, vstride, qpack, vbox);
 }
 
 void ccdk_prim_batch(cudaStream_t st, int kind, long long n, const double *pts, const double *eta, unsigned char *hit, double *t)

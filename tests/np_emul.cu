@@ -120,19 +120,11 @@ void run(long long n, const int *stencils, const double *q0, const double *q1, i
             b[k] = ldv(q1 + (long long)vstride * s[k]);
             v[k] = b[k] - a[k];
         }
-        // cull
-        Cull<IS_VF> c;
-        c.init(a, b, eta);
-        const bool far = c.stencil_apart();
-        unsigned todo = 0;
-        if (IS_VF || !far) todo = 1u;
-        if (!far)
-        {
-            for (int sub = 1; sub <= NVE; sub++)
-                if (!c.ve_apart(sub)) todo |= 1u << sub;
-            for (int k = 0; k < NVV; k++)
-                if (!c.vv_apart(k)) todo |= 1u << (NVE + 1 + k);
-        }
+        // cull (float swept boxes, as np_cull_kernel)
+        CullF<IS_VF> c;
+        for (int k = 0; k < 4; k++) c.bx[k] = swept_box_f(a[k], b[k]);
+        c.init(eta);
+        const unsigned todo = c.todo();
         // pass 1
         recs.clear();
         int code[NSUB], first[NSUB], cnt[NSUB];
