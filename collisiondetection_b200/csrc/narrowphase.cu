@@ -29,9 +29,6 @@
 #include "ccd_stages.cuh"
 #include <stdio.h>
 #include <stdlib.h>
-#include <cooperative_groups.h>
-#include <cooperative_groups/scan.h>
-namespace cg = cooperative_groups;
 
 namespace ccd {
 
@@ -78,26 +75,67 @@ struct Stitcher
     }
 };
 
-// ---- reductions -----------------------------------------------------------------------------
-// TOI >= 0, so the IEEE bit pattern orders like the value: min over unsigned 64-bit.  Warp-level only.
-__device__ __forceinline__ void reduce_warp(bool hit, double toi, unsigned long long *earliest_bits, unsigned long long *nhit)
+// ---- block-level aggregation --------------------------------------------------------------------------------
+// Appending to a global queue with one atomic per WARP (and waiting for the returned base) serialises the whole grid on
+// one L2 address: measured 1.97 ms of a 2.0 ms kernel.  These helpers spend ONE atomic per block.  They contain
+// __syncthreads(): every thread of the block must reach them, so the loops around them use block_rounded() trip counts.
+__device__ __forceinline__ unsigned long long block_rounded(unsigned long long n) { return (n + blockDim.x - 1) / blockDim.x * blockDim.x; }
+
+// reserve c (>= 0) consecutive slots of *counter for this thread; returns the index of its first slot
+__device__ __forceinline__ unsigned long long block_alloc(unsigned c, unsigned long long *counter)
 {
+    __shared__ unsigned s_w[32];
+    __shared__ unsigned long long s_b;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    unsigned incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_w[wib] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        unsigned tot = 0;
+        for (int w = 0; w < nw; w++) { const unsigned x = s_w[w]; s_w[w] = tot; tot += x; }
+        s_b = tot ? atomicAdd(counter, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    const unsigned long long r = s_b + s_w[wib] + (incl - c);
+    __syncthreads();
+    return r;
+}
+
+// earliest TOI / hit count of the block merged with one atomic pair
+__device__ __forceinline__ void reduce_block(bool hit, double toi, unsigned long long *earliest_bits, unsigned long long *nhit)
+{
+    __shared__ unsigned long long s_bits[32];
+    __shared__ unsigned s_cnt[32];
     unsigned long long bits = hit ? (unsigned long long)__double_as_longlong(toi) : 0xFFFFFFFFFFFFFFFFull;
     unsigned cnt = hit ? 1u : 0u;
-    const unsigned mask = __activemask();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
     {
-        unsigned long long ob = __shfl_xor_sync(mask, bits, o);
-        unsigned oc = __shfl_xor_sync(mask, cnt, o);
+        const unsigned long long ob = __shfl_xor_sync(0xffffffffu, bits, o);
+        const unsigned oc = __shfl_xor_sync(0xffffffffu, cnt, o);
         bits = ob < bits ? ob : bits;
         cnt += oc;
     }
-    if ((threadIdx.x & 31) == 0 && cnt)
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) { s_bits[wib] = bits; s_cnt[wib] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0)
     {
-        atomicMin(earliest_bits, bits);
-        atomicAdd(nhit, (unsigned long long)cnt);
+        for (int w = 1; w < nw; w++) { bits = s_bits[w] < bits ? s_bits[w] : bits; cnt += s_cnt[w]; }
+        if (cnt)
+        {
+            atomicMin(earliest_bits, bits);
+            atomicAdd(nhit, (unsigned long long)cnt);
+        }
     }
+    __syncthreads();
 }
 
 struct NpArgs
@@ -177,18 +215,6 @@ __device__ __forceinline__ void store_result(const NpArgs &A, long long i, int s
     if (A.stage) A.stage[i] = (unsigned char)stage;
 }
 
-// Reserve n consecutive task records; returns the index of the first.  Called from divergent code: the lanes that
-// happen to be here together share one atomic (coalesced group).
-__device__ __forceinline__ unsigned long long alloc_task_slots(const NpArgs &A, int n)
-{
-    cg::coalesced_group g = cg::coalesced_threads();
-    const int pre = cg::exclusive_scan(g, n);
-    unsigned long long base = 0;
-    if (g.thread_rank() == g.size() - 1) base = atomicAdd(A.ntask, (unsigned long long)(pre + n));
-    base = g.shfl(base, g.size() - 1);
-    return base + (unsigned long long)pre;
-}
-
 
 // ================================================================================================================
 // Single-step pipeline.  Every kernel does one kind of work for all its lanes; kernels are connected by queues in HBM
@@ -227,27 +253,6 @@ struct P1Args
     int *qgen;                   // stencils for the general routine
     unsigned long long *ctr;     // counters, K_* above
 };
-
-__device__ __forceinline__ void queue_push(bool want, int value, int *queue, unsigned long long *count)
-{
-    const unsigned m = __ballot_sync(0xffffffffu, want);
-    if (!m) return;
-    const int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (want) queue[base + __popc(m & ((1u << lane) - 1))] = value;
-}
-__device__ __forceinline__ void queue_push2(bool want, int2 value, int2 *queue, unsigned long long *count)
-{
-    const unsigned m = __ballot_sync(0xffffffffu, want);
-    if (!m) return;
-    const int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (want) queue[base + __popc(m & ((1u << lane) - 1))] = value;
-}
 
 __device__ __forceinline__ void store_record(double *dst, const double (&rec)[8])
 {
@@ -338,10 +343,9 @@ template <bool IS_VF, int S> __global__ void __launch_bounds__(128, NP_MINB) np_
     constexpr bool LAST = (S == NST - 1);
     constexpr int KOWN = Prim<IS_VF>::poly(S);
     const unsigned long long n = (S == 0) ? (IS_VF ? (unsigned long long)A.n : Q.ctr[K_NQ]) : Q.ctr[K_NSQ + S - 1];
-    const unsigned long long nround = (n + 31ull) & ~31ull;
+    const unsigned long long nround = block_rounded(n);
     const int2 *in = Q.sq[(S + 1) & 1];
     int2 *out = Q.sq[S & 1];
-    const int lane = threadIdx.x & 31;
     for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < nround; it += (unsigned long long)gridDim.x * blockDim.x)
     {
         bool alive = false, has_rec = false;
@@ -361,30 +365,18 @@ template <bool IS_VF, int S> __global__ void __launch_bounds__(128, NP_MINB) np_
             state = so;
         }
         if (!LAST)
-            queue_push2(alive, make_int2((int)i, (int)state), out, Q.ctr + K_NSQ + S);
+        {
+            const unsigned long long o = block_alloc(alive ? 1u : 0u, Q.ctr + K_NSQ + S);
+            if (alive) out[o] = make_int2((int)i, (int)state);
+        }
         else
         {
             const unsigned need = state & 0x1fu;
             const bool gen = alive && need == 0u, def = alive && need != 0u;
             if (gen) atomicOr(&Q.status[i], (unsigned)SC_GENERAL);
-            // records of the surviving stencils of this warp: one reservation
+            // records of the surviving stencils of this block: one reservation
             const int cnt = def ? __popc(need) : 0;
-            int pre = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
-            {
-                const int x = __shfl_up_sync(0xffffffffu, pre, o);
-                if (lane >= o) pre += x;
-            }
-            const int total = __shfl_sync(0xffffffffu, pre, 31);
-            pre -= cnt;
-            unsigned long long base = 0;
-            if (total)
-            {
-                if (lane == 0) base = atomicAdd(A.ntask, (unsigned long long)total);
-                base = __shfl_sync(0xffffffffu, base, 0);
-            }
-            const unsigned long long t0 = base + (unsigned long long)pre;
+            const unsigned long long t0 = block_alloc((unsigned)cnt, A.ntask);
             const bool fits = t0 + (unsigned long long)cnt <= A.task_cap && t0 + (unsigned long long)cnt < (1ull << 28);
             if (def)
             {
@@ -395,7 +387,11 @@ template <bool IS_VF, int S> __global__ void __launch_bounds__(128, NP_MINB) np_
 #pragma unroll
             for (int k = 0; k < 5; k++)
                 if (k != KOWN && k < NST)
-                    queue_push2(def && fits && ((need >> k) & 1u), make_int2((int)i, (int)(t0 + __popc(need & ((1u << k) - 1u)))), Q.xq[k], Q.ctr + K_NXQ + k);
+                {
+                    const bool want = def && fits && ((need >> k) & 1u);
+                    const unsigned long long o = block_alloc(want ? 1u : 0u, Q.ctr + K_NXQ + k);
+                    if (want) Q.xq[k][o] = make_int2((int)i, (int)(t0 + __popc(need & ((1u << k) - 1u))));
+                }
         }
     }
 }
@@ -421,30 +417,33 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_ve_kern
 {
     const NpArgs &A = Q.A;
     const unsigned long long n = Q.ctr[K_NQ + 1];
-    for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < n; it += (unsigned long long)gridDim.x * blockDim.x)
+    const unsigned long long nround = block_rounded(n);
+    for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < nround; it += (unsigned long long)gridDim.x * blockDim.x)
     {
-        const int item = Q.qve[it];
-        const long long i = item & 0x0fffffff;
-        const int sub = (unsigned)item >> 28;
-        int iv, i1, i2;
-        Subs<IS_VF>::ve(sub, iv, i1, i2);
-        const int4 s4 = reinterpret_cast<const int4 *>(A.stencils)[i];
-        const int idx[4] = {s4.x, s4.y, s4.z, s4.w};
-        const double eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
-        V3 a0, a1, a2, b0, b1, b2;
-        ldpair(A.q0, idx[iv], a0, b0);
-        ldpair(A.q0, idx[i1], a1, b1);
-        ldpair(A.q0, idx[i2], a2, b2);
-        const V3 v0 = b0 - a0, v1 = b1 - a1, v2 = b2 - a2;
+        int code = SC_MISS, nrec = 0, sub = 0;
+        long long i = 0;
         double recs[3][8];
-        int nrec;
-        const int code = ve_item(a0, a1, a2, v0, v1, v2, eta, recs, nrec);
-        if (code == SC_MISS)
-            continue;
-        if (code == SC_DEFERRED)
+        if (it < n)
         {
-            const unsigned long long t0 = alloc_task_slots(A, nrec);
-            if (t0 + (unsigned long long)nrec <= A.task_cap && t0 + (unsigned long long)nrec < (1ull << 28))
+            const int item = Q.qve[it];
+            i = item & 0x0fffffff;
+            sub = (unsigned)item >> 28;
+            int iv, i1, i2;
+            Subs<IS_VF>::ve(sub, iv, i1, i2);
+            const int4 s4 = reinterpret_cast<const int4 *>(A.stencils)[i];
+            const int idx[4] = {s4.x, s4.y, s4.z, s4.w};
+            const double eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
+            V3 a0, a1, a2, b0, b1, b2;
+            ldpair(A.q0, idx[iv], a0, b0);
+            ldpair(A.q0, idx[i1], a1, b1);
+            ldpair(A.q0, idx[i2], a2, b2);
+            code = ve_item(a0, a1, a2, b0 - a0, b1 - a1, b2 - a2, eta, recs, nrec);
+        }
+        const unsigned c = code == SC_DEFERRED ? (unsigned)nrec : 0u;
+        const unsigned long long t0 = block_alloc(c, A.ntask);
+        if (c)
+        {
+            if (t0 + c <= A.task_cap && t0 + c < (1ull << 28))
             {
 #pragma unroll
                 for (int k = 0; k < 3; k++)
@@ -452,7 +451,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_ve_kern
             }
             Q.sbase[5 * i + sub] = (int)((t0 < 0x0fffffffull ? (unsigned)t0 : 0x0fffffffu) | ((unsigned)nrec << 28));
         }
-        atomicOr(&Q.status[i], (unsigned)code << (2 * sub));
+        if (code != SC_MISS) atomicOr(&Q.status[i], (unsigned)code << (2 * sub));
     }
 }
 
@@ -531,25 +530,21 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_decide_
         }
         else { stage = -1; meta = (int)(submask | ((unsigned)later_hit << 8)); }
     }
-    queue_push(general, (int)i, Q.qgen, Q.ctr + K_NGEN);
-    // warp-aggregated append to the work list
-    const bool deferred = stage < 0;
-    const unsigned m = __ballot_sync(0xffffffffu, deferred);
-    if (m)
     {
-        const int lane = threadIdx.x & 31;
-        unsigned long long wbase = 0;
-        if (lane == 0) wbase = atomicAdd(A.nwork, (unsigned long long)__popc(m));
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        const unsigned long long o = block_alloc(general ? 1u : 0u, Q.ctr + K_NGEN);
+        if (general) Q.qgen[o] = (int)i;
+    }
+    const bool deferred = stage < 0;
+    {
+        const unsigned long long w = block_alloc(deferred ? 1u : 0u, A.nwork);
         if (deferred)
         {
-            const unsigned long long w = wbase + __popc(m & ((1u << lane) - 1));
             A.w_stencil[w] = (int)i;
             A.w_meta[w] = meta;
             for (int j = 0; j < 5; j++) A.w_base[5 * w + j] = base[j];
         }
     }
-    reduce_warp(stage > 0, toi, A.earliest_bits, A.nhit);
+    reduce_block(stage > 0, toi, A.earliest_bits, A.nhit);
 }
 
 // pending records by reduced degree (3..6); final records (closed forms) are skipped
@@ -559,7 +554,7 @@ __global__ void __launch_bounds__(256) bucket_tasks_kernel(const double *__restr
 {
     unsigned long long nt = *ntask_ptr;
     if (nt > cap) nt = cap;
-    const unsigned long long nround = (nt + 31ull) & ~31ull;
+    const unsigned long long nround = block_rounded(nt);
     for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < nround;
          j += (unsigned long long)gridDim.x * blockDim.x)
     {
@@ -569,18 +564,11 @@ __global__ void __launch_bounds__(256) bucket_tasks_kernel(const double *__restr
             const unsigned tag = rec_untag(tasks[REC_STRIDE * j + 7]);
             if (!(tag & REC_FINAL) && (phase == 1 || !(tag & REC_POS))) rd = (int)((tag >> 4) & 7u);
         }
-        const int lane = threadIdx.x & 31;
 #pragma unroll
         for (int d = 3; d <= 6; d++)
         {
-            const unsigned m = __ballot_sync(0xffffffffu, rd == d);
-            if (m)
-            {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(&counts[d - 3], (unsigned long long)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (rd == d) lists[(size_t)(d - 3) * cap + base + __popc(m & ((1u << lane) - 1))] = (int)j;
-            }
+            const unsigned long long o = block_alloc(rd == d ? 1u : 0u, &counts[d - 3]);
+            if (rd == d) lists[(size_t)(d - 3) * cap + o] = (int)j;
         }
     }
 }
@@ -612,7 +600,7 @@ __global__ void __launch_bounds__(128) ve_refine_kernel(double *tasks, const int
                                                         int *__restrict__ out, unsigned long long *out_count)
 {
     const unsigned long long nt = *count_ptr;
-    const unsigned long long nround = (nt + 31ull) & ~31ull;
+    const unsigned long long nround = block_rounded(nt);
     for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nround; w += (unsigned long long)gridDim.x * blockDim.x)
     {
         bool keep = false;
@@ -622,19 +610,13 @@ __global__ void __launch_bounds__(128) ve_refine_kernel(double *tasks, const int
             j = list[w];
             keep = !ve_refine_item(tasks + (long long)REC_STRIDE * j);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m)
-        {
-            const int lane = threadIdx.x & 31;
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(out_count, (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (keep) out[base + __popc(m & ((1u << lane) - 1))] = j;
-        }
+        const unsigned long long o = block_alloc(keep ? 1u : 0u, out_count);
+        if (keep) out[o] = j;
     }
 }
 
 #define SOLVE_MINB(D) ((D) <= 4 ? 4 : 3)
+#define SOLVE_CHUNK 64
 template <int D>
 __global__ void __launch_bounds__(128, SOLVE_MINB(D)) solve_kernel(double *tasks, const int *__restrict__ list, const unsigned long long *count_ptr,
                                                                    unsigned long long *cursor)
@@ -645,20 +627,28 @@ __global__ void __launch_bounds__(128, SOLVE_MINB(D)) solve_kernel(double *tasks
     L.done = true;
     L.solving = false;
     L.got_root = false;
-    bool have = false, exhausted = false;
+    bool have = false, exhausted = false, gex = false;
+    unsigned long long wnext = 0, wend = 0;      // the warp's current chunk of the list (warp-uniform)
     double *rec = nullptr;
     for (;;)
     {
         const unsigned need = __ballot_sync(0xffffffffu, !have && !exhausted);
         if (need)
         {
-            unsigned long long base = 0;
-            if (lane == __ffs(need) - 1) base = atomicAdd(cursor, (unsigned long long)__popc(need));
-            base = __shfl_sync(0xffffffffu, base, __ffs(need) - 1);
+            // records are taken from a chunk the warp reserved with one atomic (SOLVE_CHUNK at a time): a refill per
+            // round per warp on the one shared cursor would serialise all warps of the grid on that address
+            if (wnext >= wend && !gex)
+            {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(cursor, (unsigned long long)SOLVE_CHUNK);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= nt) { gex = true; wnext = wend = 0; }
+                else { wnext = base; wend = base + SOLVE_CHUNK < nt ? base + SOLVE_CHUNK : nt; }
+            }
             if (!have && !exhausted)
             {
-                const unsigned long long my = base + __popc(need & ((1u << lane) - 1));
-                if (my < nt)
+                const unsigned long long my = wnext + __popc(need & ((1u << lane) - 1));
+                if (my < wend)
                 {
                     rec = tasks + (long long)REC_STRIDE * list[my];
                     double c[D + 1];
@@ -668,9 +658,11 @@ __global__ void __launch_bounds__(128, SOLVE_MINB(D)) solve_kernel(double *tasks
                     L.load_start(c, aux);
                     have = true;
                 }
-                else
+                else if (gex)
                     exhausted = true;
             }
+            const unsigned long long adv = wnext + (unsigned long long)__popc(need);
+            wnext = adv < wend ? adv : wend;
         }
         if (!__any_sync(0xffffffffu, have))
             break;
@@ -738,7 +730,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_combine
 {
     const NpArgs &A = Q.A;
     const unsigned long long nw = *A.nwork;
-    const unsigned long long nround = (nw + 31ull) & ~31ull;
+    const unsigned long long nround = block_rounded(nw);
     for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nround;
          w += (unsigned long long)gridDim.x * blockDim.x)
     {
@@ -779,8 +771,11 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_combine
             if (!fb) store_result(A, i, stage, toi);
             else stage = 0;
         }
-        queue_push(fb, (int)i, Q.qgen, Q.ctr + K_NGEN);
-        reduce_warp(stage > 0, toi, A.earliest_bits, A.nhit);
+        {
+            const unsigned long long o = block_alloc(fb ? 1u : 0u, Q.ctr + K_NGEN);
+            if (fb) Q.qgen[o] = (int)i;
+        }
+        reduce_block(stage > 0, toi, A.earliest_bits, A.nhit);
     }
 }
 
@@ -788,7 +783,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(128) np_general_kernel(P
 {
     const NpArgs &A = Q.A;
     const unsigned long long n = Q.ctr[K_NGEN];
-    const unsigned long long nround = (n + 31ull) & ~31ull;
+    const unsigned long long nround = block_rounded(n);
     for (unsigned long long x = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; x < nround; x += (unsigned long long)gridDim.x * blockDim.x)
     {
         int stage = 0;
@@ -801,7 +796,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(128) np_general_kernel(P
             stage = stencil_segment_full<IS_VF>(S.a, S.b, S.eta, toi);
             store_result(A, i, stage, toi);
         }
-        reduce_warp(stage > 0, toi, A.earliest_bits, A.nhit);
+        reduce_block(stage > 0, toi, A.earliest_bits, A.nhit);
     }
 }
 
@@ -828,7 +823,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_history_ker
             }
         store_result(A, i, stage, toi);
     }
-    reduce_warp(stage != 0, toi, A.earliest_bits, A.nhit);
+    reduce_block(stage != 0, toi, A.earliest_bits, A.nhit);
 }
 
 // ---- batched public primitives (include/CTCD.h:36-79): pts = start points then end points ------
