@@ -60,7 +60,8 @@ struct ccd_context
 };
 
 // device counters layout (unsigned long long each)
-enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NQUERY = 7, C_NA_VF = 8, C_NA_EE = 9, C_KCUR_VF = 10, C_KCUR_EE = 11, C_NP_VF = 16 /* CCD_NP_COUNTERS counters per run: work-list entries, records, ... (narrowphase.cu K_*) */, C_NP_EE = 16 + CCD_NP_COUNTERS, C_TOTAL = 16 + 2 * CCD_NP_COUNTERS };
+enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NQUERY = 7, C_NA_VF = 8, C_NA_EE = 9, C_KCUR_VF = 10, C_KCUR_EE = 11, C_NP_VF = 16 /* CCD_NP_COUNTERS counters per run: work-list entries, records, ... (narrowphase.cu K_*) */, C_NP_EE = 16 + CCD_NP_COUNTERS, C_CAND_REG = 16 + 2 * CCD_NP_COUNTERS /* CCD_CAND_REGIONS candidate counters */, C_TOTAL = 16 + 2 * CCD_NP_COUNTERS + 64 };
+#define CCD_CAND_REGIONS 64
 enum { C_NWORK_VF = C_NP_VF, C_NTASK_VF = C_NP_VF + 1, C_NWORK_EE = C_NP_EE, C_NTASK_EE = C_NP_EE + 1 };
 
 #define CK(call)                                                                                      \
@@ -406,6 +407,8 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         CKR(ensure(c, c->pairL, sizeof(int) * c->pairCap));
         CKR(ensure(c, c->pairR, sizeof(int) * c->pairCap));
         CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 2, c->st));
+        CK(cudaMemsetAsync(ctr + C_CAND_REG, 0, sizeof(unsigned long long) * CCD_CAND_REGIONS, c->st));
+        const size_t regionCap = c->candCap / CCD_CAND_REGIONS;
         CK(cudaMemsetAsync(c->deg.p, 0, sizeof(int) * (size_t)(F + 2), c->st));
         CKR(ensure(c, c->vactive, (size_t)V + 16));
         CKR(ensure(c, c->eactive, (size_t)E + 16));
@@ -422,21 +425,27 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
                 c->launches += 1;
             }
             ccdk_traverse(c->st, kind, F, 0, nquery, P<int>(c->qlist), true, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p,
-                          c->cand.p, c->candCap, ctr + C_NCAND);
+                          c->cand.p, regionCap, ctr + C_CAND_REG);
         }
         else
             ccdk_traverse(c->st, kind, F, 0, F, nullptr, false, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p, c->cand.p,
-                          c->candCap, ctr + C_NCAND);
-        ccdk_exact_pairs(c->st, kind, !sharded, ctr + C_NCAND, c->candCap, c->cand.p, sortedFace, d_faces, P<double>(c->boxes), P<int>(c->pairL),
+                          regionCap, ctr + C_CAND_REG);
+        ccdk_exact_pairs(c->st, kind, !sharded, ctr + C_CAND_REG, regionCap, c->cand.p, sortedFace, d_faces, P<double>(c->boxes), P<int>(c->pairL),
                          P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg), P<int>(c->faceEdge), P<unsigned char>(c->vactive), P<unsigned char>(c->eactive));
         c->launches += 2;
         CKR(sync_counters(c));
-        unsigned long long ncand = c->h_counters[C_NCAND], npairs = c->h_counters[C_NPAIRS];
+        unsigned long long ncand = 0, maxreg = 0, npairs = c->h_counters[C_NPAIRS];
+        for (int r = 0; r < CCD_CAND_REGIONS; r++)
+        {
+            const unsigned long long x = c->h_counters[C_CAND_REG + r];
+            ncand += x;
+            maxreg = x > maxreg ? x : maxreg;
+        }
         // counts keep running past the capacities (writes are guarded), so an overflow tells the size to retry with
-        const bool cand_over = ncand > c->candCap, pair_over = npairs > c->pairCap;
+        const bool cand_over = maxreg > regionCap, pair_over = npairs > c->pairCap;
         const bool again = cand_over || pair_over;
         if (cand_over)
-            c->candCap = (size_t)(ncand + ncand / 8 + 1024);
+            c->candCap = (size_t)((maxreg + maxreg / 4 + 1024) * CCD_CAND_REGIONS);
         if (again)
         {
             // pairs found from a truncated candidate list are a lower bound only: leave generous room
