@@ -188,7 +188,9 @@ class Context(object):
         self._check(self.lib.ccd_stage_times(self.h, ms, C.c_int(9)), "ccd_stage_times")
         return dict(zip(self.STAGES, [float(x) for x in ms]))
 
-    def step(self, kind, faces, q0, q1, outerEta, eta, fixedMask=None, shard_rank=0, shard_world=1):
+    def step(self, kind, faces, q0, q1, outerEta, eta, fixedMask=None, shard_rank=0, shard_world=1, copy=True):
+        """ccd_step_shard.  The hit lists come back in pinned host buffers owned by the context (valid until its next
+        call): copy=False returns views of them — what a C caller gets — instead of fresh numpy arrays."""
         faces = np.ascontiguousarray(faces, dtype=np.int32).reshape(-1)
         q0 = _f64(q0).reshape(-1)
         q1 = _f64(q1).reshape(-1)
@@ -203,7 +205,9 @@ class Context(object):
         def arr(p, n, w, dt):
             if n == 0:
                 return np.zeros((0, w) if w > 1 else (0,), dt)
-            a = np.ctypeslib.as_array(p, shape=(n * w,)).copy()
+            a = np.ctypeslib.as_array(p, shape=(n * w,))
+            if copy:
+                a = a.copy()
             return a.reshape(n, w) if w > 1 else a
 
         out = dict(n_vf_candidates=r.n_vf_candidates, n_ee_candidates=r.n_ee_candidates, n_vf_hits=r.n_vf_hits,
