@@ -124,39 +124,82 @@ CCD_FN void read_final_record(const double *rec, Ivl3 &o, unsigned &tag)
 }
 
 // ---- the state machine ---------------------------------------------------------------------------------------
-template <int D> struct RootLane
+// STRIDE == 0: the polynomial and the two root lists live in the struct (registers, indexed through unrolled selects);
+// STRIDE > 0: they live in memory the caller binds (shared memory in solve_kernel, element k of a lane at [k * STRIDE]),
+// indexed directly — fewer registers (more resident warps for the latency-bound Newton chains) and no select chains.
+template <int D, int STRIDE = 0> struct RootLane
 {
     double c[D + 1];      // the polynomial
     double p[D + 1];      // derivative level m, right-aligned (deriv_level_padded)
     double cur[D];        // roots of the level below, ascending
     double out[D];        // roots found at this level so far
+    double *mc, *mcur, *mout;      // STRIDE > 0
     double prev;          // out[nr-1]
     double brk_lo, f_lo, x_hi, f_hi;
     double lo, hi, x, dx, dxold;      // the solve in flight
     int ncur, nr, m, m0, i, nb, it;
     bool one, plain, last, lo_neg, solving, done, got_root;      // got_root: x holds a converged root not yet recorded
 
+    CCD_FN void bind(double *mem)
+    {
+        mc = mem;
+        mcur = mem + (D + 1) * STRIDE;
+        mout = mem + (2 * D + 1) * STRIDE;
+    }
     CCD_FN double cur_at(int j) const
     {
+        if (STRIDE) return mcur[j * STRIDE];
         double r = cur[0];
 #pragma unroll
         for (int k = 1; k < D; k++)
             if (k == j) r = cur[k];
         return r;
     }
-    CCD_FN void push_out(double r)
+    CCD_FN void set_cur(int j, double r)
     {
+        if (STRIDE) { mcur[j * STRIDE] = r; return; }
 #pragma unroll
         for (int k = 0; k < D; k++)
-            if (k == nr) out[k] = r;
+            if (k == j) cur[k] = r;
+    }
+    CCD_FN double out_at(int j) const
+    {
+        if (STRIDE) return mout[j * STRIDE];
+        double r = out[0];
+#pragma unroll
+        for (int k = 1; k < D; k++)
+            if (k == j) r = out[k];
+        return r;
+    }
+    CCD_FN void push_out(double r)
+    {
+        if (STRIDE)
+        {
+            if (nr < D) mout[nr * STRIDE] = r;
+        }
+        else
+        {
+#pragma unroll
+            for (int k = 0; k < D; k++)
+                if (k == nr) out[k] = r;
+        }
         prev = r;
         nr++;
+    }
+    CCD_FN void load_c(double (&t)[D + 1]) const
+    {
+#pragma unroll
+        for (int k = 0; k <= D; k++) t[k] = STRIDE ? mc[k * STRIDE] : c[k];
     }
     CCD_FN void setup_level()
     {
         plain = one && m == m0;
         last = (m == D);
-        deriv_level_padded<D>(c, m, p);
+        {
+            double t[D + 1];
+            load_c(t);
+            deriv_level_padded<D>(t, m, p);
+        }
         nb = plain ? 2 : ncur + 2;
         i = 0;
         brk_lo = 0.0;
@@ -271,12 +314,24 @@ template <int D> struct RootLane
     }
     CCD_FN void load_start(const double (&coef)[D + 1], const double *aux)
     {
+        if (STRIDE)
+        {
 #pragma unroll
-        for (int k = 0; k <= D; k++) c[k] = coef[k];
+            for (int k = 0; k <= D; k++) mc[k * STRIDE] = coef[k];
 #pragma unroll
-        for (int k = 0; k < D; k++) { cur[k] = 0.0; out[k] = 0.0; }
-        cur[0] = aux[0];
-        cur[1] = aux[1];
+            for (int k = 0; k < D; k++) { mcur[k * STRIDE] = 0.0; mout[k * STRIDE] = 0.0; }
+            mcur[0] = aux[0];
+            mcur[STRIDE] = aux[1];
+        }
+        else
+        {
+#pragma unroll
+            for (int k = 0; k <= D; k++) c[k] = coef[k];
+#pragma unroll
+            for (int k = 0; k < D; k++) { cur[k] = 0.0; out[k] = 0.0; }
+            cur[0] = aux[0];
+            cur[1] = aux[1];
+        }
         const int pk = (int)aux[2];
         m0 = pk & 15;
         one = (pk & 16) != 0;
@@ -325,15 +380,27 @@ template <int D> struct RootLane
                 if (!plain && last && f_lo == 0.0 && (nr == 0 || prev != 1.0)) push_out(1.0);
                 const bool keep_all = last && !plain;
                 int n2 = 0;
-#pragma unroll
-                for (int k = 0; k < D; k++)
-                    if (k < nr && (keep_all || (out[k] > 0.0 && out[k] < 1.0)))
+                if (STRIDE)
+                {
+                    const int nlim = nr < D ? nr : D;
+                    for (int k = 0; k < nlim; k++)
                     {
-#pragma unroll
-                        for (int j = 0; j < D; j++)
-                            if (j == n2) cur[j] = out[k];
-                        n2++;
+                        const double o = mout[k * STRIDE];
+                        if (keep_all || (o > 0.0 && o < 1.0)) mcur[(n2++) * STRIDE] = o;
                     }
+                }
+                else
+                {
+#pragma unroll
+                    for (int k = 0; k < D; k++)
+                        if (k < nr && (keep_all || (out[k] > 0.0 && out[k] < 1.0)))
+                        {
+#pragma unroll
+                            for (int j = 0; j < D; j++)
+                                if (j == n2) cur[j] = out[k];
+                            n2++;
+                        }
+                }
                 ncur = n2;
                 if (m == D) { done = true; return; }
                 m++;
@@ -382,7 +449,7 @@ template <int D> struct RootLane
     CCD_FN int result(double (&r)[6]) const
     {
 #pragma unroll
-        for (int k = 0; k < 6; k++) r[k] = (k < D) ? cur[k < D ? k : 0] : 0.0;
+        for (int k = 0; k < 6; k++) r[k] = (k < D) ? (STRIDE ? mcur[(k < D ? k : 0) * STRIDE] : cur[k < D ? k : 0]) : 0.0;
         return ncur;
     }
 };

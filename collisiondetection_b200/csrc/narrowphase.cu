@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(128) ve_refine_kernel(double *tasks, const int
     }
 }
 
-#define SOLVE_MINB(D) ((D) <= 4 ? 4 : 3)
+#define SOLVE_MINB(D) ((D) <= 4 ? 6 : 5)
 #define SOLVE_CHUNK 64
 template <int D>
 __global__ void __launch_bounds__(128, SOLVE_MINB(D)) solve_kernel(double *tasks, const int *__restrict__ list, const unsigned long long *count_ptr,
@@ -623,7 +623,9 @@ __global__ void __launch_bounds__(128, SOLVE_MINB(D)) solve_kernel(double *tasks
 {
     const unsigned long long nt = *count_ptr;
     const int lane = threadIdx.x & 31;
-    RootLane<D> L;
+    __shared__ double s_lane[(3 * D + 1) * 128];      // polynomial + two root lists of every lane, element k at [k * 128 + thread]
+    RootLane<D, 128> L;
+    L.bind(s_lane + threadIdx.x);
     L.done = true;
     L.solving = false;
     L.got_root = false;
