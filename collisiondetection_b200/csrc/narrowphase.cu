@@ -21,6 +21,9 @@
 #ifndef NP_MINB
 #define NP_MINB 4      // resident blocks of 128 threads per SM the stencil kernels are compiled for
 #endif
+#ifndef NP_MINB_STAGE
+#define NP_MINB_STAGE 8      // ... and the per-polynomial stage / export kernels (latency-bound gathers: occupancy wins, measured)
+#endif
 #include "ccd_math.cuh"
 #include "ccd_roots_t.cuh"
 #include "ccd_stencil.cuh"
@@ -336,7 +339,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(256) np_cull_kernel(P1Ar
     }
 }
 
-template <bool IS_VF, int S> __global__ void __launch_bounds__(128, NP_MINB) np_stage_kernel(P1Args Q)
+template <bool IS_VF, int S> __global__ void __launch_bounds__(128, NP_MINB_STAGE) np_stage_kernel(P1Args Q)
 {
     const NpArgs &A = Q.A;
     constexpr int NST = Prim<IS_VF>::NST;
@@ -396,7 +399,7 @@ template <bool IS_VF, int S> __global__ void __launch_bounds__(128, NP_MINB) np_
     }
 }
 
-template <bool IS_VF, int K> __global__ void __launch_bounds__(128, NP_MINB) np_export_kernel(P1Args Q)
+template <bool IS_VF, int K> __global__ void __launch_bounds__(128, NP_MINB_STAGE) np_export_kernel(P1Args Q)
 {
     const NpArgs &A = Q.A;
     const unsigned long long n = Q.ctr[K_NXQ + K];
