@@ -443,7 +443,7 @@ CCD_FN void window_item(double *rec, int nrec, int KD)
 
 // CTCD::vertexEdgeCTCD (src/CTCD.cpp:511-602), vertex q0 against segment (q1,q2); v* = end - start.
 // Returns SC_MISS, SC_DEFERRED (nrec records in recs: polynomial 0,1 = the two inside quadratics, 2 = the distance
-// quartic; whole-[0,1] lists have no record) or SC_GENERAL (nothing constrains the test: left to the general routine).
+// quartic; whole-[0,1] lists have no record — possibly none at all).
 CCD_FN int ve_item(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, double (&recs)[3][8], int &nrec)
 {
     const double minD = eta * eta;
@@ -545,7 +545,7 @@ CCD_FN int ve_item(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, doub
             nrec++;
         }
     }
-    return nrec ? SC_DEFERRED : SC_GENERAL;
+    return SC_DEFERRED;      // nrec == 0: nothing constrains the test — combining zero records gives the whole [0,1], a hit at t = 0
 }
 
 // A pending vertex-edge distance quartic (record `rec`, its sub-test's inside-quadratic records right before it).  The

@@ -339,16 +339,19 @@ template <bool IS_VF> __global__ void __launch_bounds__(256) np_cull_kernel(P1Ar
     }
 }
 
-template <bool IS_VF, int S> __global__ void __launch_bounds__(128, NP_MINB_STAGE) np_stage_kernel(P1Args Q)
+// Stage S (and, with TWO, stage S+1 for the stencils that survive S: the edge-edge quartics reject only ~20 % each, so a
+// pair of them shares one gather of the positions).  in_q / out_q: which of the two stage queues is read / written.
+template <bool IS_VF, int S, bool TWO> __global__ void __launch_bounds__(128, NP_MINB_STAGE) np_stage_kernel(P1Args Q, int in_q, int out_q)
 {
     const NpArgs &A = Q.A;
     constexpr int NST = Prim<IS_VF>::NST;
-    constexpr bool LAST = (S == NST - 1);
-    constexpr int KOWN = Prim<IS_VF>::poly(S);
+    constexpr int SL = S + (TWO ? 1 : 0);      // the last stage this kernel runs
+    constexpr bool LAST = (SL == NST - 1);
+    constexpr int KOWN = Prim<IS_VF>::poly(SL);
     const unsigned long long n = (S == 0) ? (IS_VF ? (unsigned long long)A.n : Q.ctr[K_NQ]) : Q.ctr[K_NSQ + S - 1];
     const unsigned long long nround = block_rounded(n);
-    const int2 *in = Q.sq[(S + 1) & 1];
-    int2 *out = Q.sq[S & 1];
+    const int2 *in = Q.sq[in_q];
+    int2 *out = Q.sq[out_q];
     for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < nround; it += (unsigned long long)gridDim.x * blockDim.x)
     {
         bool alive = false, has_rec = false;
@@ -364,19 +367,30 @@ template <bool IS_VF, int S> __global__ void __launch_bounds__(128, NP_MINB_STAG
             V3 v[4];
             for (int k = 0; k < 4; k++) v[k] = St.b[k] - St.a[k];
             unsigned so = state;
-            alive = stage_item<IS_VF, S, LAST>(St.a, v, St.eta, state, so, rec, has_rec);
+            if (TWO)
+            {
+                double dummy[8];
+                bool h;
+                alive = stage_item<IS_VF, S, false>(St.a, v, St.eta, state, so, dummy, h);
+                state = so;
+                if (alive) alive = stage_item<IS_VF, SL, LAST>(St.a, v, St.eta, state, so, rec, has_rec);
+            }
+            else
+                alive = stage_item<IS_VF, S, LAST>(St.a, v, St.eta, state, so, rec, has_rec);
             state = so;
         }
         if (!LAST)
         {
-            const unsigned long long o = block_alloc(alive ? 1u : 0u, Q.ctr + K_NSQ + S);
+            const unsigned long long o = block_alloc(alive ? 1u : 0u, Q.ctr + K_NSQ + SL);
             if (alive) out[o] = make_int2((int)i, (int)state);
         }
         else
         {
+            // a survivor is deferred to the combine kernel with the records of its constrained polynomials — possibly
+            // none: every list is the whole [0,1] then, and combining zero records gives exactly that (hit at t = 0,
+            // subject to the edge-edge parallel test)
             const unsigned need = state & 0x1fu;
-            const bool gen = alive && need == 0u, def = alive && need != 0u;
-            if (gen) atomicOr(&Q.status[i], (unsigned)SC_GENERAL);
+            const bool def = alive;
             // records of the surviving stencils of this block: one reservation
             const int cnt = def ? __popc(need) : 0;
             const unsigned long long t0 = block_alloc((unsigned)cnt, A.ntask);
@@ -934,19 +948,28 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
     g_trace.mark(st, "start");
     np_cull_kernel<IS_VF><<<grid_for(n, 256), 256, 0, st>>>(Q);
     g_trace.mark(st, "cull");
-    np_stage_kernel<IS_VF, 0><<<gq, B, 0, st>>>(Q);
+    np_stage_kernel<IS_VF, 0, false><<<gq, B, 0, st>>>(Q, 0, 0);
     g_trace.mark(st, "stage0");
-    np_stage_kernel<IS_VF, 1><<<gq, B, 0, st>>>(Q);
-    np_stage_kernel<IS_VF, 2><<<gq, B, 0, st>>>(Q);
-    np_stage_kernel<IS_VF, 3><<<gq, B, 0, st>>>(Q);
-    int nl = 5;
-    if (!IS_VF)
+    int nl = 2;
+    if (IS_VF)
     {
-        np_stage_kernel<false, 4><<<gq, B, 0, st>>>(Q);
-        np_export_kernel<false, 4><<<gq, B, 0, st>>>(Q);
+        np_stage_kernel<IS_VF, 1, false><<<gq, B, 0, st>>>(Q, 0, 1);
+        np_stage_kernel<IS_VF, 2, false><<<gq, B, 0, st>>>(Q, 1, 0);
+        np_stage_kernel<IS_VF, 3, false><<<gq, B, 0, st>>>(Q, 0, 1);
+        nl += 3;
+    }
+    else
+    {
+        np_stage_kernel<false, 1, true><<<gq, B, 0, st>>>(Q, 0, 1);      // a0, a1
+        np_stage_kernel<false, 3, true><<<gq, B, 0, st>>>(Q, 1, 0);      // b0, b1 (last)
         nl += 2;
     }
     g_trace.mark(st, "stages");
+    if (!IS_VF)
+    {
+        np_export_kernel<false, 4><<<gq, B, 0, st>>>(Q);
+        nl += 1;
+    }
     np_export_kernel<IS_VF, 0><<<gq, B, 0, st>>>(Q);
     np_export_kernel<IS_VF, 1><<<gq, B, 0, st>>>(Q);
     np_export_kernel<IS_VF, 2><<<gq, B, 0, st>>>(Q);

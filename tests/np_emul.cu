@@ -84,8 +84,7 @@ template <bool IS_VF> int primitive(const V3 *a, const V3 *v, double eta, std::v
     if (!run_stage<IS_VF, 3>(a, v, eta, state, own, has)) return SC_MISS;
     if (!IS_VF)
         if (!run_stage<false, 4>(a, v, eta, state, own, has)) return SC_MISS;
-    const unsigned need = state & 0x1fu;
-    if (!need) return SC_GENERAL;
+    const unsigned need = state & 0x1fu;      // may be 0: deferred with no record
     constexpr int KOWN = Prim<IS_VF>::poly(Prim<IS_VF>::NST - 1);
     for (int k = 0; k < 5; k++)
     {
@@ -189,14 +188,14 @@ void run(long long n, const int *stencils, const double *q0, const double *q1, i
         {
             for (size_t k = 0; k < recs.size(); k++) ve_refine_item(recs[k].d);      // no-op for anything but pending VE quartics
             solve_records(recs, stats, 0);
-            if (code[0] == SC_DEFERRED) window_item(recs[first[0]].d, cnt[0], IS_VF ? 3 : 4);
+            if (code[0] == SC_DEFERRED && cnt[0] > 0) window_item(recs[first[0]].d, cnt[0], IS_VF ? 3 : 4);
             solve_records(recs, stats, 1);
             stage = 0;
             bool settled = false;
             for (int j = 0; j < nd && !settled; j++)
             {
                 const int sub = dsub[j];
-                const int r = combine_records(recs[first[sub]].d, cnt[sub], !IS_VF && sub == 0, a, v, t);
+                const int r = combine_records(cnt[sub] > 0 ? recs[first[sub]].d : nullptr, cnt[sub], !IS_VF && sub == 0, a, v, t);
                 if (r == RS_FALLBACK) { general = true; settled = true; }
                 else if (r == RS_HIT) { stage = sub + 1; settled = true; }
             }
