@@ -268,11 +268,20 @@ def main():
     hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
     nvf, nee = r.n_vf_candidates, r.n_ee_candidates
     dom = max(stages, key=stages.get)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_c5.json"))) if args.workload == "cloth1415" and world == 1 else {}
+    except Exception:
+        pass
     if dom in ("np_vf", "np_ee"):
+        # the narrowphase is a pipeline of kernels per stencil type (cull, one kernel per polynomial, root isolation,
+        # combine); its roofline is taken over the whole group: algorithmic FP64 flops of SURVEY.md 8(d) / group time
         flops = nvf * FLOP_VF if dom == "np_vf" else nee * FLOP_EE
         ach = flops / (stages[dom] * 1e-3) / 1e12
-        roof = dict(kernel="stencil_kernel<%s>" % ("VF" if dom == "np_vf" else "EE"), bound="fp64", achieved=ach, peak=fp64_peak,
-                    unit="TFLOP/s", frac=ach / fp64_peak if fp64_peak else None, traffic=None,
+        roof = dict(kernel="%s narrowphase kernel group (np_cull/np_stage/np_export/np_ve/solve_kernel/np_combine ...; largest: solve_kernel<6>)" % ("VF" if dom == "np_vf" else "EE"),
+                    bound="fp64", achieved=ach, peak=fp64_peak,
+                    unit="TFLOP/s", frac=ach / fp64_peak if fp64_peak else None, traffic=traffic.get("narrowphase_bytes"),
+                    traffic_source=traffic.get("source"),
                     peak_source="measured live: ccd_fp64_peak (16 independent DFMA chains/thread on all SMs); MEASURED_PEAKS.json has no FP64 entry",
                     algorithmic="%.0f flop/stencil x %d stencils (coefficient construction only; root isolation and early exits excluded)" % (
                         FLOP_VF if dom == "np_vf" else FLOP_EE, nvf if dom == "np_vf" else nee),
@@ -283,15 +292,22 @@ def main():
         bytes_bp = 892.0 * F + 48.0 * raw + 16.0 * (nvf + nee)
         bp_ms = sum(v for k, v in stages.items() if not k.startswith("np_") and k != "topology")
         ach = bytes_bp / (bp_ms * 1e-3) / 1e9
-        roof = dict(kernel="broadphase (dominant stage: %s)" % dom, bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s",
-                    frac=ach / hbm_peak, traffic=None, peak_source=hbm_src,
+        roof = dict(kernel="broadphase kernel group (dominant stage: %s)" % dom, bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s",
+                    frac=ach / hbm_peak, traffic=traffic.get("broadphase_bytes"), traffic_source=traffic.get("source"), peak_source=hbm_src,
                     algorithmic="892 B/face + 48 B/raw stencil + 16 B/unique stencil over all broadphase kernels")
+    # the second roofline of the step (the one not dominant), so both phases are always on the line
+    raw = 15.0 * r.n_face_pairs * (1 if world > 1 else 1)
+    bp_ms = sum(v for k, v in stages.items() if not k.startswith("np_") and k != "topology")
+    np_ms = stages.get("np_vf", 0.0) + stages.get("np_ee", 0.0)
+    phases = dict(broadphase=dict(ms=bp_ms, achieved_gbs=(892.0 * F + 48.0 * raw + 16.0 * (nvf + nee)) / (bp_ms * 1e-3) / 1e9 if bp_ms else None, peak_gbs=hbm_peak),
+                  narrowphase=dict(ms=np_ms, achieved_tflops=(nvf * FLOP_VF + nee * FLOP_EE) / (np_ms * 1e-3) / 1e12 if np_ms else None, peak_tflops=fp64_peak,
+                                   stencils_per_s=(nvf + nee) / (np_ms * 1e-3) if np_ms else None))
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warmup, ms_per_step=ms_per_step,
                higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic" if args.workload.startswith("cloth") else "reference mesh fixture",
                config=config, clocks=clocks,
                e2e=dict(value=n_stencils / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
                gpu_launches=int(launches) * args.steps,
-               roofline=roof,
+               roofline=roof, phases=phases,
                stages_ms=stages, stages_ms_max_over_ranks={k: float(st_all[:, i].max()) for i, k in enumerate(stage_names)},
                stencils_per_rank=[int(x) for x in st_all[:, -1]], stages_ms_per_rank={k: [round(float(x), 3) for x in st_all[:, i]] for i, k in enumerate(stage_names)}, kernel_ms_per_step=kern_ms / args.steps,
                counts=dict(vertices=V, faces=F, stencils=n_stencils, vf_rank0=int(nvf), ee_rank0=int(nee), hits=n_hits,

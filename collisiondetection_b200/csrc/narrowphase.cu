@@ -634,6 +634,9 @@ __global__ void __launch_bounds__(128) ve_refine_kernel(double *tasks, const int
 
 #define SOLVE_MINB(D) ((D) <= 4 ? 6 : 5)
 #define SOLVE_CHUNK 64
+#ifndef SOLVE_KEEP_NUM
+#define SOLVE_KEEP_NUM 2      // a Newton round ends when fewer than SOLVE_KEEP_NUM/4 of its lanes are still iterating
+#endif
 template <int D>
 __global__ void __launch_bounds__(128, SOLVE_MINB(D)) solve_kernel(double *tasks, const int *__restrict__ list, const unsigned long long *count_ptr,
                                                                    unsigned long long *cursor)
@@ -701,7 +704,7 @@ __global__ void __launch_bounds__(128, SOLVE_MINB(D)) solve_kernel(double *tasks
         unsigned ms = __ballot_sync(0xffffffffu, have && L.solving);
         if (ms)
         {
-            const int thresh = max(1, __popc(ms) >> 1);
+            const int thresh = max(1, (__popc(ms) * SOLVE_KEEP_NUM) >> 2);
             do
             {
                 if (have && L.solving) L.newton_step();
