@@ -584,8 +584,8 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         if (c->taskCapEe < (size_t)nee + 1024) c->taskCapEe = (size_t)nee + 1024;
         CKR(ensure(c, c->tasksVf, 128 * c->taskCapVf));
         CKR(ensure(c, c->tasksEe, 128 * c->taskCapEe));
-        CKR(ensure(c, c->tlistVf, sizeof(int) * 5 * c->taskCapVf));
-        CKR(ensure(c, c->tlistEe, sizeof(int) * 5 * c->taskCapEe));
+        CKR(ensure(c, c->tlistVf, sizeof(int) * 6 * c->taskCapVf));
+        CKR(ensure(c, c->tlistEe, sizeof(int) * 6 * c->taskCapEe));
         unsigned long long init[4] = {0xFFFFFFFFFFFFFFFFull, 0ull, 0xFFFFFFFFFFFFFFFFull, 0ull};
         memcpy(c->h_counters + 8, init, sizeof(init));
         CK(cudaMemcpyAsync(ctr + C_EARLY_VF, c->h_counters + 8, sizeof(init), cudaMemcpyHostToDevice, c->st));

@@ -162,7 +162,9 @@ struct NpArgs
     int *w_meta;
     int *w_base;                // 5 ints per entry
     unsigned long long *nwork;
-    double *tasks;              // 64-byte records: coefficients + reduced degree in, roots + count out
+    double *tasks;              // REC_STRIDE doubles per record
+    int *rtag;                  // per record: its tag, kept in a compact array for the bucket kernel (a tag read out of the
+                                // 128-byte records costs a DRAM sector per record and pass)
     unsigned long long *ntask;  // running number of task records
     unsigned long long task_cap;
 };
@@ -399,7 +401,12 @@ template <bool IS_VF, int S, bool TWO> __global__ void __launch_bounds__(128, NP
             {
                 Q.sbase[5 * i + 0] = (int)((t0 < 0x0fffffffull ? (unsigned)t0 : 0x0fffffffu) | ((unsigned)cnt << 28));
                 atomicOr(&Q.status[i], (unsigned)SC_DEFERRED);
-                if (has_rec && fits) store_record(A.tasks + (unsigned long long)REC_STRIDE * (t0 + __popc(need & ((1u << KOWN) - 1u))), rec);
+                if (has_rec && fits)
+                {
+                    const unsigned long long slot = t0 + __popc(need & ((1u << KOWN) - 1u));
+                    store_record(A.tasks + (unsigned long long)REC_STRIDE * slot, rec);
+                    A.rtag[slot] = (int)rec_untag(rec[7]);
+                }
             }
 #pragma unroll
             for (int k = 0; k < 5; k++)
@@ -427,6 +434,7 @@ template <bool IS_VF, int K> __global__ void __launch_bounds__(128, NP_MINB_STAG
         double rec[8];
         export_item<IS_VF, K>(St.a, v, St.eta, rec);
         store_record(A.tasks + (unsigned long long)REC_STRIDE * (unsigned)e.y, rec);
+        A.rtag[(unsigned)e.y] = (int)rec_untag(rec[7]);
     }
 }
 
@@ -458,13 +466,17 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_ve_kern
         }
         const unsigned c = code == SC_DEFERRED ? (unsigned)nrec : 0u;
         const unsigned long long t0 = block_alloc(c, A.ntask);
-        if (c)
+        if (code == SC_DEFERRED)      // also with nrec == 0: the combine kernel reads the record count from sbase
         {
-            if (t0 + c <= A.task_cap && t0 + c < (1ull << 28))
+            if (c && t0 + c <= A.task_cap && t0 + c < (1ull << 28))
             {
 #pragma unroll
                 for (int k = 0; k < 3; k++)
-                    if (k < nrec) store_record(A.tasks + (unsigned long long)REC_STRIDE * (t0 + k), recs[k]);
+                    if (k < nrec)
+                    {
+                        store_record(A.tasks + (unsigned long long)REC_STRIDE * (t0 + k), recs[k]);
+                        A.rtag[t0 + k] = (int)rec_untag(recs[k][7]);
+                    }
             }
             Q.sbase[5 * i + sub] = (int)((t0 < 0x0fffffffull ? (unsigned)t0 : 0x0fffffffu) | ((unsigned)nrec << 28));
         }
@@ -565,8 +577,9 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_decide_
 }
 
 // pending records by reduced degree (3..6); final records (closed forms) are skipped
-// phase 0: the distance polynomials ("<= 0 wanted": VF / EE sextic, vertex-edge quartic); phase 1: whatever is still pending
-__global__ void __launch_bounds__(256) bucket_tasks_kernel(const double *__restrict__ tasks, const unsigned long long *ntask_ptr,
+// phase 0: the distance polynomials ("<= 0 wanted": VF / EE sextic, vertex-edge quartic); phase 1: the inside
+// polynomials (">= 0 wanted") the window stage left pending
+__global__ void __launch_bounds__(256) bucket_tasks_kernel(const int *__restrict__ rtag, const unsigned long long *ntask_ptr,
                                                            unsigned long long cap, int *__restrict__ lists, unsigned long long *counts, int phase)
 {
     unsigned long long nt = *ntask_ptr;
@@ -578,8 +591,8 @@ __global__ void __launch_bounds__(256) bucket_tasks_kernel(const double *__restr
         int rd = 0;
         if (j < nt)
         {
-            const unsigned tag = rec_untag(tasks[REC_STRIDE * j + 7]);
-            if (!(tag & REC_FINAL) && (phase == 1 || !(tag & REC_POS))) rd = (int)((tag >> 4) & 7u);
+            const unsigned tag = (unsigned)rtag[j];
+            if (!(tag & REC_FINAL) && ((phase == 1) == ((tag & REC_POS) != 0))) rd = (int)((tag >> 4) & 7u);
         }
 #pragma unroll
         for (int d = 3; d <= 6; d++)
@@ -743,6 +756,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(128) np_window_kernel(P1
         const int nrec = (int)(b >> 28);
         if (t0 + (unsigned long long)nrec > A.task_cap) continue;
         window_item(A.tasks + (unsigned long long)REC_STRIDE * t0, nrec, IS_VF ? 3 : 4);
+        for (int j = 0; j + 1 < nrec; j++) A.rtag[t0 + j] = (int)rec_untag(A.tasks[(unsigned long long)REC_STRIDE * (t0 + j) + 7]);
     }
 }
 
@@ -801,16 +815,20 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_combine
     }
 }
 
+// ONE stencil per warp (lane 0): the general routine is long, branchy, local-memory code; 32 of them in one warp run one
+// after the other in divergent lock-step, and the few hundred stencils that need it set the kernel's duration
 template <bool IS_VF> __global__ void __launch_bounds__(128) np_general_kernel(P1Args Q)
 {
     const NpArgs &A = Q.A;
     const unsigned long long n = Q.ctr[K_NGEN];
-    const unsigned long long nround = block_rounded(n);
-    for (unsigned long long x = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; x < nround; x += (unsigned long long)gridDim.x * blockDim.x)
+    const unsigned long long wpb = blockDim.x >> 5, nwarps = (unsigned long long)gridDim.x * wpb;
+    const unsigned long long nround = (n + nwarps - 1) / nwarps * nwarps;      // same trip count for every warp of the grid
+    const int lane = threadIdx.x & 31;
+    for (unsigned long long x = (unsigned long long)blockIdx.x * wpb + (threadIdx.x >> 5); x < nround; x += nwarps)
     {
         int stage = 0;
         double toi = 0.0;
-        if (x < n)
+        if (x < n && lane == 0)
         {
             const long long i = Q.qgen[x];
             StencilIn S;
@@ -985,7 +1003,7 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
     for (int phase = 0; phase < 2; phase++)
     {
         unsigned long long *nd = Q.ctr + (phase ? K_NDEG2 : K_NDEG), *cu = Q.ctr + (phase ? K_CURSOR2 : K_CURSOR);
-        bucket_tasks_kernel<<<148 * 4, 256, 0, st>>>(A.tasks, A.ntask, A.task_cap, tlists, nd, phase);
+        bucket_tasks_kernel<<<148 * 4, 256, 0, st>>>(A.rtag, A.ntask, A.task_cap, tlists, nd, phase);
         g_trace.mark(st, "bucket");
         launch_solve<3>(st, A.tasks, tlists + 0 * A.task_cap, nd + 0, cu + 0);
         g_trace.mark(st, "solve3");
@@ -1006,7 +1024,7 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
     }
     np_combine_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
     g_trace.mark(st, "combine");
-    np_general_kernel<IS_VF><<<148 * 2, B, 0, st>>>(Q);
+    np_general_kernel<IS_VF><<<148 * 4, B, 0, st>>>(Q);
     g_trace.mark(st, "general");
     g_trace.flush(IS_VF ? "VF" : "EE", Q.ctr, n);
     return nl + 3 + 3 + 2 * 13 + 1 + 1 + 2;
@@ -1014,7 +1032,7 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
 
 // Single step: q0 = positions packed by ccdk_pack_positions (q1, vstride unused); multi-entry History: q0 == nullptr.
 // Scratch (sizes in elements, n = number of stencils): work list {w_stencil: n ints, w_meta: n ints, w_base: 5n ints},
-// tasks (task_cap records of REC_STRIDE doubles, task_cap < 2^28), tlists (5 x task_cap ints: pending records by degree + refined list),
+// tasks (task_cap records of REC_STRIDE doubles, task_cap < 2^28), tlists (6 x task_cap ints: pending records by degree, refined list, record tags),
 // status (n u32), sbase (5n ints), queues (9n ints: primitive / vertex-edge / vertex-vertex items), sq (2 x n int2: stage
 // queues), xq (5 x n int2: export queues), ctr (CCD_NP_COUNTERS counters, zeroed here; ctr[0] = work-list entries,
 // ctr[1] = records).  Returns the number of kernels launched.  If ctr[1] ends above task_cap the caller must grow the
@@ -1032,7 +1050,7 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
     A.hoff = hoff; A.htime = htime; A.hpos = hpos; A.hit = hit; A.toi = toi; A.stage = stage;
     A.earliest_bits = earliest_bits; A.nhit = nhit;
     A.w_stencil = w_stencil; A.w_meta = w_meta; A.w_base = w_base; A.nwork = ctr + K_NWORK;
-    A.tasks = tasks; A.ntask = ctr + K_NTASK; A.task_cap = task_cap;
+    A.tasks = tasks; A.ntask = ctr + K_NTASK; A.task_cap = task_cap; A.rtag = tlists + 5 * task_cap;
     if (q0 == nullptr)
     {
         if (is_vf) stencil_history_kernel<true><<<grid_for(n, 128), 128, 0, st>>>(A);
