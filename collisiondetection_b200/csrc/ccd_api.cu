@@ -148,8 +148,8 @@ void ccdk_shard_queries(cudaStream_t st, int F, const unsigned *sortedFace, cons
 void ccdk_shard_hist(cudaStream_t st, const int *counts, const void *edgeVerts, int begin, int end, int n, int nb, unsigned long long *hist);
 void ccdk_vert_edge_start(cudaStream_t st, int V, int E, const void *edgeVerts, int *out);
 void ccdk_exact_pairs(cudaStream_t st, int kind, bool both, const unsigned long long *ncand, unsigned long long cap, const void *cand,
-                      const unsigned *sortedFace, const int *faces, const double *boxes, int *pairL, int *pairR, unsigned long long pcap,
-                      unsigned long long *npairs, int *deg, const int *faceEdge, unsigned char *vactive, unsigned char *eactive);
+                      const unsigned *sortedFace, const int *faces, const double *boxes, const double *q0, const double *q1, double eta,
+                      int *pairL, int *pairR, unsigned long long pcap, unsigned long long *npairs, int *deg);
 void ccdk_adjacency_fill(cudaStream_t st, const unsigned long long *npairs, const int *pairL, const int *pairR, const long long *adjOff,
                          int *cursor, int *adj, bool both);
 void ccdk_topology_edges(cudaStream_t st, int F, const int *faces, unsigned long long *keys_in, unsigned long long *keys_sorted,
@@ -161,7 +161,8 @@ void ccdk_topology_faceranks(cudaStream_t st, int F, const int *faces, unsigned 
 void ccdk_topology_star(cudaStream_t st, int V, int F, const int *faces, int *vdeg, long long *starOff, int *cursor, int *star, void *temp,
                         size_t temp_bytes);
 void ccdk_hash_ints(cudaStream_t st, long long n, const int *d, unsigned long long *out);
-void ccdk_active_list(cudaStream_t st, int begin, int end, const unsigned char *active, int *counts, int *alist, unsigned long long *na);
+void ccdk_active_list(cudaStream_t st, int begin, int end, const long long *segOff64, const int *segOff32, const int *segFace, const int *deg,
+                      int *counts, int *alist, unsigned long long *na);
 void ccdk_emit_sort(cudaStream_t st, bool is_vf, const int *alist, const unsigned long long *na, const int *faces, const long long *starOff,
                     const int *star, const int *edgeStart, const int *heFace, const long long *adjOff, const int *adj, const int *faceRank,
                     const int *rankFace, const int *faceEdge, const void *edgeVerts, const unsigned char *fixed, int *counts, long long *kstart,
@@ -348,7 +349,8 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     cudaEventRecord(c->sev[ST_TOPOLOGY], c->st);
     CKR(ensure_topology(c, V, F, d_faces));
 
-    CKR(ensure(c, c->boxes, sizeof(double) * 2 * (size_t)kind * (size_t)F));
+    const bool lazy_boxes = d_q0 != nullptr;      // single step: exact boxes are recomputed in the pair test
+    if (!lazy_boxes) CKR(ensure(c, c->boxes, sizeof(double) * 2 * (size_t)kind * (size_t)F));
     CKR(ensure(c, c->faabb, sizeof(float) * 6 * (size_t)F));
     CKR(ensure(c, c->fkdop, sizeof(float) * 2 * (size_t)kind * (size_t)F));
     CKR(ensure(c, c->bounds, 64));
@@ -370,7 +372,7 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         c->pairCap = (size_t)F * 12 + (1u << 16);
 
     cudaEventRecord(c->sev[ST_BOXES], c->st);
-    ccdk_leaf_boxes(c->st, kind, F, d_faces, d_q0, d_q1, d_hoff, d_hpos, outerEta, P<double>(c->boxes), P<float>(c->faabb), P<float>(c->fkdop));
+    ccdk_leaf_boxes(c->st, kind, F, d_faces, d_q0, d_q1, d_hoff, d_hpos, outerEta, lazy_boxes ? nullptr : P<double>(c->boxes), P<float>(c->faabb), P<float>(c->fkdop));
     cudaEventRecord(c->sev[ST_TREE], c->st);
     ccdk_build_tree(c->st, F, P<float>(c->faabb), P<unsigned>(c->bounds), P<unsigned long long>(c->keysA), P<unsigned long long>(c->keysB),
                     P<unsigned>(c->valsA), P<unsigned>(c->valsB), c->temp.p, c->temp.cap, c->nodes.p, P<int>(c->leafParent),
@@ -410,10 +412,6 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         CK(cudaMemsetAsync(ctr + C_CAND_REG, 0, sizeof(unsigned long long) * CCD_CAND_REGIONS, c->st));
         const size_t regionCap = c->candCap / CCD_CAND_REGIONS;
         CK(cudaMemsetAsync(c->deg.p, 0, sizeof(int) * (size_t)(F + 2), c->st));
-        CKR(ensure(c, c->vactive, (size_t)V + 16));
-        CKR(ensure(c, c->eactive, (size_t)E + 16));
-        CK(cudaMemsetAsync(c->vactive.p, 0, (size_t)V + 16, c->st));
-        CK(cudaMemsetAsync(c->eactive.p, 0, (size_t)E + 16, c->st));
         if (sharded)
         {
             if (attempt == 0)
@@ -430,8 +428,8 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         else
             ccdk_traverse(c->st, kind, F, 0, F, nullptr, false, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p, c->cand.p,
                           regionCap, ctr + C_CAND_REG);
-        ccdk_exact_pairs(c->st, kind, !sharded, ctr + C_CAND_REG, regionCap, c->cand.p, sortedFace, d_faces, P<double>(c->boxes), P<int>(c->pairL),
-                         P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg), P<int>(c->faceEdge), P<unsigned char>(c->vactive), P<unsigned char>(c->eactive));
+        ccdk_exact_pairs(c->st, kind, !sharded, ctr + C_CAND_REG, regionCap, c->cand.p, sortedFace, d_faces, lazy_boxes ? nullptr : P<double>(c->boxes),
+                         lazy_boxes ? d_q0 : nullptr, d_q1, outerEta, P<int>(c->pairL), P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg));
         c->launches += 2;
         CKR(sync_counters(c));
         unsigned long long ncand = 0, maxreg = 0, npairs = c->h_counters[C_NPAIRS];
@@ -491,8 +489,8 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         CKR(ensure(c, c->keysV, sizeof(int) * (3 * ordered + 64)));      // every adjacency entry is seen by the face's 3 vertices
         CKR(ensure(c, c->keysE, sizeof(int) * (9 * ordered + 64)));      // ... and by its 3 edges, each against the neighbour's 3 edges
         CK(cudaMemsetAsync(ctr + C_NA_VF, 0, sizeof(unsigned long long) * 4, c->st));
-        ccdk_active_list(c->st, v0, v1, P<unsigned char>(c->vactive), P<int>(c->vfCounts), P<int>(c->alistV), ctr + C_NA_VF);
-        ccdk_active_list(c->st, e0, e1, P<unsigned char>(c->eactive), P<int>(c->eeCounts), P<int>(c->alistE), ctr + C_NA_EE);
+        ccdk_active_list(c->st, v0, v1, P<long long>(c->starOff), nullptr, P<int>(c->star), P<int>(c->deg), P<int>(c->vfCounts), P<int>(c->alistV), ctr + C_NA_VF);
+        ccdk_active_list(c->st, e0, e1, nullptr, P<int>(c->edgeStart), P<int>(c->heFace), P<int>(c->deg), P<int>(c->eeCounts), P<int>(c->alistE), ctr + C_NA_EE);
         ccdk_emit_sort(c->st, true, P<int>(c->alistV), ctr + C_NA_VF, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
                        P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceRank), P<int>(c->rankFace), P<int>(c->faceEdge),
                        c->edgeVerts.p, d_fixed, P<int>(c->vfCounts), P<long long>(c->kstartV), P<int>(c->keysV), ctr + C_KCUR_VF);
