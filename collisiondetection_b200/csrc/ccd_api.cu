@@ -53,7 +53,7 @@ struct ccd_context
     size_t candCap = 0, pairCap = 0, taskCapVf = 0, taskCapEe = 0;
     // sharding: ownership ranges chosen by the caller (ccd_set_shard_partition), load profile of the last sharded step
     std::vector<int> partV, partE;
-    DBuf qlist, hist, vactive, eactive, vertEdgeStart, alistV, alistE, kstartV, kstartE, keysV, keysE;
+    DBuf qlist, hist, needed, neededPre, nodeFirst, nodeForeign, vactive, eactive, vertEdgeStart, alistV, alistE, kstartV, kstartE, keysV, keysE;
     unsigned long long *h_hist = nullptr;      // pinned, 2 * CCD_SHARD_BUCKETS
     int histV = 0, histE = 0;
     bool hist_valid = false;
@@ -139,19 +139,20 @@ size_t ccdk_sort_temp_bytes(int n);
 void ccdk_exclusive_sum64(cudaStream_t st, void *temp, size_t temp_bytes, int n_plus_1, const int *in, long long *out);
 void ccdk_build_tree(cudaStream_t st, int F, const float *faabb, unsigned *bounds, unsigned long long *keys_in, unsigned long long *keys_sorted,
                      unsigned *vals_in, unsigned *sortedFace, void *temp, size_t temp_bytes, void *nodes, int *leafParent,
-                     int *nodeParent, int *flags);
+                     int *nodeParent, int *flags, int *nodeFirst);
 void ccdk_traverse(cudaStream_t st, int kind, int F, int qbegin, int qend, const int *qlist, bool all, const unsigned *sortedFace,
                    const float *faabb, const int *faces, const float *fkdop, const void *nodes, void *cand, unsigned long long cap,
-                   unsigned long long *count);
+                   unsigned long long *count, const int *needed, const unsigned char *nodeForeign);
 void ccdk_shard_queries(cudaStream_t st, int F, const unsigned *sortedFace, const int *faces, const int *faceEdge, int v0, int v1, int e0, int e1,
-                        int *qlist, unsigned long long *count);
+                        int *qlist, unsigned long long *count, int *needed, int *neededPre, const void *nodes, const int *nodeFirst,
+                        unsigned char *nodeForeign, void *temp, size_t temp_bytes);
 void ccdk_shard_hist(cudaStream_t st, const int *counts, const void *edgeVerts, int begin, int end, int n, int nb, unsigned long long *hist);
 void ccdk_vert_edge_start(cudaStream_t st, int V, int E, const void *edgeVerts, int *out);
 void ccdk_exact_pairs(cudaStream_t st, int kind, bool both, const unsigned long long *ncand, unsigned long long cap, const void *cand,
                       const unsigned *sortedFace, const int *faces, const double *boxes, const double *q0, const double *q1, double eta,
-                      int *pairL, int *pairR, unsigned long long pcap, unsigned long long *npairs, int *deg);
+                      int *pairL, int *pairR, unsigned long long pcap, unsigned long long *npairs, int *deg, const int *needed);
 void ccdk_adjacency_fill(cudaStream_t st, const unsigned long long *npairs, const int *pairL, const int *pairR, const long long *adjOff,
-                         int *cursor, int *adj, bool both);
+                         int *cursor, int *adj);
 void ccdk_topology_edges(cudaStream_t st, int F, const int *faces, unsigned long long *keys_in, unsigned long long *keys_sorted,
                          unsigned *vals_in, unsigned *vals_sorted, void *temp, size_t temp_bytes, int *flags, int *ids, void *edgeVerts,
                          int *edgeStart, int *faceEdge, int *heFace);
@@ -231,7 +232,7 @@ void ccd_destroy(ccd_context *c)
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->shardBounds, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->work2Vf, &c->work2Ee, &c->work2TaskVf, &c->work2TaskEe, &c->work2SubVf, &c->work2SubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->qpack, &c->qlist, &c->hist, &c->vactive, &c->eactive, &c->vertEdgeStart, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->work2Vf, &c->work2Ee, &c->work2TaskVf, &c->work2TaskEe, &c->work2SubVf, &c->work2SubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->qpack, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->nodeFirst, &c->nodeForeign, &c->vactive, &c->eactive, &c->vertEdgeStart, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
     for (DBuf *b : all)
         if (b->p)
             cudaFree(b->p);
@@ -363,6 +364,7 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     CKR(ensure(c, c->leafParent, sizeof(int) * (size_t)F));
     CKR(ensure(c, c->nodeParent, sizeof(int) * (size_t)F));
     CKR(ensure(c, c->flags, sizeof(int) * (size_t)F));
+    CKR(ensure(c, c->nodeFirst, sizeof(int) * (size_t)(F + 1)));
     CKR(ensure(c, c->deg, sizeof(int) * (size_t)(F + 2)));
     CKR(ensure(c, c->cursor, sizeof(int) * (size_t)(F + 2)));
     CKR(ensure(c, c->adjOff, sizeof(long long) * (size_t)(F + 2)));
@@ -376,7 +378,7 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     cudaEventRecord(c->sev[ST_TREE], c->st);
     ccdk_build_tree(c->st, F, P<float>(c->faabb), P<unsigned>(c->bounds), P<unsigned long long>(c->keysA), P<unsigned long long>(c->keysB),
                     P<unsigned>(c->valsA), P<unsigned>(c->valsB), c->temp.p, c->temp.cap, c->nodes.p, P<int>(c->leafParent),
-                    P<int>(c->nodeParent), P<int>(c->flags));
+                    P<int>(c->nodeParent), P<int>(c->flags), P<int>(c->nodeFirst));
     c->launches += 1 + 2 + 8 + 2;
     const unsigned *sortedFace = P<unsigned>(c->valsB);
     cudaEventRecord(c->sev[ST_TRAVERSE_EXACT], c->st);
@@ -401,6 +403,9 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
             e0 = (int)(((long long)E * shard_rank) / shard_world); e1 = (int)(((long long)E * (shard_rank + 1)) / shard_world);
         }
         CKR(ensure(c, c->qlist, sizeof(int) * (size_t)(F + 32)));
+        CKR(ensure(c, c->needed, sizeof(int) * (size_t)(F + 2)));
+        CKR(ensure(c, c->neededPre, sizeof(int) * (size_t)(F + 2)));
+        CKR(ensure(c, c->nodeForeign, (size_t)F + 16));
     }
     int nquery = F;
     for (int attempt = 0; attempt < 8; attempt++)
@@ -417,19 +422,22 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
             if (attempt == 0)
             {
                 CK(cudaMemsetAsync(ctr + C_NQUERY, 0, sizeof(unsigned long long), c->st));
-                ccdk_shard_queries(c->st, F, sortedFace, d_faces, P<int>(c->faceEdge), v0, v1, e0, e1, P<int>(c->qlist), ctr + C_NQUERY);
+                CK(cudaMemsetAsync(P<int>(c->needed) + F, 0, sizeof(int), c->st));
+                ccdk_shard_queries(c->st, F, sortedFace, d_faces, P<int>(c->faceEdge), v0, v1, e0, e1, P<int>(c->qlist), ctr + C_NQUERY, P<int>(c->needed),
+                                   P<int>(c->neededPre), c->nodes.p, P<int>(c->nodeFirst), P<unsigned char>(c->nodeForeign), c->temp.p, c->temp.cap);
                 CKR(sync_counters(c));
                 nquery = (int)c->h_counters[C_NQUERY];
                 c->launches += 1;
             }
             ccdk_traverse(c->st, kind, F, 0, nquery, P<int>(c->qlist), true, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p,
-                          c->cand.p, regionCap, ctr + C_CAND_REG);
+                          c->cand.p, regionCap, ctr + C_CAND_REG, P<int>(c->needed), P<unsigned char>(c->nodeForeign));
         }
         else
             ccdk_traverse(c->st, kind, F, 0, F, nullptr, false, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p, c->cand.p,
-                          regionCap, ctr + C_CAND_REG);
+                          regionCap, ctr + C_CAND_REG, nullptr, nullptr);
         ccdk_exact_pairs(c->st, kind, !sharded, ctr + C_CAND_REG, regionCap, c->cand.p, sortedFace, d_faces, lazy_boxes ? nullptr : P<double>(c->boxes),
-                         lazy_boxes ? d_q0 : nullptr, d_q1, outerEta, P<int>(c->pairL), P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg));
+                         lazy_boxes ? d_q0 : nullptr, d_q1, outerEta, P<int>(c->pairL), P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg),
+                         sharded ? P<int>(c->needed) : nullptr);
         c->launches += 2;
         CKR(sync_counters(c));
         unsigned long long ncand = 0, maxreg = 0, npairs = c->h_counters[C_NPAIRS];
@@ -470,7 +478,7 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, F + 1, P<int>(c->deg), P<long long>(c->adjOff));
     CKR(ensure(c, c->adj, sizeof(int) * (size_t)(2 * res->npairs + 1)));
     CK(cudaMemsetAsync(c->cursor.p, 0, sizeof(int) * (size_t)(F + 2), c->st));
-    ccdk_adjacency_fill(c->st, ctr + C_NPAIRS, P<int>(c->pairL), P<int>(c->pairR), P<long long>(c->adjOff), P<int>(c->cursor), P<int>(c->adj), !sharded);
+    ccdk_adjacency_fill(c->st, ctr + C_NPAIRS, P<int>(c->pairL), P<int>(c->pairR), P<long long>(c->adjOff), P<int>(c->cursor), P<int>(c->adj));
     c->launches += 3;
 
     // Stencil counts of the owned vertices / unique edges, scanned into write offsets (relative to the range start)
@@ -481,7 +489,7 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     cudaEventRecord(c->sev[ST_EMIT_COUNT], c->st);
     {
         // warp-cooperative emission (broadphase.cu section 6b): active items -> unique sorted keys + counts
-        const size_t ordered = (size_t)res->npairs * (sharded ? 1 : 2);      // (face, neighbour) entries in the adjacency lists
+        const size_t ordered = (size_t)res->npairs * 2;      // upper bound of the (face, neighbour) entries in the adjacency lists
         CKR(ensure(c, c->alistV, sizeof(int) * (size_t)(v1 - v0 + 32)));
         CKR(ensure(c, c->alistE, sizeof(int) * (size_t)(e1 - e0 + 32)));
         CKR(ensure(c, c->kstartV, sizeof(long long) * (size_t)(V + 2)));
