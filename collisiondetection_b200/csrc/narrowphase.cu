@@ -518,53 +518,50 @@ template <bool IS_VF> __device__ __forceinline__ double vv_toi(const StencilIn &
     return t;
 }
 
-template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_decide_kernel(P1Args Q)
+// Persistent grid-stride kernel: with one stencil per thread and a few barriers per block, 240 k tiny blocks spent their
+// time being launched.  (Pass 1 no longer produces SC_GENERAL: unconstrained sub-tests are deferred with zero records.)
+template <bool IS_VF> __global__ void __launch_bounds__(256) np_decide_kernel(P1Args Q)
 {
     const NpArgs &A = Q.A;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     constexpr int NSUB = 1 + Subs<IS_VF>::NVE + Subs<IS_VF>::NVV;
-    int stage = 0, meta = 0, nd = 0;
-    bool general = false;
-    int base[5] = {0, 0, 0, 0, 0};
-    double toi = 0.0;
-    if (i < A.n)
+    const unsigned long long n = (unsigned long long)A.n, nround = block_rounded(n);
+    for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < nround; it += (unsigned long long)gridDim.x * blockDim.x)
     {
-        const unsigned st = Q.status[i];
-        unsigned submask = 0;
-        int later_hit = 255;
-        if (st)
+        const long long i = (long long)it;
+        int stage = 0, meta = 0, nd = 0;
+        int base[5] = {0, 0, 0, 0, 0};
+        double toi = 0.0;
+        if (it < n)
         {
-            for (int sub = 0; sub < NSUB; sub++)
+            const unsigned st = Q.status[i];
+            unsigned submask = 0;
+            int later_hit = 255;
+            if (st)
             {
-                const unsigned r = (st >> (2 * sub)) & 3u;
-                if (r == (unsigned)SC_GENERAL) { general = true; break; }
-                if (r == (unsigned)SC_HIT)
+                for (int sub = 0; sub < NSUB; sub++)
                 {
-                    if (nd == 0) stage = sub + 1; else later_hit = sub;
-                    break;
+                    const unsigned r = (st >> (2 * sub)) & 3u;
+                    if (r == (unsigned)SC_HIT)
+                    {
+                        if (nd == 0) stage = sub + 1; else later_hit = sub;
+                        break;
+                    }
+                    if (r == (unsigned)SC_DEFERRED) { base[nd++] = Q.sbase[5 * i + sub]; submask |= 1u << sub; }
                 }
-                if (r == (unsigned)SC_DEFERRED) { base[nd++] = Q.sbase[5 * i + sub]; submask |= 1u << sub; }
             }
-        }
-        if (general) stage = 0;
-        else if (nd == 0)
-        {
-            if (stage)
+            if (nd == 0)
             {
-                StencilIn S;
-                load_single<IS_VF>(A, i, S);
-                toi = vv_toi<IS_VF>(S, stage - 1);
+                if (stage)
+                {
+                    StencilIn S;
+                    load_single<IS_VF>(A, i, S);
+                    toi = vv_toi<IS_VF>(S, stage - 1);
+                }
+                store_result(A, i, stage, toi);
             }
-            store_result(A, i, stage, toi);
+            else { stage = -1; meta = (int)(submask | ((unsigned)later_hit << 8)); }
         }
-        else { stage = -1; meta = (int)(submask | ((unsigned)later_hit << 8)); }
-    }
-    {
-        const unsigned long long o = block_alloc(general ? 1u : 0u, Q.ctr + K_NGEN);
-        if (general) Q.qgen[o] = (int)i;
-    }
-    const bool deferred = stage < 0;
-    {
+        const bool deferred = stage < 0;
         const unsigned long long w = block_alloc(deferred ? 1u : 0u, A.nwork);
         if (deferred)
         {
@@ -572,8 +569,8 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_decide_
             A.w_meta[w] = meta;
             for (int j = 0; j < 5; j++) A.w_base[5 * w + j] = base[j];
         }
+        if (__syncthreads_or(stage > 0)) reduce_block(stage > 0, toi, A.earliest_bits, A.nhit);      // vertex-vertex hits only: rare
     }
-    reduce_block(stage > 0, toi, A.earliest_bits, A.nhit);
 }
 
 // pending records by reduced degree (3..6); final records (closed forms) are skipped
@@ -998,7 +995,7 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
     np_ve_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
     g_trace.mark(st, "ve");
     np_vv_kernel<IS_VF><<<gq, 256, 0, st>>>(Q);
-    np_decide_kernel<IS_VF><<<grid_for(n, B), B, 0, st>>>(Q);
+    np_decide_kernel<IS_VF><<<148 * 8, 256, 0, st>>>(Q);
     g_trace.mark(st, "vv+decide");
     for (int phase = 0; phase < 2; phase++)
     {
