@@ -188,8 +188,10 @@ def main():
         r = ctx.step_device(api.KDOP, V, F, d_f.data_ptr(), d_q0.data_ptr(), d_q1.data_ptr(), wl["outer_eta"], wl["eta"], 0, rank, world)
         # the path's only exchange: earliest TOI, hit / stencil counts and the load profile that balances the next
         # step's ownership ranges — one small all-gather
+        st = ctx.stage_times()
         summary["toi"], summary["hits"], summary["stencils"] = D.exchange_step(
-            ctx, r.earliest_toi, r.n_vf_hits + r.n_ee_hits, r.n_vf_candidates, r.n_ee_candidates, device="cuda")
+            ctx, r.earliest_toi, r.n_vf_hits + r.n_ee_hits, r.n_vf_candidates, r.n_ee_candidates, device="cuda", stage_ms=st)
+        summary["stage_ms"] = st
         return r
 
     def barrier():
@@ -212,7 +214,7 @@ def main():
     for _ in range(args.steps):
         r = step_dev()
         kern_ms += r.ms_broadphase + r.ms_narrowphase
-        for k, v in ctx.stage_times().items():
+        for k, v in summary["stage_ms"].items():
             stage_sum[k] = stage_sum.get(k, 0.0) + v
     e1.record()
     barrier()

@@ -52,7 +52,7 @@ struct ccd_context
     size_t h_res_cap[4] = {0, 0, 0, 0};
     size_t candCap = 0, pairCap = 0, taskCapVf = 0, taskCapEe = 0;
     // sharding: ownership ranges chosen by the caller (ccd_set_shard_partition), load profile of the last sharded step
-    std::vector<int> partV, partE;
+    std::vector<int> partV, partE, h_vertEdgeStart;      // h_vertEdgeStart: host copy of the vertex -> first-edge table (per mesh)
     DBuf qlist, hist, needed, neededPre, nodeFirst, nodeForeign, vactive, eactive, vertEdgeStart, alistV, alistE, kstartV, kstartE, keysV, keysE;
     unsigned long long *h_hist = nullptr;      // pinned, 2 * CCD_SHARD_BUCKETS
     int histV = 0, histE = 0;
@@ -142,7 +142,7 @@ void ccdk_build_tree(cudaStream_t st, int F, const float *faabb, unsigned *bound
                      int *nodeParent, int *flags, int *nodeFirst);
 void ccdk_traverse(cudaStream_t st, int kind, int F, int qbegin, int qend, const int *qlist, bool all, const unsigned *sortedFace,
                    const float *faabb, const int *faces, const float *fkdop, const void *nodes, void *cand, unsigned long long cap,
-                   unsigned long long *count, const int *needed, const unsigned char *nodeForeign);
+                   unsigned long long *count, const int *needed, const unsigned char *nodeForeign, const unsigned long long *qcount);
 void ccdk_shard_queries(cudaStream_t st, int F, const unsigned *sortedFace, const int *faces, const int *faceEdge, int v0, int v1, int e0, int e1,
                         int *qlist, unsigned long long *count, int *needed, int *neededPre, const void *nodes, const int *nodeFirst,
                         unsigned char *nodeForeign, void *temp, size_t temp_bytes);
@@ -322,6 +322,9 @@ static int ensure_topology(ccd_context *c, int V, int F, const int *d_faces)
                        c->temp.cap);
     CKR(ensure(c, c->vertEdgeStart, sizeof(int) * (size_t)(V + 2)));
     ccdk_vert_edge_start(c->st, V, c->nEdges, c->edgeVerts.p, P<int>(c->vertEdgeStart));
+    c->h_vertEdgeStart.resize((size_t)V + 1);
+    CK(cudaMemcpyAsync(c->h_vertEdgeStart.data(), c->vertEdgeStart.p, sizeof(int) * ((size_t)V + 1), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
     c->launches += 5;
     CK(cudaGetLastError());
     c->topoF = F;
@@ -407,7 +410,6 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         CKR(ensure(c, c->neededPre, sizeof(int) * (size_t)(F + 2)));
         CKR(ensure(c, c->nodeForeign, (size_t)F + 16));
     }
-    int nquery = F;
     for (int attempt = 0; attempt < 8; attempt++)
     {
         CKR(ensure(c, c->cand, sizeof(int) * 2 * c->candCap));
@@ -425,16 +427,15 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
                 CK(cudaMemsetAsync(P<int>(c->needed) + F, 0, sizeof(int), c->st));
                 ccdk_shard_queries(c->st, F, sortedFace, d_faces, P<int>(c->faceEdge), v0, v1, e0, e1, P<int>(c->qlist), ctr + C_NQUERY, P<int>(c->needed),
                                    P<int>(c->neededPre), c->nodes.p, P<int>(c->nodeFirst), P<unsigned char>(c->nodeForeign), c->temp.p, c->temp.cap);
-                CKR(sync_counters(c));
-                nquery = (int)c->h_counters[C_NQUERY];
-                c->launches += 1;
+                c->launches += 3;
             }
-            ccdk_traverse(c->st, kind, F, 0, nquery, P<int>(c->qlist), true, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p,
-                          c->cand.p, regionCap, ctr + C_CAND_REG, P<int>(c->needed), P<unsigned char>(c->nodeForeign));
+            // the number of query faces stays on the device: the grid covers all F, the surplus threads leave at once
+            ccdk_traverse(c->st, kind, F, 0, F, P<int>(c->qlist), true, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p,
+                          c->cand.p, regionCap, ctr + C_CAND_REG, P<int>(c->needed), P<unsigned char>(c->nodeForeign), ctr + C_NQUERY);
         }
         else
             ccdk_traverse(c->st, kind, F, 0, F, nullptr, false, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p, c->cand.p,
-                          regionCap, ctr + C_CAND_REG, nullptr, nullptr);
+                          regionCap, ctr + C_CAND_REG, nullptr, nullptr, nullptr);
         ccdk_exact_pairs(c->st, kind, !sharded, ctr + C_CAND_REG, regionCap, c->cand.p, sortedFace, d_faces, lazy_boxes ? nullptr : P<double>(c->boxes),
                          lazy_boxes ? d_q0 : nullptr, d_q1, outerEta, P<int>(c->pairL), P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg),
                          sharded ? P<int>(c->needed) : nullptr);
@@ -897,14 +898,12 @@ int ccd_shard_edge_bounds(ccd_context *c, int world, const int32_t *vbounds, int
         c->err = "ccd_shard_edge_bounds: no mesh topology on this context yet (run a step first)";
         return CCD_ERR_ARG;
     }
-    CK(cudaSetDevice(c->device));
     for (int r = 0; r <= world; r++)
     {
-        if (vbounds[r] < 0 || vbounds[r] > c->topoV)
+        if (vbounds[r] < 0 || vbounds[r] > c->topoV || (size_t)vbounds[r] >= c->h_vertEdgeStart.size())
             return CCD_ERR_ARG;
-        CK(cudaMemcpyAsync(&ebounds[r], P<int>(c->vertEdgeStart) + vbounds[r], sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        ebounds[r] = c->h_vertEdgeStart[(size_t)vbounds[r]];      // host copy made when the topology tables were built
     }
-    CK(cudaStreamSynchronize(c->st));
     return CCD_OK;
 }
 

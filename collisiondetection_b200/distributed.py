@@ -50,6 +50,20 @@ def reduce_step_summary(earliest_toi, n_hits, n_stencils, device="cpu", group=No
     return (float(toi) if np.isfinite(toi) else float("inf")), int(out[1:1 + world].sum()), int(out[1 + world:].sum())
 
 
+_FIRST_CACHE = {}
+
+
+def _bucket_first(n_items, nb):
+    """first item of each bucket b = 0..nb (item i falls in bucket i * nb // n_items)"""
+    key = (int(n_items), int(nb))
+    f = _FIRST_CACHE.get(key)
+    if f is None:
+        f = -(-(np.arange(nb + 1, dtype=np.int64) * int(n_items)) // int(nb))
+        _FIRST_CACHE.clear()
+        _FIRST_CACHE[key] = f
+    return f
+
+
 def balanced_bounds(hist, n_items, world):
     """world+1 ascending item bounds such that every rank gets about the same load, from a load profile.
 
@@ -58,23 +72,20 @@ def balanced_bounds(hist, n_items, world):
     partition."""
     hist = np.asarray(hist, dtype=np.float64)
     nb = len(hist)
-    total = hist.sum()
+    total = float(hist.sum())
     bounds = np.zeros(world + 1, dtype=np.int64)
     bounds[world] = n_items
     if total <= 0 or n_items <= 0:
-        for r in range(1, world):
-            bounds[r] = (n_items * r) // world
+        bounds[1:world] = (int(n_items) * np.arange(1, world, dtype=np.int64)) // world
         return bounds.astype(np.int32)
     cum = np.concatenate([[0.0], np.cumsum(hist)])
-    # first item of bucket b
-    first = [-(-(b * n_items) // nb) for b in range(nb + 1)]
-    for r in range(1, world):
-        target = total * r / world
-        b = int(np.searchsorted(cum, target, side="right") - 1)
-        b = min(max(b, 0), nb - 1)
-        frac = (target - cum[b]) / hist[b] if hist[b] > 0 else 0.0
-        lo, hi = first[b], first[b + 1]
-        bounds[r] = min(max(int(round(lo + frac * (hi - lo))), bounds[r - 1]), n_items)
+    first = _bucket_first(n_items, nb)
+    targets = total * np.arange(1, world, dtype=np.float64) / world
+    b = np.clip(np.searchsorted(cum, targets, side="right") - 1, 0, nb - 1)
+    hb = hist[b]
+    frac = np.where(hb > 0, (targets - cum[b]) / np.where(hb > 0, hb, 1.0), 0.0)
+    raw = np.rint(first[b] + frac * (first[b + 1] - first[b])).astype(np.int64)
+    bounds[1:world] = np.minimum(np.maximum.accumulate(raw), n_items)
     return bounds.astype(np.int32)
 
 
@@ -117,7 +128,7 @@ def exchange_step(ctx, earliest_toi, n_hits, n_vf, n_ee=0, device="cpu", group=N
         c = allr[:, 8].sum() / max(tot_ee, 1.0) + emit_per_stencil
         if not (a > 0 and b > 0 and c > 0):      # no timings (CPU tests): the fixed model
             a, b, c = VERTEX_WEIGHT, 1.0, 1.0
-        items = np.diff([-(-(k * nv) // nb) for k in range(nb + 1)]).astype(np.float64)
+        items = np.diff(_bucket_first(nv, nb)).astype(np.float64)
         load = b * allr[:, nh:nh + nb].sum(axis=0) + c * allr[:, nh + nb:].sum(axis=0) + a * items
         vb = balanced_bounds(load, nv, world)
         eb = ctx.shard_edge_bounds(vb)
