@@ -51,7 +51,7 @@ EXPORTS = [
     "ccd_broadphase_step", "ccd_narrowphase", "ccd_step", "ccd_step_result_free", "ccd_step_device", "ccd_vf_batch",
     "ccd_ee_batch", "ccd_ve_batch", "ccd_vv_batch", "ccd_find_intervals_batch", "ccd_dist_vf_batch",
     "ccd_dist_ee_batch", "ccd_dist_plane_lt_batch", "ccd_dist_line_lt_batch", "ccd_mesh_self_distance",
-    "ccd_memcpy_d2h", "ccd_fp64_peak", "ccd_stage_times", "ccd_step_shard", "ccd_set_shard_partition", "ccd_shard_histogram", "ccd_shard_edge_bounds",
+    "ccd_memcpy_d2h", "ccd_fp64_peak", "ccd_stage_times", "ccd_step_shard", "ccd_set_shard_partition", "ccd_shard_histogram", "ccd_shard_edge_bounds", "ccd_narrowphase_sepplane",
 ]
 
 _LIB = None
@@ -181,6 +181,26 @@ class Context(object):
 
     # ---- whole step (example/AlecTest.cpp:86-111) ---------------------------------------------
     STAGES = ("topology", "leaf_boxes", "tree_build", "traverse_exact", "adjacency", "emit_count", "emit_write", "np_vf", "np_ee")
+
+    def findCollisionsSeparatingPlane(self, hoff, htime, hpos, vf, vf_eta, ee, ee_eta):
+        """SeparatingPlaneNarrowPhase::findCollisions (ccd_narrowphase_sepplane): hit flags per candidate."""
+        hoff = np.ascontiguousarray(hoff, dtype=np.int64)
+        htime = _f64(htime)
+        hpos = _f64(hpos).reshape(-1)
+        V = hoff.size - 1
+        vf = np.ascontiguousarray(vf, dtype=np.int32).reshape(-1, 4)
+        ee = np.ascontiguousarray(ee, dtype=np.int32).reshape(-1, 4)
+        nvf, nee = len(vf), len(ee)
+        vf_eta = np.ascontiguousarray(np.broadcast_to(np.asarray(vf_eta, dtype=np.float64), (nvf,)))
+        ee_eta = np.ascontiguousarray(np.broadcast_to(np.asarray(ee_eta, dtype=np.float64), (nee,)))
+        vf_hit = np.zeros(nvf, np.uint8)
+        ee_hit = np.zeros(nee, np.uint8)
+        nh = (C.c_int64(), C.c_int64())
+        rc = self.lib.ccd_narrowphase_sepplane(self.h, C.c_int(V), _ptr(hoff, _lp), _ptr(htime, _dp), _ptr(hpos, _dp), C.c_int64(nvf), _ptr(vf, _ip),
+                                               _ptr(vf_eta, _dp), C.c_int64(nee), _ptr(ee, _ip), _ptr(ee_eta, _dp), _ptr(vf_hit, _bp), _ptr(ee_hit, _bp),
+                                               C.byref(nh[0]), C.byref(nh[1]))
+        self._check(rc, "ccd_narrowphase_sepplane")
+        return dict(vf_hit=vf_hit, ee_hit=ee_hit, n_vf_hits=nh[0].value, n_ee_hits=nh[1].value)
 
     def stage_times(self):
         """Device ms per stage of the last step (ccd_stage_times)."""

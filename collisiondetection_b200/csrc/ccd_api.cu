@@ -752,6 +752,56 @@ int ccd_narrowphase(ccd_context *c, int V, const int64_t *hoff, const double *ht
     return CCD_OK;
 }
 
+// SeparatingPlaneNarrowPhase::findCollisions (src/SeparatingPlaneNarrowPhase.cpp:11-25)
+int ccd_narrowphase_sepplane(ccd_context *c, int V, const int64_t *hoff, const double *htime, const double *hpos, int64_t nvf, const int32_t *vf,
+                             const double *vf_eta, int64_t nee, const int32_t *ee, const double *ee_eta, uint8_t *vf_hit, uint8_t *ee_hit,
+                             int64_t *n_vf_hits, int64_t *n_ee_hits)
+{
+    if (!c || V < 0 || nvf < 0 || nee < 0 || (V > 0 && (!hoff || !htime || !hpos)) || (nvf > 0 && (!vf || !vf_eta || !vf_hit)) ||
+        (nee > 0 && (!ee || !ee_eta || !ee_hit)))
+        return CCD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    c->launches = 0;
+    const long long N = V > 0 ? (long long)hoff[V] : 0;
+    // History::computeMinimumGap (src/History.cpp:82-96) / 4
+    double gap = 1.0;
+    for (int v = 0; v < V; v++)
+        for (long long j = hoff[v] + 1; j < hoff[v + 1]; j++)
+        {
+            const double g = htime[j] - htime[j - 1];
+            gap = g < gap ? g : gap;
+        }
+    const double eps = gap / 4.0;
+    CKR(upload(c, c->hoff, hoff, sizeof(int64_t) * ((size_t)V + 1)));
+    CKR(upload(c, c->htime, htime, sizeof(double) * (size_t)N));
+    CKR(upload(c, c->hpos, hpos, sizeof(double) * 3 * (size_t)N));
+    CKR(upload(c, c->vf_in, vf, sizeof(int32_t) * 4 * (size_t)nvf));
+    CKR(upload(c, c->ee_in, ee, sizeof(int32_t) * 4 * (size_t)nee));
+    CKR(upload(c, c->vf_eta, vf_eta, sizeof(double) * (size_t)nvf));
+    CKR(upload(c, c->ee_eta, ee_eta, sizeof(double) * (size_t)nee));
+    CKR(ensure(c, c->vfHit, (size_t)nvf + 16));
+    CKR(ensure(c, c->eeHit, (size_t)nee + 16));
+    unsigned long long *ctr = P<unsigned long long>(c->counters);
+    CK(cudaMemsetAsync(ctr + C_EARLY_VF, 0, sizeof(unsigned long long) * 4, c->st));
+    ccdk_sepplane(c->st, true, nvf, P<int>(c->vf_in), P<double>(c->vf_eta), P<long long>(c->hoff), P<double>(c->htime), P<double>(c->hpos), eps,
+                  P<unsigned char>(c->vfHit), ctr + C_NHIT_VF, ctr + C_EARLY_VF);
+    ccdk_sepplane(c->st, false, nee, P<int>(c->ee_in), P<double>(c->ee_eta), P<long long>(c->hoff), P<double>(c->htime), P<double>(c->hpos), eps,
+                  P<unsigned char>(c->eeHit), ctr + C_NHIT_EE, ctr + C_EARLY_EE);
+    c->launches += 2;
+    CK(cudaGetLastError());
+    if (nvf > 0) CK(cudaMemcpyAsync(vf_hit, c->vfHit.p, (size_t)nvf, cudaMemcpyDeviceToHost, c->st));
+    if (nee > 0) CK(cudaMemcpyAsync(ee_hit, c->eeHit.p, (size_t)nee, cudaMemcpyDeviceToHost, c->st));
+    CKR(sync_counters(c));
+    if (c->h_counters[C_EARLY_VF] || c->h_counters[C_EARLY_EE])
+    {
+        c->err = "narrowphase_sepplane: interval stack overflow (History with extremely small time gaps)";
+        return CCD_ERR_NOMEM;
+    }
+    if (n_vf_hits) *n_vf_hits = (int64_t)c->h_counters[C_NHIT_VF];
+    if (n_ee_hits) *n_ee_hits = (int64_t)c->h_counters[C_NHIT_EE];
+    return CCD_OK;
+}
+
 int ccd_step_device(ccd_context *c, int kind, int V, int F, const int32_t *d_faces, const double *d_q0, const double *d_q1, double outerEta,
                     double eta, const uint8_t *d_fixedMask, int shard_rank, int shard_world, ccd_device_result *out)
 {

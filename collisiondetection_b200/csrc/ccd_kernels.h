@@ -14,3 +14,6 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
 void ccdk_pack_positions(cudaStream_t st, int V, const double *q0, const double *q1, int vstride, double *qpack, float *vbox);
 void ccdk_prim_batch(cudaStream_t st, int kind, long long n, const double *pts, const double *eta, unsigned char *hit, double *t);
 void ccdk_find_intervals(cudaStream_t st, long long n, int degree, int pos, const double *coeffs, int *cnt, double *lo, double *hi);
+// SeparatingPlaneNarrowPhase: hit flags only; *nhit += hits, *err += stencils whose interval stack overflowed
+void ccdk_sepplane(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, const long long *hoff, const double *htime,
+                   const double *hpos, double eps, unsigned char *hit, unsigned long long *nhit, unsigned long long *err);

@@ -30,6 +30,7 @@
 #include "ccd_classify.cuh"
 #include "ccd_solve.cuh"
 #include "ccd_stages.cuh"
+#include "ccd_sepplane.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -837,6 +838,26 @@ template <bool IS_VF> __global__ void __launch_bounds__(128) np_general_kernel(P
     }
 }
 
+// SeparatingPlaneNarrowPhase::findCollisions (src/SeparatingPlaneNarrowPhase.cpp:11-25): one thread per stencil runs the
+// interval search of ccd_sepplane.cuh; flag = 1 hit, 0 miss.  err counts stencils whose interval stack overflowed.
+template <bool IS_VF>
+__global__ void __launch_bounds__(128) sepplane_kernel(long long n, const int *__restrict__ stencils, const double *__restrict__ eta_arr, HistView H,
+                                                       double eps, unsigned char *__restrict__ hit, unsigned long long *nhit, unsigned long long *err)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int r = 0;
+    if (i < n)
+    {
+        const int4 s = reinterpret_cast<const int4 *>(stencils)[i];
+        const int verts[4] = {s.x, s.y, s.z, s.w};
+        r = sp_check_stencil<IS_VF>(H, verts, eta_arr[i], eps);
+        hit[i] = r > 0;
+        if (r < 0) atomicAdd(err, 1ull);
+    }
+    const unsigned long long o = block_alloc(r > 0 ? 1u : 0u, nhit);
+    (void)o;
+}
+
 // multi-entry History: stitched segments, full algorithm in one pass
 template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_history_kernel(NpArgs A)
 {
@@ -1063,6 +1084,16 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
     Q.qgen = queues;      // the primitive queue is consumed by stage 0 long before anything goes to the general routine
     Q.ctr = ctr;
     return is_vf ? launch_single_step<true>(st, Q, n, tlists) : launch_single_step<false>(st, Q, n, tlists);
+}
+
+void ccdk_sepplane(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, const long long *hoff, const double *htime,
+                   const double *hpos, double eps, unsigned char *hit, unsigned long long *nhit, unsigned long long *err)
+{
+    if (n <= 0) return;
+    HistView H;
+    H.hoff = hoff; H.htime = htime; H.hpos = hpos;
+    if (is_vf) sepplane_kernel<true><<<grid_for(n, 128), 128, 0, st>>>(n, stencils, eta_arr, H, eps, hit, nhit, err);
+    else sepplane_kernel<false><<<grid_for(n, 128), 128, 0, st>>>(n, stencils, eta_arr, H, eps, hit, nhit, err);
 }
 
 void ccdk_pack_positions(cudaStream_t st, int V, const double *q0, const double *q1, int vstride, double *qpack, float *vbox)

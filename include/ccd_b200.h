@@ -77,6 +77,14 @@ int ccd_narrowphase(ccd_context *ctx, int V, const int64_t *hoff, const double *
                     const double *ee_eta, uint8_t *vf_hit, double *vf_toi, uint8_t *vf_stage, uint8_t *ee_hit,
                     double *ee_toi, uint8_t *ee_stage, ccd_np_summary *summary);
 
+/* NarrowPhase::findCollisions as SeparatingPlaneNarrowPhase (src/SeparatingPlaneNarrowPhase.cpp:11-278), the narrowphase
+ * ActiveLayers instantiates (src/ActiveLayers.cpp:28): recursive interval culling with the plane between the closest
+ * points at an interval's midpoint, CTCD primitives on the short intervals that remain.  Same inputs as ccd_narrowphase;
+ * outputs are the hit flags (the reference returns nothing else).  eps = History::computeMinimumGap() / 4. */
+int ccd_narrowphase_sepplane(ccd_context *ctx, int V, const int64_t *hoff, const double *htime, const double *hpos,
+                             int64_t nvf, const int32_t *vf, const double *vf_eta, int64_t nee, const int32_t *ee,
+                             const double *ee_eta, uint8_t *vf_hit, uint8_t *ee_hit, int64_t *n_vf_hits, int64_t *n_ee_hits);
+
 /* ---- one whole CCD step, the flow of example/AlecTest.cpp:86-111: broadphase with outerEta, every
  * candidate wrapped with thickness `eta`, CTCD narrowphase.  Returns the colliding stencils (sorted)
  * with their TOIs; candidate arrays are returned only when the pointers are non-NULL. */

@@ -189,6 +189,53 @@ public:
     double earliestTOI;
 };
 
+// src/SeparatingPlaneNarrowPhase.h:8-22 — the narrowphase ActiveLayers owns (src/ActiveLayers.cpp:28)
+class SeparatingPlaneNarrowPhase : public ::NarrowPhase
+{
+public:
+    SeparatingPlaneNarrowPhase() { context(); }
+
+    virtual void findCollisions(const History &h, const std::set<std::pair<VertexFaceStencil, double> > &candidateVFS,
+                                const std::set<std::pair<EdgeEdgeStencil, double> > &candidateEES, std::set<VertexFaceStencil> &vfs,
+                                std::set<EdgeEdgeStencil> &ees)
+    {
+        int V = 0;
+        std::vector<int32_t> vf, ee;
+        std::vector<double> vfe, eee;
+        vf.reserve(4 * candidateVFS.size());
+        ee.reserve(4 * candidateEES.size());
+        for (std::set<std::pair<VertexFaceStencil, double> >::const_iterator it = candidateVFS.begin(); it != candidateVFS.end(); ++it)
+        {
+            const int s[4] = {it->first.p, it->first.q0, it->first.q1, it->first.q2};
+            for (int k = 0; k < 4; k++) { vf.push_back(s[k]); if (s[k] + 1 > V) V = s[k] + 1; }
+            vfe.push_back(it->second);
+        }
+        for (std::set<std::pair<EdgeEdgeStencil, double> >::const_iterator it = candidateEES.begin(); it != candidateEES.end(); ++it)
+        {
+            const int s[4] = {it->first.p0, it->first.p1, it->first.q0, it->first.q1};
+            for (int k = 0; k < 4; k++) { ee.push_back(s[k]); if (s[k] + 1 > V) V = s[k] + 1; }
+            eee.push_back(it->second);
+        }
+        FlatHistory fh(h, V);
+        const int64_t nvf = (int64_t)vfe.size(), nee = (int64_t)eee.size();
+        vfHit.assign(nvf, 0);
+        eeHit.assign(nee, 0);
+        check(ccd_narrowphase_sepplane(context(), V, fh.off.data(), fh.time.data(), fh.pos.data(), nvf, vf.data(), vfe.data(), nee, ee.data(),
+                                       eee.data(), vfHit.data(), eeHit.data(), 0, 0),
+              "ccd_narrowphase_sepplane");
+        int64_t i = 0;
+        for (std::set<std::pair<VertexFaceStencil, double> >::const_iterator it = candidateVFS.begin(); it != candidateVFS.end(); ++it, ++i)
+            if (vfHit[i])
+                vfs.insert(it->first);
+        i = 0;
+        for (std::set<std::pair<EdgeEdgeStencil, double> >::const_iterator it = candidateEES.begin(); it != candidateEES.end(); ++it, ++i)
+            if (eeHit[i])
+                ees.insert(it->first);
+    }
+
+    std::vector<uint8_t> vfHit, eeHit;      // per-candidate flags of the last call, in the iteration order of the candidate sets
+};
+
 // include/CTCD.h:36-79 — a single call is a batch of one on the GPU
 struct CTCD
 {

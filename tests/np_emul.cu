@@ -12,6 +12,7 @@
 #include "../collisiondetection_b200/csrc/ccd_classify.cuh"
 #include "../collisiondetection_b200/csrc/ccd_solve.cuh"
 #include "../collisiondetection_b200/csrc/ccd_stages.cuh"
+#include "../collisiondetection_b200/csrc/ccd_sepplane.cuh"
 #include <vector>
 #include <string.h>
 
@@ -237,4 +238,21 @@ extern "C" int np_emul_roots(int d, const double *c, double *roots)
     else return -1;
     for (int k = 0; k < n; k++) roots[k] = r[k];
     return n;
+}
+
+// SeparatingPlaneNarrowPhase (ccd_sepplane.cuh) for a list of stencils over a CSR History; returns the number of stencils
+// whose interval stack overflowed
+extern "C" int np_emul_sepplane(int is_vf, long long n, const int *stencils, const double *eta, const long long *hoff, const double *htime,
+                                const double *hpos, double eps, unsigned char *hit)
+{
+    HistView H;
+    H.hoff = hoff; H.htime = htime; H.hpos = hpos;
+    int bad = 0;
+    for (long long i = 0; i < n; i++)
+    {
+        const int r = is_vf ? sp_check_stencil<true>(H, stencils + 4 * i, eta[i], eps) : sp_check_stencil<false>(H, stencils + 4 * i, eta[i], eps);
+        hit[i] = r > 0;
+        bad += r < 0;
+    }
+    return bad;
 }

@@ -120,6 +120,23 @@ def test_multi_entry_history(ctx, port):
         assert np.array_equal(out[k + "_toi"].view(np.uint64), p[k + "_toi"].view(np.uint64))
 
 
+@pytest.mark.parametrize("name", ["alec_prob11_835", "history_prob3_402", "alec_prob3_402_thick"])
+def test_separating_plane_narrowphase(ctx, name):
+    """ccd_narrowphase_sepplane against the UNMODIFIED reference's SeparatingPlaneNarrowPhase (oracle/_ref, which travels to
+    the GPU box): same hit flags (the host build of the same code matches it with 0 mismatches, tests/test_np_emul.py)."""
+    from oracle import bind
+    if not bind.have_ref():
+        pytest.skip("oracle/_ref not built")
+    g = golden(name + ".npz")
+    H = (g["hoff"], g["htime"], g["hpos"]) if "hoff" in g.files else _single(g)
+    eta = float(g["eta"])
+    vf, ee = g["ref_vf"], g["ref_ee"]
+    r = bind.Ref().narrowphase(*H, vf, eta, ee, eta, which=1)
+    out = ctx.findCollisionsSeparatingPlane(*H, vf, eta, ee, eta)
+    assert np.array_equal(out["vf_hit"], r["vf_hit"]) and np.array_equal(out["ee_hit"], r["ee_hit"])
+    assert out["n_vf_hits"] == int(r["vf_hit"].sum()) and out["n_ee_hits"] == int(r["ee_hit"].sum())
+
+
 def test_per_stencil_eta(ctx, port):
     """Thickness comes per stencil (ActiveLayers.cpp:196-207 varies it with layer depth)."""
     g = golden("alec_prob3_402_thick.npz")
