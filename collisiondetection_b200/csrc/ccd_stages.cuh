@@ -26,9 +26,11 @@ enum { SC_MISS = 0, SC_HIT = 1, SC_DEFERRED = 2, SC_GENERAL = 3 };
 template <bool IS_VF> struct Prim
 {
     static constexpr int NST = IS_VF ? 4 : 5;      // polynomials = stages
-    // polynomial handled by stage s, in the reference's order: VF e1,e2,e3,coplanarity (src/CTCD.cpp:433-475);
-    // EE distance sextic first, then a0,a1,b0,b1 (src/CTCD.cpp:266-350)
-    static CCD_HD constexpr int poly(int s) { return IS_VF ? s : (s == 0 ? 4 : s - 1); }
+    // polynomial handled by stage s: VF e1,e2,e3,coplanarity (src/CTCD.cpp:433-475); EE a0,a1,b0,b1 and the distance sextic
+    // LAST (the reference tests it first, src/CTCD.cpp:266-350, but the verdict is a conjunction: once the swept-box cull
+    // has run the sextic rejects only ~6 % of the stencils while each quartic rejects ~20 %, so the expensive polynomial
+    // is built for half as many stencils this way — and its record is written by the stage itself, not rebuilt)
+    static CCD_HD constexpr int poly(int s) { return s; }
     static CCD_HD constexpr int degree(int k) { return IS_VF ? (k < 3 ? 3 : 6) : (k < 4 ? 4 : 6); }
     static CCD_HD constexpr bool pos(int k) { return IS_VF ? (k < 3) : (k < 4); }
 };

@@ -228,7 +228,7 @@ __device__ __forceinline__ void store_result(const NpArgs &A, long long i, int s
 //   cull      one thread per stencil: swept-box culling -> the sub-tests that have to be evaluated at all become items
 //             of three queues (primitive / vertex-edge / vertex-vertex);
 //   stage<S>  one thread per surviving stencil, ONE polynomial of the primitive per kernel (VF: e1,e2,e3,coplanarity;
-//             EE: distance sextic, a0,a1,b0,b1): most stencils leave at the first or second polynomial, and the
+//             EE: a0,a1,b0,b1, distance sextic): most stencils leave at the first or second polynomial, and the
 //             survivors are compacted before the next one, so warps stay full.  The last stage reserves the records of
 //             a surviving stencil and feeds one export queue per polynomial;
 //   export<K> rebuilds polynomial K for the survivors that need its record (all lanes build the same polynomial);
@@ -987,28 +987,26 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
     g_trace.mark(st, "start");
     np_cull_kernel<IS_VF><<<grid_for(n, 256), 256, 0, st>>>(Q);
     g_trace.mark(st, "cull");
-    np_stage_kernel<IS_VF, 0, false><<<gq, B, 0, st>>>(Q, 0, 0);
-    g_trace.mark(st, "stage0");
-    int nl = 2;
+    int nl = 1;
     if (IS_VF)
     {
-        np_stage_kernel<IS_VF, 1, false><<<gq, B, 0, st>>>(Q, 0, 1);
-        np_stage_kernel<IS_VF, 2, false><<<gq, B, 0, st>>>(Q, 1, 0);
-        np_stage_kernel<IS_VF, 3, false><<<gq, B, 0, st>>>(Q, 0, 1);
-        nl += 3;
+        np_stage_kernel<true, 0, false><<<gq, B, 0, st>>>(Q, 0, 0);
+        g_trace.mark(st, "stage0");
+        np_stage_kernel<true, 1, false><<<gq, B, 0, st>>>(Q, 0, 1);
+        np_stage_kernel<true, 2, false><<<gq, B, 0, st>>>(Q, 1, 0);
+        np_stage_kernel<true, 3, false><<<gq, B, 0, st>>>(Q, 0, 1);
+        nl += 4;
     }
     else
     {
-        np_stage_kernel<false, 1, true><<<gq, B, 0, st>>>(Q, 0, 1);      // a0, a1
-        np_stage_kernel<false, 3, true><<<gq, B, 0, st>>>(Q, 1, 0);      // b0, b1 (last)
-        nl += 2;
+        np_stage_kernel<false, 0, true><<<gq, B, 0, st>>>(Q, 0, 0);      // a0, a1
+        g_trace.mark(st, "stage0");
+        np_stage_kernel<false, 2, true><<<gq, B, 0, st>>>(Q, 0, 1);      // b0, b1
+        np_stage_kernel<false, 4, false><<<gq, B, 0, st>>>(Q, 1, 0);     // distance sextic (last: writes its own record)
+        np_export_kernel<false, 3><<<gq, B, 0, st>>>(Q);
+        nl += 4;
     }
     g_trace.mark(st, "stages");
-    if (!IS_VF)
-    {
-        np_export_kernel<false, 4><<<gq, B, 0, st>>>(Q);
-        nl += 1;
-    }
     np_export_kernel<IS_VF, 0><<<gq, B, 0, st>>>(Q);
     np_export_kernel<IS_VF, 1><<<gq, B, 0, st>>>(Q);
     np_export_kernel<IS_VF, 2><<<gq, B, 0, st>>>(Q);

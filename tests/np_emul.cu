@@ -95,7 +95,7 @@ template <bool IS_VF> int primitive(const V3 *a, const V3 *v, double eta, std::v
         else if (k == 0) run_export<IS_VF, 0>(a, v, eta, r);
         else if (k == 1) run_export<IS_VF, 1>(a, v, eta, r);
         else if (k == 2) run_export<IS_VF, 2>(a, v, eta, r);
-        else if (k == 4) run_export<false, 4>(a, v, eta, r);
+        else if (k == 3) run_export<false, 3>(a, v, eta, r);
         recs.push_back(r);
         nrec++;
     }
