@@ -42,9 +42,9 @@ struct ccd_context
     int topoF = -1, topoV = -1, nEdges = 0;
     unsigned long long topoHashVal = 0;
     // emission
-    DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut, shardBounds;
+    DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut;
     // narrowphase
-    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, work2Vf, work2Ee, work2TaskVf, work2TaskEe, work2SubVf, work2SubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, qpack, selTmp, selA, selB, selC, selD, selCount;
+    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, qpack, selTmp, selA, selB, selC, selD, selCount;
     // pinned host scratch
     unsigned long long *h_counters = nullptr; // C_TOTAL entries
     // pinned host buffers for the hit lists returned by ccd_step (valid until the next call on the context)
@@ -53,7 +53,7 @@ struct ccd_context
     size_t candCap = 0, pairCap = 0, taskCapVf = 0, taskCapEe = 0;
     // sharding: ownership ranges chosen by the caller (ccd_set_shard_partition), load profile of the last sharded step
     std::vector<int> partV, partE, h_vertEdgeStart;      // h_vertEdgeStart: host copy of the vertex -> first-edge table (per mesh)
-    DBuf qlist, hist, needed, neededPre, nodeFirst, nodeForeign, vactive, eactive, vertEdgeStart, alistV, alistE, kstartV, kstartE, keysV, keysE;
+    DBuf qlist, hist, needed, neededPre, nodeFirst, nodeForeign, vertEdgeStart, alistV, alistE, kstartV, kstartE, keysV, keysE;
     unsigned long long *h_hist = nullptr;      // pinned, 2 * CCD_SHARD_BUCKETS
     int histV = 0, histE = 0;
     bool hist_valid = false;
@@ -172,7 +172,6 @@ void ccdk_emit_write(cudaStream_t st, bool is_vf, const int *alist, const unsign
                      const int *star, const int *edgeStart, const int *heFace, const long long *adjOff, const int *adj, const int *faceRank,
                      const int *rankFace, const int *faceEdge, const void *edgeVerts, const unsigned char *fixed, const int *counts,
                      const long long *kstart, const int *keys_in, const long long *offsets, int *out);
-void ccdk_shard_bounds(cudaStream_t st, const long long *offsets, int n, int rank, int world, int *out);
 void ccdk_dist_batch(cudaStream_t st, int which, long long n, const double *pts, const double *eta, double *vec, double *bary, unsigned char *flag);
 void ccdk_vertex_min_dist2(cudaStream_t st, int V, int F, const double *verts, const int *faces, unsigned long long *out_bits);
 void ccdk_stencil_min_dist(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *verts, unsigned long long *out_bits);
@@ -231,8 +230,8 @@ void ccd_destroy(ccd_context *c)
                    &c->leafParent, &c->nodeParent, &c->flags, &c->cand, &c->counters, &c->pairL, &c->pairR, &c->deg, &c->adjOff,
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
-                   &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->shardBounds, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->work2Vf, &c->work2Ee, &c->work2TaskVf, &c->work2TaskEe, &c->work2SubVf, &c->work2SubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->qpack, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->nodeFirst, &c->nodeForeign, &c->vactive, &c->eactive, &c->vertEdgeStart, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
+                   &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->qpack, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->nodeFirst, &c->nodeForeign, &c->vertEdgeStart, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
     for (DBuf *b : all)
         if (b->p)
             cudaFree(b->p);
