@@ -592,6 +592,8 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         CKR(ensure(c, c->tasksEe, 128 * c->taskCapEe));
         CKR(ensure(c, c->tlistVf, sizeof(int) * 6 * c->taskCapVf));
         CKR(ensure(c, c->tlistEe, sizeof(int) * 6 * c->taskCapEe));
+        // (a run with no stencils of one type launches nothing for it: its counters must not keep an earlier call's values)
+        CK(cudaMemsetAsync(ctr + C_NP_VF, 0, sizeof(unsigned long long) * 2 * CCD_NP_COUNTERS, c->st));
         unsigned long long init[4] = {0xFFFFFFFFFFFFFFFFull, 0ull, 0xFFFFFFFFFFFFFFFFull, 0ull};
         memcpy(c->h_counters + 8, init, sizeof(init));
         CK(cudaMemcpyAsync(ctr + C_EARLY_VF, c->h_counters + 8, sizeof(init), cudaMemcpyHostToDevice, c->st));
