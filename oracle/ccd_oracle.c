@@ -911,6 +911,10 @@ void orc_narrowphase_flat(int V, const long long *hoff, const double *htime, con
     }
 }
 
+int orc_narrowphase_sepplane(int V, const long long *hoff, const double *htime, const double *hpos, long long nvf, const int *vf,
+                             const double *vf_eta, long long nee, const int *ee, const double *ee_eta, unsigned char *vf_hit,
+                             unsigned char *ee_hit);
+
 /* CTCDNarrowPhase::findCollisions, src/CTCDNarrowPhase.cpp:9-22 (flat arrays instead of sets) */
 int orc_narrowphase(int which, int V, const long long *hoff, const double *htime, const double *hpos,
                     long long nvf, const int *vf, const double *vf_eta, long long nee, const int *ee,
@@ -921,7 +925,13 @@ int orc_narrowphase(int which, int V, const long long *hoff, const double *htime
     double t0 = now_s();
     (void)V;
     if (which != 0)
-        return -1;
+    {
+        /* SeparatingPlaneNarrowPhase: flags only (no TOI / stage) */
+        int rc = orc_narrowphase_sepplane(V, hoff, htime, hpos, nvf, vf, vf_eta, nee, ee, ee_eta, vf_hit, ee_hit);
+        if (seconds)
+            *seconds = now_s() - t0;
+        return rc;
+    }
     for (i = 0; i < nvf; i++)
     {
         double t = 0; int st = 0;
@@ -1385,4 +1395,212 @@ double orc_mesh_self_distance(int V, const double *verts, int F, const int *face
     if (seconds)
         *seconds = now_s() - t0;
     return closest;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * SeparatingPlaneNarrowPhase  (src/SeparatingPlaneNarrowPhase.cpp:11-278), recursive like the reference
+ * ---------------------------------------------------------------------------------------- */
+typedef struct
+{
+    const long long *hoff;
+    const double *htime;
+    const double *hpos;
+} hist_t;
+
+/* History::getPosAtTime, src/History.cpp:49-80 (the bisection there only moves the start of this scan) */
+static void sp_pos_at(const hist_t *H, int vert, double time, v3 *pos, int *idx)
+{
+    const long long b = H->hoff[vert], e = H->hoff[vert + 1];
+    long long next = b, prev;
+    while (next < e && H->htime[next] <= time)
+        next++;
+    prev = next - 1;
+    if (next == e)
+    {
+        *pos = ld(H->hpos + 3 * prev);
+        *idx = (int)(prev - b);
+        return;
+    }
+    {
+        double dt = H->htime[next] - H->htime[prev];
+        double alpha = (time - H->htime[prev]) / dt;
+        *pos = add(scl(1.0 - alpha, ld(H->hpos + 3 * prev)), scl(alpha, ld(H->hpos + 3 * next)));
+        *idx = (int)(prev - b);
+    }
+}
+
+/* planeIntersect, :266-276 */
+static double sp_plane_intersect(v3 planePos, v3 planeVel, v3 planeNormal, v3 ptOld, v3 ptNew, double ptdt, double eta)
+{
+    double numerator = 0.5 * eta - dot(sub(ptOld, planePos), planeNormal);
+    double denom = -dot(planeVel, planeNormal);
+    if (ptdt != 0.0)
+        denom += dot(sub(ptNew, ptOld), planeNormal) / ptdt;
+    return numerator / denom;
+}
+
+/* planeTrajectoryIntersect, :220-264 */
+static double sp_trajectory(const hist_t *H, int vert, int startidx, int forward, v3 planePos, v3 planeVel, v3 planeNormal,
+                            v3 ptstart, double timestart, double eta)
+{
+    const long long b = H->hoff[vert];
+    const int size = (int)(H->hoff[vert + 1] - b);
+    const double *ht = H->htime + b, *hp = H->hpos + 3 * b;
+    int i;
+    {
+        double dt = forward ? ht[startidx] - timestart : timestart - ht[startidx];
+        double t = sp_plane_intersect(planePos, scl(forward ? 1.0 : -1.0, planeVel), planeNormal, ptstart, ld(hp + 3 * startidx), dt, eta);
+        if (t >= 0 && t <= dt)
+            return t;
+    }
+    if (forward)
+    {
+        for (i = startidx; i < size; i++)
+        {
+            double dt, t;
+            if (i == size - 1)
+                return INFINITY;
+            dt = ht[i + 1] - ht[i];
+            t = sp_plane_intersect(add(planePos, scl(ht[i] - timestart, planeVel)), planeVel, planeNormal, ld(hp + 3 * i), ld(hp + 3 * (i + 1)), dt, eta);
+            if (t >= 0 && t <= dt)
+                return ht[i] + t - timestart;
+        }
+    }
+    else
+    {
+        for (i = startidx; i >= 0; i--)
+        {
+            double dt, t;
+            if (i == 0)
+                return INFINITY;
+            dt = ht[i] - ht[i - 1];
+            t = sp_plane_intersect(sub(planePos, scl(timestart - ht[i], planeVel)), scl(-1.0, planeVel), planeNormal, ld(hp + 3 * i), ld(hp + 3 * (i - 1)), dt, eta);
+            if (t >= 0 && t <= dt)
+                return timestart - (ht[i] - t);
+        }
+    }
+    return INFINITY;
+}
+
+/* the CTCD tests of a short interval inside one History segment, :76-140 */
+static int sp_segment(int is_vf, const v3 *oldpos, const v3 *newpos, double eta)
+{
+    static const int ve_ee[4][3] = {{0, 2, 3}, {1, 2, 3}, {2, 0, 1}, {3, 0, 1}};
+    static const int vv_ee[4][2] = {{0, 2}, {0, 3}, {1, 2}, {1, 3}};
+    double p[24], q[18], t;
+    int i, e, v;
+    for (i = 0; i < 4; i++)
+    {
+        p[3 * i] = oldpos[i].x; p[3 * i + 1] = oldpos[i].y; p[3 * i + 2] = oldpos[i].z;
+        p[12 + 3 * i] = newpos[i].x; p[12 + 3 * i + 1] = newpos[i].y; p[12 + 3 * i + 2] = newpos[i].z;
+    }
+    if (is_vf ? vertex_face(p, eta, &t) : edge_edge(p, eta, &t))
+        return 1;
+    for (e = 0; e < (is_vf ? 3 : 4); e++)
+    {
+        int iv = is_vf ? 0 : ve_ee[e][0], i1 = is_vf ? 1 + (e % 3) : ve_ee[e][1], i2 = is_vf ? 1 + ((e + 1) % 3) : ve_ee[e][2];
+        memcpy(q, p + 3 * iv, 3 * sizeof(double)); memcpy(q + 3, p + 3 * i1, 3 * sizeof(double)); memcpy(q + 6, p + 3 * i2, 3 * sizeof(double));
+        memcpy(q + 9, p + 12 + 3 * iv, 3 * sizeof(double)); memcpy(q + 12, p + 12 + 3 * i1, 3 * sizeof(double)); memcpy(q + 15, p + 12 + 3 * i2, 3 * sizeof(double));
+        if (vertex_edge(q, eta, &t))
+            return 1;
+    }
+    for (v = 0; v < (is_vf ? 3 : 4); v++)
+    {
+        int i1 = is_vf ? 0 : vv_ee[v][0], i2 = is_vf ? 1 + v : vv_ee[v][1];
+        memcpy(q, p + 3 * i1, 3 * sizeof(double)); memcpy(q + 3, p + 3 * i2, 3 * sizeof(double));
+        memcpy(q + 6, p + 12 + 3 * i1, 3 * sizeof(double)); memcpy(q + 9, p + 12 + 3 * i2, 3 * sizeof(double));
+        if (vertex_vertex(q, eta, &t))
+            return 1;
+    }
+    return 0;
+}
+
+/* checkInterval, :47-218 */
+static int sp_check(int is_vf, const hist_t *H, const int *verts, double eta, double mint, double maxt, double eps)
+{
+    v3 midpos[4], closest, planepos, planevel, term[4], wpos[4];
+    int mididx[4], i, vert;
+    double midt, b1, b2, b3, b4 = 0, w[4], t;
+    if (maxt < mint)
+        return 0;
+    if (maxt - mint < 3 * eps)
+    {
+        int ok = 1;
+        v3 oldpos[4], newpos[4];
+        for (i = 0; i < 4; i++)
+        {
+            int oldidx, newidx;
+            sp_pos_at(H, verts[i], mint, &oldpos[i], &oldidx);
+            sp_pos_at(H, verts[i], maxt, &newpos[i], &newidx);
+            if (oldidx != newidx) { ok = 0; break; }
+        }
+        if (ok)
+            return sp_segment(is_vf, oldpos, newpos, eta);
+    }
+    midt = 0.5 * (mint + maxt);
+    for (i = 0; i < 4; i++)
+        sp_pos_at(H, verts[i], midt, &midpos[i], &mididx[i]);
+    if (is_vf)
+        closest = dist_vf(midpos[0], midpos[1], midpos[2], midpos[3], &b1, &b2, &b3);
+    else
+        closest = dist_ee(midpos[0], midpos[1], midpos[2], midpos[3], &b1, &b2, &b3, &b4);
+    if (dot(closest, closest) < eta * eta)
+        return 1;
+    /* separating plane, :167-189: bary * (next - prev) / dt term by term */
+    w[0] = is_vf ? 1.0 : b1; w[1] = is_vf ? b1 : b2; w[2] = is_vf ? b2 : b3; w[3] = is_vf ? b3 : b4;
+    for (i = 0; i < 4; i++)
+    {
+        const long long e0 = H->hoff[verts[i]] + mididx[i];
+        double dts = H->htime[e0 + 1] - H->htime[e0];
+        v3 d = sub(ld(H->hpos + 3 * (e0 + 1)), ld(H->hpos + 3 * e0));
+        if (!(is_vf && i == 0)) d = scl(w[i], d);
+        term[i] = mk(d.x / dts, d.y / dts, d.z / dts);
+        wpos[i] = (is_vf && i == 0) ? midpos[0] : scl(w[i], midpos[i]);
+    }
+    planepos = scl(0.5, add(add(add(wpos[0], wpos[1]), wpos[2]), wpos[3]));
+    planevel = scl(0.5, add(add(add(term[0], term[1]), term[2]), term[3]));
+    {
+        double cn = sqrt(dot(closest, closest));
+        closest = mk(closest.x / cn, closest.y / cn, closest.z / cn);
+    }
+    t = INFINITY;
+    for (vert = 0; vert < 4; vert++)
+    {
+        double sign = (vert == 0 || (vert == 1 && !is_vf)) ? -1.0 : 1.0;
+        t = smin(t, sp_trajectory(H, verts[vert], mididx[vert], 0, planepos, planevel, scl(sign, closest), midpos[vert], midt, eta));
+    }
+    if (t < 1.0)
+        if (sp_check(is_vf, H, verts, eta, mint, midt - smax(0.0, t - eps), eps))
+            return 1;
+    t = INFINITY;
+    for (vert = 0; vert < 4; vert++)
+    {
+        double sign = (vert == 0 || (vert == 1 && !is_vf)) ? -1.0 : 1.0;
+        t = smin(t, sp_trajectory(H, verts[vert], mididx[vert] + 1, 1, planepos, planevel, scl(sign, closest), midpos[vert], midt, eta));
+    }
+    if (t < 1.0)
+        if (sp_check(is_vf, H, verts, eta, midt + smax(0.0, t - eps), maxt, eps))
+            return 1;
+    return 0;
+}
+
+/* SeparatingPlaneNarrowPhase::findCollisions, :11-25: eps = History::computeMinimumGap() / 4 (src/History.cpp:82-96) */
+int orc_narrowphase_sepplane(int V, const long long *hoff, const double *htime, const double *hpos, long long nvf, const int *vf,
+                             const double *vf_eta, long long nee, const int *ee, const double *ee_eta, unsigned char *vf_hit,
+                             unsigned char *ee_hit)
+{
+    hist_t H;
+    double gap = 1.0, eps;
+    long long i, j;
+    int v;
+    H.hoff = hoff; H.htime = htime; H.hpos = hpos;
+    for (v = 0; v < V; v++)
+        for (j = hoff[v] + 1; j < hoff[v + 1]; j++)
+            gap = smin(htime[j] - htime[j - 1], gap);
+    eps = gap / 4.0;
+    for (i = 0; i < nvf; i++)
+        vf_hit[i] = (unsigned char)sp_check(1, &H, vf + 4 * i, vf_eta[i], 0.0, 1.0, eps);
+    for (i = 0; i < nee; i++)
+        ee_hit[i] = (unsigned char)sp_check(0, &H, ee + 4 * i, ee_eta[i], 0.0, 1.0, eps);
+    return 0;
 }

@@ -120,21 +120,24 @@ def test_multi_entry_history(ctx, port):
         assert np.array_equal(out[k + "_toi"].view(np.uint64), p[k + "_toi"].view(np.uint64))
 
 
-@pytest.mark.parametrize("name", ["alec_prob11_835", "history_prob3_402", "alec_prob3_402_thick"])
-def test_separating_plane_narrowphase(ctx, name):
-    """ccd_narrowphase_sepplane against the UNMODIFIED reference's SeparatingPlaneNarrowPhase (oracle/_ref, which travels to
-    the GPU box): same hit flags (the host build of the same code matches it with 0 mismatches, tests/test_np_emul.py)."""
+@pytest.mark.parametrize("name", ["alec_prob3_402", "alec_prob11_835", "alec_prob18_834", "history_prob3_402", "alec_prob3_402_thick", "alec_prob3_402_fixed"])
+def test_separating_plane_narrowphase(ctx, port, name):
+    """ccd_narrowphase_sepplane against the golden flags of the UNMODIFIED reference's SeparatingPlaneNarrowPhase
+    (tests/golden/sepplane.npz), against the plain-C restatement, and — when oracle/_ref travelled — the reference itself."""
     from oracle import bind
-    if not bind.have_ref():
-        pytest.skip("oracle/_ref not built")
     g = golden(name + ".npz")
+    sp = golden("sepplane.npz")
     H = (g["hoff"], g["htime"], g["hpos"]) if "hoff" in g.files else _single(g)
     eta = float(g["eta"])
     vf, ee = g["ref_vf"], g["ref_ee"]
-    r = bind.Ref().narrowphase(*H, vf, eta, ee, eta, which=1)
     out = ctx.findCollisionsSeparatingPlane(*H, vf, eta, ee, eta)
-    assert np.array_equal(out["vf_hit"], r["vf_hit"]) and np.array_equal(out["ee_hit"], r["ee_hit"])
-    assert out["n_vf_hits"] == int(r["vf_hit"].sum()) and out["n_ee_hits"] == int(r["ee_hit"].sum())
+    assert np.array_equal(out["vf_hit"], sp[name + "_vf"]) and np.array_equal(out["ee_hit"], sp[name + "_ee"])
+    assert out["n_vf_hits"] == int(sp[name + "_vf"].sum()) and out["n_ee_hits"] == int(sp[name + "_ee"].sum())
+    p = port.narrowphase(*H, vf, eta, ee, eta, which=1)
+    assert np.array_equal(out["vf_hit"], p["vf_hit"]) and np.array_equal(out["ee_hit"], p["ee_hit"])
+    if bind.have_ref():
+        r = bind.Ref().narrowphase(*H, vf, eta, ee, eta, which=1)
+        assert np.array_equal(out["vf_hit"], r["vf_hit"]) and np.array_equal(out["ee_hit"], r["ee_hit"])
 
 
 def test_per_stencil_eta(ctx, port):

@@ -131,11 +131,11 @@ def _sepplane_emul(lib, is_vf, st, eta, H):
 
 
 @pytest.mark.skipif(not bind.have_ref(), reason="needs oracle/_ref (the unmodified reference; built where /root/reference exists)")
-@pytest.mark.parametrize("name,allowed", [("alec_prob3_402", 0), ("alec_prob11_835", 4), ("alec_prob18_834", 2), ("history_prob3_402", 0)])
+@pytest.mark.parametrize("name,allowed", [("alec_prob3_402", 0), ("alec_prob11_835", 0), ("alec_prob18_834", 0), ("history_prob3_402", 0)])
 def test_sepplane_emul_matches_reference(emul, name, allowed):
     """SeparatingPlaneNarrowPhase (ccd_sepplane.cuh, host build) against the UNMODIFIED reference class on the golden scenes.
-    Flags may differ only where the reference's rpoly and the new root isolator disagree (a handful per
-    scene, classified); prob11's reference counts are 840 VF / 2,212 EE."""
+    Measured: 0 mismatches on every scene (rpoly and the new root isolator agree on all the short intervals these scenes
+    produce); prob11's reference counts are 840 VF / 2,212 EE."""
     g = np.load(os.path.join(HERE, "golden", name + ".npz"))
     ref = bind.Ref()
     if "hoff" in g.files:

@@ -200,3 +200,21 @@ def test_prob17_full_size(port):
     print("prob17 flag mismatches vs reference:", verdicts)
     assert verdicts.get("unexplained", 0) == 0, verdicts
     assert sum(verdicts.values()) <= 200, verdicts
+
+
+SP_SCENES = ["alec_prob3_402", "alec_prob11_835", "alec_prob18_834", "history_prob3_402", "alec_prob3_402_thick", "alec_prob3_402_fixed"]
+
+
+@pytest.mark.parametrize("name", SP_SCENES)
+def test_separating_plane_restatement_matches_golden(port, name):
+    """SeparatingPlaneNarrowPhase (src/SeparatingPlaneNarrowPhase.cpp:11-278) restated in plain C (oracle/ccd_oracle.c:
+    orc_narrowphase_sepplane) against the flags of the unmodified reference class (tests/golden/sepplane.npz, made by
+    tests/golden/make_golden_sepplane.py): identical on every candidate.  prob11: 840 VF / 2,212 EE."""
+    g = golden(name + ".npz")
+    sp = golden("sepplane.npz")
+    H = (g["hoff"], g["htime"], g["hpos"]) if "hoff" in g.files else _single(g)
+    eta = float(g["eta"])
+    p = port.narrowphase(*H, g["ref_vf"], eta, g["ref_ee"], eta, which=1)
+    assert np.array_equal(p["vf_hit"], sp[name + "_vf"]) and np.array_equal(p["ee_hit"], sp[name + "_ee"])
+    if name == "alec_prob11_835":
+        assert int(p["vf_hit"].sum()) == 840 and int(p["ee_hit"].sum()) == 2212
