@@ -140,6 +140,28 @@ def test_separating_plane_narrowphase(ctx, port, name):
         assert np.array_equal(out["vf_hit"], r["vf_hit"]) and np.array_equal(out["ee_hit"], r["ee_hit"])
 
 
+@pytest.mark.parametrize("k", [0, 1, 60, 135])
+def test_model1_flow_frames(ctx, port, k):
+    """BASELINE config C3 (Model1_flow frame k -> k+1, coarse mesh dynamic, fine frame fixed): candidate sets with the
+    fixed-vertex filter and both narrowphases against the unmodified reference's golden vectors; TOI bits against the restatement."""
+    g = golden("model1_flow.npz")
+    p = "f%d_" % k
+    q0, q1, f, fixed = g[p + "q0"], g[p + "q1"], g[p + "faces"], g[p + "fixed"]
+    vf, ee = ctx.findCollisionCandidatesStep(13, f, q0, q1, float(g["outer_eta"]), fixed)
+    assert np.array_equal(vf, g[p + "vf"]) and np.array_equal(ee, g[p + "ee"])
+    from oracle import bind
+    H = bind.single_step_history(q0, q1)
+    eta = float(g["eta"])
+    out = ctx.findCollisions(*H, vf, eta, ee, eta)
+    ref = port.narrowphase(*H, vf, eta, ee, eta)
+    for nm in ("vf", "ee"):
+        assert np.array_equal(out[nm + "_hit"], g[p + nm + "_hit"])
+        assert np.array_equal(out[nm + "_toi"].view(np.uint64), ref[nm + "_toi"].view(np.uint64))
+        assert np.array_equal(out[nm + "_stage"], ref[nm + "_stage"].astype(np.uint8))
+    sp = ctx.findCollisionsSeparatingPlane(*H, vf, eta, ee, eta)
+    assert np.array_equal(sp["vf_hit"], g[p + "sp_vf_hit"]) and np.array_equal(sp["ee_hit"], g[p + "sp_ee_hit"])
+
+
 def test_per_stencil_eta(ctx, port):
     """Thickness comes per stencil (ActiveLayers.cpp:196-207 varies it with layer depth)."""
     g = golden("alec_prob3_402_thick.npz")

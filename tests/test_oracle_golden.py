@@ -218,3 +218,24 @@ def test_separating_plane_restatement_matches_golden(port, name):
     assert np.array_equal(p["vf_hit"], sp[name + "_vf"]) and np.array_equal(p["ee_hit"], sp[name + "_ee"])
     if name == "alec_prob11_835":
         assert int(p["vf_hit"].sum()) == 840 and int(p["ee_hit"].sum()) == 2212
+
+
+@pytest.mark.parametrize("k", [0, 1, 60, 135])
+def test_model1_flow_frames(port, k):
+    """BASELINE config C3: Model1_flow frame k -> k+1 as example/testNewSequence.cpp:150-203 assembles it (coarse mesh
+    dynamic, fine frame fixed, outer / inner radius 1e-3 / 1e-4).  Restatement against the unmodified reference
+    (tests/golden/model1_flow.npz): candidate sets with the fixed-vertex filter, CTCD flags / TOI / stage, SeparatingPlane flags."""
+    g = golden("model1_flow.npz")
+    p = "f%d_" % k
+    H = bind.single_step_history(g[p + "q0"], g[p + "q1"])
+    vf, ee, _ = port.broadphase(13, g[p + "faces"], *H, float(g["outer_eta"]), g[p + "fixed"])
+    assert np.array_equal(vf, g[p + "vf"]) and np.array_equal(ee, g[p + "ee"])
+    eta = float(g["eta"])
+    a = port.narrowphase(*H, vf, eta, ee, eta)
+    for nm in ("vf", "ee"):
+        assert np.array_equal(a[nm + "_hit"], g[p + nm + "_hit"])
+        hit = g[p + nm + "_hit"] > 0
+        assert np.array_equal(a[nm + "_stage"][hit], g[p + nm + "_stage"][hit])
+        assert np.allclose(a[nm + "_toi"][hit], g[p + nm + "_toi"][hit], rtol=1e-9, atol=0)
+    b = port.narrowphase(*H, vf, eta, ee, eta, which=1)
+    assert np.array_equal(b["vf_hit"], g[p + "sp_vf_hit"]) and np.array_equal(b["ee_hit"], g[p + "sp_ee_hit"])
