@@ -152,3 +152,17 @@ def test_sepplane_emul_matches_reference(emul, name, allowed):
     assert mism <= allowed, mism
     if name == "alec_prob11_835":
         assert int(r["vf_hit"].sum()) == 840 and int(r["ee_hit"].sum()) == 2212
+
+
+@pytest.mark.parametrize("variant", ["static", "reverse", "scaled1e3", "half-static", "big-eta"])
+def test_emul_matches_checker_on_degenerate_variants(emul, port, variant):
+    """Shapes the staged pipeline has special paths for: no motion at all (every polynomial degenerates to a constant), half of
+    the vertices static (exactly-zero leading coefficients, closed-form records), coordinates scaled by 1e3, the step run
+    backwards, and a thickness of 5e-2 (nearly everything is deferred, many hits) — flags, TOI bits and stage must still
+    equal the checker's on every candidate of prob11."""
+    g = np.load(os.path.join(HERE, "golden", "alec_prob11_835.npz"))
+    q0, q1, vf, ee = g["q0"], g["q1"], g["ref_vf"], g["ref_ee"]
+    even = (np.arange(len(q0)) % 2 == 0)[:, None]
+    a, b, eta = {"static": (q0, q0.copy(), 1e-3), "reverse": (q1, q0, 1e-8), "scaled1e3": (q0 * 1e3, q1 * 1e3, 1e-5),
+                 "half-static": (q0, np.where(even, q0, q1), 1e-6), "big-eta": (q0, q1, 5e-2)}[variant]
+    check_scene(emul, port, a, b, vf, ee, eta)
