@@ -162,6 +162,25 @@ def test_model1_flow_frames(ctx, port, k):
     assert np.array_equal(sp["vf_hit"], g[p + "sp_vf_hit"]) and np.array_equal(sp["ee_hit"], g[p + "sp_ee_hit"])
 
 
+@pytest.mark.parametrize("variant", ["static", "reverse", "scaled1e3", "half-static", "big-eta"])
+def test_degenerate_variants_bit_exact(ctx, port, variant):
+    """prob11's candidates with no motion at all, half of the vertices static (exactly-zero leading coefficients), coordinates
+    x 1e3, the step reversed, and eta = 5e-2 (nearly everything deferred): flags, TOI bits and stage equal the restatement's."""
+    g = golden("alec_prob11_835.npz")
+    q0, q1, vf, ee = g["q0"], g["q1"], g["ref_vf"], g["ref_ee"]
+    even = (np.arange(len(q0)) % 2 == 0)[:, None]
+    a, b, eta = {"static": (q0, q0.copy(), 1e-3), "reverse": (q1, q0, 1e-8), "scaled1e3": (q0 * 1e3, q1 * 1e3, 1e-5),
+                 "half-static": (q0, np.where(even, q0, q1), 1e-6), "big-eta": (q0, q1, 5e-2)}[variant]
+    from oracle import bind
+    H = bind.single_step_history(a, b)
+    out = ctx.findCollisions(*H, vf, eta, ee, eta)
+    p = port.narrowphase(*H, vf, eta, ee, eta)
+    for k in ("vf", "ee"):
+        assert np.array_equal(out[k + "_hit"], p[k + "_hit"]), k
+        assert np.array_equal(out[k + "_stage"], p[k + "_stage"].astype(np.uint8)), k
+        assert np.array_equal(out[k + "_toi"].view(np.uint64), p[k + "_toi"].view(np.uint64)), k
+
+
 def test_per_stencil_eta(ctx, port):
     """Thickness comes per stencil (ActiveLayers.cpp:196-207 varies it with layer depth)."""
     g = golden("alec_prob3_402_thick.npz")
