@@ -181,6 +181,20 @@ def test_degenerate_variants_bit_exact(ctx, port, variant):
         assert np.array_equal(out[k + "_toi"].view(np.uint64), p[k + "_toi"].view(np.uint64)), k
 
 
+@pytest.mark.parametrize("p", [0, 1, 2, 3, 4])
+def test_velocityfilter_detection_passes(ctx, p):
+    """BASELINE config C4: the detection calls of the unmodified VelocityFilter run on mesh1 -> mesh2 (tests/golden/
+    velocityfilter.npz, recorded from the reference): broadphase over the growing multi-entry History, SeparatingPlane
+    narrowphase with ActiveLayers' per-stencil thickness — same candidate sets, same hits."""
+    g = golden("velocityfilter.npz")
+    k = "mesh12_p%d_" % p
+    H = (g[k + "hoff"], g[k + "htime"], g[k + "hpos"])
+    vf, ee = ctx.findCollisionCandidates(13, g["mesh12_faces"], *H, float(g["mesh12_outer"]))
+    assert np.array_equal(vf, g[k + "vf"]) and np.array_equal(ee, g[k + "ee"])
+    out = ctx.findCollisionsSeparatingPlane(*H, vf, g[k + "vf_eta"], ee, g[k + "ee_eta"])
+    assert np.array_equal(out["vf_hit"], g[k + "vf_hit"]) and np.array_equal(out["ee_hit"], g[k + "ee_hit"])
+
+
 def test_per_stencil_eta(ctx, port):
     """Thickness comes per stencil (ActiveLayers.cpp:196-207 varies it with layer depth)."""
     g = golden("alec_prob3_402_thick.npz")

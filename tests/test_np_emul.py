@@ -166,3 +166,15 @@ def test_emul_matches_checker_on_degenerate_variants(emul, port, variant):
     a, b, eta = {"static": (q0, q0.copy(), 1e-3), "reverse": (q1, q0, 1e-8), "scaled1e3": (q0 * 1e3, q1 * 1e3, 1e-5),
                  "half-static": (q0, np.where(even, q0, q1), 1e-6), "big-eta": (q0, q1, 5e-2)}[variant]
     check_scene(emul, port, a, b, vf, ee, eta)
+
+
+@pytest.mark.parametrize("p", [0, 2, 4])
+def test_sepplane_emul_on_velocityfilter_passes(emul, p):
+    """The host build of ccd_sepplane.cuh on the growing Histories of the reference's own VelocityFilter run (config C4,
+    tests/golden/velocityfilter.npz): per-stencil thickness, up to ~10 entries per vertex, eps = minimum gap / 4."""
+    g = np.load(os.path.join(HERE, "golden", "velocityfilter.npz"))
+    k = "mesh12_p%d_" % p
+    H = (g[k + "hoff"], g[k + "htime"], g[k + "hpos"])
+    for nm, is_vf in (("vf", True), ("ee", False)):
+        hit = _sepplane_emul(emul, is_vf, g[k + nm], g[k + nm + "_eta"], H)
+        assert np.array_equal(hit, g[k + nm + "_hit"]), nm

@@ -239,3 +239,21 @@ def test_model1_flow_frames(port, k):
         assert np.allclose(a[nm + "_toi"][hit], g[p + nm + "_toi"][hit], rtol=1e-9, atol=0)
     b = port.narrowphase(*H, vf, eta, ee, eta, which=1)
     assert np.array_equal(b["vf_hit"], g[p + "sp_vf_hit"]) and np.array_equal(b["ee_hit"], g[p + "sp_ee_hit"])
+
+
+@pytest.mark.parametrize("p", [0, 1, 2, 3, 4])
+def test_velocityfilter_detection_passes(port, p):
+    """BASELINE config C4: detection pass p of ActiveLayers inside the unmodified VelocityFilter::velocityFilter on
+    mesh1.obj -> mesh2.obj (example/testVelocityFilter.cpp, radii 2e-8 / 1e-8), recorded by oracle/ref_recorder.* into
+    tests/golden/velocityfilter.npz: a History that grows from 394 to 1,038 entries, every broadphase candidate with the
+    per-stencil thickness ActiveLayers assigns, the SeparatingPlane hits.  SURVEY.md 8(c) lists the same counts:
+    (394; 2299/3682 -> 30/23), (858; 2304/3691 -> 30/11), (1022; 2287/3658 -> 18/8), (1038; ... -> 6/0), (1038; ... -> 3/0)."""
+    g = golden("velocityfilter.npz")
+    k = "mesh12_p%d_" % p
+    H = (g[k + "hoff"], g[k + "htime"], g[k + "hpos"])
+    expect = [(394, 2299, 3682, 30, 23), (858, 2304, 3691, 30, 11), (1022, 2287, 3658, 18, 8), (1038, 2287, 3658, 6, 0), (1038, 2287, 3658, 3, 0)][p]
+    assert (len(H[1]), len(g[k + "vf"]), len(g[k + "ee"]), int(g[k + "vf_hit"].sum()), int(g[k + "ee_hit"].sum())) == expect
+    vf, ee, _ = port.broadphase(13, g["mesh12_faces"], *H, float(g["mesh12_outer"]))
+    assert np.array_equal(vf, g[k + "vf"]) and np.array_equal(ee, g[k + "ee"])
+    r = port.narrowphase(*H, vf, g[k + "vf_eta"], ee, g[k + "ee_eta"], which=1)
+    assert np.array_equal(r["vf_hit"], g[k + "vf_hit"]) and np.array_equal(r["ee_hit"], g[k + "ee_hit"])
