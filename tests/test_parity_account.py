@@ -1,0 +1,110 @@
+"""The parity account against the UNMODIFIED reference's golden vectors (CPU; the GPU is bit-identical to the restatement,
+tests/test_gpu_parity.py): every flag difference and EVERY hit whose time of impact differs from the reference's by more
+than north_star's 1e-9 relative is classified by the 60-digit arbiter (tests/parity_account.py); nothing may stay
+unexplained, and the classified sets are pinned exactly.
+
+Measured account (profiles/r02_parity_account.json holds the full-size runs):
+  prob3_402    0 flags, 0 TOI out of tolerance
+  prob18_834   0 flags; 17 VF + 68 EE TOI out of tolerance, all reference-artefact (restatement within 1e-9 of the exact root)
+  prob11_835   2 EE flags (reference-artefact); 71 VF + 657 EE TOI: 726 reference-artefact, 2 ill-conditioned
+  prob17_30957 2 VF + 123 EE flags (92 reference-artefact, 32 noise-sign, 1 degenerate-poly); TOI: see the json
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden, ROOT
+from oracle import bind
+import parity_account as PA
+from arbiter import Arbiter
+
+EXPECT = {
+    # name: (vf flag classes, ee flag classes, vf toi out-of-tolerance classes, ee toi classes)
+    "alec_prob3_402": ({}, {}, {}, {}),
+    "alec_prob18_834": ({}, {}, {"reference-artefact": 17}, {"reference-artefact": 68}),
+    "alec_prob11_835": ({}, {"reference-artefact": 2}, {"reference-artefact": 71}, {"reference-artefact": 655, "ill-conditioned": 2}),
+    "alec_prob3_402_thick": None,
+}
+
+
+def _classes(r, prefix):
+    return {k[len(prefix):]: v for k, v in r.items() if k.startswith(prefix)}
+
+
+@pytest.mark.parametrize("name", sorted(EXPECT))
+def test_account_small_configs(port, name):
+    g = golden(name + ".npz")
+    eta = float(g["eta"])
+    H = bind.single_step_history(g["q0"], g["q1"])
+    out = port.narrowphase(*H, g["ref_vf"], eta, g["ref_ee"], eta)
+    arb = Arbiter(port)
+    got = []
+    for k in ("vf", "ee"):
+        r = PA.account(arb, port, k, g["q0"], g["q1"], g["ref_" + k], eta, out[k + "_hit"], out[k + "_toi"], out[k + "_stage"],
+                       g["ref_%s_hit" % k], g["ref_%s_toi" % k], g["ref_%s_stage" % k])
+        assert r["unexplained"] == 0, (name, k, r)
+        assert r["toi_arbitrated"] == r["toi_out_of_1e-9"]          # every one of them, not a sample
+        got.append(r)
+    if EXPECT[name] is not None:
+        fv, fe, tv, te = EXPECT[name]
+        assert _classes(got[0], "flag:") == fv and _classes(got[1], "flag:") == fe, (got[0], got[1])
+        assert _classes(got[0], "toi:") == tv and _classes(got[1], "toi:") == te, (got[0], got[1])
+
+
+def _prob17(port, max_toi):
+    g = golden("alec_prob17_30957.npz")
+    q0, q1 = g["q0"], g["q1"]
+    H = bind.single_step_history(q0, q1)
+    vf, ee, _ = port.broadphase(13, g["faces"], *H, 1e-8)
+    assert bind.fnv1a64(vf) == str(g["vf_fnv"]) and bind.fnv1a64(ee) == str(g["ee_fnv"])
+    out = port.narrowphase(*H, vf, 1e-8, ee, 1e-8)
+    arb = Arbiter(port)
+    res = {}
+    for k, st in (("vf", vf), ("ee", ee)):
+        # the golden holds the reference's hit list (sorted, a subset of the candidates) and the hits' TOI
+        key = lambda a: (a[:, 0].astype(np.int64) << 42) ^ (a[:, 1].astype(np.int64) << 28) ^ (a[:, 2].astype(np.int64) << 14) ^ a[:, 3].astype(np.int64)
+        idx = np.nonzero(np.isin(key(st), key(g["ref_%s_hits" % k])))[0]
+        assert len(idx) == len(g["ref_%s_hits" % k]) and np.array_equal(st[idx], g["ref_%s_hits" % k])
+        rh = np.zeros(len(st), np.uint8)
+        rh[idx] = 1
+        rt = np.zeros(len(st))
+        rt[idx] = g["ref_%s_hit_toi" % k]
+        res[k] = PA.account(arb, port, k, q0, q1, st, 1e-8, out[k + "_hit"], out[k + "_toi"], out[k + "_stage"], rh, rt, None, max_toi=max_toi)
+    return res
+
+
+def test_account_prob17_sampled(port):
+    """BASELINE config C2: all 125 flag differences classified and pinned; a deterministic sample of the TOI differences."""
+    res = _prob17(port, max_toi=150)
+    assert res["vf"]["unexplained"] == 0 and res["ee"]["unexplained"] == 0, res
+    assert res["vf"]["flag_mismatch"] == 2 and res["ee"]["flag_mismatch"] == 123, res
+    tot = {}
+    for k in ("vf", "ee"):
+        for c, v in _classes(res[k], "flag:").items():
+            tot[c] = tot.get(c, 0) + v
+    assert tot == {"reference-artefact": 92, "noise-sign": 32, "degenerate-poly": 1}, tot
+
+
+@pytest.mark.slow
+def test_account_prob17_every_toi(port):
+    res = _prob17(port, max_toi=None)
+    print(json.dumps(res))
+    assert res["vf"]["unexplained"] == 0 and res["ee"]["unexplained"] == 0, res
+    assert res["vf"]["toi_arbitrated"] == res["vf"]["toi_out_of_1e-9"] and res["ee"]["toi_arbitrated"] == res["ee"]["toi_out_of_1e-9"]
+
+
+def test_account_c5_golden_is_closed():
+    """BASELINE config C5: the committed full-size golden (tests/golden/make_golden_c5.py, 30.5 M stencils through the
+    unmodified reference) carries the classified list of every flag difference of the restatement; none unexplained."""
+    path = os.path.join(ROOT, "tests", "golden", "cloth_1415.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/cloth_1415.npz not generated")
+    g = np.load(path)
+    assert (int(g["n_vf"]), int(g["n_ee"])) == (11265150, 19238022)
+    assert (int(g["ref_vf_n_hits"]), int(g["ref_ee_n_hits"])) == (698934, 2561228)
+    for k in ("vf", "ee"):
+        cls = list(g["%s_mismatch_class" % k])
+        assert "unexplained" not in cls, (k, cls)
+        assert "unexplained" not in list(g["%s_toi_sample_class" % k])
