@@ -35,7 +35,8 @@ struct ccd_context
     DBuf faces, q0, q1, hoff, htime, hpos, fixed, vf_in, ee_in, vf_eta, ee_eta, pts, eta;
     // broadphase
     DBuf boxes, faabb, fkdop, bounds, keysA, keysB, valsA, valsB, temp, nodes, leafParent, nodeParent, flags;
-    DBuf cand, counters, pairL, pairR, deg, adjOff, cursor, adj;
+    DBuf cand, counters, pairL, pairR, deg, adjOff, cursor, adj, heap, srec, unsure, frontA, frontB;
+    size_t frontCap = 0, unsureCap = 0;
     DBuf k32A, k32B, scanFlags, scanIds;
     // topology cache (function of `faces` only)
     DBuf edgeVerts, edgeStart, faceEdge, heFace, faceRank, rankFace, vdeg, starOff, starCur, star, topoHash;
@@ -44,7 +45,7 @@ struct ccd_context
     // emission
     DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut;
     // narrowphase
-    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, qpack, selTmp, selA, selB, selC, selD, selCount;
+    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, p1Ve, qpack, selTmp, selA, selB, selC, selD, selCount;
     // pinned host scratch
     unsigned long long *h_counters = nullptr; // C_TOTAL entries
     // pinned host buffers for the hit lists returned by ccd_step (valid until the next call on the context)
@@ -60,7 +61,7 @@ struct ccd_context
 };
 
 // device counters layout (unsigned long long each)
-enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NQUERY = 7, C_NA_VF = 8, C_NA_EE = 9, C_KCUR_VF = 10, C_KCUR_EE = 11, C_NP_VF = 16 /* CCD_NP_COUNTERS counters per run: work-list entries, records, ... (narrowphase.cu K_*) */, C_NP_EE = 16 + CCD_NP_COUNTERS, C_CAND_REG = 16 + 2 * CCD_NP_COUNTERS /* CCD_CAND_REGIONS candidate counters */, C_TOTAL = 16 + 2 * CCD_NP_COUNTERS + 64 };
+enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NQUERY = 7, C_NA_VF = 8, C_NA_EE = 9, C_KCUR_VF = 10, C_KCUR_EE = 11, C_FRONT = 12 /* 4 counters: frontier sizes (ping-pong), their maximum, undecided face pairs */, C_NP_VF = 16 /* CCD_NP_COUNTERS counters per run: work-list entries, records, ... (narrowphase.cu K_*) */, C_NP_EE = 16 + CCD_NP_COUNTERS, C_CAND_REG = 16 + 2 * CCD_NP_COUNTERS /* CCD_CAND_REGIONS candidate counters */, C_TOTAL = 16 + 2 * CCD_NP_COUNTERS + 64 };
 #define CCD_CAND_REGIONS 64
 enum { C_NWORK_VF = C_NP_VF, C_NTASK_VF = C_NP_VF + 1, C_NWORK_EE = C_NP_EE, C_NTASK_EE = C_NP_EE + 1 };
 
@@ -172,6 +173,17 @@ void ccdk_emit_write(cudaStream_t st, bool is_vf, const int *alist, const unsign
                      const int *star, const int *edgeStart, const int *heFace, const long long *adjOff, const int *adj, const int *faceRank,
                      const int *rankFace, const int *faceEdge, const void *edgeVerts, const unsigned char *fixed, const int *counts,
                      const long long *kstart, const int *keys_in, const long long *offsets, int *out);
+void ccdk_face_aabb(cudaStream_t st, int F, const int *faces, const double *q0, const double *q1, double eta, float *faabb);
+int ccdk_cluster_count_pow2(int F);
+int ccdk_cluster_size(void);
+void ccdk_build_cluster_tree(cudaStream_t st, int kind, int F, const int *faces, const float *faabb, const double *q0, const double *q1, double eta,
+                             const double *boxes, unsigned *bounds, unsigned long long *keys_in, unsigned long long *keys_sorted, unsigned *vals_in,
+                             unsigned *sortedFace, void *temp, size_t temp_bytes, float *heap, float *rec);
+int ccdk_leaf_record_words(void);
+int ccdk_pair_traversal(cudaStream_t st, int kind, int F, const float *heap, const float *rec, const double *boxes,
+                        const double *q0, const double *q1, double eta, void *fr0, void *fr1, unsigned long long fcap, unsigned long long *fcount,
+                        void *unsure, unsigned long long ucap, int *pairL, int *pairR, unsigned long long pcap, unsigned long long *npairs, int *deg,
+                        const int *own, const int *ownPre, void *cand, unsigned long long ccap, unsigned long long *ncand);
 void ccdk_dist_batch(cudaStream_t st, int which, long long n, const double *pts, const double *eta, double *vec, double *bary, unsigned char *flag);
 void ccdk_vertex_min_dist2(cudaStream_t st, int V, int F, const double *verts, const int *faces, unsigned long long *out_bits);
 void ccdk_stencil_min_dist(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *verts, unsigned long long *out_bits);
@@ -231,7 +243,7 @@ void ccd_destroy(ccd_context *c)
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->qpack, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->nodeFirst, &c->nodeForeign, &c->vertEdgeStart, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount};
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1Ve, &c->qpack, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->nodeFirst, &c->nodeForeign, &c->vertEdgeStart, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->unsure, &c->frontA, &c->frontB};
     for (DBuf *b : all)
         if (b->p)
             cudaFree(b->p);
@@ -355,7 +367,8 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     const bool lazy_boxes = d_q0 != nullptr;      // single step: exact boxes are recomputed in the pair test
     if (!lazy_boxes) CKR(ensure(c, c->boxes, sizeof(double) * 2 * (size_t)kind * (size_t)F));
     CKR(ensure(c, c->faabb, sizeof(float) * 6 * (size_t)F));
-    CKR(ensure(c, c->fkdop, sizeof(float) * 2 * (size_t)kind * (size_t)F));
+    static const bool old_traverse = getenv("CCD_TRAVERSE_OLD") != nullptr;      // A/B switch, development only
+    if (old_traverse) CKR(ensure(c, c->fkdop, sizeof(float) * 2 * (size_t)kind * (size_t)F));
     CKR(ensure(c, c->bounds, 64));
     CKR(ensure(c, c->temp, ccdk_sort_temp_bytes(3 * F > V + 1 ? 3 * F : V + 1)));
     CKR(ensure(c, c->keysA, sizeof(unsigned long long) * (size_t)(3 * F + 1)));
@@ -376,12 +389,26 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         c->pairCap = (size_t)F * 12 + (1u << 16);
 
     cudaEventRecord(c->sev[ST_BOXES], c->st);
-    ccdk_leaf_boxes(c->st, kind, F, d_faces, d_q0, d_q1, d_hoff, d_hpos, outerEta, lazy_boxes ? nullptr : P<double>(c->boxes), P<float>(c->faabb), P<float>(c->fkdop));
+    if (lazy_boxes && !old_traverse) ccdk_face_aabb(c->st, F, d_faces, d_q0, d_q1, outerEta, P<float>(c->faabb));
+    else ccdk_leaf_boxes(c->st, kind, F, d_faces, d_q0, d_q1, d_hoff, d_hpos, outerEta, lazy_boxes ? nullptr : P<double>(c->boxes), P<float>(c->faabb), old_traverse ? P<float>(c->fkdop) : nullptr);
     cudaEventRecord(c->sev[ST_TREE], c->st);
-    ccdk_build_tree(c->st, F, P<float>(c->faabb), P<unsigned>(c->bounds), P<unsigned long long>(c->keysA), P<unsigned long long>(c->keysB),
-                    P<unsigned>(c->valsA), P<unsigned>(c->valsB), c->temp.p, c->temp.cap, c->nodes.p, P<int>(c->leafParent),
-                    P<int>(c->nodeParent), P<int>(c->flags), P<int>(c->nodeFirst));
-    c->launches += 1 + 2 + 8 + 2;
+    if (old_traverse)
+    {
+        ccdk_build_tree(c->st, F, P<float>(c->faabb), P<unsigned>(c->bounds), P<unsigned long long>(c->keysA), P<unsigned long long>(c->keysB),
+                        P<unsigned>(c->valsA), P<unsigned>(c->valsB), c->temp.p, c->temp.cap, c->nodes.p, P<int>(c->leafParent),
+                        P<int>(c->nodeParent), P<int>(c->flags), P<int>(c->nodeFirst));
+        c->launches += 1 + 2 + 8 + 2;
+    }
+    else
+    {
+        const size_t NLc = (size_t)ccdk_cluster_count_pow2(F), NLf = NLc * (size_t)ccdk_cluster_size();
+        CKR(ensure(c, c->heap, sizeof(float) * 6 * (2 * NLc)));
+        CKR(ensure(c, c->srec, sizeof(float) * (size_t)ccdk_leaf_record_words() * NLf));
+        ccdk_build_cluster_tree(c->st, kind, F, d_faces, P<float>(c->faabb), lazy_boxes ? d_q0 : nullptr, d_q1, outerEta, lazy_boxes ? nullptr : P<double>(c->boxes),
+                                P<unsigned>(c->bounds), P<unsigned long long>(c->keysA), P<unsigned long long>(c->keysB), P<unsigned>(c->valsA),
+                                P<unsigned>(c->valsB), c->temp.p, c->temp.cap, P<float>(c->heap), P<float>(c->srec));
+        c->launches += 1 + 2 + 8 + 2 + 3;
+    }
     const unsigned *sortedFace = P<unsigned>(c->valsB);
     cudaEventRecord(c->sev[ST_TRAVERSE_EXACT], c->st);
 
@@ -425,20 +452,37 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
                 CK(cudaMemsetAsync(ctr + C_NQUERY, 0, sizeof(unsigned long long), c->st));
                 CK(cudaMemsetAsync(P<int>(c->needed) + F, 0, sizeof(int), c->st));
                 ccdk_shard_queries(c->st, F, sortedFace, d_faces, P<int>(c->faceEdge), v0, v1, e0, e1, P<int>(c->qlist), ctr + C_NQUERY, P<int>(c->needed),
-                                   P<int>(c->neededPre), c->nodes.p, P<int>(c->nodeFirst), P<unsigned char>(c->nodeForeign), c->temp.p, c->temp.cap);
+                                   P<int>(c->neededPre), old_traverse ? c->nodes.p : nullptr, P<int>(c->nodeFirst), P<unsigned char>(c->nodeForeign), c->temp.p, c->temp.cap);
                 c->launches += 3;
             }
             // the number of query faces stays on the device: the grid covers all F, the surplus threads leave at once
-            ccdk_traverse(c->st, kind, F, 0, F, P<int>(c->qlist), true, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p,
-                          c->cand.p, regionCap, ctr + C_CAND_REG, P<int>(c->needed), P<unsigned char>(c->nodeForeign), ctr + C_NQUERY);
+            if (old_traverse)
+                ccdk_traverse(c->st, kind, F, 0, F, P<int>(c->qlist), true, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p,
+                              c->cand.p, regionCap, ctr + C_CAND_REG, P<int>(c->needed), P<unsigned char>(c->nodeForeign), ctr + C_NQUERY);
         }
-        else
+        else if (old_traverse)
             ccdk_traverse(c->st, kind, F, 0, F, nullptr, false, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p, c->cand.p,
                           regionCap, ctr + C_CAND_REG, nullptr, nullptr, nullptr);
-        ccdk_exact_pairs(c->st, kind, !sharded, ctr + C_CAND_REG, regionCap, c->cand.p, sortedFace, d_faces, lazy_boxes ? nullptr : P<double>(c->boxes),
-                         lazy_boxes ? d_q0 : nullptr, d_q1, outerEta, P<int>(c->pairL), P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg),
-                         sharded ? P<int>(c->needed) : nullptr);
-        c->launches += 2;
+        if (old_traverse)
+        {
+            ccdk_exact_pairs(c->st, kind, !sharded, ctr + C_CAND_REG, regionCap, c->cand.p, sortedFace, d_faces, lazy_boxes ? nullptr : P<double>(c->boxes),
+                             lazy_boxes ? d_q0 : nullptr, d_q1, outerEta, P<int>(c->pairL), P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg),
+                             sharded ? P<int>(c->needed) : nullptr);
+            c->launches += 2;
+        }
+        else
+        {
+            // simultaneous pair traversal of the cluster tree, then the cluster pairs' face tests: pairs + degrees
+            if (c->frontCap == 0) c->frontCap = (size_t)F * 2 + (1u << 16);
+            CKR(ensure(c, c->frontA, sizeof(int) * 2 * c->frontCap));
+            CKR(ensure(c, c->frontB, sizeof(int) * 2 * c->frontCap));
+            if (c->unsureCap == 0) c->unsureCap = (size_t)F / 16 + (1u << 14);
+            CKR(ensure(c, c->unsure, sizeof(int) * 2 * c->unsureCap));
+            c->launches += ccdk_pair_traversal(c->st, kind, F, P<float>(c->heap), P<float>(c->srec), lazy_boxes ? nullptr : P<double>(c->boxes),
+                                               lazy_boxes ? d_q0 : nullptr, d_q1, outerEta, c->frontA.p, c->frontB.p, c->frontCap, ctr + C_FRONT, c->unsure.p,
+                                               c->unsureCap, P<int>(c->pairL), P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg),
+                                               sharded ? P<int>(c->needed) : nullptr, sharded ? P<int>(c->neededPre) : nullptr, c->cand.p, c->candCap, ctr + C_NCAND);
+        }
         CKR(sync_counters(c));
         unsigned long long ncand = 0, maxreg = 0, npairs = c->h_counters[C_NPAIRS];
         for (int r = 0; r < CCD_CAND_REGIONS; r++)
@@ -448,8 +492,13 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
             maxreg = x > maxreg ? x : maxreg;
         }
         // counts keep running past the capacities (writes are guarded), so an overflow tells the size to retry with
+        const bool front_over = !old_traverse && c->h_counters[C_FRONT + 2] > c->frontCap;
+        if (front_over) c->frontCap = (size_t)(c->h_counters[C_FRONT + 2] * 2 + 1024);      // a truncated level hides the size of the next: leave room
+        const bool unsure_over = !old_traverse && c->h_counters[C_FRONT + 3] > c->unsureCap;
+        if (unsure_over) c->unsureCap = (size_t)(c->h_counters[C_FRONT + 3] * 2 + 1024);
+        if (!old_traverse) { ncand = c->h_counters[C_NCAND]; maxreg = (ncand + CCD_CAND_REGIONS - 1) / CCD_CAND_REGIONS; }      // one list of candCap entries
         const bool cand_over = maxreg > regionCap, pair_over = npairs > c->pairCap;
-        const bool again = cand_over || pair_over;
+        const bool again = cand_over || pair_over || front_over || unsure_over;
         if (cand_over)
             c->candCap = (size_t)((maxreg + maxreg / 4 + 1024) * CCD_CAND_REGIONS);
         if (again)
@@ -461,7 +510,8 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         }
         if (!again)
         {
-            res->ncand = (long long)ncand;
+            res->ncand = old_traverse ? (long long)ncand : (long long)c->h_counters[C_FRONT + 2];      // cluster path: the largest frontier (= cluster pairs)
+            if (getenv("CCD_BP_TRACE")) fprintf(stderr, "[bp] cluster pairs %llu, face-pair candidates %llu, undecided %llu, face pairs %llu\n", c->h_counters[C_FRONT + 2], c->h_counters[C_NCAND], c->h_counters[C_FRONT + 3], npairs);
             res->npairs = (long long)npairs;
             break;
         }
@@ -567,9 +617,10 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         const size_t nmax = (size_t)(nvf > nee ? nvf : nee) + 32;
         CKR(ensure(c, c->p1Status, sizeof(unsigned) * nmax));
         CKR(ensure(c, c->p1Sbase, sizeof(int) * 5 * nmax));
-        CKR(ensure(c, c->p1Queues, sizeof(int) * 9 * nmax));
+        CKR(ensure(c, c->p1Queues, sizeof(int) * 13 * nmax));
         CKR(ensure(c, c->p1Sq, sizeof(int) * 4 * nmax));
         CKR(ensure(c, c->p1Xq, sizeof(int) * 10 * nmax));
+        CKR(ensure(c, c->p1Ve, 12 * (size_t)ccdk_np_ve_slots((long long)nmax) + 48 * nmax));
     }
     const float *d_vbox = nullptr;
     if (d_q0)
@@ -601,12 +652,12 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         nl += ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
                                P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF, P<int>(c->workVf),
                                P<int>(c->workTaskVf), P<int>(c->workSubVf), P<double>(c->tasksVf), P<int>(c->tlistVf), c->taskCapVf, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
-                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_VF);
+                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_VF, c->p1Ve.p, ccdk_np_ve_slots(nvf), V);
         cudaEventRecord(c->sev[ST_NP_EE], c->st);
         nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
                                P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE, P<int>(c->workEe),
                                P<int>(c->workTaskEe), P<int>(c->workSubEe), P<double>(c->tasksEe), P<int>(c->tlistEe), c->taskCapEe, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
-                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_EE);
+                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_EE, c->p1Ve.p, ccdk_np_ve_slots(nee), V);
         cudaEventRecord(c->sev[CCD_N_STAGES], c->st);
         CK(cudaGetLastError());
         CKR(sync_counters(c));

@@ -8,8 +8,10 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
                      const double *q0, const double *q1, int vstride, const float *vbox, const long long *hoff, const double *htime, const double *hpos,
                      unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits,
                      unsigned long long *nhit, int *w_stencil, int *w_meta, int *w_base, double *tasks, int *tlists,
-                     unsigned long long task_cap, unsigned *status, int *sbase, int *queues, int *sq, int *xq, unsigned long long *ctr);
-#define CCD_NP_COUNTERS 32      // counters per narrowphase run (narrowphase.cu: K_*)
+                     unsigned long long task_cap, unsigned *status, int *sbase, int *queues, int *sq, int *xq, unsigned long long *ctr,
+                     void *ve_scratch, unsigned ve_slots, int V);
+unsigned ccdk_np_ve_slots(long long n);
+#define CCD_NP_COUNTERS 40      // counters per narrowphase run (narrowphase.cu: K_*)
 // {x0,y0,z0,-,x1,y1,z1,-} per vertex (8 doubles) for the single-step narrowphase kernels
 void ccdk_pack_positions(cudaStream_t st, int V, const double *q0, const double *q1, int vstride, double *qpack, float *vbox);
 void ccdk_prim_batch(cudaStream_t st, int kind, long long n, const double *pts, const double *eta, unsigned char *hit, double *t);

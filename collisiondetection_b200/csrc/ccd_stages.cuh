@@ -555,7 +555,7 @@ CCD_FN int ve_item(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, doub
 // Bernstein hull is rarely conclusive.  Only the times at which the vertex projects inside the segment count ([0,1]
 // narrowed by the quadratics' intervals), and on those windows the hull, refined down to 64ths, usually proves "further
 // than eta": the record is then finalised with no interval and no root is isolated.  Returns true in that case.
-CCD_FN bool ve_refine_item(double *rec)
+template <int STRIDE> CCD_FN bool ve_refine_item_s(double *rec)
 {
     const unsigned tag = rec_untag(rec[7]);
     const int rd = (int)((tag >> 4) & 7u);
@@ -568,7 +568,7 @@ CCD_FN bool ve_refine_item(double *rec)
     {
         Ivl3 o;
         unsigned t;
-        read_final_record(rec - REC_STRIDE * s, o, t);
+        read_final_record(rec - STRIDE * s, o, t);
         if (o.bad) return false;
         narrow_ivl(R, o, false, z, z, z, z);
     }
@@ -600,6 +600,27 @@ CCD_FN bool ve_refine_item(double *rec)
     for (int k = 0; k < 3; k++) { none.l[k] = 0.0; none.u[k] = 0.0; }
     write_final_record(rec, none, tag);
     return true;
+}
+
+CCD_FN bool ve_refine_item(double *rec) { return ve_refine_item_s<REC_STRIDE>(rec); }
+
+// ve_item followed at once by the refinement of its pending distance quartic on the windows its inside quadratics leave:
+// a test whose quartic is proven "further than eta" there has no common time at all — combining its records would give
+// RS_MISS — so it is reported as SC_MISS and none of its records is ever written (four out of five deferred vertex-edge
+// tests of the 4M-triangle cloth end this way).
+CCD_FN int ve_item_refined(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, double (&recs)[3][8], int &nrec)
+{
+    const int code = ve_item(q0s, q1s, q2s, v0, v1, v2, eta, recs, nrec);
+    if (code != SC_DEFERRED || nrec == 0) return code;
+    bool gone = false;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if (k == nrec - 1)
+        {
+            const unsigned tag = rec_untag(recs[k][7]);
+            if (!(tag & (REC_FINAL | REC_POS)) && (tag & 7u) == 2u) gone = ve_refine_item_s<8>(&recs[k][0]);
+        }
+    return gone ? SC_MISS : code;
 }
 
 // turn a pending record into a final one: isolate the roots of its polynomial, apply the interval rules

@@ -245,7 +245,7 @@ __device__ __forceinline__ void store_result(const NpArgs &A, long long i, int s
 enum
 {
     K_NWORK = 0, K_NTASK = 1, K_NDEG = 2 /* 4 */, K_NQ = 6 /* prim, ve, vv */, K_NGEN = 9, K_NSQ = 10 /* after stage 0..3 */,
-    K_NXQ = 14 /* polynomial 0..4 */, K_CURSOR = 19 /* degree 3..6 */, K_NDEG2 = 23 /* second solve round */, K_CURSOR2 = 27, K_NREF = 31 /* vertex-edge quartics left after ve_refine */, K_COUNT = 32
+    K_NXQ = 14 /* polynomial 0..4 */, K_CURSOR = 19 /* degree 3..6 */, K_NDEG2 = 23 /* second solve round */, K_CURSOR2 = 27, K_NVE2 = 31 /* unique vertex-edge tests that need records */, K_NVEU = 32 /* unique vertex-edge tests */, K_COUNT = 33
 };
 
 struct P1Args
@@ -254,6 +254,15 @@ struct P1Args
     unsigned *status;            // per stencil: 2 bits per sub-test (SC_*)
     int *sbase;                  // per stencil, per deferred sub-test 0..4: first record | number of records << 28
     int *qprim, *qve, *qvv;      // queues out of cull: stencil index (| sub-test << 28)
+    int *qve2;                   // unique vertex-edge tests whose first look did not settle them (np_ve_kernel -> np_ve_rec_kernel)
+    // vertex-edge de-duplication (np_ve_key_kernel): the same (vertex, edge) meets in ~6 stencils
+    unsigned long long *vkeys;   // hash set of packed (vertex, edge vertex, edge vertex) triples, vslots entries (power of two)
+    int *vslotval;               // per slot: index of the unique test
+    int *vitem;                  // per queued item: its unique test (| VE_DIRECT) or the slot that holds it
+    int *vulist;                 // unique tests: a representative item (stencil | sub-test << 28)
+    int *vures;                  // per unique test: -1 miss, else first record | number of records << 28
+    unsigned vslots;
+    bool vdedup;                 // false: per-stencil eta or vertex ids beyond 21 bits -> every item is its own test
     int2 *sq[2];                 // stage queues (ping-pong): {stencil, state}
     int2 *xq[5];                 // export queues per polynomial: {stencil, record slot}
     int *qgen;                   // stencils for the general routine
@@ -439,31 +448,123 @@ template <bool IS_VF, int K> __global__ void __launch_bounds__(128, NP_MINB_STAG
     }
 }
 
-template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_ve_kernel(P1Args Q)
+// Vertex-edge tests.  The test of vertex v against edge (a, b) depends on nothing else of the stencil, and the same triple
+// comes up in every stencil that pairs an edge at v with (a, b) and in both faces at (a, b): ~5 times at the 4M-triangle
+// cloth.  np_ve_key_kernel therefore folds the queued items into UNIQUE tests through a hash set of packed triples (one
+// 64-bit compare-and-swap per item; an item that cannot be placed within VE_PROBES probes simply becomes its own test), the
+// two dense kernels below run once per unique test, and np_ve_resolve_kernel hands every item the result of its test —
+// the records of a deferred test are shared by all its stencils (they are read-only once solved).
+//   np_ve_kernel      classifies a unique test (miss / needs records) and compacts the survivors;
+//   np_ve_rec_kernel  rebuilds those (the gather hits L2, the arithmetic is ~200 flop), refines the pending distance
+//                     quartic on the windows of its inside quadratics (ve_item_refined: four out of five end here as a
+//                     miss) and writes records only for the rest.
+#define VE_DIRECT 0x80000000u
+#define VE_PROBES 48
+#define VE_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+template <bool IS_VF> __device__ __forceinline__ void ve_item_verts(const NpArgs &A, int item, long long &i, int &sub, int &v, int &a, int &b)
+{
+    i = item & 0x0fffffff;
+    sub = (unsigned)item >> 28;
+    int iv, i1, i2;
+    Subs<IS_VF>::ve(sub, iv, i1, i2);
+    const int4 s4 = reinterpret_cast<const int4 *>(A.stencils)[i];
+    const int idx[4] = {s4.x, s4.y, s4.z, s4.w};
+    v = idx[iv]; a = idx[i1]; b = idx[i2];
+}
+
+template <bool IS_VF> __global__ void __launch_bounds__(256) np_ve_key_kernel(P1Args Q)
 {
     const NpArgs &A = Q.A;
     const unsigned long long n = Q.ctr[K_NQ + 1];
     const unsigned long long nround = block_rounded(n);
+    const unsigned mask = Q.vslots - 1u;
     for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < nround; it += (unsigned long long)gridDim.x * blockDim.x)
     {
-        int code = SC_MISS, nrec = 0, sub = 0;
-        long long i = 0;
+        bool mine = false, placed = false;
+        int item = 0;
+        unsigned h = 0;
+        if (it < n)
+        {
+            item = Q.qve[it];
+            mine = true;
+            if (Q.vdedup)
+            {
+                long long i;
+                int sub, v, a, b;
+                ve_item_verts<IS_VF>(A, item, i, sub, v, a, b);
+                const unsigned long long key = (unsigned long long)(unsigned)v | ((unsigned long long)(unsigned)a << 21) | ((unsigned long long)(unsigned)b << 42);
+                unsigned long long x = key * 0x9E3779B97F4A7C15ull;
+                x ^= x >> 29;
+                h = (unsigned)x & mask;
+                for (int probe = 0; probe < VE_PROBES; probe++)
+                {
+                    const unsigned long long old = atomicCAS(&Q.vkeys[h], VE_EMPTY, key);
+                    if (old == VE_EMPTY) { placed = true; break; }
+                    if (old == key) { mine = false; break; }
+                    h = (h + 1u) & mask;
+                }
+            }
+        }
+        const unsigned long long u = block_alloc(mine ? 1u : 0u, Q.ctr + K_NVEU);
+        if (mine)
+        {
+            Q.vulist[u] = item;
+            if (placed) Q.vslotval[h] = (int)u;
+        }
+        if (it < n) Q.vitem[it] = mine ? (int)((unsigned)u | VE_DIRECT) : (int)h;
+    }
+}
+
+template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_ve_kernel(P1Args Q)
+{
+    const NpArgs &A = Q.A;
+    const unsigned long long n = Q.ctr[K_NVEU];
+    const unsigned long long nround = block_rounded(n);
+    for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < nround; it += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        int code = SC_MISS;
+        if (it < n)
+        {
+            long long i;
+            int sub, iv, i1, i2;
+            ve_item_verts<IS_VF>(A, Q.vulist[it], i, sub, iv, i1, i2);
+            const double eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
+            V3 a0, a1, a2, b0, b1, b2;
+            ldpair(A.q0, iv, a0, b0);
+            ldpair(A.q0, i1, a1, b1);
+            ldpair(A.q0, i2, a2, b2);
+            double recs[3][8];
+            int nrec = 0;
+            code = ve_item(a0, a1, a2, b0 - a0, b1 - a1, b2 - a2, eta, recs, nrec);
+            Q.vures[it] = -1;
+        }
+        const unsigned long long o = block_alloc(code == SC_DEFERRED ? 1u : 0u, Q.ctr + K_NVE2);
+        if (code == SC_DEFERRED) Q.qve2[o] = (int)it;
+    }
+}
+
+template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_ve_rec_kernel(P1Args Q)
+{
+    const NpArgs &A = Q.A;
+    const unsigned long long n = Q.ctr[K_NVE2];
+    const unsigned long long nround = block_rounded(n);
+    for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < nround; it += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        int code = SC_MISS, nrec = 0, u = 0;
         double recs[3][8];
         if (it < n)
         {
-            const int item = Q.qve[it];
-            i = item & 0x0fffffff;
-            sub = (unsigned)item >> 28;
-            int iv, i1, i2;
-            Subs<IS_VF>::ve(sub, iv, i1, i2);
-            const int4 s4 = reinterpret_cast<const int4 *>(A.stencils)[i];
-            const int idx[4] = {s4.x, s4.y, s4.z, s4.w};
+            u = Q.qve2[it];
+            long long i;
+            int sub, iv, i1, i2;
+            ve_item_verts<IS_VF>(A, Q.vulist[u], i, sub, iv, i1, i2);
             const double eta = A.eta_arr ? A.eta_arr[i] : A.eta_all;
             V3 a0, a1, a2, b0, b1, b2;
-            ldpair(A.q0, idx[iv], a0, b0);
-            ldpair(A.q0, idx[i1], a1, b1);
-            ldpair(A.q0, idx[i2], a2, b2);
-            code = ve_item(a0, a1, a2, b0 - a0, b1 - a1, b2 - a2, eta, recs, nrec);
+            ldpair(A.q0, iv, a0, b0);
+            ldpair(A.q0, i1, a1, b1);
+            ldpair(A.q0, i2, a2, b2);
+            code = ve_item_refined(a0, a1, a2, b0 - a0, b1 - a1, b2 - a2, eta, recs, nrec);
         }
         const unsigned c = code == SC_DEFERRED ? (unsigned)nrec : 0u;
         const unsigned long long t0 = block_alloc(c, A.ntask);
@@ -479,9 +580,26 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_ve_kern
                         A.rtag[t0 + k] = (int)rec_untag(recs[k][7]);
                     }
             }
-            Q.sbase[5 * i + sub] = (int)((t0 < 0x0fffffffull ? (unsigned)t0 : 0x0fffffffu) | ((unsigned)nrec << 28));
+            Q.vures[u] = (int)((t0 < 0x0fffffffull ? (unsigned)t0 : 0x0fffffffu) | ((unsigned)nrec << 28));
         }
-        if (code != SC_MISS) atomicOr(&Q.status[i], (unsigned)code << (2 * sub));
+    }
+}
+
+// every queued item takes the result of its unique test
+template <bool IS_VF> __global__ void __launch_bounds__(256) np_ve_resolve_kernel(P1Args Q)
+{
+    const unsigned long long n = Q.ctr[K_NQ + 1];
+    for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < n; it += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        const unsigned ref = (unsigned)Q.vitem[it];
+        const int u = (ref & VE_DIRECT) ? (int)(ref & ~VE_DIRECT) : Q.vslotval[ref];
+        const int res = Q.vures[u];
+        if (res < 0) continue;
+        const int item = Q.qve[it];
+        const long long i = item & 0x0fffffff;
+        const int sub = (unsigned)item >> 28;
+        Q.sbase[5 * i + sub] = res;
+        atomicOr(&Q.status[i], (unsigned)SC_DEFERRED << (2 * sub));
     }
 }
 
@@ -619,27 +737,6 @@ template <int D> __global__ void __launch_bounds__(128) prepare_kernel(double *t
         RootLane<D> L;
         L.prepare(c);
         L.save_start(rec + 8);
-    }
-}
-
-// first-round degree-3 / degree-4 lists (= the vertex-edge distance quartics): ve_refine_item settles most of them without
-// the root isolator; the rest are compacted into `out`
-__global__ void __launch_bounds__(128) ve_refine_kernel(double *tasks, const int *__restrict__ list, const unsigned long long *count_ptr,
-                                                        int *__restrict__ out, unsigned long long *out_count)
-{
-    const unsigned long long nt = *count_ptr;
-    const unsigned long long nround = block_rounded(nt);
-    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nround; w += (unsigned long long)gridDim.x * blockDim.x)
-    {
-        bool keep = false;
-        int j = 0;
-        if (w < nt)
-        {
-            j = list[w];
-            keep = !ve_refine_item(tasks + (long long)REC_STRIDE * j);
-        }
-        const unsigned long long o = block_alloc(keep ? 1u : 0u, out_count);
-        if (keep) out[o] = j;
     }
 }
 
@@ -1011,7 +1108,11 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
     np_export_kernel<IS_VF, 1><<<gq, B, 0, st>>>(Q);
     np_export_kernel<IS_VF, 2><<<gq, B, 0, st>>>(Q);
     g_trace.mark(st, "export");
+    np_ve_key_kernel<IS_VF><<<148 * 8, 256, 0, st>>>(Q);
+    g_trace.mark(st, "ve_key");
     np_ve_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
+    np_ve_rec_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
+    np_ve_resolve_kernel<IS_VF><<<148 * 8, 256, 0, st>>>(Q);
     g_trace.mark(st, "ve");
     np_vv_kernel<IS_VF><<<gq, 256, 0, st>>>(Q);
     np_decide_kernel<IS_VF><<<148 * 8, 256, 0, st>>>(Q);
@@ -1023,14 +1124,7 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
         g_trace.mark(st, "bucket");
         launch_solve<3>(st, A.tasks, tlists + 0 * A.task_cap, nd + 0, cu + 0);
         g_trace.mark(st, "solve3");
-        if (phase == 0)
-        {
-            ve_refine_kernel<<<148 * 8, 128, 0, st>>>(A.tasks, tlists + 1 * A.task_cap, nd + 1, tlists + 4 * A.task_cap, Q.ctr + K_NREF);
-            g_trace.mark(st, "ve_refine");
-            launch_solve<4>(st, A.tasks, tlists + 4 * A.task_cap, Q.ctr + K_NREF, cu + 1);
-        }
-        else
-            launch_solve<4>(st, A.tasks, tlists + 1 * A.task_cap, nd + 1, cu + 1);
+        launch_solve<4>(st, A.tasks, tlists + 1 * A.task_cap, nd + 1, cu + 1);
         g_trace.mark(st, "solve4");
         launch_solve<5>(st, A.tasks, tlists + 2 * A.task_cap, nd + 2, cu + 2);
         g_trace.mark(st, "solve5");
@@ -1043,21 +1137,22 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
     np_general_kernel<IS_VF><<<148 * 4, B, 0, st>>>(Q);
     g_trace.mark(st, "general");
     g_trace.flush(IS_VF ? "VF" : "EE", Q.ctr, n);
-    return nl + 3 + 3 + 2 * 13 + 1 + 1 + 2;
+    return nl + 3 + 6 + 2 * 13 + 1 + 2;
 }
 
 // Single step: q0 = positions packed by ccdk_pack_positions (q1, vstride unused); multi-entry History: q0 == nullptr.
 // Scratch (sizes in elements, n = number of stencils): work list {w_stencil: n ints, w_meta: n ints, w_base: 5n ints},
 // tasks (task_cap records of REC_STRIDE doubles, task_cap < 2^28), tlists (6 x task_cap ints: pending records by degree, refined list, record tags),
-// status (n u32), sbase (5n ints), queues (9n ints: primitive / vertex-edge / vertex-vertex items), sq (2 x n int2: stage
+// status (n u32), sbase (5n ints), queues (13n ints: primitive / vertex-edge / vertex-vertex items / vertex-edge items that need records), sq (2 x n int2: stage
 // queues), xq (5 x n int2: export queues), ctr (CCD_NP_COUNTERS counters, zeroed here; ctr[0] = work-list entries,
-// ctr[1] = records).  Returns the number of kernels launched.  If ctr[1] ends above task_cap the caller must grow the
+// ctr[1] = records), ve_scratch (12 bytes x ve_slots + 48 bytes x n; ve_slots a power of two, see ccdk_np_ve_slots).  Returns the number of kernels launched.  If ctr[1] ends above task_cap the caller must grow the
 // record buffer and call again.
 int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, double eta_all,
                      const double *q0, const double *q1, int vstride, const float *vbox, const long long *hoff, const double *htime, const double *hpos,
                      unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits,
                      unsigned long long *nhit, int *w_stencil, int *w_meta, int *w_base, double *tasks, int *tlists,
-                     unsigned long long task_cap, unsigned *status, int *sbase, int *queues, int *sq, int *xq, unsigned long long *ctr)
+                     unsigned long long task_cap, unsigned *status, int *sbase, int *queues, int *sq, int *xq, unsigned long long *ctr,
+                     void *ve_scratch, unsigned ve_slots, int V)
 {
     static_assert(K_COUNT <= CCD_NP_COUNTERS, "counter block too small");
     if (n <= 0) return 0;
@@ -1076,12 +1171,30 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
     cudaMemsetAsync(ctr, 0, CCD_NP_COUNTERS * sizeof(unsigned long long), st);
     P1Args Q;
     Q.A = A; Q.status = status; Q.sbase = sbase;
-    Q.qprim = queues; Q.qve = queues + n; Q.qvv = queues + 5 * n;
+    Q.qprim = queues; Q.qve = queues + n; Q.qvv = queues + 5 * n; Q.qve2 = queues + 9 * n;
     Q.sq[0] = reinterpret_cast<int2 *>(sq); Q.sq[1] = reinterpret_cast<int2 *>(sq) + n;
     for (int k = 0; k < 5; k++) Q.xq[k] = reinterpret_cast<int2 *>(xq) + (size_t)k * n;
     Q.qgen = queues;      // the primitive queue is consumed by stage 0 long before anything goes to the general routine
     Q.ctr = ctr;
+    // vertex-edge de-duplication scratch: ve_slots keys (8 bytes) + ve_slots slot values + 3 x 4n ints
+    Q.vslots = ve_slots;
+    Q.vkeys = reinterpret_cast<unsigned long long *>(ve_scratch);
+    Q.vslotval = reinterpret_cast<int *>(Q.vkeys + ve_slots);
+    Q.vitem = Q.vslotval + ve_slots;
+    Q.vulist = Q.vitem + 4 * n;
+    Q.vures = Q.vulist + 4 * n;
+    Q.vdedup = eta_arr == nullptr && V <= (1 << 21) && ve_slots >= 2;
+    if (Q.vdedup) cudaMemsetAsync(Q.vkeys, 0xff, sizeof(unsigned long long) * ve_slots, st);
     return is_vf ? launch_single_step<true>(st, Q, n, tlists) : launch_single_step<false>(st, Q, n, tlists);
+}
+
+// hash-set size for the vertex-edge de-duplication of a run over n stencils: the unique tests number ~0.15 n (4M-triangle
+// cloth), at most 4 n; a set that fills up only loses de-duplication (np_ve_key_kernel), never correctness
+unsigned ccdk_np_ve_slots(long long n)
+{
+    unsigned s = 1u << 12;
+    while ((long long)s < n && s < (1u << 30)) s <<= 1;
+    return s;
 }
 
 void ccdk_sepplane(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, const long long *hoff, const double *htime,

@@ -110,7 +110,18 @@ def stage_pack():
         d["%s_toi_out_of_1e9" % k] = len(out_tol)
         d["%s_toi_rel_max" % k] = float(rel.max(initial=0))
         d["%s_toi_rel_median" % k] = float(np.median(rel)) if len(rel) else 0.0
-        d["%s_stage_differs" % k] = int((ps[both] != rs[both]).sum())
+        # both hit, but through different sub-tests (e.g. the reference's primitive missed and a vertex-edge test caught
+        # it): the earlier of the two sub-tests is where the runs disagree -> that disagreement is classified
+        sd = both[ps[both] != rs[both]]
+        sdc = []
+        for i in sd:
+            pts = np.concatenate([q0[st[i]].reshape(-1), q1[st[i]].reshape(-1)])
+            first = int(min(ps[i], rs[i]))
+            sdc.append(PA.classify_flag(arb, k, pts, eta, bool(ps[i] == first), bool(rs[i] == first), first, first))
+        d["%s_stage_differs" % k] = len(sd)
+        d["%s_stage_differs_index" % k] = sd.astype(np.int64)
+        d["%s_stage_differs_class" % k] = np.array(sdc, dtype="U24")
+        print(k, "both hit, different sub-test:", len(sd), dict(zip(*np.unique(np.array(sdc, dtype="U24"), return_counts=True))) if len(sd) else {}, flush=True)
         # the out-of-tolerance ones: a deterministic sample of at most 2000 is arbitrated (all of them when fewer)
         pick = out_tol if len(out_tol) <= 2000 else out_tol[np.linspace(0, len(out_tol) - 1, 2000).astype(np.int64)]
         tcls = []

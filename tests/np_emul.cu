@@ -21,6 +21,7 @@ using namespace ccd;
 namespace {
 
 struct Rec { double d[REC_STRIDE]; };
+long long *g_stats = nullptr;      // funnel counters (np_emul's stats array)
 
 template <int D> void solve_one(Rec &r)
 {
@@ -80,12 +81,18 @@ template <bool IS_VF> int primitive(const V3 *a, const V3 *v, double eta, std::v
     bool has = false;
     nrec = 0;
     if (!run_stage<IS_VF, 0>(a, v, eta, state, own, has)) return SC_MISS;
+    if (g_stats) g_stats[20]++;
     if (!run_stage<IS_VF, 1>(a, v, eta, state, own, has)) return SC_MISS;
+    if (g_stats) g_stats[21]++;
     if (!run_stage<IS_VF, 2>(a, v, eta, state, own, has)) return SC_MISS;
+    if (g_stats) g_stats[22]++;
     if (!run_stage<IS_VF, 3>(a, v, eta, state, own, has)) return SC_MISS;
+    if (g_stats) g_stats[23]++;
     if (!IS_VF)
         if (!run_stage<false, 4>(a, v, eta, state, own, has)) return SC_MISS;
+    if (g_stats) g_stats[24]++;
     const unsigned need = state & 0x1fu;      // may be 0: deferred with no record
+    if (g_stats) for (int k = 0; k < 5; k++) g_stats[25 + k] += (need >> k) & 1u;
     constexpr int KOWN = Prim<IS_VF>::poly(Prim<IS_VF>::NST - 1);
     for (int k = 0; k < 5; k++)
     {
@@ -125,6 +132,13 @@ void run(long long n, const int *stencils, const double *q0, const double *q1, i
         for (int k = 0; k < 4; k++) c.bx[k] = swept_box_f(a[k], b[k]);
         c.init(eta);
         const unsigned todo = c.todo();
+        if (g_stats)
+        {
+            g_stats[16] += (todo & 1u);
+            g_stats[17] += ccd_popc((todo >> 1) & ((1u << NVE) - 1u));
+            g_stats[18] += ccd_popc(todo >> (NVE + 1));
+            g_stats[19] += (todo == (IS_VF ? 1u : 0u));
+        }
         // pass 1
         recs.clear();
         int code[NSUB], first[NSUB], cnt[NSUB];
@@ -143,7 +157,12 @@ void run(long long n, const int *stencils, const double *q0, const double *q1, i
                 Subs<IS_VF>::ve(sub, iv, i1, i2);
                 double r3[3][8];
                 int nrec;
-                code[sub] = ve_item(a[iv], a[i1], a[i2], v[iv], v[i1], v[i2], eta, r3, nrec);
+                code[sub] = ve_item(a[iv], a[i1], a[i2], v[iv], v[i1], v[i2], eta, r3, nrec);      // np_ve_kernel: classify
+                if (code[sub] == SC_DEFERRED)                                                       // np_ve_rec_kernel: rebuild + refine
+                {
+                    code[sub] = ve_item_refined(a[iv], a[i1], a[i2], v[iv], v[i1], v[i2], eta, r3, nrec);
+                    if (g_stats) g_stats[31] += (code[sub] == SC_MISS);
+                }
                 if (code[sub] == SC_DEFERRED)
                 {
                     first[sub] = (int)recs.size();
@@ -187,7 +206,7 @@ void run(long long n, const int *stencils, const double *q0, const double *q1, i
         }
         else if (!general)
         {
-            for (size_t k = 0; k < recs.size(); k++) ve_refine_item(recs[k].d);      // no-op for anything but pending VE quartics
+                  // no-op for anything but pending VE quartics
             solve_records(recs, stats, 0);
             if (code[0] == SC_DEFERRED && cnt[0] > 0) window_item(recs[first[0]].d, cnt[0], IS_VF ? 3 : 4);
             solve_records(recs, stats, 1);
@@ -201,6 +220,7 @@ void run(long long n, const int *stencils, const double *q0, const double *q1, i
                 else if (r == RS_HIT) { stage = sub + 1; settled = true; }
             }
             if (!settled && later_hit != 255) { stage = later_hit + 1; t = vv_time(later_hit); }
+            if (g_stats) { g_stats[32]++; g_stats[33] += (stage != 0); g_stats[40 + (stage < 10 ? stage : 9)]++; }
         }
         if (general)
         {
@@ -221,6 +241,7 @@ extern "C" int np_emul(int is_vf, long long n, const int *stencils, const double
                        double eta_all, unsigned char *hit, double *toi, unsigned char *stage, long long *stats)
 {
     for (int k = 0; k < 11; k++) stats[k] = 0;
+    g_stats = nullptr;
     if (is_vf) run<true>(n, stencils, q0, q1, vstride, eta_arr, eta_all, hit, toi, stage, stats);
     else run<false>(n, stencils, q0, q1, vstride, eta_arr, eta_all, hit, toi, stage, stats);
     return 0;
@@ -255,4 +276,19 @@ extern "C" int np_emul_sepplane(int is_vf, long long n, const int *stencils, con
         bad += r < 0;
     }
     return bad;
+}
+
+// same as np_emul with the funnel counters: stats has 64 entries (0..10 as np_emul; 16 primitives after the cull, 17 / 18
+// vertex-edge / vertex-vertex items after the cull, 19 stencils with nothing to do, 20..24 survivors of stage 0..4,
+// 25..29 records needed per polynomial, 31 vertex-edge quartics settled by ve_refine, 32 deferred stencils, 33 of them hits,
+// 40..49 deferred stencils by final stage)
+extern "C" int np_emul_funnel(int is_vf, long long n, const int *stencils, const double *q0, const double *q1, int vstride, const double *eta_arr,
+                              double eta_all, unsigned char *hit, double *toi, unsigned char *stage, long long *stats)
+{
+    for (int k = 0; k < 64; k++) stats[k] = 0;
+    g_stats = stats;
+    if (is_vf) run<true>(n, stencils, q0, q1, vstride, eta_arr, eta_all, hit, toi, stage, stats);
+    else run<false>(n, stencils, q0, q1, vstride, eta_arr, eta_all, hit, toi, stage, stats);
+    g_stats = nullptr;
+    return 0;
 }

@@ -353,21 +353,92 @@ def test_cloth_sharded_union_equals_whole(ctx):
 
 
 @pytest.mark.slow
-def test_cloth_full_size_properties(ctx):
-    """BASELINE config C5 (1415 x 1415 vertices, 3,998,792 triangles): no CPU oracle at this size inside the test
-    budget, so size-independent properties — canonical form, strict lexicographic order (sorted + unique),
-    idempotence, hits a subset with TOI in [0,1] — plus the ribbon check: a 48-column ribbon of the same cloth run
-    on its own must give exactly the stencils of the full run that lie wholly inside the ribbon's interior."""
+def test_cloth_full_size_against_golden(ctx, port):
+    """BASELINE config C5 (1415 x 1415 vertices, 3,998,792 triangles) against the golden the UNMODIFIED reference produced at
+    full size (tests/golden/cloth_1415.npz, tests/golden/make_golden_c5.py: KDOPBroadPhase + CTCDNarrowPhase over all
+    30,503,172 candidates, the flow of example/AlecTest.cpp:86-111):
+
+      * candidate sets: counts and FNV-1a-64 of the sorted lists equal the reference's (bit-exact sets);
+      * hit flags: the set of stencils on which the GPU differs from the reference is EXACTLY the classified list in the
+        golden (56 edge-edge stencils, 0 vertex-face; every one arbitrated, none unexplained), flag by flag;
+      * the sub-test that fired equals the reference's except on the classified list;
+      * time of impact: every 16th reference hit is compared at full precision, 1e-9 relative (north_star), except the
+        arbitrated out-of-tolerance list (reference artefacts of rpoly on nearly-double roots);
+      * earliest time of impact within 1e-9 relative of the reference's;
+      * size-independent properties (canonical form, strict order, idempotence of the fused step) and the ribbon check:
+        a 48-column ribbon of the same cloth run on its own gives exactly the CPU restatement's lists, which are exactly
+        the stencils of the full run that lie wholly inside the ribbon's interior."""
+    import os
+    from conftest import GOLDEN
     from collisiondetection_b200 import scenes
-    n = 1415
+    path = os.path.join(GOLDEN, "cloth_1415.npz")
+    assert os.path.exists(path), "tests/golden/cloth_1415.npz missing (python tests/golden/make_golden_c5.py)"
+    g = np.load(path)
+    n = int(g["n"])
     q0, q1, f, eta = scenes.cloth(n)
+    assert len(f) == 3998792 and eta == float(g["eta"])
     vf, ee = ctx.findCollisionCandidatesStep(13, f, q0, q1, eta)
-    assert len(f) == 3998792
+    assert (len(vf), len(ee)) == (int(g["n_vf"]), int(g["n_ee"])) == (11265150, 19238022)
+    assert bind.fnv1a64(vf) == str(g["vf_fnv"]) and bind.fnv1a64(ee) == str(g["ee_fnv"])
     _check_canonical_sorted_unique(vf, ee)
+
+    H = bind.single_step_history(q0, q1)
+    out = ctx.findCollisions(*H, vf, eta, ee, eta)
+    account = {}
+    for k, st in (("vf", vf), ("ee", ee)):
+        hit = out[k + "_hit"] > 0
+        rh = np.unpackbits(g["ref_%s_hit_bits" % k])[:len(st)] > 0
+        assert int(rh.sum()) == int(g["ref_%s_n_hits" % k])
+        mism = np.nonzero(hit != rh)[0]
+        assert np.array_equal(mism, g["%s_mismatch_index" % k]), (k, len(mism))
+        assert np.array_equal(hit[mism].astype(np.uint8), g["%s_mismatch_mine" % k])
+        assert np.array_equal(st[mism], g["%s_mismatch_stencil" % k])
+        cls = [str(c) for c in g["%s_mismatch_class" % k]]
+        assert "unexplained" not in cls
+        # the sub-test that fired, on the reference's hits that are hits here too
+        ridx = np.nonzero(rh)[0]
+        both = hit[ridx]
+        sd = ridx[both][out[k + "_stage"][ridx[both]] != g["ref_%s_hit_stage" % k][both]]
+        assert np.array_equal(sd, g["%s_stage_differs_index" % k]), (k, len(sd))
+        assert "unexplained" not in [str(c) for c in g["%s_stage_differs_class" % k]]
+        # time of impact of every 16th reference hit
+        samp = ridx[::16]
+        rt = g["ref_%s_hit_toi_16th" % k]
+        ok = hit[samp]
+        rel = np.abs(out[k + "_toi"][samp[ok]] - rt[ok]) / np.maximum(np.abs(rt[ok]), 1e-300)
+        bad = samp[ok][rel > 1e-9]
+        assert np.all(np.isin(bad, g["%s_toi_sample_index" % k])), (k, bad[:10])
+        assert "unexplained" not in [str(c) for c in g["%s_toi_sample_class" % k]]
+        account[k] = dict(matched=int((hit == rh).sum()), flag_classes={c: cls.count(c) for c in sorted(set(cls))},
+                          toi_out_of_1e9=int(g["%s_toi_out_of_1e9" % k]), unexplained=0)
+    print("C5 parity account:", account)
+    ref_early = float(g["ref_earliest_toi"])
+    assert abs(out["earliest_toi"] - ref_early) <= 1e-9 * ref_early
+
+    # the fused step (what bench.py times): same counts, hit lists = the flagged subsets of the candidate lists
     r = ctx.step(13, f, q0, q1, eta, eta)
     assert (r["n_vf_candidates"], r["n_ee_candidates"]) == (len(vf), len(ee))
-    assert 0 <= r["earliest_toi"] <= 1
-    assert r["n_vf_hits"] > 0 and r["n_ee_hits"] > 0
+    assert np.array_equal(r["vf_hits"], vf[out["vf_hit"] > 0]) and np.array_equal(r["ee_hits"], ee[out["ee_hit"] > 0])
+    assert np.array_equal(r["vf_hit_toi"].view(np.uint64), out["vf_toi"][out["vf_hit"] > 0].view(np.uint64))
+    assert r["earliest_toi"] == out["earliest_toi"] == min(r["vf_hit_toi"].min(), r["ee_hit_toi"].min())
+
+    # ribbon check: columns [j0, j1) of the same cloth on their own
+    j0, j1 = 600, 648
+    rq0, rq1, rf, reta = scenes.cloth(n, cols=(j0, j1))
+    assert reta == eta
+    rvf, ree = ctx.findCollisionCandidatesStep(13, rf, rq0, rq1, eta)
+    pvf, pee, _ = port.broadphase(13, rf, *bind.single_step_history(rq0, rq1), eta)
+    assert np.array_equal(rvf, pvf) and np.array_equal(ree, pee)
+    nc = j1 - j0
+    for full, rib in ((vf, rvf), (ee, ree)):
+        # a vertex whose column is strictly inside the ribbon has all its faces (and their neighbours' boxes) in it
+        col = full % n
+        inside = np.all((col >= j0 + 2) & (col < j1 - 2), axis=1)
+        mapped = ((full[inside] // n) * nc + (full[inside] % n - j0)).astype(np.int32)
+        rcol = rib % nc
+        rin = np.all((rcol >= 2) & (rcol < nc - 2), axis=1)
+        assert inside.sum() > 1000
+        assert np.array_equal(mapped, rib[rin])
 
 
 def _write_obj(path, q, f):
