@@ -180,7 +180,7 @@ class Context(object):
         return out
 
     # ---- whole step (example/AlecTest.cpp:86-111) ---------------------------------------------
-    STAGES = ("topology", "leaf_boxes", "tree_build", "traverse_exact", "adjacency", "emit_count", "emit_write", "np_vf", "np_ee")
+    STAGES = ("topology", "leaf_boxes", "tree_build", "traverse_exact", "adjacency", "emit_count", "emit_write", "np_ee", "np_vf")
 
     def findCollisionsSeparatingPlane(self, hoff, htime, hpos, vf, vf_eta, ee, ee_eta):
         """SeparatingPlaneNarrowPhase::findCollisions (ccd_narrowphase_sepplane): hit flags per candidate."""

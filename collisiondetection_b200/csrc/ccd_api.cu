@@ -13,7 +13,7 @@
 #include <vector>
 
 // per-stage device timing (CUDA events on the context's stream); see ccd_stage_times()
-enum { ST_TOPOLOGY = 0, ST_BOXES, ST_TREE, ST_TRAVERSE_EXACT, ST_ADJACENCY, ST_EMIT_COUNT, ST_EMIT_WRITE, ST_NP_VF, ST_NP_EE, CCD_N_STAGES };
+enum { ST_TOPOLOGY = 0, ST_BOXES, ST_TREE, ST_TRAVERSE_EXACT, ST_ADJACENCY, ST_EMIT_COUNT, ST_EMIT_WRITE, ST_NP_EE, ST_NP_VF, CCD_N_STAGES };
 
 struct DBuf
 {
@@ -25,6 +25,8 @@ struct ccd_context
 {
     int device = 0;
     cudaStream_t st = nullptr;
+    cudaStream_t st2 = nullptr;      // side stream: the edge-edge run's general routine overlaps the vertex-face run
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t sev[CCD_N_STAGES + 1];
     bool stage_valid = false;
@@ -35,7 +37,7 @@ struct ccd_context
     DBuf faces, q0, q1, hoff, htime, hpos, fixed, vf_in, ee_in, vf_eta, ee_eta, pts, eta;
     // broadphase
     DBuf boxes, faabb, fkdop, bounds, keysA, keysB, valsA, valsB, temp, nodes, leafParent, nodeParent, flags;
-    DBuf cand, counters, pairL, pairR, deg, adjOff, cursor, adj, heap, srec, unsure, frontA, frontB;
+    DBuf cand, counters, pairL, pairR, deg, adjOff, cursor, adj, heap, srec, sbox, sfaces, unsure, frontA, frontB;
     size_t frontCap = 0, unsureCap = 0;
     DBuf k32A, k32B, scanFlags, scanIds;
     // topology cache (function of `faces` only)
@@ -178,9 +180,9 @@ int ccdk_cluster_count_pow2(int F);
 int ccdk_cluster_size(void);
 void ccdk_build_cluster_tree(cudaStream_t st, int kind, int F, const int *faces, const float *faabb, const double *q0, const double *q1, double eta,
                              const double *boxes, unsigned *bounds, unsigned long long *keys_in, unsigned long long *keys_sorted, unsigned *vals_in,
-                             unsigned *sortedFace, void *temp, size_t temp_bytes, float *heap, float *rec);
+                             unsigned *sortedFace, void *temp, size_t temp_bytes, float *heap, float *rec, float *sbox, void *sfaces);
 int ccdk_leaf_record_words(void);
-int ccdk_pair_traversal(cudaStream_t st, int kind, int F, const float *heap, const float *rec, const double *boxes,
+int ccdk_pair_traversal(cudaStream_t st, int kind, int F, const float *heap, const float *rec, const float *sbox, const void *sfaces, const double *boxes,
                         const double *q0, const double *q1, double eta, void *fr0, void *fr1, unsigned long long fcap, unsigned long long *fcount,
                         void *unsure, unsigned long long ucap, int *pairL, int *pairR, unsigned long long pcap, unsigned long long *npairs, int *deg,
                         const int *own, const int *ownPre, void *cand, unsigned long long ccap, unsigned long long *ncand);
@@ -213,18 +215,32 @@ int ccd_create(ccd_context **out, int device)
         delete c;
         return CCD_ERR_CUDA;
     }
-    for (int i = 0; i < 4; i++)
-        cudaEventCreate(&c->ev[i]);
-    for (int i = 0; i <= CCD_N_STAGES; i++)
-        cudaEventCreate(&c->sev[i]);
-    cudaMallocHost((void **)&c->h_counters, sizeof(unsigned long long) * C_TOTAL);
-    cudaMallocHost((void **)&c->h_hist, sizeof(unsigned long long) * 2 * CCD_SHARD_BUCKETS);
+    for (int i = 0; i <= CCD_N_STAGES; i++) c->sev[i] = nullptr;
+    bool ok = cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; i++)
+        ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+    for (int i = 0; i <= CCD_N_STAGES && ok; i++)
+        ok = cudaEventCreate(&c->sev[i]) == cudaSuccess;
+    if (!ok)
+    {
+        cudaGetLastError();
+        ccd_destroy(c);
+        return CCD_ERR_CUDA;
+    }
+    if (cudaMallocHost((void **)&c->h_counters, sizeof(unsigned long long) * C_TOTAL) != cudaSuccess ||
+        cudaMallocHost((void **)&c->h_hist, sizeof(unsigned long long) * 2 * CCD_SHARD_BUCKETS) != cudaSuccess)
+    {
+        cudaGetLastError();
+        ccd_destroy(c);
+        return CCD_ERR_NOMEM;
+    }
     double ax[13][3];
     kdop_axes(ax);
     ccdk_set_axes(ax);
     if (ensure(c, c->counters, sizeof(unsigned long long) * C_TOTAL) != CCD_OK)
     {
-        delete c;
+        ccd_destroy(c);
         return CCD_ERR_NOMEM;
     }
     *out = c;
@@ -236,14 +252,15 @@ void ccd_destroy(ccd_context *c)
     if (!c)
         return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->st);
+    if (c->st) cudaStreamSynchronize(c->st);
+    if (c->st2) cudaStreamSynchronize(c->st2);
     DBuf *all[] = {&c->faces, &c->q0, &c->q1, &c->hoff, &c->htime, &c->hpos, &c->fixed, &c->vf_in, &c->ee_in, &c->vf_eta, &c->ee_eta,
                    &c->pts, &c->eta, &c->boxes, &c->faabb, &c->fkdop, &c->bounds, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->temp, &c->nodes,
                    &c->leafParent, &c->nodeParent, &c->flags, &c->cand, &c->counters, &c->pairL, &c->pairR, &c->deg, &c->adjOff,
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1Ve, &c->qpack, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->nodeFirst, &c->nodeForeign, &c->vertEdgeStart, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->unsure, &c->frontA, &c->frontB};
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1Ve, &c->qpack, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->nodeFirst, &c->nodeForeign, &c->vertEdgeStart, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->sbox, &c->sfaces, &c->unsure, &c->frontA, &c->frontB};
     for (DBuf *b : all)
         if (b->p)
             cudaFree(b->p);
@@ -258,8 +275,12 @@ void ccd_destroy(ccd_context *c)
         if (c->ev[i])
             cudaEventDestroy(c->ev[i]);
     for (int i = 0; i <= CCD_N_STAGES; i++)
-        cudaEventDestroy(c->sev[i]);
-    cudaStreamDestroy(c->st);
+        if (c->sev[i])
+            cudaEventDestroy(c->sev[i]);
+    if (c->evFork) cudaEventDestroy(c->evFork);
+    if (c->evJoin) cudaEventDestroy(c->evJoin);
+    if (c->st2) cudaStreamDestroy(c->st2);
+    if (c->st) cudaStreamDestroy(c->st);
     delete c;
 }
 
@@ -404,9 +425,11 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         const size_t NLc = (size_t)ccdk_cluster_count_pow2(F), NLf = NLc * (size_t)ccdk_cluster_size();
         CKR(ensure(c, c->heap, sizeof(float) * 6 * (2 * NLc)));
         CKR(ensure(c, c->srec, sizeof(float) * (size_t)ccdk_leaf_record_words() * NLf));
+        CKR(ensure(c, c->sbox, sizeof(float) * 6 * NLf));
+        CKR(ensure(c, c->sfaces, sizeof(int) * 4 * NLf));
         ccdk_build_cluster_tree(c->st, kind, F, d_faces, P<float>(c->faabb), lazy_boxes ? d_q0 : nullptr, d_q1, outerEta, lazy_boxes ? nullptr : P<double>(c->boxes),
                                 P<unsigned>(c->bounds), P<unsigned long long>(c->keysA), P<unsigned long long>(c->keysB), P<unsigned>(c->valsA),
-                                P<unsigned>(c->valsB), c->temp.p, c->temp.cap, P<float>(c->heap), P<float>(c->srec));
+                                P<unsigned>(c->valsB), c->temp.p, c->temp.cap, P<float>(c->heap), P<float>(c->srec), P<float>(c->sbox), c->sfaces.p);
         c->launches += 1 + 2 + 8 + 2 + 3;
     }
     const unsigned *sortedFace = P<unsigned>(c->valsB);
@@ -478,7 +501,7 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
             CKR(ensure(c, c->frontB, sizeof(int) * 2 * c->frontCap));
             if (c->unsureCap == 0) c->unsureCap = (size_t)F / 16 + (1u << 14);
             CKR(ensure(c, c->unsure, sizeof(int) * 2 * c->unsureCap));
-            c->launches += ccdk_pair_traversal(c->st, kind, F, P<float>(c->heap), P<float>(c->srec), lazy_boxes ? nullptr : P<double>(c->boxes),
+            c->launches += ccdk_pair_traversal(c->st, kind, F, P<float>(c->heap), P<float>(c->srec), P<float>(c->sbox), c->sfaces.p, lazy_boxes ? nullptr : P<double>(c->boxes),
                                                lazy_boxes ? d_q0 : nullptr, d_q1, outerEta, c->frontA.p, c->frontB.p, c->frontCap, ctr + C_FRONT, c->unsure.p,
                                                c->unsureCap, P<int>(c->pairL), P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg),
                                                sharded ? P<int>(c->needed) : nullptr, sharded ? P<int>(c->neededPre) : nullptr, c->cand.p, c->candCap, ctr + C_NCAND);
@@ -596,7 +619,7 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
 
 // Narrowphase over device-resident stencils; results left in c->vfHit/... ; summary via counters.
 static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d_vf, const double *d_vf_eta, long long nee, const int *d_ee,
-                              const double *d_ee_eta, double eta_all, const double *d_q0, const double *d_q1, int vstride, const long long *d_hoff,
+                              const double *d_ee_eta, double eta_all_vf, double eta_all_ee, const double *d_q0, const double *d_q1, int vstride, const long long *d_hoff,
                               const double *d_htime, const double *d_hpos, ccd_np_summary *sum)
 {
     unsigned long long *ctr = P<unsigned long long>(c->counters);
@@ -648,16 +671,20 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         unsigned long long init[4] = {0xFFFFFFFFFFFFFFFFull, 0ull, 0xFFFFFFFFFFFFFFFFull, 0ull};
         memcpy(c->h_counters + 8, init, sizeof(init));
         CK(cudaMemcpyAsync(ctr + C_EARLY_VF, c->h_counters + 8, sizeof(init), cudaMemcpyHostToDevice, c->st));
-        cudaEventRecord(c->sev[ST_NP_VF], c->st);
-        nl += ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
-                               P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF, P<int>(c->workVf),
-                               P<int>(c->workTaskVf), P<int>(c->workSubVf), P<double>(c->tasksVf), P<int>(c->tlistVf), c->taskCapVf, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
-                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_VF, c->p1Ve.p, ccdk_np_ve_slots(nvf), V);
+        // the edge-edge run goes first: its general routine (a few hundred long single-lane walks) then runs on the side
+        // stream beside the vertex-face run
+        const bool single_step = d_q0 != nullptr;
         cudaEventRecord(c->sev[ST_NP_EE], c->st);
-        nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
+        nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all_ee, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
                                P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE, P<int>(c->workEe),
                                P<int>(c->workTaskEe), P<int>(c->workSubEe), P<double>(c->tasksEe), P<int>(c->tlistEe), c->taskCapEe, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
-                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_EE, c->p1Ve.p, ccdk_np_ve_slots(nee), V);
+                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_EE, c->p1Ve.p, ccdk_np_ve_slots(nee), V, c->st2, c->evFork, c->evJoin);
+        cudaEventRecord(c->sev[ST_NP_VF], c->st);
+        nl += ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all_vf, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
+                               P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF, P<int>(c->workVf),
+                               P<int>(c->workTaskVf), P<int>(c->workSubVf), P<double>(c->tasksVf), P<int>(c->tlistVf), c->taskCapVf, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
+                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_VF, c->p1Ve.p, ccdk_np_ve_slots(nvf), V, nullptr, nullptr, nullptr);
+        if (single_step && nee > 0 && !getenv("CCD_NP_TRACE")) CK(cudaStreamWaitEvent(c->st, c->evJoin, 0));
         cudaEventRecord(c->sev[CCD_N_STAGES], c->st);
         CK(cudaGetLastError());
         CKR(sync_counters(c));
@@ -778,12 +805,22 @@ int ccd_narrowphase(ccd_context *c, int V, const int64_t *hoff, const double *ht
     CKR(upload(c, c->hpos, hpos, sizeof(double) * 3 * (size_t)N));
     CKR(upload(c, c->vf_in, vf, sizeof(int32_t) * 4 * (size_t)nvf));
     CKR(upload(c, c->ee_in, ee, sizeof(int32_t) * 4 * (size_t)nee));
-    CKR(upload(c, c->vf_eta, vf_eta, sizeof(double) * (size_t)nvf));
-    CKR(upload(c, c->ee_eta, ee_eta, sizeof(double) * (size_t)nee));
+    // one thickness for every stencil of a type (the common case: include/CTCD.h callers pass one eta) is passed by value:
+    // no per-stencil array to upload or read, and the vertex-edge de-duplication applies (it needs a shared eta)
+    auto uniform = [](const double *a, int64_t n) {
+        if (n <= 0) return false;
+        for (int64_t i = 1; i < n; i++)
+            if (a[i] != a[0]) return false;
+        return true;
+    };
+    const bool uvf = uniform(vf_eta, nvf), uee = uniform(ee_eta, nee);
+    if (!uvf) CKR(upload(c, c->vf_eta, vf_eta, sizeof(double) * (size_t)nvf));
+    if (!uee) CKR(upload(c, c->ee_eta, ee_eta, sizeof(double) * (size_t)nee));
     ccd_np_summary s;
     // two entries per vertex = one linear segment: read q0/q1 straight out of hpos (stride 6)
     const bool single = history_is_single_step(V, hoff);
-    CKR(narrowphase_device(c, V, nvf, P<int>(c->vf_in), P<double>(c->vf_eta), nee, P<int>(c->ee_in), P<double>(c->ee_eta), 0.0,
+    CKR(narrowphase_device(c, V, nvf, P<int>(c->vf_in), uvf ? nullptr : P<double>(c->vf_eta), nee, P<int>(c->ee_in), uee ? nullptr : P<double>(c->ee_eta),
+                           uvf ? vf_eta[0] : 0.0, uee ? ee_eta[0] : 0.0,
                            single ? P<double>(c->hpos) : nullptr, single ? P<double>(c->hpos) + 3 : nullptr, 6, P<long long>(c->hoff),
                            P<double>(c->htime), P<double>(c->hpos), &s));
     if (nvf > 0)
@@ -867,7 +904,7 @@ int ccd_step_device(ccd_context *c, int kind, int V, int F, const int32_t *d_fac
     CKR(broadphase_device(c, kind, V, F, d_faces, d_q0, d_q1, nullptr, nullptr, outerEta, d_fixedMask, shard_rank, shard_world, &r));
     CK(cudaEventRecord(c->ev[1], c->st));
     ccd_np_summary s;
-    CKR(narrowphase_device(c, V, r.nvf, P<int>(c->vfOut), nullptr, r.nee, P<int>(c->eeOut), nullptr, eta, d_q0, d_q1, 3, nullptr, nullptr, nullptr, &s));
+    CKR(narrowphase_device(c, V, r.nvf, P<int>(c->vfOut), nullptr, r.nee, P<int>(c->eeOut), nullptr, eta, eta, d_q0, d_q1, 3, nullptr, nullptr, nullptr, &s));
     CK(cudaEventRecord(c->ev[2], c->st));
     CK(cudaEventSynchronize(c->ev[2]));
     cudaEventElapsedTime(&out->ms_broadphase, c->ev[0], c->ev[1]);

@@ -637,58 +637,87 @@ template <bool IS_VF> __device__ __forceinline__ double vv_toi(const StencilIn &
     return t;
 }
 
-// Persistent grid-stride kernel: with one stencil per thread and a few barriers per block, 240 k tiny blocks spent their
-// time being launched.  (Pass 1 no longer produces SC_GENERAL: unconstrained sub-tests are deferred with zero records.)
+// Persistent grid-stride kernel, FOUR consecutive stencils per thread: the status words arrive as one 16-byte load, the
+// results leave as 4-byte / 32-byte stores, and the block's barriers (work-list reservation, reduction) are paid once per
+// 1024 stencils.  (Pass 1 no longer produces SC_GENERAL: unconstrained sub-tests are deferred with zero records.)
 template <bool IS_VF> __global__ void __launch_bounds__(256) np_decide_kernel(P1Args Q)
 {
     const NpArgs &A = Q.A;
     constexpr int NSUB = 1 + Subs<IS_VF>::NVE + Subs<IS_VF>::NVV;
-    const unsigned long long n = (unsigned long long)A.n, nround = block_rounded(n);
+    const unsigned long long n = (unsigned long long)A.n, nquad = (n + 3) / 4, nround = block_rounded(nquad);
     for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < nround; it += (unsigned long long)gridDim.x * blockDim.x)
     {
-        const long long i = (long long)it;
-        int stage = 0, meta = 0, nd = 0;
-        int base[5] = {0, 0, 0, 0, 0};
-        double toi = 0.0;
-        if (it < n)
+        const long long i0 = 4ll * (long long)it;
+        unsigned st4[4] = {0, 0, 0, 0};
+        if (i0 + 3 < (long long)n)
         {
-            const unsigned st = Q.status[i];
+            const uint4 s = reinterpret_cast<const uint4 *>(Q.status)[it];
+            st4[0] = s.x; st4[1] = s.y; st4[2] = s.z; st4[3] = s.w;
+        }
+        else
+            for (int k = 0; k < 4; k++)
+                if (i0 + k < (long long)n) st4[k] = Q.status[i0 + k];
+        int stage[4] = {0, 0, 0, 0}, meta[4] = {0, 0, 0, 0};
+        double toi[4] = {0.0, 0.0, 0.0, 0.0};
+        unsigned ndef = 0;
+        bool any_hit = false;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            const unsigned st = st4[k];
+            if (!st) continue;
             unsigned submask = 0;
-            int later_hit = 255;
-            if (st)
+            int later_hit = 255, nd = 0;
+            for (int sub = 0; sub < NSUB; sub++)
             {
-                for (int sub = 0; sub < NSUB; sub++)
+                const unsigned r = (st >> (2 * sub)) & 3u;
+                if (r == (unsigned)SC_HIT)
                 {
-                    const unsigned r = (st >> (2 * sub)) & 3u;
-                    if (r == (unsigned)SC_HIT)
-                    {
-                        if (nd == 0) stage = sub + 1; else later_hit = sub;
-                        break;
-                    }
-                    if (r == (unsigned)SC_DEFERRED) { base[nd++] = Q.sbase[5 * i + sub]; submask |= 1u << sub; }
+                    if (nd == 0) stage[k] = sub + 1; else later_hit = sub;
+                    break;
                 }
+                if (r == (unsigned)SC_DEFERRED) { nd++; submask |= 1u << sub; }
             }
             if (nd == 0)
             {
-                if (stage)
+                if (stage[k])
                 {
                     StencilIn S;
-                    load_single<IS_VF>(A, i, S);
-                    toi = vv_toi<IS_VF>(S, stage - 1);
+                    load_single<IS_VF>(A, i0 + k, S);
+                    toi[k] = vv_toi<IS_VF>(S, stage[k] - 1);
+                    any_hit = true;
                 }
-                store_result(A, i, stage, toi);
             }
-            else { stage = -1; meta = (int)(submask | ((unsigned)later_hit << 8)); }
+            else { stage[k] = -1; meta[k] = (int)(submask | ((unsigned)later_hit << 8)); ndef++; }
         }
-        const bool deferred = stage < 0;
-        const unsigned long long w = block_alloc(deferred ? 1u : 0u, A.nwork);
-        if (deferred)
+        // results of the stencils that are settled
+        if (i0 + 3 < (long long)n)
         {
-            A.w_stencil[w] = (int)i;
-            A.w_meta[w] = meta;
-            for (int j = 0; j < 5; j++) A.w_base[5 * w + j] = base[j];
+            reinterpret_cast<uchar4 *>(A.hit)[it] = make_uchar4(stage[0] > 0, stage[1] > 0, stage[2] > 0, stage[3] > 0);
+            if (A.stage) reinterpret_cast<uchar4 *>(A.stage)[it] = make_uchar4((unsigned char)max(stage[0], 0), (unsigned char)max(stage[1], 0),
+                                                                              (unsigned char)max(stage[2], 0), (unsigned char)max(stage[3], 0));
+            double2 *t2 = reinterpret_cast<double2 *>(A.toi + i0);
+            t2[0] = make_double2(toi[0], toi[1]);
+            t2[1] = make_double2(toi[2], toi[3]);
         }
-        if (__syncthreads_or(stage > 0)) reduce_block(stage > 0, toi, A.earliest_bits, A.nhit);      // vertex-vertex hits only: rare
+        else
+            for (int k = 0; k < 4; k++)
+                if (i0 + k < (long long)n) store_result(A, i0 + k, max(stage[k], 0), toi[k]);
+        unsigned long long w = block_alloc(ndef, A.nwork);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (stage[k] < 0)
+            {
+                const long long i = i0 + k;
+                A.w_stencil[w] = (int)i;
+                A.w_meta[w] = meta[k];
+                int j = 0;
+                for (unsigned m = (unsigned)meta[k] & 0xffu; m; m &= m - 1) A.w_base[5 * w + (j++)] = Q.sbase[5 * i + (__ffs(m) - 1)];
+                for (; j < 5; j++) A.w_base[5 * w + j] = 0;
+                w++;
+            }
+        if (__syncthreads_or(any_hit))      // vertex-vertex hits only: rare
+            for (int k = 0; k < 4; k++) reduce_block(stage[k] > 0, toi[k], A.earliest_bits, A.nhit);
     }
 }
 
@@ -1076,7 +1105,8 @@ template <int D> static void launch_solve(cudaStream_t st, double *tasks, const 
     finalize_kernel<D><<<148 * 8, 128, 0, st>>>(tasks, list, count);
 }
 
-template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Args &Q, long long n, int *tlists)
+template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Args &Q, long long n, int *tlists, cudaStream_t side, cudaEvent_t ev_fork,
+                                                    cudaEvent_t ev_join)
 {
     const NpArgs &A = Q.A;
     const int B = 128;
@@ -1134,7 +1164,17 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
     }
     np_combine_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
     g_trace.mark(st, "combine");
-    np_general_kernel<IS_VF><<<148 * 4, B, 0, st>>>(Q);
+    if (side && !g_trace.on)
+    {
+        // the few stencils of the general routine are long single-lane walks (0.3 ms for ~300 stencils at the 4M-triangle
+        // cloth): they run beside whatever the caller launches next and are joined through ev_join
+        cudaEventRecord(ev_fork, st);
+        cudaStreamWaitEvent(side, ev_fork, 0);
+        np_general_kernel<IS_VF><<<148 * 4, B, 0, side>>>(Q);
+        cudaEventRecord(ev_join, side);
+    }
+    else
+        np_general_kernel<IS_VF><<<148 * 4, B, 0, st>>>(Q);
     g_trace.mark(st, "general");
     g_trace.flush(IS_VF ? "VF" : "EE", Q.ctr, n);
     return nl + 3 + 6 + 2 * 13 + 1 + 2;
@@ -1145,14 +1185,15 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
 // tasks (task_cap records of REC_STRIDE doubles, task_cap < 2^28), tlists (6 x task_cap ints: pending records by degree, refined list, record tags),
 // status (n u32), sbase (5n ints), queues (13n ints: primitive / vertex-edge / vertex-vertex items / vertex-edge items that need records), sq (2 x n int2: stage
 // queues), xq (5 x n int2: export queues), ctr (CCD_NP_COUNTERS counters, zeroed here; ctr[0] = work-list entries,
-// ctr[1] = records), ve_scratch (12 bytes x ve_slots + 48 bytes x n; ve_slots a power of two, see ccdk_np_ve_slots).  Returns the number of kernels launched.  If ctr[1] ends above task_cap the caller must grow the
-// record buffer and call again.
+// ctr[1] = records; tlists region 4 holds the general routine's list), ve_scratch (12 bytes x ve_slots + 48 bytes x n; ve_slots a power of two, see ccdk_np_ve_slots).  Returns the number of kernels launched.  If ctr[1] ends above task_cap the caller must grow the
+// record buffer and call again.  side != nullptr: the general routine is launched on that stream (after ev_fork) and
+// signals ev_join; the caller must make its stream wait for ev_join before it reads the results.
 int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, double eta_all,
                      const double *q0, const double *q1, int vstride, const float *vbox, const long long *hoff, const double *htime, const double *hpos,
                      unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits,
                      unsigned long long *nhit, int *w_stencil, int *w_meta, int *w_base, double *tasks, int *tlists,
                      unsigned long long task_cap, unsigned *status, int *sbase, int *queues, int *sq, int *xq, unsigned long long *ctr,
-                     void *ve_scratch, unsigned ve_slots, int V)
+                     void *ve_scratch, unsigned ve_slots, int V, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join)
 {
     static_assert(K_COUNT <= CCD_NP_COUNTERS, "counter block too small");
     if (n <= 0) return 0;
@@ -1174,7 +1215,7 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
     Q.qprim = queues; Q.qve = queues + n; Q.qvv = queues + 5 * n; Q.qve2 = queues + 9 * n;
     Q.sq[0] = reinterpret_cast<int2 *>(sq); Q.sq[1] = reinterpret_cast<int2 *>(sq) + n;
     for (int k = 0; k < 5; k++) Q.xq[k] = reinterpret_cast<int2 *>(xq) + (size_t)k * n;
-    Q.qgen = queues;      // the primitive queue is consumed by stage 0 long before anything goes to the general routine
+    Q.qgen = tlists + 4 * task_cap;      // a list of its own: the general routine may still be running when the next run reuses the queues
     Q.ctr = ctr;
     // vertex-edge de-duplication scratch: ve_slots keys (8 bytes) + ve_slots slot values + 3 x 4n ints
     Q.vslots = ve_slots;
@@ -1185,7 +1226,7 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
     Q.vures = Q.vulist + 4 * n;
     Q.vdedup = eta_arr == nullptr && V <= (1 << 21) && ve_slots >= 2;
     if (Q.vdedup) cudaMemsetAsync(Q.vkeys, 0xff, sizeof(unsigned long long) * ve_slots, st);
-    return is_vf ? launch_single_step<true>(st, Q, n, tlists) : launch_single_step<false>(st, Q, n, tlists);
+    return is_vf ? launch_single_step<true>(st, Q, n, tlists, side, ev_fork, ev_join) : launch_single_step<false>(st, Q, n, tlists, side, ev_fork, ev_join);
 }
 
 // hash-set size for the vertex-edge de-duplication of a run over n stencils: the unique tests number ~0.15 n (4M-triangle
