@@ -643,7 +643,8 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         CKR(ensure(c, c->p1Queues, sizeof(int) * 13 * nmax));
         CKR(ensure(c, c->p1Sq, sizeof(int) * 4 * nmax));
         CKR(ensure(c, c->p1Xq, sizeof(int) * 10 * nmax));
-        CKR(ensure(c, c->p1Ve, 12 * (size_t)ccdk_np_ve_slots((long long)nmax) + 48 * nmax));
+        // vertex-edge de-duplication scratch: one region per run (the vertex-face run consults the edge-edge run's table)
+        CKR(ensure(c, c->p1Ve, 12 * (size_t)ccdk_np_ve_slots(nee) + 48 * ((size_t)nee + 32) + 12 * (size_t)ccdk_np_ve_slots(nvf) + 48 * ((size_t)nvf + 32) + 64));
     }
     const float *d_vbox = nullptr;
     if (d_q0)
@@ -674,16 +675,19 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         // the edge-edge run goes first: its general routine (a few hundred long single-lane walks) then runs on the side
         // stream beside the vertex-face run
         const bool single_step = d_q0 != nullptr;
+        const size_t ve_off_vf = (12 * (size_t)ccdk_np_ve_slots(nee) + 48 * ((size_t)nee + 32) + 15) & ~(size_t)15;
+        const bool share_ve = single_step && nee > 0 && nvf > 0 && !d_vf_eta && !d_ee_eta && eta_all_vf == eta_all_ee && !getenv("CCD_NO_VE_SHARE");
         cudaEventRecord(c->sev[ST_NP_EE], c->st);
         nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all_ee, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
                                P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE, P<int>(c->workEe),
                                P<int>(c->workTaskEe), P<int>(c->workSubEe), P<double>(c->tasksEe), P<int>(c->tlistEe), c->taskCapEe, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
-                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_EE, c->p1Ve.p, ccdk_np_ve_slots(nee), V, c->st2, c->evFork, c->evJoin);
+                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_EE, c->p1Ve.p, ccdk_np_ve_slots(nee), V, c->st2, c->evFork, c->evJoin, nullptr, 0, 0, nullptr);
         cudaEventRecord(c->sev[ST_NP_VF], c->st);
         nl += ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all_vf, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
                                P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF, P<int>(c->workVf),
                                P<int>(c->workTaskVf), P<int>(c->workSubVf), P<double>(c->tasksVf), P<int>(c->tlistVf), c->taskCapVf, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
-                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_VF, c->p1Ve.p, ccdk_np_ve_slots(nvf), V, nullptr, nullptr, nullptr);
+                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_VF, (char *)c->p1Ve.p + ve_off_vf, ccdk_np_ve_slots(nvf), V, nullptr, nullptr, nullptr,
+                               share_ve ? c->p1Ve.p : nullptr, share_ve ? ccdk_np_ve_slots(nee) : 0u, nee, share_ve ? P<double>(c->tasksEe) : nullptr);
         if (single_step && nee > 0 && !getenv("CCD_NP_TRACE")) CK(cudaStreamWaitEvent(c->st, c->evJoin, 0));
         cudaEventRecord(c->sev[CCD_N_STAGES], c->st);
         CK(cudaGetLastError());

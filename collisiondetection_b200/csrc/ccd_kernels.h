@@ -9,7 +9,8 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
                      unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits,
                      unsigned long long *nhit, int *w_stencil, int *w_meta, int *w_base, double *tasks, int *tlists,
                      unsigned long long task_cap, unsigned *status, int *sbase, int *queues, int *sq, int *xq, unsigned long long *ctr,
-                     void *ve_scratch, unsigned ve_slots, int V, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join);
+                     void *ve_scratch, unsigned ve_slots, int V, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join,
+                     const void *prev_ve_scratch, unsigned prev_ve_slots, long long prev_n, const double *prev_tasks);
 unsigned ccdk_np_ve_slots(long long n);
 #define CCD_NP_COUNTERS 40      // counters per narrowphase run (narrowphase.cu: K_*)
 // {x0,y0,z0,-,x1,y1,z1,-} per vertex (8 doubles) for the single-step narrowphase kernels

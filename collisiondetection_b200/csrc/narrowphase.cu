@@ -164,6 +164,7 @@ struct NpArgs
     int *w_base;                // 5 ints per entry
     unsigned long long *nwork;
     double *tasks;              // REC_STRIDE doubles per record
+    const double *tasks_other;  // records of the run before this one (vertex-edge tests shared across the two runs: sbase bit 31)
     int *rtag;                  // per record: its tag, kept in a compact array for the bucket kernel (a tag read out of the
                                 // 128-byte records costs a DRAM sector per record and pass)
     unsigned long long *ntask;  // running number of task records
@@ -262,6 +263,12 @@ struct P1Args
     int *vulist;                 // unique tests: a representative item (stencil | sub-test << 28)
     int *vures;                  // per unique test: -1 miss, else first record | number of records << 28
     unsigned vslots;
+    // the run before this one (edge-edge, when this is the vertex-face run of the same step with the same eta): its hash
+    // set is consulted first, and a test found there is never evaluated again — its records are read out of that run's
+    // record buffer (sbase bit 31)
+    const unsigned long long *pkeys;
+    const int *pslotval, *pures;
+    unsigned pslots;             // 0: no previous run to consult
     bool vdedup;                 // false: per-stencil eta or vertex ids beyond 21 bits -> every item is its own test
     int2 *sq[2];                 // stage queues (ping-pong): {stencil, state}
     int2 *xq[5];                 // export queues per polynomial: {stencil, record slot}
@@ -459,6 +466,7 @@ template <bool IS_VF, int K> __global__ void __launch_bounds__(128, NP_MINB_STAG
 //                     quartic on the windows of its inside quadratics (ve_item_refined: four out of five end here as a
 //                     miss) and writes records only for the rest.
 #define VE_DIRECT 0x80000000u
+#define VE_PREV 0x40000000u      // the item's test lives in the previous run's table (slot in the low bits)
 #define VE_PROBES 48
 #define VE_EMPTY 0xFFFFFFFFFFFFFFFFull
 
@@ -481,7 +489,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(256) np_ve_key_kernel(P1
     const unsigned mask = Q.vslots - 1u;
     for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < nround; it += (unsigned long long)gridDim.x * blockDim.x)
     {
-        bool mine = false, placed = false;
+        bool mine = false, placed = false, prev = false;
         int item = 0;
         unsigned h = 0;
         if (it < n)
@@ -496,8 +504,20 @@ template <bool IS_VF> __global__ void __launch_bounds__(256) np_ve_key_kernel(P1
                 const unsigned long long key = (unsigned long long)(unsigned)v | ((unsigned long long)(unsigned)a << 21) | ((unsigned long long)(unsigned)b << 42);
                 unsigned long long x = key * 0x9E3779B97F4A7C15ull;
                 x ^= x >> 29;
-                h = (unsigned)x & mask;
-                for (int probe = 0; probe < VE_PROBES; probe++)
+                if (Q.pslots)
+                {
+                    const unsigned pmask = Q.pslots - 1u;
+                    unsigned hp = (unsigned)x & pmask;
+                    for (int probe = 0; probe < VE_PROBES; probe++)
+                    {
+                        const unsigned long long old = Q.pkeys[hp];
+                        if (old == VE_EMPTY) break;
+                        if (old == key) { mine = false; prev = true; h = hp; break; }
+                        hp = (hp + 1u) & pmask;
+                    }
+                }
+                if (!prev) h = (unsigned)x & mask;
+                for (int probe = 0; probe < VE_PROBES && !prev; probe++)
                 {
                     const unsigned long long old = atomicCAS(&Q.vkeys[h], VE_EMPTY, key);
                     if (old == VE_EMPTY) { placed = true; break; }
@@ -512,7 +532,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(256) np_ve_key_kernel(P1
             Q.vulist[u] = item;
             if (placed) Q.vslotval[h] = (int)u;
         }
-        if (it < n) Q.vitem[it] = mine ? (int)((unsigned)u | VE_DIRECT) : (int)h;
+        if (it < n) Q.vitem[it] = mine ? (int)((unsigned)u | VE_DIRECT) : (int)(prev ? (h | VE_PREV) : h);
     }
 }
 
@@ -592,9 +612,16 @@ template <bool IS_VF> __global__ void __launch_bounds__(256) np_ve_resolve_kerne
     for (unsigned long long it = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; it < n; it += (unsigned long long)gridDim.x * blockDim.x)
     {
         const unsigned ref = (unsigned)Q.vitem[it];
-        const int u = (ref & VE_DIRECT) ? (int)(ref & ~VE_DIRECT) : Q.vslotval[ref];
-        const int res = Q.vures[u];
-        if (res < 0) continue;
+        int res;
+        if (ref & VE_DIRECT) res = Q.vures[ref & ~VE_DIRECT];
+        else if (ref & VE_PREV)
+        {
+            res = Q.pures[Q.pslotval[ref & ~VE_PREV]];
+            if (res >= 0) res = (int)((unsigned)res | 0x80000000u);      // records in the previous run's buffer
+            else res = -1;
+        }
+        else res = Q.vures[Q.vslotval[ref]];
+        if (res == -1) continue;
         const int item = Q.qve[it];
         const long long i = item & 0x0fffffff;
         const int sub = (unsigned)item >> 28;
@@ -727,9 +754,14 @@ template <bool IS_VF> __global__ void __launch_bounds__(256) np_decide_kernel(P1
 __global__ void __launch_bounds__(256) bucket_tasks_kernel(const int *__restrict__ rtag, const unsigned long long *ntask_ptr,
                                                            unsigned long long cap, int *__restrict__ lists, unsigned long long *counts, int phase)
 {
+    // the four degrees share ONE block-wide scan: their running counts are packed 16 bits each into a 64-bit word (a block
+    // of 256 threads adds at most 256 to any of them)
+    __shared__ unsigned long long s_w[8];
+    __shared__ unsigned long long s_base[4];
     unsigned long long nt = *ntask_ptr;
     if (nt > cap) nt = cap;
     const unsigned long long nround = block_rounded(nt);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < nround;
          j += (unsigned long long)gridDim.x * blockDim.x)
     {
@@ -739,12 +771,35 @@ __global__ void __launch_bounds__(256) bucket_tasks_kernel(const int *__restrict
             const unsigned tag = (unsigned)rtag[j];
             if (!(tag & REC_FINAL) && ((phase == 1) == ((tag & REC_POS) != 0))) rd = (int)((tag >> 4) & 7u);
         }
+        const unsigned long long mine = (rd >= 3 && rd <= 6) ? 1ull << (16 * (rd - 3)) : 0ull;
+        unsigned long long incl = mine;
 #pragma unroll
-        for (int d = 3; d <= 6; d++)
+        for (int o = 1; o < 32; o <<= 1)
         {
-            const unsigned long long o = block_alloc(rd == d ? 1u : 0u, &counts[d - 3]);
-            if (rd == d) lists[(size_t)(d - 3) * cap + o] = (int)j;
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
         }
+        if (lane == 31) s_w[wib] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            unsigned long long tot = 0;
+            for (int w = 0; w < 8; w++) { const unsigned long long x = s_w[w]; s_w[w] = tot; tot += x; }
+#pragma unroll
+            for (int d = 0; d < 4; d++)
+            {
+                const unsigned long long c = (tot >> (16 * d)) & 0xffffull;
+                s_base[d] = c ? atomicAdd(&counts[d], c) : 0ull;
+            }
+        }
+        __syncthreads();
+        if (mine)
+        {
+            const int d = rd - 3;
+            const unsigned long long before = ((s_w[wib] + incl - mine) >> (16 * d)) & 0xffffull;
+            lists[(size_t)d * cap + s_base[d] + before] = (int)j;
+        }
+        __syncthreads();
     }
 }
 
@@ -877,7 +932,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(128) np_window_kernel(P1
         if (!(A.w_meta[w] & 1)) continue;      // primitive not deferred
         const unsigned b = (unsigned)A.w_base[5 * w];
         const unsigned long long t0 = b & 0x0fffffffu;
-        const int nrec = (int)(b >> 28);
+        const int nrec = (int)((b >> 28) & 7u);
         if (t0 + (unsigned long long)nrec > A.task_cap) continue;
         window_item(A.tasks + (unsigned long long)REC_STRIDE * t0, nrec, IS_VF ? 3 : 4);
         for (int j = 0; j + 1 < nrec; j++) A.rtag[t0 + j] = (int)rec_untag(A.tasks[(unsigned long long)REC_STRIDE * (t0 + j) + 7]);
@@ -902,12 +957,20 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_combine
         {
             i = A.w_stencil[w];
             const int meta = A.w_meta[w];
-            StencilIn S;
-            load_single<IS_VF>(A, i, S);
-            V3 v[4];
-            for (int k = 0; k < 4; k++) v[k] = S.b[k] - S.a[k];
             unsigned submask = (unsigned)meta & 0xffu;
             const int later_hit = (meta >> 8) & 0xff;
+            // the positions are needed only by the edge-edge primitive's parallel test and by a vertex-vertex hit behind
+            // the deferred sub-tests
+            StencilIn S;
+            V3 v[4];
+            const bool need_pos = (!IS_VF && (submask & 1u)) || later_hit != 255;
+            if (need_pos)
+            {
+                load_single<IS_VF>(A, i, S);
+                for (int k = 0; k < 4; k++) v[k] = S.b[k] - S.a[k];
+            }
+            else
+                for (int k = 0; k < 4; k++) { S.a[k] = mk(0, 0, 0); S.b[k] = mk(0, 0, 0); v[k] = mk(0, 0, 0); }
             int j = 0;
             bool settled = false;
             while (submask)
@@ -917,9 +980,11 @@ template <bool IS_VF> __global__ void __launch_bounds__(128, NP_MINB) np_combine
                 const unsigned b = (unsigned)A.w_base[5 * w + j];
                 j++;
                 const unsigned long long t0 = b & 0x0fffffffu;
-                const int nrec = (int)(b >> 28);
-                if (t0 + (unsigned long long)nrec > A.task_cap) { settled = true; break; }      // never written: the caller grows the buffer and reruns
-                const int r = combine_records(A.tasks + (unsigned long long)REC_STRIDE * t0, nrec, !IS_VF && sub == 0, S.a, v, toi);
+                const int nrec = (int)((b >> 28) & 7u);
+                const bool other = (b & 0x80000000u) != 0;
+                if (!other && t0 + (unsigned long long)nrec > A.task_cap) { settled = true; break; }      // never written: the caller grows the buffer and reruns
+                const double *tb = other ? A.tasks_other : A.tasks;
+                const int r = combine_records(tb + (unsigned long long)REC_STRIDE * t0, nrec, !IS_VF && sub == 0, S.a, v, toi);
                 if (r == RS_FALLBACK) { fb = true; settled = true; break; }
                 if (r == RS_HIT) { stage = sub + 1; settled = true; break; }
             }
@@ -1188,12 +1253,15 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
 // ctr[1] = records; tlists region 4 holds the general routine's list), ve_scratch (12 bytes x ve_slots + 48 bytes x n; ve_slots a power of two, see ccdk_np_ve_slots).  Returns the number of kernels launched.  If ctr[1] ends above task_cap the caller must grow the
 // record buffer and call again.  side != nullptr: the general routine is launched on that stream (after ev_fork) and
 // signals ev_join; the caller must make its stream wait for ev_join before it reads the results.
+// prev_*: the vertex-edge scratch, stencil count and record buffer of the run just before this one when both belong to the
+// same step and use the same eta (nullptr otherwise): tests already made there are looked up instead of repeated.
 int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, double eta_all,
                      const double *q0, const double *q1, int vstride, const float *vbox, const long long *hoff, const double *htime, const double *hpos,
                      unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits,
                      unsigned long long *nhit, int *w_stencil, int *w_meta, int *w_base, double *tasks, int *tlists,
                      unsigned long long task_cap, unsigned *status, int *sbase, int *queues, int *sq, int *xq, unsigned long long *ctr,
-                     void *ve_scratch, unsigned ve_slots, int V, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join)
+                     void *ve_scratch, unsigned ve_slots, int V, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join,
+                     const void *prev_ve_scratch, unsigned prev_ve_slots, long long prev_n, const double *prev_tasks)
 {
     static_assert(K_COUNT <= CCD_NP_COUNTERS, "counter block too small");
     if (n <= 0) return 0;
@@ -1202,7 +1270,7 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
     A.hoff = hoff; A.htime = htime; A.hpos = hpos; A.hit = hit; A.toi = toi; A.stage = stage;
     A.earliest_bits = earliest_bits; A.nhit = nhit;
     A.w_stencil = w_stencil; A.w_meta = w_meta; A.w_base = w_base; A.nwork = ctr + K_NWORK;
-    A.tasks = tasks; A.ntask = ctr + K_NTASK; A.task_cap = task_cap; A.rtag = tlists + 5 * task_cap;
+    A.tasks = tasks; A.tasks_other = nullptr; A.ntask = ctr + K_NTASK; A.task_cap = task_cap; A.rtag = tlists + 5 * task_cap;
     if (q0 == nullptr)
     {
         if (is_vf) stencil_history_kernel<true><<<grid_for(n, 128), 128, 0, st>>>(A);
@@ -1226,6 +1294,15 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
     Q.vures = Q.vulist + 4 * n;
     Q.vdedup = eta_arr == nullptr && V <= (1 << 21) && ve_slots >= 2;
     if (Q.vdedup) cudaMemsetAsync(Q.vkeys, 0xff, sizeof(unsigned long long) * ve_slots, st);
+    Q.pslots = 0; Q.pkeys = nullptr; Q.pslotval = nullptr; Q.pures = nullptr;
+    Q.A.tasks_other = prev_tasks;
+    if (Q.vdedup && prev_ve_scratch && prev_ve_slots >= 2 && prev_tasks)
+    {
+        Q.pslots = prev_ve_slots;
+        Q.pkeys = reinterpret_cast<const unsigned long long *>(prev_ve_scratch);
+        Q.pslotval = reinterpret_cast<const int *>(Q.pkeys + prev_ve_slots);
+        Q.pures = Q.pslotval + prev_ve_slots + 8 * prev_n;      // behind that run's vitem and vulist (4 n ints each)
+    }
     return is_vf ? launch_single_step<true>(st, Q, n, tlists, side, ev_fork, ev_join) : launch_single_step<false>(st, Q, n, tlists, side, ev_fork, ev_join);
 }
 
