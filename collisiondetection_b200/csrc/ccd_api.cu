@@ -37,7 +37,7 @@ struct ccd_context
     DBuf faces, q0, q1, hoff, htime, hpos, fixed, vf_in, ee_in, vf_eta, ee_eta, pts, eta;
     // broadphase
     DBuf boxes, faabb, fkdop, bounds, keysA, keysB, valsA, valsB, temp, nodes, leafParent, nodeParent, flags;
-    DBuf cand, counters, pairL, pairR, deg, adjOff, cursor, adj, heap, srec, sbox, sfaces, unsure, frontA, frontB;
+    DBuf cand, counters, pairL, pairR, deg, adjOff, cursor, adj, heap, srec, sbox, sfaces, unsure, frontA, frontB, bigV, bigE;
     size_t frontCap = 0, unsureCap = 0;
     DBuf k32A, k32B, scanFlags, scanIds;
     // topology cache (function of `faces` only)
@@ -63,7 +63,7 @@ struct ccd_context
 };
 
 // device counters layout (unsigned long long each)
-enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NQUERY = 7, C_NA_VF = 8, C_NA_EE = 9, C_KCUR_VF = 10, C_KCUR_EE = 11, C_FRONT = 12 /* 4 counters: frontier sizes (ping-pong), their maximum, undecided face pairs */, C_NP_VF = 16 /* CCD_NP_COUNTERS counters per run: work-list entries, records, ... (narrowphase.cu K_*) */, C_NP_EE = 16 + CCD_NP_COUNTERS, C_CAND_REG = 16 + 2 * CCD_NP_COUNTERS /* CCD_CAND_REGIONS candidate counters */, C_TOTAL = 16 + 2 * CCD_NP_COUNTERS + 64 };
+enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NQUERY = 7, C_NA_VF = 8, C_NA_EE = 9, C_KCUR_VF = 10, C_KCUR_EE = 11, C_FRONT = 12 /* 4 counters: frontier sizes (ping-pong), their maximum, undecided face pairs */, C_NP_VF = 16 /* CCD_NP_COUNTERS counters per run: work-list entries, records, ... (narrowphase.cu K_*) */, C_NP_EE = 16 + CCD_NP_COUNTERS, C_CAND_REG = 16 + 2 * CCD_NP_COUNTERS /* CCD_CAND_REGIONS candidate counters */, C_NBIG = 16 + 2 * CCD_NP_COUNTERS + 64 /* 2 counters: items of the block-per-item emission (VF, EE) */, C_TOTAL = 16 + 2 * CCD_NP_COUNTERS + 64 + 2 };
 #define CCD_CAND_REGIONS 64
 enum { C_NWORK_VF = C_NP_VF, C_NTASK_VF = C_NP_VF + 1, C_NWORK_EE = C_NP_EE, C_NTASK_EE = C_NP_EE + 1 };
 
@@ -170,7 +170,7 @@ void ccdk_active_list(cudaStream_t st, int begin, int end, const long long *segO
 void ccdk_emit_sort(cudaStream_t st, bool is_vf, const int *alist, const unsigned long long *na, const int *faces, const long long *starOff,
                     const int *star, const int *edgeStart, const int *heFace, const long long *adjOff, const int *adj, const int *faceRank,
                     const int *rankFace, const int *faceEdge, const void *edgeVerts, const unsigned char *fixed, int *counts, long long *kstart,
-                    int *keys_out, unsigned long long *kcursor);
+                    int *keys_out, unsigned long long *kcursor, int *biglist, unsigned long long *nbig);
 void ccdk_emit_write(cudaStream_t st, bool is_vf, const int *alist, const unsigned long long *na, int begin, const int *faces, const long long *starOff,
                      const int *star, const int *edgeStart, const int *heFace, const long long *adjOff, const int *adj, const int *faceRank,
                      const int *rankFace, const int *faceEdge, const void *edgeVerts, const unsigned char *fixed, const int *counts,
@@ -260,7 +260,7 @@ void ccd_destroy(ccd_context *c)
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1Ve, &c->qpack, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->nodeFirst, &c->nodeForeign, &c->vertEdgeStart, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->sbox, &c->sfaces, &c->unsure, &c->frontA, &c->frontB};
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1Ve, &c->qpack, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->nodeFirst, &c->nodeForeign, &c->vertEdgeStart, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->sbox, &c->sfaces, &c->unsure, &c->frontA, &c->frontB, &c->bigV, &c->bigE};
     for (DBuf *b : all)
         if (b->p)
             cudaFree(b->p);
@@ -570,15 +570,18 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         CKR(ensure(c, c->keysV, sizeof(int) * (3 * ordered + 64)));      // every adjacency entry is seen by the face's 3 vertices
         CKR(ensure(c, c->keysE, sizeof(int) * (9 * ordered + 64)));      // ... and by its 3 edges, each against the neighbour's 3 edges
         CK(cudaMemsetAsync(ctr + C_NA_VF, 0, sizeof(unsigned long long) * 4, c->st));
+        CK(cudaMemsetAsync(ctr + C_NBIG, 0, sizeof(unsigned long long) * 2, c->st));
+        CKR(ensure(c, c->bigV, sizeof(int) * (size_t)(v1 - v0 + 32)));
+        CKR(ensure(c, c->bigE, sizeof(int) * (size_t)(e1 - e0 + 32)));
         ccdk_active_list(c->st, v0, v1, P<long long>(c->starOff), nullptr, P<int>(c->star), P<int>(c->deg), P<int>(c->vfCounts), P<int>(c->alistV), ctr + C_NA_VF);
         ccdk_active_list(c->st, e0, e1, nullptr, P<int>(c->edgeStart), P<int>(c->heFace), P<int>(c->deg), P<int>(c->eeCounts), P<int>(c->alistE), ctr + C_NA_EE);
         ccdk_emit_sort(c->st, true, P<int>(c->alistV), ctr + C_NA_VF, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
                        P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceRank), P<int>(c->rankFace), P<int>(c->faceEdge),
-                       c->edgeVerts.p, d_fixed, P<int>(c->vfCounts), P<long long>(c->kstartV), P<int>(c->keysV), ctr + C_KCUR_VF);
+                       c->edgeVerts.p, d_fixed, P<int>(c->vfCounts), P<long long>(c->kstartV), P<int>(c->keysV), ctr + C_KCUR_VF, P<int>(c->bigV), ctr + C_NBIG);
         ccdk_emit_sort(c->st, false, P<int>(c->alistE), ctr + C_NA_EE, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
                        P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceRank), P<int>(c->rankFace), P<int>(c->faceEdge),
-                       c->edgeVerts.p, d_fixed, P<int>(c->eeCounts), P<long long>(c->kstartE), P<int>(c->keysE), ctr + C_KCUR_EE);
-        c->launches += 2;
+                       c->edgeVerts.p, d_fixed, P<int>(c->eeCounts), P<long long>(c->kstartE), P<int>(c->keysE), ctr + C_KCUR_EE, P<int>(c->bigE), ctr + C_NBIG + 1);
+        c->launches += 4;
     }
     // the scan reads one element past the range (never added to anything it outputs)
     ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, v1 - v0 + 1, P<int>(c->vfCounts) + v0, P<long long>(c->vfOffsets) + v0);
