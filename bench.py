@@ -268,7 +268,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    config = dict(workload=args.workload, kind="KDOP-13", sharding="vertex/edge ownership ranges over %d rank(s), rebalanced every step from the previous step's load profile; replicated LBVH, sharded traversal / emission / narrowphase" % world,
+    config = dict(workload=args.workload, kind="KDOP-13", sharding="ownership by Morton (LBVH subtree) range over %d rank(s), rebalanced every step from the previous step's load profile; replicated cluster tree, sharded tree intersection / emission / narrowphase" % world,
                   l2="working set (inputs 144 MB at cloth1415 + GBs of intermediates) exceeds the 126 MB L2; nothing is reused across steps")
 
     if args.impl == "reference":
@@ -311,6 +311,7 @@ def main():
     if world > 1:
         # replicated positions: rank 0's arrays are the step's input on every GPU (NCCL broadcast over NVLink)
         D.broadcast_positions(d_q0, d_q1, src=0)
+        ctx.wait_stream(torch.cuda.current_stream().cuda_stream)      # the context's private stream must not read before the broadcast lands
     summary = {}
 
     def step_dev():
@@ -367,20 +368,35 @@ def main():
 
     # ---- end to end through the host-buffer C-ABI call (pinned host arrays; H2D + D2H inside the timed region)
     np_q0, np_q1, np_f = h_q0.numpy(), h_q1.numpy(), h_f.numpy()
+    if world == 1:
+        def step_e2e():
+            # copy=False: the hit lists are read where the C ABI leaves them (pinned host buffers of the context)
+            return ctx.step(api.KDOP, np_f, np_q0, np_q1, wl["outer_eta"], wl["eta"], None, rank, world, copy=False)
+        h2d = 48 * V + 12 * F
+    else:
+        # sharded job: every rank copies its 1/N slice of the positions from pinned host memory, the slices are all-gathered over
+        # NVLink, the step runs on the replicated arrays and the rank's hit lists come back to pinned host memory.  The faces
+        # (static topology) stay resident.
+        fq0, fq1 = d_q0.view(-1), d_q1.view(-1)
+        hq0, hq1 = h_q0.view(-1), h_q1.view(-1)
+
+        def step_e2e():
+            D.gather_positions(fq0, fq1, hq0, hq1, rank, world)
+            ctx.wait_stream(torch.cuda.current_stream().cuda_stream)
+            return ctx.step_device_hits(api.KDOP, V, F, d_f.data_ptr(), d_q0.data_ptr(), d_q1.data_ptr(), wl["outer_eta"], wl["eta"], 0, rank, world)
+        h2d = -(-48 * V // world)
     for _ in range(2):
-        ctx.step(api.KDOP, np_f, np_q0, np_q1, wl["outer_eta"], wl["eta"], None, rank, world, copy=False)
+        step_e2e()
     barrier()
     e0.record()
     for _ in range(args.steps):
-        # copy=False: the hit lists are read where the C ABI leaves them (pinned host buffers of the context)
-        er = ctx.step(api.KDOP, np_f, np_q0, np_q1, wl["outer_eta"], wl["eta"], None, rank, world, copy=False)
+        er = step_e2e()
     e1.record()
     barrier()
     te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te[0]) / args.steps
-    h2d = 48 * V + 12 * F
     d2h = 24 * (er["n_vf_hits"] + er["n_ee_hits"])
 
     if rank != 0:

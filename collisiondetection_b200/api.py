@@ -51,7 +51,7 @@ EXPORTS = [
     "ccd_broadphase_step", "ccd_narrowphase", "ccd_step", "ccd_step_result_free", "ccd_step_device", "ccd_vf_batch",
     "ccd_ee_batch", "ccd_ve_batch", "ccd_vv_batch", "ccd_find_intervals_batch", "ccd_dist_vf_batch",
     "ccd_dist_ee_batch", "ccd_dist_plane_lt_batch", "ccd_dist_line_lt_batch", "ccd_mesh_self_distance",
-    "ccd_memcpy_d2h", "ccd_fp64_peak", "ccd_stage_times", "ccd_step_shard", "ccd_set_shard_partition", "ccd_shard_histogram", "ccd_shard_edge_bounds", "ccd_narrowphase_sepplane",
+    "ccd_memcpy_d2h", "ccd_fp64_peak", "ccd_stage_times", "ccd_step_shard", "ccd_set_shard_partition", "ccd_shard_histogram", "ccd_step_device_hits", "ccd_wait_stream", "ccd_narrowphase_sepplane",
 ]
 
 _LIB = None
@@ -248,31 +248,45 @@ class Context(object):
         self._check(rc, "ccd_step_device")
         return r
 
+    def wait_stream(self, cuda_stream):
+        """ccd_wait_stream: order the context's next calls after what is enqueued on `cuda_stream` (a raw cudaStream_t
+        address, e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._check(self.lib.ccd_wait_stream(self.h, C.c_void_p(cuda_stream)), "ccd_wait_stream")
+
+    def step_device_hits(self, kind, V, F, d_faces, d_q0, d_q1, outerEta, eta, d_fixed=0, shard_rank=0, shard_world=1):
+        """ccd_step_device_hits: device inputs, hit lists in the context's pinned host buffers (views, valid until the next call)."""
+        r = StepResult()
+        rc = self.lib.ccd_step_device_hits(self.h, C.c_int(kind), C.c_int(V), C.c_int(F), C.c_void_p(d_faces), C.c_void_p(d_q0), C.c_void_p(d_q1),
+                                           C.c_double(outerEta), C.c_double(eta), C.c_void_p(d_fixed) if d_fixed else None,
+                                           C.c_int(shard_rank), C.c_int(shard_world), C.byref(r))
+        self._check(rc, "ccd_step_device_hits")
+
+        def arr(p, n, w, dt):
+            if n == 0:
+                return np.zeros((0, w) if w > 1 else (0,), dt)
+            a = np.ctypeslib.as_array(p, shape=(n * w,))
+            return a.reshape(n, w) if w > 1 else a
+
+        return dict(n_vf_candidates=r.n_vf_candidates, n_ee_candidates=r.n_ee_candidates, n_vf_hits=r.n_vf_hits, n_ee_hits=r.n_ee_hits,
+                    earliest_toi=r.earliest_toi, vf_hits=arr(r.vf_hits, r.n_vf_hits, 4, np.int32), vf_hit_toi=arr(r.vf_hit_toi, r.n_vf_hits, 1, np.float64),
+                    ee_hits=arr(r.ee_hits, r.n_ee_hits, 4, np.int32), ee_hit_toi=arr(r.ee_hit_toi, r.n_ee_hits, 1, np.float64))
+
     SHARD_BUCKETS = 1024
 
     def shard_histogram(self):
-        """Load profile of the last sharded step (ccd_shard_histogram): (vf_hist, ee_hist, n_vertices, n_edges)."""
+        """Load profile of the last sharded step (ccd_shard_histogram): (vf_hist, ee_hist, n_positions)."""
         vf = np.zeros(self.SHARD_BUCKETS, np.int64)
         ee = np.zeros(self.SHARD_BUCKETS, np.int64)
-        nv, ne = C.c_int32(), C.c_int32()
-        self._check(self.lib.ccd_shard_histogram(self.h, vf.ctypes.data_as(C.c_void_p), ee.ctypes.data_as(C.c_void_p), C.byref(nv), C.byref(ne)),
+        npos = C.c_int32()
+        self._check(self.lib.ccd_shard_histogram(self.h, vf.ctypes.data_as(C.c_void_p), ee.ctypes.data_as(C.c_void_p), C.byref(npos)),
                     "ccd_shard_histogram")
-        return vf, ee, nv.value, ne.value
+        return vf, ee, npos.value
 
-    def shard_edge_bounds(self, vbounds):
-        """Unique-edge bounds that go with vertex bounds (ccd_shard_edge_bounds)."""
-        vb = np.ascontiguousarray(vbounds, dtype=np.int32)
-        eb = np.zeros(len(vb), np.int32)
-        self._check(self.lib.ccd_shard_edge_bounds(self.h, C.c_int(len(vb) - 1), vb.ctypes.data_as(C.c_void_p), eb.ctypes.data_as(C.c_void_p)),
-                    "ccd_shard_edge_bounds")
-        return eb
-
-    def set_shard_partition(self, vbounds, ebounds):
-        """Ownership ranges of the next sharded steps (ccd_set_shard_partition): world+1 ascending bounds each."""
-        vb = np.ascontiguousarray(vbounds, dtype=np.int32)
-        eb = np.ascontiguousarray(ebounds, dtype=np.int32)
-        self._check(self.lib.ccd_set_shard_partition(self.h, C.c_int(len(vb) - 1), vb.ctypes.data_as(C.c_void_p), eb.ctypes.data_as(C.c_void_p)),
-                    "ccd_set_shard_partition")
+    def set_shard_partition(self, pbounds):
+        """Ownership ranges of the next sharded steps (ccd_set_shard_partition): world+1 ascending bounds over the faces'
+        sorted (Morton) positions."""
+        pb = np.ascontiguousarray(pbounds, dtype=np.int32)
+        self._check(self.lib.ccd_set_shard_partition(self.h, C.c_int(len(pb) - 1), pb.ctypes.data_as(C.c_void_p)), "ccd_set_shard_partition")
 
     def download(self, d_ptr, shape, dtype):
         """Copy a device array owned by this context (e.g. DeviceResult.d_vf) to a new numpy array."""

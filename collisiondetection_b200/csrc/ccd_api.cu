@@ -36,7 +36,7 @@ struct ccd_context
     // staging of host inputs
     DBuf faces, q0, q1, hoff, htime, hpos, fixed, vf_in, ee_in, vf_eta, ee_eta, pts, eta;
     // broadphase
-    DBuf boxes, faabb, fkdop, bounds, keysA, keysB, valsA, valsB, temp, nodes, leafParent, nodeParent, flags;
+    DBuf boxes, faabb, bounds, keysA, keysB, valsA, valsB, temp, facePos, cmark;
     DBuf cand, counters, pairL, pairR, deg, adjOff, cursor, adj, heap, srec, sbox, sfaces, unsure, frontA, frontB, bigV, bigE;
     size_t frontCap = 0, unsureCap = 0;
     DBuf k32A, k32B, scanFlags, scanIds;
@@ -55,16 +55,15 @@ struct ccd_context
     size_t h_res_cap[4] = {0, 0, 0, 0};
     size_t candCap = 0, pairCap = 0, taskCapVf = 0, taskCapEe = 0;
     // sharding: ownership ranges chosen by the caller (ccd_set_shard_partition), load profile of the last sharded step
-    std::vector<int> partV, partE, h_vertEdgeStart;      // h_vertEdgeStart: host copy of the vertex -> first-edge table (per mesh)
-    DBuf qlist, hist, needed, neededPre, nodeFirst, nodeForeign, vertEdgeStart, alistV, alistE, kstartV, kstartE, keysV, keysE;
+    std::vector<int> partP;      // ownership bounds over the sorted (Morton) positions of a sharded step (ccd_set_shard_partition)
+    DBuf qlist, hist, needed, neededPre, alistV, alistE, kstartV, kstartE, keysV, keysE;
     unsigned long long *h_hist = nullptr;      // pinned, 2 * CCD_SHARD_BUCKETS
-    int histV = 0, histE = 0;
+    int histF = 0;
     bool hist_valid = false;
 };
 
 // device counters layout (unsigned long long each)
-enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NQUERY = 7, C_NA_VF = 8, C_NA_EE = 9, C_KCUR_VF = 10, C_KCUR_EE = 11, C_FRONT = 12 /* 4 counters: frontier sizes (ping-pong), their maximum, undecided face pairs */, C_NP_VF = 16 /* CCD_NP_COUNTERS counters per run: work-list entries, records, ... (narrowphase.cu K_*) */, C_NP_EE = 16 + CCD_NP_COUNTERS, C_CAND_REG = 16 + 2 * CCD_NP_COUNTERS /* CCD_CAND_REGIONS candidate counters */, C_NBIG = 16 + 2 * CCD_NP_COUNTERS + 64 /* 2 counters: items of the block-per-item emission (VF, EE) */, C_TOTAL = 16 + 2 * CCD_NP_COUNTERS + 64 + 2 };
-#define CCD_CAND_REGIONS 64
+enum { C_NCAND = 0, C_NPAIRS = 1, C_EARLY_VF = 2, C_NHIT_VF = 3, C_EARLY_EE = 4, C_NHIT_EE = 5, C_HASH = 6, C_NQUERY = 7, C_NA_VF = 8, C_NA_EE = 9, C_KCUR_VF = 10, C_KCUR_EE = 11, C_FRONT = 12 /* 4 counters: frontier sizes (ping-pong), their maximum, undecided face pairs */, C_NP_VF = 16 /* CCD_NP_COUNTERS counters per run: work-list entries, records, ... (narrowphase.cu K_*) */, C_NP_EE = 16 + CCD_NP_COUNTERS, C_NBIG = 16 + 2 * CCD_NP_COUNTERS /* 2 counters: items of the block-per-item emission (VF, EE) */, C_TOTAL = 16 + 2 * CCD_NP_COUNTERS + 2 };
 enum { C_NWORK_VF = C_NP_VF, C_NTASK_VF = C_NP_VF + 1, C_NWORK_EE = C_NP_EE, C_NTASK_EE = C_NP_EE + 1 };
 
 #define CK(call)                                                                                      \
@@ -140,20 +139,11 @@ void ccdk_leaf_boxes(cudaStream_t st, int kind, int F, const int *faces, const d
                      const double *hpos, double eta, double *boxes, float *faabb, float *fkdop);
 size_t ccdk_sort_temp_bytes(int n);
 void ccdk_exclusive_sum64(cudaStream_t st, void *temp, size_t temp_bytes, int n_plus_1, const int *in, long long *out);
-void ccdk_build_tree(cudaStream_t st, int F, const float *faabb, unsigned *bounds, unsigned long long *keys_in, unsigned long long *keys_sorted,
-                     unsigned *vals_in, unsigned *sortedFace, void *temp, size_t temp_bytes, void *nodes, int *leafParent,
-                     int *nodeParent, int *flags, int *nodeFirst);
-void ccdk_traverse(cudaStream_t st, int kind, int F, int qbegin, int qend, const int *qlist, bool all, const unsigned *sortedFace,
-                   const float *faabb, const int *faces, const float *fkdop, const void *nodes, void *cand, unsigned long long cap,
-                   unsigned long long *count, const int *needed, const unsigned char *nodeForeign, const unsigned long long *qcount);
-void ccdk_shard_queries(cudaStream_t st, int F, const unsigned *sortedFace, const int *faces, const int *faceEdge, int v0, int v1, int e0, int e1,
-                        int *qlist, unsigned long long *count, int *needed, int *neededPre, const void *nodes, const int *nodeFirst,
-                        unsigned char *nodeForeign, void *temp, size_t temp_bytes);
-void ccdk_shard_hist(cudaStream_t st, const int *counts, const void *edgeVerts, int begin, int end, int n, int nb, unsigned long long *hist);
-void ccdk_vert_edge_start(cudaStream_t st, int V, int E, const void *edgeVerts, int *out);
-void ccdk_exact_pairs(cudaStream_t st, int kind, bool both, const unsigned long long *ncand, unsigned long long cap, const void *cand,
-                      const unsigned *sortedFace, const int *faces, const double *boxes, const double *q0, const double *q1, double eta,
-                      int *pairL, int *pairR, unsigned long long pcap, unsigned long long *npairs, int *deg, const int *needed);
+void ccdk_shard_queries(cudaStream_t st, int F, const unsigned *sortedFace, const int *faces, const int *faceEdge, int *facePos, const long long *starOff,
+                        const int *star, const int *edgeStart, const int *heFace, int p0, int p1, int *qlist, unsigned long long *count, int *needed,
+                        int *neededPre, void *temp, size_t temp_bytes);
+void ccdk_shard_hist(cudaStream_t st, const int *counts, int n_items, const long long *segOff64, const int *segOff32, const int *segFace,
+                     const int *facePos, int F, int nb, unsigned long long *hist);
 void ccdk_adjacency_fill(cudaStream_t st, const unsigned long long *npairs, const int *pairL, const int *pairR, const long long *adjOff,
                          int *cursor, int *adj);
 void ccdk_topology_edges(cudaStream_t st, int F, const int *faces, unsigned long long *keys_in, unsigned long long *keys_sorted,
@@ -166,7 +156,7 @@ void ccdk_topology_star(cudaStream_t st, int V, int F, const int *faces, int *vd
                         size_t temp_bytes);
 void ccdk_hash_ints(cudaStream_t st, long long n, const int *d, unsigned long long *out);
 void ccdk_active_list(cudaStream_t st, int begin, int end, const long long *segOff64, const int *segOff32, const int *segFace, const int *deg,
-                      int *counts, int *alist, unsigned long long *na);
+                      int *counts, int *alist, unsigned long long *na, const int *facePos, int p0, int p1);
 void ccdk_emit_sort(cudaStream_t st, bool is_vf, const int *alist, const unsigned long long *na, const int *faces, const long long *starOff,
                     const int *star, const int *edgeStart, const int *heFace, const long long *adjOff, const int *adj, const int *faceRank,
                     const int *rankFace, const int *faceEdge, const void *edgeVerts, const unsigned char *fixed, int *counts, long long *kstart,
@@ -178,11 +168,12 @@ void ccdk_emit_write(cudaStream_t st, bool is_vf, const int *alist, const unsign
 void ccdk_face_aabb(cudaStream_t st, int F, const int *faces, const double *q0, const double *q1, double eta, float *faabb);
 int ccdk_cluster_count_pow2(int F);
 int ccdk_cluster_size(void);
-void ccdk_build_cluster_tree(cudaStream_t st, int kind, int F, const int *faces, const float *faabb, const double *q0, const double *q1, double eta,
-                             const double *boxes, unsigned *bounds, unsigned long long *keys_in, unsigned long long *keys_sorted, unsigned *vals_in,
-                             unsigned *sortedFace, void *temp, size_t temp_bytes, float *heap, float *rec, float *sbox, void *sfaces);
+void ccdk_build_cluster_tree(cudaStream_t st, int F, const int *faces, const float *faabb, unsigned *bounds, unsigned long long *keys_in,
+                             unsigned long long *keys_sorted, unsigned *vals_in, unsigned *sortedFace, void *temp, size_t temp_bytes, float *heap,
+                             float *sbox, void *sfaces);
 int ccdk_leaf_record_words(void);
-int ccdk_pair_traversal(cudaStream_t st, int kind, int F, const float *heap, const float *rec, const float *sbox, const void *sfaces, const double *boxes,
+int ccdk_pair_traversal(cudaStream_t st, int kind, int F, const int *faces, const unsigned *sortedFace, const float *heap, float *rec, unsigned char *cmark,
+                        const float *sbox, const void *sfaces, const double *boxes,
                         const double *q0, const double *q1, double eta, void *fr0, void *fr1, unsigned long long fcap, unsigned long long *fcount,
                         void *unsure, unsigned long long ucap, int *pairL, int *pairR, unsigned long long pcap, unsigned long long *npairs, int *deg,
                         const int *own, const int *ownPre, void *cand, unsigned long long ccap, unsigned long long *ncand);
@@ -255,12 +246,12 @@ void ccd_destroy(ccd_context *c)
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->st2) cudaStreamSynchronize(c->st2);
     DBuf *all[] = {&c->faces, &c->q0, &c->q1, &c->hoff, &c->htime, &c->hpos, &c->fixed, &c->vf_in, &c->ee_in, &c->vf_eta, &c->ee_eta,
-                   &c->pts, &c->eta, &c->boxes, &c->faabb, &c->fkdop, &c->bounds, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->temp, &c->nodes,
-                   &c->leafParent, &c->nodeParent, &c->flags, &c->cand, &c->counters, &c->pairL, &c->pairR, &c->deg, &c->adjOff,
+                   &c->pts, &c->eta, &c->boxes, &c->faabb, &c->bounds, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->temp, &c->facePos, &c->cmark,
+                   &c->cand, &c->counters, &c->pairL, &c->pairR, &c->deg, &c->adjOff,
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1Ve, &c->qpack, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->nodeFirst, &c->nodeForeign, &c->vertEdgeStart, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->sbox, &c->sfaces, &c->unsure, &c->frontA, &c->frontB, &c->bigV, &c->bigE};
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1Ve, &c->qpack, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->sbox, &c->sfaces, &c->unsure, &c->frontA, &c->frontB, &c->bigV, &c->bigE};
     for (DBuf *b : all)
         if (b->p)
             cudaFree(b->p);
@@ -352,12 +343,7 @@ static int ensure_topology(ccd_context *c, int V, int F, const int *d_faces)
     }
     ccdk_topology_star(c->st, V, F, d_faces, P<int>(c->vdeg), P<long long>(c->starOff), P<int>(c->starCur), P<int>(c->star), c->temp.p,
                        c->temp.cap);
-    CKR(ensure(c, c->vertEdgeStart, sizeof(int) * (size_t)(V + 2)));
-    ccdk_vert_edge_start(c->st, V, c->nEdges, c->edgeVerts.p, P<int>(c->vertEdgeStart));
-    c->h_vertEdgeStart.resize((size_t)V + 1);
-    CK(cudaMemcpyAsync(c->h_vertEdgeStart.data(), c->vertEdgeStart.p, sizeof(int) * ((size_t)V + 1), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
-    c->launches += 5;
+    c->launches += 3;
     CK(cudaGetLastError());
     c->topoF = F;
     c->topoV = V;
@@ -385,22 +371,15 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     cudaEventRecord(c->sev[ST_TOPOLOGY], c->st);
     CKR(ensure_topology(c, V, F, d_faces));
 
-    const bool lazy_boxes = d_q0 != nullptr;      // single step: exact boxes are recomputed in the pair test
+    const bool lazy_boxes = d_q0 != nullptr;      // single step: exact boxes are recomputed where they are needed
     if (!lazy_boxes) CKR(ensure(c, c->boxes, sizeof(double) * 2 * (size_t)kind * (size_t)F));
     CKR(ensure(c, c->faabb, sizeof(float) * 6 * (size_t)F));
-    static const bool old_traverse = getenv("CCD_TRAVERSE_OLD") != nullptr;      // A/B switch, development only
-    if (old_traverse) CKR(ensure(c, c->fkdop, sizeof(float) * 2 * (size_t)kind * (size_t)F));
     CKR(ensure(c, c->bounds, 64));
     CKR(ensure(c, c->temp, ccdk_sort_temp_bytes(3 * F > V + 1 ? 3 * F : V + 1)));
     CKR(ensure(c, c->keysA, sizeof(unsigned long long) * (size_t)(3 * F + 1)));
     CKR(ensure(c, c->keysB, sizeof(unsigned long long) * (size_t)(3 * F + 1)));
     CKR(ensure(c, c->valsA, sizeof(unsigned) * (size_t)(3 * F + 1)));
     CKR(ensure(c, c->valsB, sizeof(unsigned) * (size_t)(3 * F + 1)));
-    CKR(ensure(c, c->nodes, 64 * (size_t)F));
-    CKR(ensure(c, c->leafParent, sizeof(int) * (size_t)F));
-    CKR(ensure(c, c->nodeParent, sizeof(int) * (size_t)F));
-    CKR(ensure(c, c->flags, sizeof(int) * (size_t)F));
-    CKR(ensure(c, c->nodeFirst, sizeof(int) * (size_t)(F + 1)));
     CKR(ensure(c, c->deg, sizeof(int) * (size_t)(F + 2)));
     CKR(ensure(c, c->cursor, sizeof(int) * (size_t)(F + 2)));
     CKR(ensure(c, c->adjOff, sizeof(long long) * (size_t)(F + 2)));
@@ -410,132 +389,94 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         c->pairCap = (size_t)F * 12 + (1u << 16);
 
     cudaEventRecord(c->sev[ST_BOXES], c->st);
-    if (lazy_boxes && !old_traverse) ccdk_face_aabb(c->st, F, d_faces, d_q0, d_q1, outerEta, P<float>(c->faabb));
-    else ccdk_leaf_boxes(c->st, kind, F, d_faces, d_q0, d_q1, d_hoff, d_hpos, outerEta, lazy_boxes ? nullptr : P<double>(c->boxes), P<float>(c->faabb), old_traverse ? P<float>(c->fkdop) : nullptr);
+    if (lazy_boxes) ccdk_face_aabb(c->st, F, d_faces, d_q0, d_q1, outerEta, P<float>(c->faabb));
+    else ccdk_leaf_boxes(c->st, kind, F, d_faces, d_q0, d_q1, d_hoff, d_hpos, outerEta, P<double>(c->boxes), P<float>(c->faabb), nullptr);
     cudaEventRecord(c->sev[ST_TREE], c->st);
-    if (old_traverse)
-    {
-        ccdk_build_tree(c->st, F, P<float>(c->faabb), P<unsigned>(c->bounds), P<unsigned long long>(c->keysA), P<unsigned long long>(c->keysB),
-                        P<unsigned>(c->valsA), P<unsigned>(c->valsB), c->temp.p, c->temp.cap, c->nodes.p, P<int>(c->leafParent),
-                        P<int>(c->nodeParent), P<int>(c->flags), P<int>(c->nodeFirst));
-        c->launches += 1 + 2 + 8 + 2;
-    }
-    else
     {
         const size_t NLc = (size_t)ccdk_cluster_count_pow2(F), NLf = NLc * (size_t)ccdk_cluster_size();
         CKR(ensure(c, c->heap, sizeof(float) * 6 * (2 * NLc)));
         CKR(ensure(c, c->srec, sizeof(float) * (size_t)ccdk_leaf_record_words() * NLf));
         CKR(ensure(c, c->sbox, sizeof(float) * 6 * NLf));
         CKR(ensure(c, c->sfaces, sizeof(int) * 4 * NLf));
-        ccdk_build_cluster_tree(c->st, kind, F, d_faces, P<float>(c->faabb), lazy_boxes ? d_q0 : nullptr, d_q1, outerEta, lazy_boxes ? nullptr : P<double>(c->boxes),
-                                P<unsigned>(c->bounds), P<unsigned long long>(c->keysA), P<unsigned long long>(c->keysB), P<unsigned>(c->valsA),
-                                P<unsigned>(c->valsB), c->temp.p, c->temp.cap, P<float>(c->heap), P<float>(c->srec), P<float>(c->sbox), c->sfaces.p);
+        CKR(ensure(c, c->cmark, NLc + 16));
+        ccdk_build_cluster_tree(c->st, F, d_faces, P<float>(c->faabb), P<unsigned>(c->bounds), P<unsigned long long>(c->keysA), P<unsigned long long>(c->keysB),
+                                P<unsigned>(c->valsA), P<unsigned>(c->valsB), c->temp.p, c->temp.cap, P<float>(c->heap), P<float>(c->sbox), c->sfaces.p);
         c->launches += 1 + 2 + 8 + 2 + 3;
     }
     const unsigned *sortedFace = P<unsigned>(c->valsB);
     cudaEventRecord(c->sev[ST_TRAVERSE_EXACT], c->st);
 
-    // Ownership of a shard: vertices [v0,v1) for VF stencils, unique edges [e0,e1) for EE stencils.  With one rank the
-    // ranges are everything and the traversal visits unordered pairs once; with several ranks the ranges come from the
-    // caller (ccd_set_shard_partition, balanced on the previous step's load profile; equal index split until then) and
-    // the rank traverses, tests and counts only for the faces its own emission reads.
+    // Ownership of a shard: the vertices (VF stencils) and unique edges (EE stencils) anchored in its range [p0, p1) of
+    // sorted (Morton) positions — see shard_queries_kernel.  With one rank the range is everything; with several the
+    // ranges come from the caller (ccd_set_shard_partition, balanced on the previous step's load profile; equal split
+    // until then) and the rank traverses, tests and counts only for the faces its own emission reads.
     const bool sharded = shard_world > 1;
     const int E = c->nEdges;
-    int v0 = 0, v1 = V, e0 = 0, e1 = E;
+    int p0 = 0, p1 = F;
     if (sharded)
     {
-        if ((int)c->partV.size() == shard_world + 1 && (int)c->partE.size() == shard_world + 1 && c->partV[shard_world] == V && c->partE[shard_world] == E)
+        if ((int)c->partP.size() == shard_world + 1 && c->partP[shard_world] == F)
         {
-            v0 = c->partV[shard_rank]; v1 = c->partV[shard_rank + 1];
-            e0 = c->partE[shard_rank]; e1 = c->partE[shard_rank + 1];
+            p0 = c->partP[shard_rank]; p1 = c->partP[shard_rank + 1];
         }
         else
         {
-            v0 = (int)(((long long)V * shard_rank) / shard_world); v1 = (int)(((long long)V * (shard_rank + 1)) / shard_world);
-            e0 = (int)(((long long)E * shard_rank) / shard_world); e1 = (int)(((long long)E * (shard_rank + 1)) / shard_world);
+            p0 = (int)(((long long)F * shard_rank) / shard_world); p1 = (int)(((long long)F * (shard_rank + 1)) / shard_world);
         }
         CKR(ensure(c, c->qlist, sizeof(int) * (size_t)(F + 32)));
         CKR(ensure(c, c->needed, sizeof(int) * (size_t)(F + 2)));
         CKR(ensure(c, c->neededPre, sizeof(int) * (size_t)(F + 2)));
-        CKR(ensure(c, c->nodeForeign, (size_t)F + 16));
+        CKR(ensure(c, c->facePos, sizeof(int) * (size_t)(F + 2)));
     }
+    const int *facePos = sharded ? P<int>(c->facePos) : nullptr;
     for (int attempt = 0; attempt < 8; attempt++)
     {
         CKR(ensure(c, c->cand, sizeof(int) * 2 * c->candCap));
         CKR(ensure(c, c->pairL, sizeof(int) * c->pairCap));
         CKR(ensure(c, c->pairR, sizeof(int) * c->pairCap));
         CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 2, c->st));
-        CK(cudaMemsetAsync(ctr + C_CAND_REG, 0, sizeof(unsigned long long) * CCD_CAND_REGIONS, c->st));
-        const size_t regionCap = c->candCap / CCD_CAND_REGIONS;
         CK(cudaMemsetAsync(c->deg.p, 0, sizeof(int) * (size_t)(F + 2), c->st));
-        if (sharded)
+        if (sharded && attempt == 0)
         {
-            if (attempt == 0)
-            {
-                CK(cudaMemsetAsync(ctr + C_NQUERY, 0, sizeof(unsigned long long), c->st));
-                CK(cudaMemsetAsync(P<int>(c->needed) + F, 0, sizeof(int), c->st));
-                ccdk_shard_queries(c->st, F, sortedFace, d_faces, P<int>(c->faceEdge), v0, v1, e0, e1, P<int>(c->qlist), ctr + C_NQUERY, P<int>(c->needed),
-                                   P<int>(c->neededPre), old_traverse ? c->nodes.p : nullptr, P<int>(c->nodeFirst), P<unsigned char>(c->nodeForeign), c->temp.p, c->temp.cap);
-                c->launches += 3;
-            }
-            // the number of query faces stays on the device: the grid covers all F, the surplus threads leave at once
-            if (old_traverse)
-                ccdk_traverse(c->st, kind, F, 0, F, P<int>(c->qlist), true, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p,
-                              c->cand.p, regionCap, ctr + C_CAND_REG, P<int>(c->needed), P<unsigned char>(c->nodeForeign), ctr + C_NQUERY);
+            CK(cudaMemsetAsync(ctr + C_NQUERY, 0, sizeof(unsigned long long), c->st));
+            CK(cudaMemsetAsync(P<int>(c->needed) + F, 0, sizeof(int), c->st));
+            ccdk_shard_queries(c->st, F, sortedFace, d_faces, P<int>(c->faceEdge), P<int>(c->facePos), P<long long>(c->starOff), P<int>(c->star),
+                               P<int>(c->edgeStart), P<int>(c->heFace), p0, p1, P<int>(c->qlist), ctr + C_NQUERY, P<int>(c->needed), P<int>(c->neededPre),
+                               c->temp.p, c->temp.cap);
+            c->launches += 4;
         }
-        else if (old_traverse)
-            ccdk_traverse(c->st, kind, F, 0, F, nullptr, false, sortedFace, P<float>(c->faabb), d_faces, P<float>(c->fkdop), c->nodes.p, c->cand.p,
-                          regionCap, ctr + C_CAND_REG, nullptr, nullptr, nullptr);
-        if (old_traverse)
-        {
-            ccdk_exact_pairs(c->st, kind, !sharded, ctr + C_CAND_REG, regionCap, c->cand.p, sortedFace, d_faces, lazy_boxes ? nullptr : P<double>(c->boxes),
-                             lazy_boxes ? d_q0 : nullptr, d_q1, outerEta, P<int>(c->pairL), P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg),
-                             sharded ? P<int>(c->needed) : nullptr);
-            c->launches += 2;
-        }
-        else
-        {
-            // simultaneous pair traversal of the cluster tree, then the cluster pairs' face tests: pairs + degrees
-            if (c->frontCap == 0) c->frontCap = (size_t)F * 2 + (1u << 16);
-            CKR(ensure(c, c->frontA, sizeof(int) * 2 * c->frontCap));
-            CKR(ensure(c, c->frontB, sizeof(int) * 2 * c->frontCap));
-            if (c->unsureCap == 0) c->unsureCap = (size_t)F / 16 + (1u << 14);
-            CKR(ensure(c, c->unsure, sizeof(int) * 2 * c->unsureCap));
-            c->launches += ccdk_pair_traversal(c->st, kind, F, P<float>(c->heap), P<float>(c->srec), P<float>(c->sbox), c->sfaces.p, lazy_boxes ? nullptr : P<double>(c->boxes),
-                                               lazy_boxes ? d_q0 : nullptr, d_q1, outerEta, c->frontA.p, c->frontB.p, c->frontCap, ctr + C_FRONT, c->unsure.p,
-                                               c->unsureCap, P<int>(c->pairL), P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg),
-                                               sharded ? P<int>(c->needed) : nullptr, sharded ? P<int>(c->neededPre) : nullptr, c->cand.p, c->candCap, ctr + C_NCAND);
-        }
+        // simultaneous pair traversal of the cluster tree, then the cluster pairs' face tests: pairs + degrees
+        if (c->frontCap == 0) c->frontCap = (size_t)F * 2 + (1u << 16);
+        CKR(ensure(c, c->frontA, sizeof(int) * 2 * c->frontCap));
+        CKR(ensure(c, c->frontB, sizeof(int) * 2 * c->frontCap));
+        if (c->unsureCap == 0) c->unsureCap = (size_t)F / 16 + (1u << 14);
+        CKR(ensure(c, c->unsure, sizeof(int) * 2 * c->unsureCap));
+        c->launches += ccdk_pair_traversal(c->st, kind, F, d_faces, sortedFace, P<float>(c->heap), P<float>(c->srec), P<unsigned char>(c->cmark), P<float>(c->sbox), c->sfaces.p, lazy_boxes ? nullptr : P<double>(c->boxes),
+                                           lazy_boxes ? d_q0 : nullptr, d_q1, outerEta, c->frontA.p, c->frontB.p, c->frontCap, ctr + C_FRONT, c->unsure.p,
+                                           c->unsureCap, P<int>(c->pairL), P<int>(c->pairR), c->pairCap, ctr + C_NPAIRS, P<int>(c->deg),
+                                           sharded ? P<int>(c->needed) : nullptr, sharded ? P<int>(c->neededPre) : nullptr, c->cand.p, c->candCap, ctr + C_NCAND);
         CKR(sync_counters(c));
-        unsigned long long ncand = 0, maxreg = 0, npairs = c->h_counters[C_NPAIRS];
-        for (int r = 0; r < CCD_CAND_REGIONS; r++)
-        {
-            const unsigned long long x = c->h_counters[C_CAND_REG + r];
-            ncand += x;
-            maxreg = x > maxreg ? x : maxreg;
-        }
+        const unsigned long long ncand = c->h_counters[C_NCAND], npairs = c->h_counters[C_NPAIRS];
         // counts keep running past the capacities (writes are guarded), so an overflow tells the size to retry with
-        const bool front_over = !old_traverse && c->h_counters[C_FRONT + 2] > c->frontCap;
+        const bool front_over = c->h_counters[C_FRONT + 2] > c->frontCap;
         if (front_over) c->frontCap = (size_t)(c->h_counters[C_FRONT + 2] * 2 + 1024);      // a truncated level hides the size of the next: leave room
-        const bool unsure_over = !old_traverse && c->h_counters[C_FRONT + 3] > c->unsureCap;
+        const bool unsure_over = c->h_counters[C_FRONT + 3] > c->unsureCap;
         if (unsure_over) c->unsureCap = (size_t)(c->h_counters[C_FRONT + 3] * 2 + 1024);
-        if (!old_traverse) { ncand = c->h_counters[C_NCAND]; maxreg = (ncand + CCD_CAND_REGIONS - 1) / CCD_CAND_REGIONS; }      // one list of candCap entries
-        const bool cand_over = maxreg > regionCap, pair_over = npairs > c->pairCap;
+        const bool cand_over = ncand > c->candCap, pair_over = npairs > c->pairCap;
         const bool again = cand_over || pair_over || front_over || unsure_over;
-        if (cand_over)
-            c->candCap = (size_t)((maxreg + maxreg / 4 + 1024) * CCD_CAND_REGIONS);
+        if (cand_over) c->candCap = (size_t)(ncand + ncand / 4 + 1024);
         if (again)
         {
             // pairs found from a truncated candidate list are a lower bound only: leave generous room
             size_t want = (size_t)(npairs + npairs / 4 + 1024);
-            if (cand_over) want = want > c->candCap / 2 ? want : c->candCap / 2;
+            if (cand_over || front_over) want = want > c->candCap / 2 ? want : c->candCap / 2;
             if (want > c->pairCap) c->pairCap = want;
         }
         if (!again)
         {
-            res->ncand = old_traverse ? (long long)ncand : (long long)c->h_counters[C_FRONT + 2];      // cluster path: the largest frontier (= cluster pairs)
-            if (getenv("CCD_BP_TRACE")) fprintf(stderr, "[bp] cluster pairs %llu, face-pair candidates %llu, undecided %llu, face pairs %llu\n", c->h_counters[C_FRONT + 2], c->h_counters[C_NCAND], c->h_counters[C_FRONT + 3], npairs);
+            res->ncand = (long long)c->h_counters[C_FRONT + 2];      // the largest frontier (= cluster pairs)
             res->npairs = (long long)npairs;
+            if (getenv("CCD_BP_TRACE")) fprintf(stderr, "[bp] cluster pairs %llu, face-pair candidates %llu, undecided %llu, face pairs %llu\n", c->h_counters[C_FRONT + 2], ncand, c->h_counters[C_FRONT + 3], npairs);
             break;
         }
         if (attempt == 7)
@@ -554,7 +495,7 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     ccdk_adjacency_fill(c->st, ctr + C_NPAIRS, P<int>(c->pairL), P<int>(c->pairR), P<long long>(c->adjOff), P<int>(c->cursor), P<int>(c->adj));
     c->launches += 3;
 
-    // Stencil counts of the owned vertices / unique edges, scanned into write offsets (relative to the range start)
+    // Stencil counts of the owned vertices / unique edges (zero for everything else), scanned into write offsets
     CKR(ensure(c, c->vfCounts, sizeof(int) * (size_t)(V + 2)));
     CKR(ensure(c, c->vfOffsets, sizeof(long long) * (size_t)(V + 2)));
     CKR(ensure(c, c->eeCounts, sizeof(int) * (size_t)(E + 2)));
@@ -563,56 +504,55 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     {
         // warp-cooperative emission (broadphase.cu section 6b): active items -> unique sorted keys + counts
         const size_t ordered = (size_t)res->npairs * 2;      // upper bound of the (face, neighbour) entries in the adjacency lists
-        CKR(ensure(c, c->alistV, sizeof(int) * (size_t)(v1 - v0 + 32)));
-        CKR(ensure(c, c->alistE, sizeof(int) * (size_t)(e1 - e0 + 32)));
+        CKR(ensure(c, c->alistV, sizeof(int) * (size_t)(V + 32)));
+        CKR(ensure(c, c->alistE, sizeof(int) * (size_t)(E + 32)));
         CKR(ensure(c, c->kstartV, sizeof(long long) * (size_t)(V + 2)));
         CKR(ensure(c, c->kstartE, sizeof(long long) * (size_t)(E + 2)));
         CKR(ensure(c, c->keysV, sizeof(int) * (3 * ordered + 64)));      // every adjacency entry is seen by the face's 3 vertices
         CKR(ensure(c, c->keysE, sizeof(int) * (9 * ordered + 64)));      // ... and by its 3 edges, each against the neighbour's 3 edges
         CK(cudaMemsetAsync(ctr + C_NA_VF, 0, sizeof(unsigned long long) * 4, c->st));
         CK(cudaMemsetAsync(ctr + C_NBIG, 0, sizeof(unsigned long long) * 2, c->st));
-        CKR(ensure(c, c->bigV, sizeof(int) * (size_t)(v1 - v0 + 32)));
-        CKR(ensure(c, c->bigE, sizeof(int) * (size_t)(e1 - e0 + 32)));
-        ccdk_active_list(c->st, v0, v1, P<long long>(c->starOff), nullptr, P<int>(c->star), P<int>(c->deg), P<int>(c->vfCounts), P<int>(c->alistV), ctr + C_NA_VF);
-        ccdk_active_list(c->st, e0, e1, nullptr, P<int>(c->edgeStart), P<int>(c->heFace), P<int>(c->deg), P<int>(c->eeCounts), P<int>(c->alistE), ctr + C_NA_EE);
+        CKR(ensure(c, c->bigV, sizeof(int) * (size_t)(V + 32)));
+        CKR(ensure(c, c->bigE, sizeof(int) * (size_t)(E + 32)));
+        ccdk_active_list(c->st, 0, V, P<long long>(c->starOff), nullptr, P<int>(c->star), P<int>(c->deg), P<int>(c->vfCounts), P<int>(c->alistV), ctr + C_NA_VF, facePos, p0, p1);
+        ccdk_active_list(c->st, 0, E, nullptr, P<int>(c->edgeStart), P<int>(c->heFace), P<int>(c->deg), P<int>(c->eeCounts), P<int>(c->alistE), ctr + C_NA_EE, facePos, p0, p1);
         ccdk_emit_sort(c->st, true, P<int>(c->alistV), ctr + C_NA_VF, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
                        P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceRank), P<int>(c->rankFace), P<int>(c->faceEdge),
                        c->edgeVerts.p, d_fixed, P<int>(c->vfCounts), P<long long>(c->kstartV), P<int>(c->keysV), ctr + C_KCUR_VF, P<int>(c->bigV), ctr + C_NBIG);
         ccdk_emit_sort(c->st, false, P<int>(c->alistE), ctr + C_NA_EE, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
                        P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceRank), P<int>(c->rankFace), P<int>(c->faceEdge),
                        c->edgeVerts.p, d_fixed, P<int>(c->eeCounts), P<long long>(c->kstartE), P<int>(c->keysE), ctr + C_KCUR_EE, P<int>(c->bigE), ctr + C_NBIG + 1);
-        c->launches += 4;
+        c->launches += 6;
     }
     // the scan reads one element past the range (never added to anything it outputs)
-    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, v1 - v0 + 1, P<int>(c->vfCounts) + v0, P<long long>(c->vfOffsets) + v0);
-    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, e1 - e0 + 1, P<int>(c->eeCounts) + e0, P<long long>(c->eeOffsets) + e0);
+    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, V + 1, P<int>(c->vfCounts), P<long long>(c->vfOffsets));
+    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, E + 1, P<int>(c->eeCounts), P<long long>(c->eeOffsets));
     c->launches += 4;
     c->hist_valid = false;
     if (sharded)
     {
         CKR(ensure(c, c->hist, sizeof(unsigned long long) * 2 * CCD_SHARD_BUCKETS));
         CK(cudaMemsetAsync(c->hist.p, 0, sizeof(unsigned long long) * 2 * CCD_SHARD_BUCKETS, c->st));
-        ccdk_shard_hist(c->st, P<int>(c->vfCounts), nullptr, v0, v1, V, CCD_SHARD_BUCKETS, P<unsigned long long>(c->hist));
-        ccdk_shard_hist(c->st, P<int>(c->eeCounts), c->edgeVerts.p, e0, e1, V, CCD_SHARD_BUCKETS, P<unsigned long long>(c->hist) + CCD_SHARD_BUCKETS);
+        ccdk_shard_hist(c->st, P<int>(c->vfCounts), V, P<long long>(c->starOff), nullptr, P<int>(c->star), facePos, F, CCD_SHARD_BUCKETS, P<unsigned long long>(c->hist));
+        ccdk_shard_hist(c->st, P<int>(c->eeCounts), E, nullptr, P<int>(c->edgeStart), P<int>(c->heFace), facePos, F, CCD_SHARD_BUCKETS, P<unsigned long long>(c->hist) + CCD_SHARD_BUCKETS);
         CK(cudaMemcpyAsync(c->h_hist, c->hist.p, sizeof(unsigned long long) * 2 * CCD_SHARD_BUCKETS, cudaMemcpyDeviceToHost, c->st));
-        c->histV = V;
-        c->histE = E;
+        c->histF = F;
         c->hist_valid = true;
         c->launches += 2;
     }
-    long long range[4] = {0, 0, 0, 0};
-    CK(cudaMemcpyAsync(&range[1], P<long long>(c->vfOffsets) + v1, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaMemcpyAsync(&range[3], P<long long>(c->eeOffsets) + e1, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+    long long range[2] = {0, 0};
+    CK(cudaMemcpyAsync(&range[0], P<long long>(c->vfOffsets) + V, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(&range[1], P<long long>(c->eeOffsets) + E, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    res->nvf = range[1] - range[0];
-    res->nee = range[3] - range[2];
+    res->nvf = range[0];
+    res->nee = range[1];
     CKR(ensure(c, c->vfOut, sizeof(int) * 4 * (size_t)(res->nvf + 1)));
     CKR(ensure(c, c->eeOut, sizeof(int) * 4 * (size_t)(res->nee + 1)));
     cudaEventRecord(c->sev[ST_EMIT_WRITE], c->st);
-    ccdk_emit_write(c->st, true, P<int>(c->alistV), ctr + C_NA_VF, v0, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
+    ccdk_emit_write(c->st, true, P<int>(c->alistV), ctr + C_NA_VF, 0, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
                     P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceRank), P<int>(c->rankFace), P<int>(c->faceEdge),
                     c->edgeVerts.p, d_fixed, P<int>(c->vfCounts), P<long long>(c->kstartV), P<int>(c->keysV), P<long long>(c->vfOffsets), P<int>(c->vfOut));
-    ccdk_emit_write(c->st, false, P<int>(c->alistE), ctr + C_NA_EE, e0, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
+    ccdk_emit_write(c->st, false, P<int>(c->alistE), ctr + C_NA_EE, 0, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
                     P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceRank), P<int>(c->rankFace), P<int>(c->faceEdge),
                     c->edgeVerts.p, d_fixed, P<int>(c->eeCounts), P<long long>(c->kstartE), P<int>(c->keysE), P<long long>(c->eeOffsets), P<int>(c->eeOut));
     c->launches += 2;
@@ -1014,6 +954,39 @@ int ccd_step_shard(ccd_context *c, int kind, int V, int F, const int32_t *faces,
     return CCD_OK;
 }
 
+int ccd_step_device_hits(ccd_context *c, int kind, int V, int F, const int32_t *d_faces, const double *d_q0, const double *d_q1, double outerEta,
+                         double eta, const uint8_t *d_fixedMask, int shard_rank, int shard_world, ccd_step_result *out)
+{
+    if (!c || !out)
+        return CCD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    memset(out, 0, sizeof(*out));
+    ccd_device_result d;
+    CKR(ccd_step_device(c, kind, V, F, d_faces, d_q0, d_q1, outerEta, eta, d_fixedMask, shard_rank, shard_world, &d));
+    out->n_vf_candidates = d.n_vf_candidates;
+    out->n_ee_candidates = d.n_ee_candidates;
+    out->n_vf_hits = d.n_vf_hits;
+    out->n_ee_hits = d.n_ee_hits;
+    out->earliest_toi = d.earliest_toi;
+    out->ms_broadphase = d.ms_broadphase;
+    out->ms_narrowphase = d.ms_narrowphase;
+    CKR(select_hits(c, 0, d.n_vf_candidates, d.d_vf, d.d_vf_toi, d.d_vf_hit, d.n_vf_hits, &out->vf_hits, &out->vf_hit_toi));
+    CKR(select_hits(c, 2, d.n_ee_candidates, d.d_ee, d.d_ee_toi, d.d_ee_hit, d.n_ee_hits, &out->ee_hits, &out->ee_hit_toi));
+    return CCD_OK;
+}
+
+int ccd_wait_stream(ccd_context *c, void *producer_stream)
+{
+    if (!c)
+        return CCD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    // everything enqueued so far on the caller's stream (the copy / broadcast that fills the device inputs) is ordered before
+    // everything this context enqueues from now on; no host synchronisation
+    CK(cudaEventRecord(c->evFork, (cudaStream_t)producer_stream));
+    CK(cudaStreamWaitEvent(c->st, c->evFork, 0));
+    return CCD_OK;
+}
+
 void ccd_step_result_free(ccd_step_result *r)
 {
     if (!r)
@@ -1023,37 +996,18 @@ void ccd_step_result_free(ccd_step_result *r)
     r->vf_hit_toi = r->ee_hit_toi = nullptr;
 }
 
-int ccd_set_shard_partition(ccd_context *c, int world, const int32_t *vbounds, const int32_t *ebounds)
+int ccd_set_shard_partition(ccd_context *c, int world, const int32_t *pbounds)
 {
-    if (!c || world < 1 || !vbounds || !ebounds || vbounds[0] != 0 || ebounds[0] != 0)
+    if (!c || world < 1 || !pbounds || pbounds[0] != 0)
         return CCD_ERR_ARG;
     for (int r = 0; r < world; r++)
-        if (vbounds[r + 1] < vbounds[r] || ebounds[r + 1] < ebounds[r])
+        if (pbounds[r + 1] < pbounds[r])
             return CCD_ERR_ARG;
-    c->partV.assign(vbounds, vbounds + world + 1);
-    c->partE.assign(ebounds, ebounds + world + 1);
+    c->partP.assign(pbounds, pbounds + world + 1);
     return CCD_OK;
 }
 
-int ccd_shard_edge_bounds(ccd_context *c, int world, const int32_t *vbounds, int32_t *ebounds)
-{
-    if (!c || world < 1 || !vbounds || !ebounds)
-        return CCD_ERR_ARG;
-    if (c->topoV < 0 || !c->vertEdgeStart.p)
-    {
-        c->err = "ccd_shard_edge_bounds: no mesh topology on this context yet (run a step first)";
-        return CCD_ERR_ARG;
-    }
-    for (int r = 0; r <= world; r++)
-    {
-        if (vbounds[r] < 0 || vbounds[r] > c->topoV || (size_t)vbounds[r] >= c->h_vertEdgeStart.size())
-            return CCD_ERR_ARG;
-        ebounds[r] = c->h_vertEdgeStart[(size_t)vbounds[r]];      // host copy made when the topology tables were built
-    }
-    return CCD_OK;
-}
-
-int ccd_shard_histogram(ccd_context *c, int64_t *vf_hist, int64_t *ee_hist, int32_t *n_vertices, int32_t *n_edges)
+int ccd_shard_histogram(ccd_context *c, int64_t *vf_hist, int64_t *ee_hist, int32_t *n_positions)
 {
     if (!c || !vf_hist || !ee_hist)
         return CCD_ERR_ARG;
@@ -1067,8 +1021,7 @@ int ccd_shard_histogram(ccd_context *c, int64_t *vf_hist, int64_t *ee_hist, int3
         vf_hist[i] = (int64_t)c->h_hist[i];
         ee_hist[i] = (int64_t)c->h_hist[CCD_SHARD_BUCKETS + i];
     }
-    if (n_vertices) *n_vertices = c->histV;
-    if (n_edges) *n_edges = c->histE;
+    if (n_positions) *n_positions = c->histF;
     return CCD_OK;
 }
 

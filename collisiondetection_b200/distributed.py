@@ -1,10 +1,11 @@
 """Multi-GPU plumbing of the CCD step: one process per GPU, torch.distributed (NCCL on the GPUs, gloo in CPU tests).
 
-The path shards without a data-path collective: positions and faces are replicated (every rank uploads or receives
-the same q0/q1 — `broadcast_positions`), every rank builds the same LBVH, and rank r traverses it, emits and tests only
-for the stencils it owns: a contiguous vertex range (VF) and unique-edge range (EE).
+The path shards without a data-path collective: positions and faces are replicated (every rank uploads its slice and
+all-gathers, or receives the same q0/q1 — `gather_positions` / `broadcast_positions`), every rank builds the same LBVH,
+and rank r intersects it, emits and tests only for the stencils it owns: the vertices (VF) and unique edges (EE) anchored
+in a contiguous range of the faces' Morton order — a range of LBVH subtrees, i.e. a region of space.
 The only exchange is the step summary, ONE small all-gather per step (`exchange_step`): earliest TOI, hit / stencil
-counts, and each rank's load profile (stencils per bucket of vertex / edge ids), from which every rank derives the same
+counts, and each rank's load profile (stencils per bucket of sorted positions), from which every rank derives the same
 ownership ranges for the next step (`balanced_bounds`) — the rebalancing SURVEY.md section 8(e) asks for.
 """
 import numpy as np
@@ -12,9 +13,9 @@ import torch
 import torch.distributed as dist
 
 
-# fallback cost model when no stage times are available: cost of owning a vertex (box tests and LBVH traversal for the
-# ~2 faces around it) in units of the cost of one stencil (emission + narrowphase)
-VERTEX_WEIGHT = 4.0
+# fallback cost model when no stage times are available: cost of owning one sorted position (box tests and tree
+# intersection around that face) in units of the cost of one stencil (emission + narrowphase)
+VERTEX_WEIGHT = 2.0
 
 
 def shard_range(n, rank, world):
@@ -89,26 +90,51 @@ def balanced_bounds(hist, n_items, world):
     return bounds.astype(np.int32)
 
 
+def gather_positions(d_q0, d_q1, h_q0, h_q1, rank, world, group=None):
+    """End-to-end input path of a sharded job: every rank copies only ITS 1/world slice of the step's positions from (pinned)
+    host memory and the slices are all-gathered over NVLink (NCCL) into the replicated device arrays — the host-to-device
+    traffic of the job is one copy of the positions, not `world` copies.  d_q* / h_q*: flat float64 tensors of equal
+    length (device / pinned host)."""
+    n = d_q0.numel()
+    if not (dist.is_available() and dist.is_initialized()) or world == 1:
+        d_q0.copy_(h_q0, non_blocking=True)
+        d_q1.copy_(h_q1, non_blocking=True)
+        return
+    per = -(-n // world)
+    for d, h in ((d_q0, h_q0), (d_q1, h_q1)):
+        if n % world == 0:
+            a, b = rank * per, (rank + 1) * per
+            d[a:b].copy_(h[a:b], non_blocking=True)
+            dist.all_gather_into_tensor(d, d[a:b], group=group)
+        else:      # ragged tail: gather padded slices, then trim
+            buf = torch.zeros(per * world, dtype=d.dtype, device=d.device)
+            a, b = rank * per, min((rank + 1) * per, n)
+            if b > a:
+                buf[a:b].copy_(h[a:b], non_blocking=True)
+            dist.all_gather_into_tensor(buf, buf[rank * per:(rank + 1) * per].clone(), group=group)
+            d.copy_(buf[:n])
+
+
 def exchange_step(ctx, earliest_toi, n_hits, n_vf, n_ee=0, device="cpu", group=None, rebalance=True, stage_ms=None):
     """The step's only exchange: ONE all-gather of a small vector per rank — earliest TOI, hit / stencil counts, the rank's
-    measured stage times and its load profile (stencils per bucket of vertex ids).
+    measured stage times and its load profile (stencils per bucket of sorted positions).
 
     Returns the global (earliest TOI, hits, stencils).  With `rebalance`, every rank also installs the ownership ranges
     for its next step (ccd_set_shard_partition), balanced on the summed profile under a cost model whose three
-    coefficients are re-measured every step from the gathered times: cost of a rank = a * vertices owned (box tests and
-    LBVH traversal around them) + b * VF stencils + c * EE stencils (emission + narrowphase).
+    coefficients are re-measured every step from the gathered times: cost of a rank = a * positions owned (box tests and
+    tree intersection around them) + b * VF stencils + c * EE stencils (emission + narrowphase).
     `stage_ms`: this rank's ccd_stage_times() of the step (taken from ctx when omitted)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return float(earliest_toi), int(n_hits), int(n_vf + n_ee)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    vf_hist, ee_hist, nv, ne = ctx.shard_histogram()
+    vf_hist, ee_hist, npos = ctx.shard_histogram()
     nb = len(vf_hist)
     if stage_ms is None:
         stage_ms = ctx.stage_times()
     t_item = stage_ms.get("traverse_exact", 0.0) + stage_ms.get("adjacency", 0.0)
     t_emit = stage_ms.get("emit_count", 0.0) + stage_ms.get("emit_write", 0.0)
     part = getattr(ctx, "shard_partition", None)
-    owned = float(part[0][rank + 1] - part[0][rank]) if part is not None and len(part[0]) == world + 1 else float(nv) / world
+    owned = float(part[rank + 1] - part[rank]) if part is not None and len(part) == world + 1 else float(npos) / world
     head = [earliest_toi if np.isfinite(earliest_toi) else np.inf, float(n_hits), float(n_vf), float(n_ee), owned, t_item, t_emit,
             stage_ms.get("np_vf", 0.0), stage_ms.get("np_ee", 0.0)]
     nh = len(head)
@@ -128,11 +154,10 @@ def exchange_step(ctx, earliest_toi, n_hits, n_vf, n_ee=0, device="cpu", group=N
         c = allr[:, 8].sum() / max(tot_ee, 1.0) + emit_per_stencil
         if not (a > 0 and b > 0 and c > 0):      # no timings (CPU tests): the fixed model
             a, b, c = VERTEX_WEIGHT, 1.0, 1.0
-        items = np.diff(_bucket_first(nv, nb)).astype(np.float64)
+        items = np.diff(_bucket_first(npos, nb)).astype(np.float64)
         load = b * allr[:, nh:nh + nb].sum(axis=0) + c * allr[:, nh + nb:].sum(axis=0) + a * items
-        vb = balanced_bounds(load, nv, world)
-        eb = ctx.shard_edge_bounds(vb)
-        ctx.set_shard_partition(vb, eb)
-        ctx.shard_partition = (list(map(int, vb)), list(map(int, eb)))
+        pb = balanced_bounds(load, npos, world)
+        ctx.set_shard_partition(pb)
+        ctx.shard_partition = list(map(int, pb))
     toi = allr[:, 0].min()
     return (float(toi) if np.isfinite(toi) else float("inf")), int(allr[:, 1].sum()), int(allr[:, 2].sum() + allr[:, 3].sum())

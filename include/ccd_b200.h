@@ -109,13 +109,13 @@ int ccd_step_shard(ccd_context *ctx, int kind, int V, int F, const int32_t *face
                    ccd_step_result *out);
 
 /* Device-resident variant: inputs already in HBM, results stay in HBM (pointers valid until the next
- * call on this context).  shard_rank / shard_world partition the step across GPUs of one job: rank r owns a
- * contiguous range of vertices (its VF stencils) and of unique edges (its EE stencils).  Every rank builds the
- * (replicated) LBVH, but traverses it, tests face pairs and counts stencils only for the faces its own ranges
- * touch.  The ranges are an equal index split until the caller installs better ones with
- * ccd_set_shard_partition — normally computed from the load profiles of the previous step
- * (ccd_shard_histogram, summed over ranks).  Whatever the ranges, the concatenation over ranks of the
- * stencil lists equals the single-GPU lists exactly.  world = 1 means the whole step. */
+ * call on this context).  shard_rank / shard_world partition the step across GPUs of one job: rank r owns the
+ * vertices (its VF stencils) and unique edges (its EE stencils) anchored in a contiguous range of the faces' Morton
+ * order, i.e. a subtree range of the step's LBVH.  Every rank builds the (replicated) tree, but intersects it, tests
+ * face pairs and counts stencils only around the faces its own range touches.  The ranges are an equal split until
+ * the caller installs better ones with ccd_set_shard_partition — normally computed from the load profiles of the
+ * previous step (ccd_shard_histogram, summed over ranks).  Whatever the ranges, the ranks' stencil lists are sorted,
+ * pairwise disjoint, and their union is the single-GPU list exactly.  world = 1 means the whole step. */
 typedef struct
 {
     int64_t n_vf_candidates, n_ee_candidates;
@@ -138,20 +138,30 @@ int ccd_step_device(ccd_context *ctx, int kind, int V, int F, const int32_t *d_f
                     const double *d_q1, double outerEta, double eta, const uint8_t *d_fixedMask, int shard_rank,
                     int shard_world, ccd_device_result *out);
 
-/* Ownership ranges for sharded steps on this context: vbounds / ebounds have world+1 ascending entries,
- * vbounds[0] = ebounds[0] = 0, vbounds[world] = V, ebounds[world] = number of unique edges (returned by
- * ccd_shard_histogram).  Ignored (equal split) when they do not match the mesh of a later call. */
-int ccd_set_shard_partition(ccd_context *ctx, int world, const int32_t *vbounds, const int32_t *ebounds);
-/* Edge bounds that go with vertex bounds: ebounds[r] = first unique edge (ids are in lexicographic (min,max) order)
- * whose smaller vertex is >= vbounds[r].  With these a rank's edges only touch faces of its own vertices, so the
- * set of faces it has to traverse for is as small as it can be. */
-int ccd_shard_edge_bounds(ccd_context *ctx, int world, const int32_t *vbounds, int32_t *ebounds);
-/* Load profile of the last sharded step on this context: stencils owned by this rank per bucket of vertex ids,
- * CCD_SHARD_BUCKETS equal-width buckets (vertex v falls in bucket v * CCD_SHARD_BUCKETS / n_vertices): vf_hist counts
- * VF stencils by their vertex, ee_hist EE stencils by the smaller vertex of their first edge.  Summing over ranks
- * gives the whole step's profile.  n_vertices / n_edges: the id ranges. */
+/* ccd_step_device with the hit lists copied to (pinned) host memory like ccd_step_shard: device inputs in, host results
+ * out — the end-to-end call of a multi-GPU job whose positions reach the GPUs by an all-gather over NVLink. */
+int ccd_step_device_hits(ccd_context *ctx, int kind, int V, int F, const int32_t *d_faces, const double *d_q0,
+                         const double *d_q1, double outerEta, double eta, const uint8_t *d_fixedMask, int shard_rank,
+                         int shard_world, ccd_step_result *out);
+/* The context runs its kernels on a private non-blocking stream.  Device inputs (d_faces, d_q0, d_q1, d_fixedMask) that
+ * are still being produced on another stream — a copy, an NCCL broadcast / all-gather — must be ordered before the next
+ * call: ccd_wait_stream(ctx, stream) makes everything the context enqueues afterwards wait for what is on `stream`
+ * (a cudaStream_t; NULL = the legacy default stream) at the time of the call.  No host synchronisation.  Alternatively
+ * synchronise the producer stream yourself. */
+int ccd_wait_stream(ccd_context *ctx, void *producer_stream);
+
+/* Ownership ranges for sharded steps on this context: pbounds has world+1 ascending entries over the F sorted (Morton)
+ * positions of the faces, pbounds[0] = 0, pbounds[world] = F.  Rank r owns the vertices and unique edges whose anchor face
+ * (the first face of the vertex's star / of the edge's face list) sorts into [pbounds[r], pbounds[r+1]) — a region of
+ * space, whatever the mesh numbering (BASELINE north_star: "pairs are partitioned by BVH subtree").  Ignored (equal
+ * split) when the last bound does not match F of a later call. */
+int ccd_set_shard_partition(ccd_context *ctx, int world, const int32_t *pbounds);
+/* Load profile of the last sharded step on this context: stencils owned by this rank per bucket of sorted positions,
+ * CCD_SHARD_BUCKETS equal-width buckets (position p falls in bucket p * CCD_SHARD_BUCKETS / n_positions): vf_hist counts
+ * VF stencils by the anchor of their vertex, ee_hist EE stencils by the anchor of their first edge.  Summing over ranks
+ * gives the whole step's profile.  n_positions = F. */
 #define CCD_SHARD_BUCKETS 1024
-int ccd_shard_histogram(ccd_context *ctx, int64_t *vf_hist, int64_t *ee_hist, int32_t *n_vertices, int32_t *n_edges);
+int ccd_shard_histogram(ccd_context *ctx, int64_t *vf_hist, int64_t *ee_hist, int32_t *n_positions);
 
 /* Utilities for bindings that hold device results: copy `bytes` from a device pointer of this context to host
  * memory, and a measured FP64 roofline denominator (dependent-free DFMA streams on every SM) in TFLOP/s. */

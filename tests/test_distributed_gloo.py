@@ -97,8 +97,8 @@ class _FakeCtx(object):
     """Stands in for api.Context in the CPU test of the exchange: a fixed load profile per rank, records the partition."""
     SHARD_BUCKETS = 1024
 
-    def __init__(self, rank, world, nv, ne):
-        self.rank, self.world, self.nv, self.ne = rank, world, nv, ne
+    def __init__(self, rank, world, npos):
+        self.rank, self.world, self.npos = rank, world, npos
         self.partition = None
 
     def shard_histogram(self):
@@ -107,13 +107,10 @@ class _FakeCtx(object):
         lo, hi = (self.SHARD_BUCKETS * self.rank) // self.world, (self.SHARD_BUCKETS * (self.rank + 1)) // self.world
         vf[lo:hi] = 10 * (self.rank + 1)      # later ranks are heavier
         ee[lo:hi] = 7
-        return vf, ee, self.nv, self.ne
+        return vf, ee, self.npos
 
-    def shard_edge_bounds(self, vb):
-        return np.asarray(vb, dtype=np.int64) * 3
-
-    def set_shard_partition(self, vb, eb):
-        self.partition = (list(map(int, vb)), list(map(int, eb)))
+    def set_shard_partition(self, pb):
+        self.partition = list(map(int, pb))
 
 
 def _exchange_worker(rank, world, port_no, results):
@@ -121,8 +118,15 @@ def _exchange_worker(rank, world, port_no, results):
     os.environ["MASTER_PORT"] = str(port_no)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from collisiondetection_b200 import distributed as D
-    ctx = _FakeCtx(rank, world, 100000, 300000)
+    ctx = _FakeCtx(rank, world, 100000)
     toi, nh, ns = D.exchange_step(ctx, 0.25 + 0.1 * rank if rank else float("inf"), 10 + rank, 600 * (rank + 1), 400 * (rank + 1), stage_ms={})
+    # the end-to-end input path: every rank contributes its slice, all ranks end with the whole arrays
+    n = 1000 + rank * 0 + (3 if world == 3 else 0)
+    h0 = torch.arange(n, dtype=torch.float64)
+    h1 = h0 * 2.0
+    d0, d1 = torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+    D.gather_positions(d0, d1, h0, h1, rank, world)
+    assert torch.equal(d0, h0) and torch.equal(d1, h1)
     results[rank] = (toi, nh, ns, ctx.partition)
     dist.destroy_process_group()
 
@@ -132,13 +136,12 @@ def test_exchange_step_gathers_and_rebalances(world):
     mgr = mp.get_context("spawn").Manager()
     results = mgr.dict()
     mp.spawn(_exchange_worker, args=(world, 29650 + world, results), nprocs=world, join=True)
-    parts = {results[r][3] and (tuple(results[r][3][0]), tuple(results[r][3][1])) for r in range(world)}
+    parts = {results[r][3] and tuple(results[r][3]) for r in range(world)}
     assert len(parts) == 1, "ranks derived different partitions"
-    vb, eb = results[0][3]
-    assert vb[0] == 0 and vb[-1] == 100000
-    # heavier late ranks -> their vertex ranges shrink; edge bounds follow the vertex bounds
-    assert vb[1] > 100000 // world
-    assert eb == [3 * v for v in vb]
+    pb = results[0][3]
+    assert pb[0] == 0 and pb[-1] == 100000
+    # heavier late ranks -> their position ranges shrink
+    assert pb[1] > 100000 // world
     for r in range(world):
         toi, nh, ns, _ = results[r]
         assert toi == (0.35 if world > 1 else float("inf"))

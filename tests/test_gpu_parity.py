@@ -304,9 +304,14 @@ def test_cloth_twin_355(ctx):
     assert np.all((r["vf_hit_toi"] >= 0) & (r["vf_hit_toi"] <= 1))
 
 
+def _rows_sorted(a):
+    a = np.asarray(a)
+    return a[np.lexsort(a.T[::-1])] if len(a) else a
+
+
 def test_cloth_sharded_union_equals_whole(ctx):
-    """ccd_step_device with (rank, world): the union of the shards' stencil lists is the unsharded list, hit counts add
-    up and the earliest TOI is the min over shards — what the multi-GPU reduction relies on."""
+    """ccd_step_device with (rank, world): the shards' stencil lists are each sorted, pairwise disjoint, and their union is the
+    unsharded list; hit counts add up and the earliest TOI is the min over shards — what the multi-GPU reduction relies on."""
     import torch
     from collisiondetection_b200 import scenes
     q0, q1, f, eta = scenes.cloth(201)
@@ -322,13 +327,19 @@ def test_cloth_sharded_union_equals_whole(ctx):
         ee = ctx.download(r.d_ee, (r.n_ee_candidates, 4), np.int32)
         return r.n_vf_hits, r.n_ee_hits, r.earliest_toi, vf, ee
 
-    whole = run(0, 1)
-    for world in (2, 3, 8):
-        parts = [run(r, world) for r in range(world)]
-        assert np.array_equal(np.concatenate([p[3] for p in parts]), whole[3])
-        assert np.array_equal(np.concatenate([p[4] for p in parts]), whole[4])
+    def check(parts, whole):
+        for p in parts:
+            if len(p[3]) and len(p[4]):
+                _check_canonical_sorted_unique(p[3], p[4])      # every shard's list is sorted on its own
+        assert sum(len(p[3]) for p in parts) == len(whole[3]) and sum(len(p[4]) for p in parts) == len(whole[4])      # disjoint
+        assert np.array_equal(_rows_sorted(np.concatenate([p[3] for p in parts])), whole[3])
+        assert np.array_equal(_rows_sorted(np.concatenate([p[4] for p in parts])), whole[4])
         assert sum(p[0] for p in parts) == whole[0] and sum(p[1] for p in parts) == whole[1]
         assert min(p[2] for p in parts) == whole[2]
+
+    whole = run(0, 1)
+    for world in (2, 3, 8):
+        check([run(r, world) for r in range(world)], whole)
     # rebalanced ownership (what distributed.exchange_step installs every step): same union, loads within a few per cent
     from collisiondetection_b200.distributed import balanced_bounds
     world = 4
@@ -336,20 +347,20 @@ def test_cloth_sharded_union_equals_whole(ctx):
     he = np.zeros(ctx.SHARD_BUCKETS, np.int64)
     for r in range(world):
         run(r, world)
-        a, b, nv, ne = ctx.shard_histogram()
+        a, b, npos = ctx.shard_histogram()
         hv += a
         he += b
-    assert hv.sum() == len(whole[3]) and he.sum() == len(whole[4]) and nv == V
-    vb = balanced_bounds(hv + he, nv, world)
-    ctx.set_shard_partition(vb, ctx.shard_edge_bounds(vb))
+    assert hv.sum() == len(whole[3]) and he.sum() == len(whole[4]) and npos == F
+    pb = balanced_bounds(hv + he, npos, world)
+    ctx.set_shard_partition(pb)
     parts = [run(r, world) for r in range(world)]
-    assert np.array_equal(np.concatenate([p[3] for p in parts]), whole[3])
-    assert np.array_equal(np.concatenate([p[4] for p in parts]), whole[4])
+    check(parts, whole)
     loads = [len(p[3]) + len(p[4]) for p in parts]
     assert max(loads) <= 1.1 * (sum(loads) / world), loads
-    ctx.set_shard_partition([0, V], [0, ne])      # a partition for another world size is ignored (equal split)
-    parts = [run(r, 2) for r in range(2)]
-    assert np.array_equal(np.concatenate([p[3] for p in parts]), whole[3])
+    ctx.set_shard_partition([0, F // 3, F])      # a partition for another world size is ignored (equal split)
+    check([run(r, 4) for r in range(4)], whole)
+    ctx.set_shard_partition([0, F // 3, F])
+    check([run(r, 2) for r in range(2)], whole)
 
 
 @pytest.mark.slow
