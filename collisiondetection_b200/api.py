@@ -52,6 +52,7 @@ EXPORTS = [
     "ccd_ee_batch", "ccd_ve_batch", "ccd_vv_batch", "ccd_find_intervals_batch", "ccd_dist_vf_batch",
     "ccd_dist_ee_batch", "ccd_dist_plane_lt_batch", "ccd_dist_line_lt_batch", "ccd_mesh_self_distance",
     "ccd_memcpy_d2h", "ccd_fp64_peak", "ccd_stage_times", "ccd_step_shard", "ccd_set_shard_partition", "ccd_shard_histogram", "ccd_step_device_hits", "ccd_wait_stream", "ccd_narrowphase_sepplane",
+    "ccd_penalty_group_force", "ccd_penalty_group_force_device",
 ]
 
 _LIB = None
@@ -363,6 +364,25 @@ class Context(object):
 
     def lineLineDistanceLessThan(self, pts, eta):
         return self._lt(self.lib.ccd_dist_line_lt_batch, pts, eta)
+
+    def penaltyGroupAddForce(self, q, v, vf, ee, dt, outerEta, innerEta, stiffness, CoR, F, vf_isnew=None, ee_isnew=None):
+        """PenaltyGroup::addForce (src/PenaltyGroup.cpp:34-52) over the group's stencil lists: returns (F + dt * group force,
+        fired flags of the vertex-face then the edge-edge stencils, newused)."""
+        q = _f64(q).reshape(-1)
+        v = _f64(v).reshape(-1)
+        F = np.array(F, dtype=np.float64).reshape(-1)
+        vf = np.ascontiguousarray(vf, dtype=np.int32).reshape(-1, 4)
+        ee = np.ascontiguousarray(ee, dtype=np.int32).reshape(-1, 4)
+        vn = None if vf_isnew is None else np.ascontiguousarray(vf_isnew, dtype=np.uint8)
+        en = None if ee_isnew is None else np.ascontiguousarray(ee_isnew, dtype=np.uint8)
+        vfired = np.zeros(len(vf), dtype=np.uint8)
+        efired = np.zeros(len(ee), dtype=np.uint8)
+        nf, nu = C.c_int64(), C.c_int()
+        self._check(self.lib.ccd_penalty_group_force(
+            self.h, C.c_int(q.size // 3), _ptr(q, _dp), _ptr(v, _dp), C.c_int64(len(vf)), _ptr(vf, _ip), _ptr(vn, _bp), C.c_int64(len(ee)),
+            _ptr(ee, _ip), _ptr(en, _bp), C.c_double(dt), C.c_double(outerEta), C.c_double(innerEta), C.c_double(stiffness), C.c_double(CoR),
+            _ptr(F, _dp), _ptr(vfired, _bp), _ptr(efired, _bp), C.byref(nf), C.byref(nu)), "ccd_penalty_group_force")
+        return F, np.concatenate([vfired, efired]), bool(nu.value), int(nf.value)
 
     def meshSelfDistance(self, verts, faces, fixedMask=None):
         verts = _f64(verts).reshape(-1)

@@ -48,6 +48,8 @@ struct ccd_context
     DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut;
     // narrowphase
     DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, p1Ve, qpack, selTmp, selA, selB, selC, selD, selCount;
+    // penalty forces (penalty.cu)
+    DBuf penF, penGroup, penContrib, penKeysA, penKeysB, penItemsA, penItemsB, penFired, penNewVf, penNewEe, penCtr;
     // pinned host scratch
     unsigned long long *h_counters = nullptr; // C_TOTAL entries
     // pinned host buffers for the hit lists returned by ccd_step (valid until the next call on the context)
@@ -251,7 +253,8 @@ void ccd_destroy(ccd_context *c)
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1Ve, &c->qpack, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->sbox, &c->sfaces, &c->unsure, &c->frontA, &c->frontB, &c->bigV, &c->bigE};
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1Ve, &c->qpack, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->sbox, &c->sfaces, &c->unsure, &c->frontA, &c->frontB, &c->bigV, &c->bigE,
+                   &c->penF, &c->penGroup, &c->penContrib, &c->penKeysA, &c->penKeysB, &c->penItemsA, &c->penItemsB, &c->penFired, &c->penNewVf, &c->penNewEe, &c->penCtr};
     for (DBuf *b : all)
         if (b->p)
             cudaFree(b->p);
@@ -1170,6 +1173,72 @@ int ccd_dist_line_lt_batch(ccd_context *c, int64_t n, const double *pts, const d
 {
     if (n > 0 && (!eta || !out)) return CCD_ERR_ARG;
     return dist_batch(c, 3, n, pts, eta, nullptr, nullptr, 0, out);
+}
+
+// ---- PenaltyGroup::addForce, src/PenaltyGroup.cpp:34-52 -----------------------------------------
+// device pointers: q, v, F (3 V doubles each), stencil lists, optional isnew flags, optional fired flags (nvf + nee bytes)
+static int penalty_device(ccd_context *c, int V, const double *d_q, const double *d_v, int64_t nvf, const int *d_vf, const unsigned char *d_vf_isnew,
+                          int64_t nee, const int *d_ee, const unsigned char *d_ee_isnew, double dt, double outerEta, double innerEta, double stiffness,
+                          double CoR, double *d_F, unsigned char *d_fired, int64_t *n_fired, int *newused)
+{
+    const int64_t n = nvf + nee;
+    if (4 * n >= (int64_t)1 << 31) return CCD_ERR_ARG;
+    const size_t tb = n > 0 ? ccdk_penalty_temp_bytes(4 * n) : 0;
+    CKR(ensure(c, c->temp, tb + 16));
+    CKR(ensure(c, c->penGroup, sizeof(double) * 3 * (size_t)V + 16));
+    CKR(ensure(c, c->penContrib, sizeof(double) * 12 * (size_t)n + 16));
+    CKR(ensure(c, c->penKeysA, sizeof(unsigned) * 4 * (size_t)n + 16));
+    CKR(ensure(c, c->penKeysB, sizeof(unsigned) * 4 * (size_t)n + 16));
+    CKR(ensure(c, c->penItemsA, sizeof(unsigned) * 4 * (size_t)n + 16));
+    CKR(ensure(c, c->penItemsB, sizeof(unsigned) * 4 * (size_t)n + 16));
+    CKR(ensure(c, c->penCtr, 2 * sizeof(unsigned long long)));
+    c->launches += ccdk_penalty_group_force(c->st, V, d_q, d_v, nvf, d_vf, d_vf_isnew, nee, d_ee, d_ee_isnew, dt, outerEta, innerEta, stiffness, CoR, d_F,
+                                            d_fired, P<double>(c->penContrib), P<unsigned>(c->penKeysA), P<unsigned>(c->penKeysB), P<unsigned>(c->penItemsA),
+                                            P<unsigned>(c->penItemsB), c->temp.p, tb, P<double>(c->penGroup), P<unsigned long long>(c->penCtr));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_counters, c->penCtr.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (n_fired) *n_fired = (int64_t)c->h_counters[0];
+    if (newused) *newused = c->h_counters[1] != 0;
+    return CCD_OK;
+}
+
+int ccd_penalty_group_force(ccd_context *c, int V, const double *q, const double *v, int64_t nvf, const int32_t *vf, const uint8_t *vf_isnew,
+                            int64_t nee, const int32_t *ee, const uint8_t *ee_isnew, double dt, double outerEta, double innerEta, double stiffness,
+                            double CoR, double *F, uint8_t *vf_fired, uint8_t *ee_fired, int64_t *n_fired, int *newused)
+{
+    if (!c || V < 0 || nvf < 0 || nee < 0 || (V > 0 && (!q || !v || !F)) || (nvf > 0 && !vf) || (nee > 0 && !ee))
+        return CCD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    c->launches = 0;
+    const size_t vb = sizeof(double) * 3 * (size_t)V;
+    CKR(upload(c, c->q0, q, vb));
+    CKR(upload(c, c->q1, v, vb));
+    CKR(upload(c, c->penF, F, vb));
+    CKR(upload(c, c->vf_in, vf, sizeof(int32_t) * 4 * (size_t)nvf));
+    CKR(upload(c, c->ee_in, ee, sizeof(int32_t) * 4 * (size_t)nee));
+    if (vf_isnew) CKR(upload(c, c->penNewVf, vf_isnew, (size_t)nvf));
+    if (ee_isnew) CKR(upload(c, c->penNewEe, ee_isnew, (size_t)nee));
+    CKR(ensure(c, c->penFired, (size_t)(nvf + nee) + 16));
+    CKR(penalty_device(c, V, P<double>(c->q0), P<double>(c->q1), nvf, P<int>(c->vf_in), vf_isnew ? P<unsigned char>(c->penNewVf) : nullptr, nee,
+                       P<int>(c->ee_in), ee_isnew ? P<unsigned char>(c->penNewEe) : nullptr, dt, outerEta, innerEta, stiffness, CoR, P<double>(c->penF),
+                       P<unsigned char>(c->penFired), n_fired, newused));
+    if (vb) CK(cudaMemcpyAsync(F, c->penF.p, vb, cudaMemcpyDeviceToHost, c->st));
+    if (vf_fired && nvf) CK(cudaMemcpyAsync(vf_fired, c->penFired.p, (size_t)nvf, cudaMemcpyDeviceToHost, c->st));
+    if (ee_fired && nee) CK(cudaMemcpyAsync(ee_fired, P<unsigned char>(c->penFired) + nvf, (size_t)nee, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return CCD_OK;
+}
+
+int ccd_penalty_group_force_device(ccd_context *c, int V, const double *d_q, const double *d_v, int64_t nvf, const int32_t *d_vf, const uint8_t *d_vf_isnew,
+                                   int64_t nee, const int32_t *d_ee, const uint8_t *d_ee_isnew, double dt, double outerEta, double innerEta,
+                                   double stiffness, double CoR, double *d_F, uint8_t *d_fired, int64_t *n_fired, int *newused)
+{
+    if (!c || V < 0 || nvf < 0 || nee < 0 || (V > 0 && (!d_q || !d_v || !d_F)) || (nvf > 0 && !d_vf) || (nee > 0 && !d_ee))
+        return CCD_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    c->launches = 0;
+    return penalty_device(c, V, d_q, d_v, nvf, d_vf, d_vf_isnew, nee, d_ee, d_ee_isnew, dt, outerEta, innerEta, stiffness, CoR, d_F, d_fired, n_fired, newused);
 }
 
 // Distance::meshSelfDistance, src/Distance.cpp:12-66

@@ -20,3 +20,9 @@ void ccdk_find_intervals(cudaStream_t st, long long n, int degree, int pos, cons
 // SeparatingPlaneNarrowPhase: hit flags only; *nhit += hits, *err += stencils whose interval stack overflowed
 void ccdk_sepplane(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, const long long *hoff, const double *htime,
                    const double *hpos, double eps, unsigned char *hit, unsigned long long *nhit, unsigned long long *err);
+// penalty.cu: PenaltyGroup::addForce over device arrays (see the file header for the scratch layout)
+size_t ccdk_penalty_temp_bytes(long long nitems);
+int ccdk_penalty_group_force(cudaStream_t st, int V, const double *q, const double *v, long long nvf, const int *vf, const unsigned char *vf_isnew,
+                             long long nee, const int *ee, const unsigned char *ee_isnew, double dt, double outerEta, double innerEta, double stiffness,
+                             double CoR, double *F, unsigned char *fired, double *contrib, unsigned *keysA, unsigned *keysB, unsigned *itemsA,
+                             unsigned *itemsB, void *temp, size_t temp_bytes, double *group, unsigned long long *ctr);

@@ -44,6 +44,7 @@ struct Stitcher
     const double *hpos;
     long long it[4], end[4];
     double curtime;
+    double postime;      // History time of the positions the last next() produced
 
     __device__ void begin(const long long *ho, const double *ht, const double *hp, const int *verts)
     {
@@ -55,6 +56,7 @@ struct Stitcher
     {
         if (!(curtime <= 1.0))
             return false;
+        postime = curtime;
         double newtime = INFINITY;
         for (int i = 0; i < 4; i++)
         {
@@ -1064,12 +1066,17 @@ template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_history_ker
         Stitcher st;
         st.begin(A.hoff, A.htime, A.hpos, verts);
         if (st.next(a))
+        {
+            double ta = st.postime;
             while (st.next(b))
             {
                 stage = stencil_segment_full<IS_VF>(a, b, eta, toi);
-                if (stage) break;
+                // the primitives return the parameter inside the stitched segment: map it back to History time
+                if (stage) { toi = ta + toi * (st.postime - ta); break; }
                 for (int k = 0; k < 4; k++) a[k] = b[k];
+                ta = st.postime;
             }
+        }
         store_result(A, i, stage, toi);
     }
     reduce_block(stage != 0, toi, A.earliest_bits, A.nhit);

@@ -65,6 +65,8 @@ int ccd_broadphase_step(ccd_context *ctx, int kind, int V, int F, const int32_t 
  * reference has in hand when it returns true (it discards it; this ABI surfaces it) and the index of
  * the sub-test that fired (1 = VF/EE primitive, 2.. = vertex-edge, then vertex-vertex; 0 = miss).
  * vf_eta / ee_eta: per-stencil thickness (the `.second` of the reference's pairs).
+ * The time of impact is in History time: for a multi-entry History the primitive's parameter inside the stitched
+ * segment [ta, tb] that hit is mapped back as ta + t (tb - ta) (which is t itself for a single step, ta = 0, tb = 1).
  * Any of the *_toi / *_stage outputs may be NULL. */
 typedef struct
 {
@@ -197,6 +199,23 @@ int ccd_dist_vf_batch(ccd_context *ctx, int64_t n, const double *pts, double *ve
 int ccd_dist_ee_batch(ccd_context *ctx, int64_t n, const double *pts, double *vec, double *bary);
 int ccd_dist_plane_lt_batch(ccd_context *ctx, int64_t n, const double *pts, const double *eta, uint8_t *out);
 int ccd_dist_line_lt_batch(ccd_context *ctx, int64_t n, const double *pts, const double *eta, uint8_t *out);
+
+/* ---- PenaltyGroup::addForce (src/PenaltyGroup.cpp:34-52) with VertexFacePenaltyPotential::addForce and
+ * EdgeEdgePenaltyPotential::addForce (src/PenaltyPotential.cpp:7-64) per stencil: F += dt * (sum of the fired stencils'
+ * forces), every vertex's sum taken in the order of the lists (vertex-face stencils, then edge-edge stencils) as the
+ * reference's sequential loop does, so F is bit-identical to the CPU result.  q, v, F: 3 V doubles (F in/out).
+ * vf / ee: canonical stencils (4 ints each); *_isnew (may be NULL = all new): the stencils' `isnew` members;
+ * *_fired (may be NULL): whether the potential fired; *n_fired: their number; *newused: the reference's return value
+ * (a stencil that is new fired).  The _device form takes device pointers (d_fired: nvf + nee bytes, may be NULL) so that
+ * positions, velocities and forces can stay in HBM between the passes of a VelocityFilter-style loop. */
+int ccd_penalty_group_force(ccd_context *ctx, int V, const double *q, const double *v, int64_t nvf, const int32_t *vf,
+                            const uint8_t *vf_isnew, int64_t nee, const int32_t *ee, const uint8_t *ee_isnew, double dt,
+                            double outerEta, double innerEta, double stiffness, double CoR, double *F, uint8_t *vf_fired,
+                            uint8_t *ee_fired, int64_t *n_fired, int *newused);
+int ccd_penalty_group_force_device(ccd_context *ctx, int V, const double *d_q, const double *d_v, int64_t nvf,
+                                   const int32_t *d_vf, const uint8_t *d_vf_isnew, int64_t nee, const int32_t *d_ee,
+                                   const uint8_t *d_ee_isnew, double dt, double outerEta, double innerEta, double stiffness,
+                                   double CoR, double *d_F, uint8_t *d_fired, int64_t *n_fired, int *newused);
 
 /* Distance::meshSelfDistance (src/Distance.cpp:12-66); n_vf / n_ee (may be NULL) receive the stencil
  * counts the reference prints ("Checking N vertex-face and M edge-edge stencils"). */

@@ -253,9 +253,56 @@ class Ref(_Lib):
         return times[:n], pos[:n]
 
 
+def _penalty_args(q, v, vf, ee, F):
+    q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1)
+    v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1)
+    vf = np.ascontiguousarray(vf, dtype=np.int32).reshape(-1, 4)
+    ee = np.ascontiguousarray(ee, dtype=np.int32).reshape(-1, 4)
+    F = np.array(F, dtype=np.float64).reshape(-1)      # copy: in/out
+    return q, v, vf, ee, F
+
+
 class Port(_Lib):
     prefix = "orc"
     path = PORT_SO
+
+    def penalty_group_force(self, q, v, vf, ee, dt, outer_eta, inner_eta, stiffness, cor, F, vf_isnew=None, ee_isnew=None):
+        """PenaltyGroup::addForce restated (src/PenaltyGroup.cpp:34-52).  Returns (F, fired flags, newused)."""
+        q, v, vf, ee, F = _penalty_args(q, v, vf, ee, F)
+        fired = np.zeros(len(vf) + len(ee), dtype=np.uint8)
+        vn = None if vf_isnew is None else np.ascontiguousarray(vf_isnew, dtype=np.uint8)
+        en = None if ee_isnew is None else np.ascontiguousarray(ee_isnew, dtype=np.uint8)
+        nf = C.c_longlong()
+        r = self.f("penalty_group_force", C.c_int)(
+            C.c_int(q.size // 3), _d(q), _d(v), C.c_longlong(len(vf)), _i(vf), _b(vn), C.c_longlong(len(ee)), _i(ee), _b(en),
+            C.c_double(dt), C.c_double(outer_eta), C.c_double(inner_eta), C.c_double(stiffness), C.c_double(cor), _d(F), _b(fired), C.byref(nf))
+        return F, fired, bool(r)
+
+
+VF_SO = os.path.join(HERE, "_ref", "libccdvf.so")
+
+
+class RefVF(object):
+    """oracle/_ref/libccdvf.so: the reference's VelocityFilter / ActiveLayers / PenaltyGroup objects (oracle/ref_recorder.cpp)."""
+
+    def __init__(self):
+        if not os.path.exists(VF_SO):
+            raise FileNotFoundError(VF_SO + " not built (run `make -C oracle ref`)")
+        self.lib = C.CDLL(VF_SO)
+
+    def penalty_group_force(self, q, v, vf, ee, dt, outer_eta, inner_eta, stiffness, cor, F, rolled_back=False):
+        """The reference's own PenaltyGroup::addForce over the lists (all stencils new, or none after rollback())."""
+        q, v, vf, ee, F = _penalty_args(q, v, vf, ee, F)
+        fired = np.zeros(len(vf) + len(ee), dtype=np.uint8)
+        fn = self.lib.ref_penalty_group_force
+        fn.restype = C.c_int
+        r = fn(C.c_int(q.size // 3), _d(q), _d(v), C.c_longlong(len(vf)), _i(vf), C.c_longlong(len(ee)), _i(ee), C.c_int(int(rolled_back)),
+               C.c_double(dt), C.c_double(outer_eta), C.c_double(inner_eta), C.c_double(stiffness), C.c_double(cor), _d(F), _b(fired))
+        return F, fired, bool(r)
+
+
+def have_refvf():
+    return os.path.exists(VF_SO)
 
 
 def have_ref():

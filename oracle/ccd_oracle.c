@@ -758,6 +758,7 @@ typedef struct
     int verts[4];
     long long it[4];
     double curtime;
+    double postime; /* History time of the entry the last stitch_next produced */
 } stitcher;
 
 static void stitch_begin(stitcher *s, const long long *hoff, const double *htime, const double *hpos, const int *verts)
@@ -775,6 +776,7 @@ static int stitch_next(stitcher *s, double *pos12)
     int i;
     if (!(s->curtime <= 1.0))
         return 0;
+    s->postime = s->curtime;
     for (i = 0; i < 4; i++)
     {
         long long end = s->hoff[s->verts[i] + 1];
@@ -805,22 +807,26 @@ static int stitch_next(stitcher *s, double *pos12)
     return 1;
 }
 
-/* CTCDNarrowPhase::checkVFS, src/CTCDNarrowPhase.cpp:24-72 (TOI/stage kept, see ref_harness.cpp) */
+/* CTCDNarrowPhase::checkVFS, src/CTCDNarrowPhase.cpp:24-72 (TOI/stage kept, see ref_harness.cpp; the TOI is mapped from the
+ * stitched segment's own parameter back to History time: ta + t (tb - ta), which is t itself for a single step) */
 static int check_vfs(const long long *hoff, const double *htime, const double *hpos, const int *s, double eta,
                      double *toi, int *stage)
 {
     stitcher st;
     double a[12], b[12], p[24];
     int e, v, c;
+    double ta, tb;
     stitch_begin(&st, hoff, htime, hpos, s);
     if (!stitch_next(&st, a))
         return 0;
+    ta = st.postime;
     while (stitch_next(&st, b))
     {
         double t;
+        tb = st.postime;
         memcpy(p, a, sizeof(a));
         memcpy(p + 12, b, sizeof(b));
-        if (vertex_face(p, eta, &t)) { *toi = t; *stage = 1; return 1; }
+        if (vertex_face(p, eta, &t)) { *toi = ta + t * (tb - ta); *stage = 1; return 1; }
         for (e = 0; e < 3; e++)
         {
             int i1 = 1 + (e % 3), i2 = 1 + ((e + 1) % 3);
@@ -830,7 +836,7 @@ static int check_vfs(const long long *hoff, const double *htime, const double *h
                 q[c] = a[c]; q[3 + c] = a[3 * i1 + c]; q[6 + c] = a[3 * i2 + c];
                 q[9 + c] = b[c]; q[12 + c] = b[3 * i1 + c]; q[15 + c] = b[3 * i2 + c];
             }
-            if (vertex_edge(q, eta, &t)) { *toi = t; *stage = 2 + e; return 1; }
+            if (vertex_edge(q, eta, &t)) { *toi = ta + t * (tb - ta); *stage = 2 + e; return 1; }
         }
         for (v = 0; v < 3; v++)
         {
@@ -840,9 +846,10 @@ static int check_vfs(const long long *hoff, const double *htime, const double *h
                 q[c] = a[c]; q[3 + c] = a[3 * (1 + v) + c];
                 q[6 + c] = b[c]; q[9 + c] = b[3 * (1 + v) + c];
             }
-            if (vertex_vertex(q, eta, &t)) { *toi = t; *stage = 5 + v; return 1; }
+            if (vertex_vertex(q, eta, &t)) { *toi = ta + t * (tb - ta); *stage = 5 + v; return 1; }
         }
         memcpy(a, b, sizeof(a));
+        ta = tb;
     }
     return 0;
 }
@@ -856,15 +863,18 @@ static int check_ees(const long long *hoff, const double *htime, const double *h
     stitcher st;
     double a[12], b[12], p[24];
     int e, v, c;
+    double ta, tb;
     stitch_begin(&st, hoff, htime, hpos, s);
     if (!stitch_next(&st, a))
         return 0;
+    ta = st.postime;
     while (stitch_next(&st, b))
     {
         double t;
+        tb = st.postime;
         memcpy(p, a, sizeof(a));
         memcpy(p + 12, b, sizeof(b));
-        if (edge_edge(p, eta, &t)) { *toi = t; *stage = 1; return 1; }
+        if (edge_edge(p, eta, &t)) { *toi = ta + t * (tb - ta); *stage = 1; return 1; }
         for (e = 0; e < 4; e++)
         {
             double q[18];
@@ -873,7 +883,7 @@ static int check_ees(const long long *hoff, const double *htime, const double *h
                 q[c] = a[3 * ve[e][0] + c]; q[3 + c] = a[3 * ve[e][1] + c]; q[6 + c] = a[3 * ve[e][2] + c];
                 q[9 + c] = b[3 * ve[e][0] + c]; q[12 + c] = b[3 * ve[e][1] + c]; q[15 + c] = b[3 * ve[e][2] + c];
             }
-            if (vertex_edge(q, eta, &t)) { *toi = t; *stage = 2 + e; return 1; }
+            if (vertex_edge(q, eta, &t)) { *toi = ta + t * (tb - ta); *stage = 2 + e; return 1; }
         }
         for (v = 0; v < 4; v++)
         {
@@ -883,9 +893,10 @@ static int check_ees(const long long *hoff, const double *htime, const double *h
                 q[c] = a[3 * vv[v][0] + c]; q[3 + c] = a[3 * vv[v][1] + c];
                 q[6 + c] = b[3 * vv[v][0] + c]; q[9 + c] = b[3 * vv[v][1] + c];
             }
-            if (vertex_vertex(q, eta, &t)) { *toi = t; *stage = 6 + v; return 1; }
+            if (vertex_vertex(q, eta, &t)) { *toi = ta + t * (tb - ta); *stage = 6 + v; return 1; }
         }
         memcpy(a, b, sizeof(a));
+        ta = tb;
     }
     return 0;
 }
@@ -1298,6 +1309,61 @@ static v3 dist_ee(v3 p0, v3 p1, v3 q0, v3 q1, double *bp0, double *bp1, double *
     c2 = add(q0, scl(t, d2));
     *bp0 = 1.0 - s; *bp1 = s; *bq0 = 1.0 - t; *bq1 = t;
     return sub(c2, c1);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * PenaltyGroup::addForce (src/PenaltyGroup.cpp:34-52): the group's vertex-face stencils, then its edge-edge stencils,
+ * each through its potential (src/PenaltyPotential.cpp:7-64); F += groupforce * dt.  Sequential, like the reference.
+ * fired (may be NULL): nvf + nee flags.  Returns the reference's return value (a stencil that is new fired).
+ * ---------------------------------------------------------------------------------------- */
+int orc_penalty_group_force(int V, const double *q, const double *v, long long nvf, const int *vf, const unsigned char *vf_isnew,
+                            long long nee, const int *ee, const unsigned char *ee_isnew, double dt, double outerEta, double innerEta,
+                            double stiffness0, double CoR, double *F, unsigned char *fired, long long *n_fired)
+{
+    double *g = (double *)calloc(3 * (size_t)V + 1, sizeof(double));
+    long long i, nf = 0;
+    int newused = 0, k, c;
+    for (i = 0; i < nvf + nee; i++)
+    {
+        const int is_vf = i < nvf;
+        const int *s = is_vf ? vf + 4 * i : ee + 4 * (i - nvf);
+        v3 x[4], vel[4], cv, relvel, localF, t;
+        double w[4] = {0, 0, 0, 0}, dist, stiffness = stiffness0, sc;
+        if (fired) fired[i] = 0;
+        for (k = 0; k < 4; k++) { x[k] = ld(q + 3 * (size_t)s[k]); vel[k] = ld(v + 3 * (size_t)s[k]); }
+        if (!(is_vf ? plane_lt(x[0], x[1], x[2], x[3], outerEta) : line_lt(x[0], x[1], x[2], x[3], outerEta)))
+            continue;                                                            /* PenaltyPotential.cpp:14-15 / :44-45 */
+        if (is_vf) cv = dist_vf(x[0], x[1], x[2], x[3], &w[1], &w[2], &w[3]);
+        else cv = dist_ee(x[0], x[1], x[2], x[3], &w[0], &w[1], &w[2], &w[3]);
+        dist = sqrt(dot(cv, cv));
+        if (dist >= outerEta || dist < innerEta)
+            continue;                                                            /* :19-21 / :50-52 */
+        if (is_vf)                                                               /* :23 */
+            relvel = add(add(add(mk(-vel[0].x, -vel[0].y, -vel[0].z), scl(w[1], vel[1])), scl(w[2], vel[2])), scl(w[3], vel[3]));
+        else                                                                     /* :54 */
+            relvel = add(add(sub(scl(-w[0], vel[0]), scl(w[1], vel[1])), scl(w[2], vel[2])), scl(w[3], vel[3]));
+        if (dot(relvel, cv) > 0)
+            stiffness *= CoR;
+        sc = stiffness * (outerEta - dist) / (outerEta - innerEta);             /* :27 / :58 */
+        t = scl(sc, cv);
+        localF = mk(t.x / dist, t.y / dist, t.z / dist);
+        for (k = 0; k < 4; k++)
+        {
+            /* VF: F[p] -= localF, F[q_k] += bary_k localF;  EE: F[p_k] -= baryp_k localF, F[q_k] += baryq_k localF */
+            const int minus = is_vf ? k == 0 : k < 2;
+            const v3 f = (is_vf && k == 0) ? localF : scl(w[k], localF);
+            double *gv = g + 3 * (size_t)s[k];
+            const double fc[3] = {f.x, f.y, f.z};
+            for (c = 0; c < 3; c++) gv[c] = minus ? gv[c] - fc[c] : gv[c] + fc[c];
+        }
+        if (fired) fired[i] = 1;
+        nf++;
+        if (is_vf ? (vf_isnew ? vf_isnew[i] : 1) : (ee_isnew ? ee_isnew[i - nvf] : 1)) newused = 1;
+    }
+    for (i = 0; i < 3 * (long long)V; i++) F[i] = F[i] + g[i] * dt;              /* PenaltyGroup.cpp:50 */
+    free(g);
+    if (n_fired) *n_fired = nf;
+    return newused;
 }
 
 void orc_dist_vf_batch(long long n, const double *pts, double *vec, double *bary)

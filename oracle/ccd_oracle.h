@@ -47,6 +47,11 @@ void orc_dist_line_lt_batch(long long n, const double *pts, const double *eta, u
 double orc_mesh_self_distance(int V, const double *verts, int F, const int *faces,
                               const unsigned char *fixedMask, double *seconds);
 
+/* PenaltyGroup::addForce restated (src/PenaltyGroup.cpp:34-52, src/PenaltyPotential.cpp:7-64); F is in/out */
+int orc_penalty_group_force(int V, const double *q, const double *v, long long nvf, const int *vf, const unsigned char *vf_isnew,
+                            long long nee, const int *ee, const unsigned char *ee_isnew, double dt, double outerEta, double innerEta,
+                            double stiffness, double CoR, double *F, unsigned char *fired, long long *n_fired);
+
 /* Real roots in [0,1] of c[0] t^d + ... + c[d] (c[0] != 0, 3 <= d <= 6), ascending; returns count. */
 int orc_roots01(const double *c, int d, double *roots);
 

@@ -126,7 +126,7 @@ int ref_broadphase(int kind, int V, int F, const int *faces, const long long *ho
 
 // Per-stencil replay of CTCDNarrowPhase::checkVFS / checkEES (src/CTCDNarrowPhase.cpp:24-135)
 // through the PUBLIC CTCD:: statics so the time of impact the reference has in hand when it
-// returns true is kept.  `stage` = 0 miss, 1 VF/EE primitive, 2..4 / 2..5 VE, then VV.
+// returns true is kept (mapped from the stitched segment's parameter to History time).  `stage` = 0 miss, 1 VF/EE primitive, 2..4 / 2..5 VE, then VV.
 static bool replay_vf(const History &h, const int *s, double eta, double *toi, int *stage)
 {
     std::vector<int> verts(s, s + 4);
@@ -136,11 +136,11 @@ static bool replay_vf(const History &h, const int *s, double eta, double *toi, i
     {
         const std::vector<Vector3d> &a = sh[i].pos, &b = sh[i + 1].pos;
         double t;
-        if (CTCD::vertexFaceCTCD(a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3], eta, t)) { *toi = t; *stage = 1; return true; }
+        if (CTCD::vertexFaceCTCD(a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3], eta, t)) { *toi = sh[i].time + t * (sh[i + 1].time - sh[i].time); *stage = 1; return true; }
         for (int e = 0; e < 3; e++)
-            if (CTCD::vertexEdgeCTCD(a[0], a[1 + (e % 3)], a[1 + ((e + 1) % 3)], b[0], b[1 + (e % 3)], b[1 + ((e + 1) % 3)], eta, t)) { *toi = t; *stage = 2 + e; return true; }
+            if (CTCD::vertexEdgeCTCD(a[0], a[1 + (e % 3)], a[1 + ((e + 1) % 3)], b[0], b[1 + (e % 3)], b[1 + ((e + 1) % 3)], eta, t)) { *toi = sh[i].time + t * (sh[i + 1].time - sh[i].time); *stage = 2 + e; return true; }
         for (int v = 0; v < 3; v++)
-            if (CTCD::vertexVertexCTCD(a[0], a[1 + v], b[0], b[1 + v], eta, t)) { *toi = t; *stage = 5 + v; return true; }
+            if (CTCD::vertexVertexCTCD(a[0], a[1 + v], b[0], b[1 + v], eta, t)) { *toi = sh[i].time + t * (sh[i + 1].time - sh[i].time); *stage = 5 + v; return true; }
     }
     return false;
 }
@@ -156,11 +156,11 @@ static bool replay_ee(const History &h, const int *s, double eta, double *toi, i
     {
         const std::vector<Vector3d> &a = sh[i].pos, &b = sh[i + 1].pos;
         double t;
-        if (CTCD::edgeEdgeCTCD(a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3], eta, t)) { *toi = t; *stage = 1; return true; }
+        if (CTCD::edgeEdgeCTCD(a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3], eta, t)) { *toi = sh[i].time + t * (sh[i + 1].time - sh[i].time); *stage = 1; return true; }
         for (int e = 0; e < 4; e++)
-            if (CTCD::vertexEdgeCTCD(a[ve[e][0]], a[ve[e][1]], a[ve[e][2]], b[ve[e][0]], b[ve[e][1]], b[ve[e][2]], eta, t)) { *toi = t; *stage = 2 + e; return true; }
+            if (CTCD::vertexEdgeCTCD(a[ve[e][0]], a[ve[e][1]], a[ve[e][2]], b[ve[e][0]], b[ve[e][1]], b[ve[e][2]], eta, t)) { *toi = sh[i].time + t * (sh[i + 1].time - sh[i].time); *stage = 2 + e; return true; }
         for (int v = 0; v < 4; v++)
-            if (CTCD::vertexVertexCTCD(a[vv[v][0]], a[vv[v][1]], b[vv[v][0]], b[vv[v][1]], eta, t)) { *toi = t; *stage = 6 + v; return true; }
+            if (CTCD::vertexVertexCTCD(a[vv[v][0]], a[vv[v][1]], b[vv[v][0]], b[vv[v][1]], eta, t)) { *toi = sh[i].time + t * (sh[i + 1].time - sh[i].time); *stage = 6 + v; return true; }
     }
     return false;
 }

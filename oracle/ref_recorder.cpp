@@ -2,6 +2,8 @@
 // (src/VelocityFilter.cpp) until `npasses` detection passes of its ActiveLayers have been recorded, then read them back.
 #include "ref_recorder.h"
 #include "VelocityFilter.h"
+#include "PenaltyGroup.h"
+#include "PenaltyPotential.h"
 #include <cstring>
 #include <iostream>
 #include <sstream>
@@ -94,6 +96,31 @@ void vfrec_get(int p, long long *hoff, double *htime, double *hpos, int *np_vf, 
     CP(np_vf, P.np_vf); CP(np_ee, P.np_ee); CP(np_vf_eta, P.np_vf_eta); CP(np_ee_eta, P.np_ee_eta);
     CP(np_vf_hit, P.np_vf_hit); CP(np_ee_hit, P.np_ee_hit);
 #undef CP
+}
+
+// The reference's own PenaltyGroup (src/PenaltyGroup.cpp) over given stencil lists: addVFStencil / addEEStencil in list order,
+// optional rollback() (clears every stencil's isnew), then addForce(q, v, F).  fired: VertexFacePenaltyPotential::addForce /
+// EdgeEdgePenaltyPotential::addForce called once more per stencil on a scratch force vector (their return value).
+int ref_penalty_group_force(int V, const double *q, const double *v, long long nvf, const int *vf, long long nee, const int *ee, int rolled_back,
+                            double dt, double outerEta, double innerEta, double stiffness, double CoR, double *F, unsigned char *fired)
+{
+    VectorXd Q(3 * (long)V), Vv(3 * (long)V), Ff(3 * (long)V), scratch(3 * (long)V);
+    for (long i = 0; i < 3 * (long)V; i++) { Q[i] = q[i]; Vv[i] = v[i]; Ff[i] = F[i]; }
+    scratch.setZero();
+    PenaltyGroup g(dt, outerEta, innerEta, stiffness, CoR);
+    for (long long i = 0; i < nvf; i++) g.addVFStencil(VertexFaceStencil(vf[4 * i], vf[4 * i + 1], vf[4 * i + 2], vf[4 * i + 3]));
+    for (long long i = 0; i < nee; i++) g.addEEStencil(EdgeEdgeStencil(ee[4 * i], ee[4 * i + 1], ee[4 * i + 2], ee[4 * i + 3]));
+    if (rolled_back) g.rollback();
+    const bool newused = g.addForce(Q, Vv, Ff);
+    for (long i = 0; i < 3 * (long)V; i++) F[i] = Ff[i];
+    if (fired)
+    {
+        for (long long i = 0; i < nvf; i++)
+            fired[i] = VertexFacePenaltyPotential::addForce(Q, Vv, scratch, VertexFaceStencil(vf[4 * i], vf[4 * i + 1], vf[4 * i + 2], vf[4 * i + 3]), outerEta, innerEta, stiffness, CoR);
+        for (long long i = 0; i < nee; i++)
+            fired[nvf + i] = EdgeEdgePenaltyPotential::addForce(Q, Vv, scratch, EdgeEdgeStencil(ee[4 * i], ee[4 * i + 1], ee[4 * i + 2], ee[4 * i + 3]), outerEta, innerEta, stiffness, CoR);
+    }
+    return newused ? 1 : 0;
 }
 
 } // extern "C"
