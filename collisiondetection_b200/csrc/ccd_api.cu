@@ -56,6 +56,7 @@ struct ccd_context
     void *h_res[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t h_res_cap[4] = {0, 0, 0, 0};
     size_t candCap = 0, pairCap = 0, taskCapVf = 0, taskCapEe = 0;
+    long long veUniqueEe = 0, veUniqueVf = 0;      // unique vertex-edge tests of the last single-step narrowphase call
     // sharding: ownership ranges chosen by the caller (ccd_set_shard_partition), load profile of the last sharded step
     std::vector<int> partP;      // ownership bounds over the sorted (Morton) positions of a sharded step (ccd_set_shard_partition)
     DBuf qlist, hist, needed, neededPre, alistV, alistE, kstartV, kstartE, keysV, keysE;
@@ -621,24 +622,34 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         // the edge-edge run goes first: its general routine (a few hundred long single-lane walks) then runs on the side
         // stream beside the vertex-face run
         const bool single_step = d_q0 != nullptr;
+        // hash-set sizes of the vertex-edge de-duplication: 4 x the unique tests the previous call saw (the set then fits in
+        // L2: 2.1M unique tests of 19M edge-edge stencils at the 4M-triangle cloth), never more than the first-call size
+        unsigned slotsEe = ccdk_np_ve_slots(nee), slotsVf = ccdk_np_ve_slots(nvf);
+        if (c->veUniqueEe > 0) { const unsigned s2 = ccdk_np_ve_slots(4 * c->veUniqueEe); if (s2 < slotsEe) slotsEe = s2; }
+        if (c->veUniqueVf > 0) { const unsigned s2 = ccdk_np_ve_slots(4 * c->veUniqueVf); if (s2 < slotsVf) slotsVf = s2; }
         const size_t ve_off_vf = (12 * (size_t)ccdk_np_ve_slots(nee) + 48 * ((size_t)nee + 32) + 15) & ~(size_t)15;
         const bool share_ve = single_step && nee > 0 && nvf > 0 && !d_vf_eta && !d_ee_eta && eta_all_vf == eta_all_ee && !getenv("CCD_NO_VE_SHARE");
         cudaEventRecord(c->sev[ST_NP_EE], c->st);
         nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all_ee, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
                                P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE, P<int>(c->workEe),
                                P<int>(c->workTaskEe), P<int>(c->workSubEe), P<double>(c->tasksEe), P<int>(c->tlistEe), c->taskCapEe, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
-                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_EE, c->p1Ve.p, ccdk_np_ve_slots(nee), V, c->st2, c->evFork, c->evJoin, nullptr, 0, 0, nullptr);
+                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_EE, c->p1Ve.p, slotsEe, V, c->st2, c->evFork, c->evJoin, nullptr, 0, 0, nullptr);
         cudaEventRecord(c->sev[ST_NP_VF], c->st);
         nl += ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all_vf, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
                                P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF, P<int>(c->workVf),
                                P<int>(c->workTaskVf), P<int>(c->workSubVf), P<double>(c->tasksVf), P<int>(c->tlistVf), c->taskCapVf, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
-                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_VF, (char *)c->p1Ve.p + ve_off_vf, ccdk_np_ve_slots(nvf), V, nullptr, nullptr, nullptr,
-                               share_ve ? c->p1Ve.p : nullptr, share_ve ? ccdk_np_ve_slots(nee) : 0u, nee, share_ve ? P<double>(c->tasksEe) : nullptr);
+                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_VF, (char *)c->p1Ve.p + ve_off_vf, slotsVf, V, nullptr, nullptr, nullptr,
+                               share_ve ? c->p1Ve.p : nullptr, share_ve ? slotsEe : 0u, nee, share_ve ? P<double>(c->tasksEe) : nullptr);
         if (single_step && nee > 0 && !getenv("CCD_NP_TRACE")) CK(cudaStreamWaitEvent(c->st, c->evJoin, 0));
         cudaEventRecord(c->sev[CCD_N_STAGES], c->st);
         CK(cudaGetLastError());
         CKR(sync_counters(c));
         const bool single = d_q0 != nullptr;
+        if (single)
+        {
+            c->veUniqueEe = nee > 0 ? (long long)c->h_counters[C_NP_EE + CCD_NP_KVEU] : 0;
+            c->veUniqueVf = nvf > 0 ? (long long)c->h_counters[C_NP_VF + CCD_NP_KVEU] : 0;
+        }
         const unsigned long long tv = single ? c->h_counters[C_NTASK_VF] : 0, te = single ? c->h_counters[C_NTASK_EE] : 0;
         if (tv + 5 <= c->taskCapVf && te + 5 <= c->taskCapEe)
             break;

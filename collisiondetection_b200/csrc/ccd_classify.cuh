@@ -46,16 +46,28 @@ template <int RD> CCD_FN bool no_root_static(const double *c)
 // lies in their convex hull, so the polynomial has that sign on the whole closed eighth).  If the masks of a
 // primitive's polynomials have no common bit, no time satisfies all of them, whatever the exact roots are: the
 // interval lists the reference would build cannot overlap, and the primitive misses without any root being isolated.
-template <int RD, int LEVEL> CCD_FN unsigned dyadic_sub(const double (&b)[RD + 1], bool pos)
+// want: the eighths (bits of this subtree, lowest first) the caller will look at — the others are reported as 0 without
+// being examined (the masks are only ever AND-ed into the running occupancy, so a stencil whose earlier polynomials
+// already ruled most of [0,1] out pays for the few eighths that are left)
+template <int RD, int LEVEL> CCD_FN unsigned dyadic_sub(const double (&b)[RD + 1], bool pos, unsigned want = 0xffu)
 {
-    bool possible = false;
+    if (!(want & ((1u << (1 << LEVEL)) - 1u)))
+        return 0u;
+    bool possible = false, everywhere = true;
 #pragma unroll
     for (int i = 0; i <= RD; i++)
-        possible = possible || (pos ? (b[i] >= -1e-12) : (b[i] <= 1e-12));
+    {
+        const bool ok = pos ? (b[i] >= -1e-12) : (b[i] <= 1e-12);
+        possible = possible || ok;
+        everywhere = everywhere && ok;
+    }
     if (!possible)
         return 0u;
-    if (LEVEL == 0)
-        return 1u;
+    // every coefficient within the margin: so is every coefficient of every sub-interval (de Casteljau halving takes
+    // 0.5 * (a + b) of neighbours, and rounding is monotone: a, b >= t gives fl(a + b) >= 2 t exactly), i.e. every eighth
+    // below this node would report "possible" — no need to split any further
+    if (LEVEL == 0 || everywhere)
+        return (1u << (1 << LEVEL)) - 1u;
     double l[RD + 1], r[RD + 1], t[RD + 1];
 #pragma unroll
     for (int i = 0; i <= RD; i++)
@@ -69,12 +81,12 @@ template <int RD, int LEVEL> CCD_FN unsigned dyadic_sub(const double (&b)[RD + 1
         for (int i = 0; i < RD - k; i++)
             t[i] = 0.5 * (t[i] + t[i + 1]);
     }
-    const unsigned ml = dyadic_sub<RD, (LEVEL > 0 ? LEVEL - 1 : 0)>(l, pos);
-    const unsigned mr = dyadic_sub<RD, (LEVEL > 0 ? LEVEL - 1 : 0)>(r, pos);
+    const unsigned ml = dyadic_sub<RD, (LEVEL > 0 ? LEVEL - 1 : 0)>(l, pos, want);
+    const unsigned mr = dyadic_sub<RD, (LEVEL > 0 ? LEVEL - 1 : 0)>(r, pos, want >> (1 << (LEVEL > 0 ? LEVEL - 1 : 0)));
     return ml | (mr << (1 << (LEVEL > 0 ? LEVEL - 1 : 0)));
 }
 
-template <int RD> CCD_FN unsigned dyadic_mask(const double *c, bool pos)
+template <int RD> CCD_FN unsigned dyadic_mask(const double *c, bool pos, unsigned want = 0xffu)
 {
     double b[RD + 1];
 #pragma unroll
@@ -85,16 +97,16 @@ template <int RD> CCD_FN unsigned dyadic_mask(const double *c, bool pos)
 #pragma unroll
         for (int i = RD; i >= k; i--)
             b[i] = b[i] + b[i - 1];
-    return dyadic_sub<RD, 3>(b, pos);
+    return dyadic_sub<RD, 3>(b, pos, want);
 }
 
 // mask for the normalised polynomial op[0..N] of reduced degree rd >= 3
-template <int N> CCD_FN unsigned dyadic_mask_reduced(const double (&op)[N + 1], int rd, bool pos)
+template <int N> CCD_FN unsigned dyadic_mask_reduced(const double (&op)[N + 1], int rd, bool pos, unsigned want = 0xffu)
 {
-    if (N >= 6 && rd == 6) return dyadic_mask<(N >= 6 ? 6 : 3)>(&op[N >= 6 ? N - 6 : 0], pos);
-    if (N >= 5 && rd == 5) return dyadic_mask<(N >= 5 ? 5 : 3)>(&op[N >= 5 ? N - 5 : 0], pos);
-    if (N >= 4 && rd == 4) return dyadic_mask<(N >= 4 ? 4 : 3)>(&op[N >= 4 ? N - 4 : 0], pos);
-    return dyadic_mask<3>(&op[N - 3], pos);
+    if (N >= 6 && rd == 6) return dyadic_mask<(N >= 6 ? 6 : 3)>(&op[N >= 6 ? N - 6 : 0], pos, want);
+    if (N >= 5 && rd == 5) return dyadic_mask<(N >= 5 ? 5 : 3)>(&op[N >= 5 ? N - 5 : 0], pos, want);
+    if (N >= 4 && rd == 4) return dyadic_mask<(N >= 4 ? 4 : 3)>(&op[N >= 4 ? N - 4 : 0], pos, want);
+    return dyadic_mask<3>(&op[N - 3], pos, want);
 }
 
 // would CTCD::checkInterval(t1,t2) push an interval?  Unfused Horner over op[0..N] (exactly-zero leading coefficients

@@ -13,6 +13,7 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
                      const void *prev_ve_scratch, unsigned prev_ve_slots, long long prev_n, const double *prev_tasks);
 unsigned ccdk_np_ve_slots(long long n);
 #define CCD_NP_COUNTERS 40      // counters per narrowphase run (narrowphase.cu: K_*)
+#define CCD_NP_KVEU 32          // unique vertex-edge tests of the run
 // {x0,y0,z0,-,x1,y1,z1,-} per vertex (8 doubles) for the single-step narrowphase kernels
 void ccdk_pack_positions(cudaStream_t st, int V, const double *q0, const double *q1, int vstride, double *qpack, float *vbox);
 void ccdk_prim_batch(cudaStream_t st, int kind, long long n, const double *pts, const double *eta, unsigned char *hit, double *t);

@@ -118,7 +118,7 @@ CCD_FN bool stage_item(const V3 *a, const V3 *v, double eta, unsigned state_in, 
     if (r == PC_PENDING)
     {
         need |= 1u << K;
-        occ &= dyadic_mask_reduced<N>(op, rd, POS);
+        occ &= dyadic_mask_reduced<N>(op, rd, POS, occ);
         if (!occ) return false;
         if (WANT_REC) { pending_record<N>(op, rd, make_tag(K, POS, rd), rec); has_rec = true; }
     }
@@ -513,7 +513,7 @@ CCD_FN int ve_item(V3 q0s, V3 q1s, V3 q2s, V3 v0, V3 v1, V3 v2, double eta, doub
     if (r == PC_EMPTY) return SC_MISS;
     if (r == PC_PENDING)
     {
-        occ &= dyadic_mask_reduced<4>(op, rd, false);
+        occ &= dyadic_mask_reduced<4>(op, rd, false, occ);
         if (!occ) return SC_MISS;
         double rec[8];
         pending_record<4>(op, rd, make_tag(2, false, rd), rec);

@@ -248,7 +248,7 @@ __device__ __forceinline__ void store_result(const NpArgs &A, long long i, int s
 enum
 {
     K_NWORK = 0, K_NTASK = 1, K_NDEG = 2 /* 4 */, K_NQ = 6 /* prim, ve, vv */, K_NGEN = 9, K_NSQ = 10 /* after stage 0..3 */,
-    K_NXQ = 14 /* polynomial 0..4 */, K_CURSOR = 19 /* degree 3..6 */, K_NDEG2 = 23 /* second solve round */, K_CURSOR2 = 27, K_NVE2 = 31 /* unique vertex-edge tests that need records */, K_NVEU = 32 /* unique vertex-edge tests */, K_COUNT = 33
+    K_NXQ = 14 /* polynomial 0..4 */, K_CURSOR = 19 /* degree 3..6 */, K_NDEG2 = 23 /* second solve round */, K_CURSOR2 = 27, K_NVE2 = 31 /* unique vertex-edge tests that need records */, K_NVEU = CCD_NP_KVEU /* unique vertex-edge tests */, K_COUNT = 33
 };
 
 struct P1Args
