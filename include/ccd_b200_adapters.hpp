@@ -1,10 +1,13 @@
 // C++ drop-in adapters over the C ABI (include/ccd_b200.h) for evouga/collisiondetection.
 //
 // Compile this header inside the reference tree (it includes the reference's own headers) and swap one type name
-// at the three call sites of the hot path:
+// at the call sites of the hot path (or change no source line at all and link examples/dropin_link.cpp in place of the
+// reference's detection objects):
 //
 //   src/ActiveLayers.cpp:26     bp_ = new KDOPBroadPhase();             ->  new ccdgpu::KDOPBroadPhase();
-//   src/ActiveLayers.cpp:28     np_ = new SeparatingPlaneNarrowPhase(); ->  new ccdgpu::CTCDNarrowPhase();   (same interface)
+//   src/ActiveLayers.cpp:28     np_ = new SeparatingPlaneNarrowPhase(); ->  new ccdgpu::SeparatingPlaneNarrowPhase();
+//                               (ccdgpu::CTCDNarrowPhase has the same interface but is the OTHER algorithm: swapping it in changes
+//                               the hit set of the VelocityFilter path, e.g. 2210 instead of 2212 edge-edge hits on prob11)
 //   src/Distance.cpp:43         AABBBroadPhase bp;                      ->  ccdgpu::AABBBroadPhase bp;
 //   example/AlecTest.cpp:97,111 KDOPBroadPhase() / CTCDNarrowPhase()    ->  ccdgpu::...
 //
@@ -33,18 +36,20 @@
 namespace ccdgpu {
 
 // One context per process, created on first use (device from CCD_B200_DEVICE, default 0).
+inline ccd_context *create_context()
+{
+    ccd_context *ctx = 0;
+    int dev = 0;
+    if (const char *e = getenv("CCD_B200_DEVICE"))
+        dev = atoi(e);
+    int rc = ccd_create(&ctx, dev);
+    if (rc != CCD_OK)
+        throw std::runtime_error("ccd_create failed (" + std::to_string(rc) + "): a CUDA device is required, there is no CPU fallback");
+    return ctx;
+}
 inline ccd_context *context()
 {
-    static ccd_context *ctx = 0;
-    if (!ctx)
-    {
-        int dev = 0;
-        if (const char *e = getenv("CCD_B200_DEVICE"))
-            dev = atoi(e);
-        int rc = ccd_create(&ctx, dev);
-        if (rc != CCD_OK)
-            throw std::runtime_error("ccd_create failed (" + std::to_string(rc) + "): a CUDA device is required, there is no CPU fallback");
-    }
+    static ccd_context *ctx = create_context();      // initialised once, thread-safe (C++11 function-local static)
     return ctx;
 }
 

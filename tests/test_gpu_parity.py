@@ -454,9 +454,9 @@ def test_cloth_full_size_against_golden(ctx, port):
 
 def _write_obj(path, q, f):
     with open(path, "w") as fh:
-        for p in q:
+        for p in np.asarray(q).reshape(-1, 3):
             fh.write("v %.17g %.17g %.17g\n" % tuple(p))
-        for t in f:
+        for t in np.asarray(f).reshape(-1, 3):
             fh.write("f %d %d %d\n" % (t[0] + 1, t[1] + 1, t[2] + 1))
 
 
@@ -482,3 +482,56 @@ def test_cpp_adapters_alec_flow(tmp_path):
     assert "  2212 ee collisions" in txt          # reference (rpoly): 2210; the two extra are arbitrated in test_oracle_golden
     assert "vertexFaceCTCD 1 0.66666517599038733" in txt
     assert "meshSelfDistance 1.5796406595086589e-07" in txt
+
+
+def _run_lines(exe, args, cwd, seconds):
+    import subprocess
+    try:
+        p = subprocess.run([exe] + args, cwd=cwd, capture_output=True, text=True, timeout=seconds)
+        assert p.returncode in (0, 255), p.stderr[-2000:]      # testNewSequence returns -1 from main on a failed filter
+        return p.stdout.splitlines()
+    except subprocess.TimeoutExpired as e:
+        out = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+        return out[:out.rfind("\n") + 1].splitlines()
+
+
+@pytest.mark.parametrize("driver", ["AlecTest", "testVelocityFilter", "testNewSequence"])
+def test_reference_drivers_with_gpu_detection(tmp_path, driver):
+    """The reference's UNMODIFIED example drivers — main(), VelocityFilter, ActiveLayers, PenaltyGroup all its own object code —
+    linked against the GPU library in place of its detection classes (examples/dropin_link.cpp, oracle/Makefile) print what the
+    all-CPU build printed (tests/golden/drivers.npz): candidate and collision counts of every detection pass, History sizes,
+    layer depths, self distances.  testVelocityFilter on mesh1 -> mesh2 never finishes: a prefix of its log is
+    compared.  Skipped when the binaries were never built (no /root/reference at build time)."""
+    import os
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "oracle", "_ref", driver + "_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/%s_gpu not built" % driver)
+    g = golden("drivers.npz")
+    d = str(tmp_path)
+    if driver == "AlecTest":
+        _write_obj(os.path.join(d, "V0.obj"), g["alec_q0"], g["alec_f"])
+        _write_obj(os.path.join(d, "V1.obj"), g["alec_q1"], g["alec_f"])
+        want = str(g["alec_stdout"]).splitlines()
+        got = _run_lines(exe, ["V0.obj", "V1.obj"], d, 300)
+        # the one known difference: CTCDNarrowPhase over rpoly reports 2210 edge-edge hits on prob11, the new root isolator
+        # 2212 — the two extra stencils are arbitrated as reference artefacts in tests/test_parity_account.py
+        assert "  2210 ee collisions" in want
+        want[want.index("  2210 ee collisions")] = "  2212 ee collisions"
+        assert got == want
+        return
+    if driver == "testVelocityFilter":
+        _write_obj(os.path.join(d, "mesh1.obj"), g["vf_q1"], g["vf_f"])
+        _write_obj(os.path.join(d, "mesh2.obj"), g["vf_q2"], g["vf_f"])
+        want = str(g["vf_stdout"]).splitlines()
+        got = _run_lines(exe, ["mesh1.obj", "mesh2.obj", "0"], d, 40)
+        n = min(len(got), len(want))
+        assert n >= 13, got                      # at least two detection passes inside the time limit
+        assert got[:n] == want[:n]
+        return
+    _write_obj(os.path.join(d, "coarse.obj"), g["seq_coarse_q"], g["seq_coarse_f"])
+    for k in range(int(g["seq_nframes"])):
+        _write_obj(os.path.join(d, "fine_%d.obj" % k), g["seq_fine_q%d" % k], g["seq_fine_f"])
+    want = str(g["seq_stdout"]).splitlines()
+    got = _run_lines(exe, ["1e-3", "1e-4", "coarse.obj", "fine_"], d, 600)
+    assert got == want
