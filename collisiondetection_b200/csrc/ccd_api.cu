@@ -47,7 +47,7 @@ struct ccd_context
     // emission
     DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut;
     // narrowphase
-    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, p1Ve, qpack, selTmp, selA, selB, selC, selD, selCount;
+    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, p1Ve, qpack, histCntVf, histCntEe, histOffVf, histOffEe, histQ0, histQ1, histVst, histEta, histTime, histHit, histStage, histToi, selTmp, selA, selB, selC, selD, selCount;
     // penalty forces (penalty.cu)
     DBuf penF, penGroup, penContrib, penKeysA, penKeysB, penItemsA, penItemsB, penFired, penNewVf, penNewEe, penCtr;
     // pinned host scratch
@@ -254,7 +254,7 @@ void ccd_destroy(ccd_context *c)
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1Ve, &c->qpack, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->sbox, &c->sfaces, &c->unsure, &c->frontA, &c->frontB, &c->bigV, &c->bigE,
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1Ve, &c->qpack, &c->histCntVf, &c->histCntEe, &c->histOffVf, &c->histOffEe, &c->histQ0, &c->histQ1, &c->histVst, &c->histEta, &c->histTime, &c->histHit, &c->histStage, &c->histToi, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->sbox, &c->sfaces, &c->unsure, &c->frontA, &c->frontB, &c->bigV, &c->bigE,
                    &c->penF, &c->penGroup, &c->penContrib, &c->penKeysA, &c->penKeysB, &c->penItemsA, &c->penItemsB, &c->penFired, &c->penNewVf, &c->penNewEe, &c->penCtr};
     for (DBuf *b : all)
         if (b->p)
@@ -674,6 +674,104 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
     return CCD_OK;
 }
 
+// Narrowphase over a multi-entry History (narrowphase.cu, "multi-entry History, staged"): every (stencil, stitched segment)
+// pair becomes a virtual single-step stencil on four virtual vertices, the single-step pipeline runs on all of them, and
+// each stencil takes its first hitting segment.  CCD_HISTORY_ONE_THREAD=1 keeps the one-thread-per-stencil kernel
+// (diagnostics: both give the same bits).
+static int narrowphase_history_device(ccd_context *c, int V, long long nvf, const int *d_vf, const double *d_vf_eta, long long nee, const int *d_ee,
+                                      const double *d_ee_eta, double eta_all_vf, double eta_all_ee, const long long *d_hoff, const double *d_htime,
+                                      const double *d_hpos, ccd_np_summary *sum)
+{
+    if (getenv("CCD_HISTORY_ONE_THREAD") || nvf + nee == 0)
+        return narrowphase_device(c, V, nvf, d_vf, d_vf_eta, nee, d_ee, d_ee_eta, eta_all_vf, eta_all_ee, nullptr, nullptr, 0, d_hoff, d_htime, d_hpos, sum);
+    unsigned long long *ctr = P<unsigned long long>(c->counters);
+    const long long nmax = nvf > nee ? nvf : nee;
+    CKR(ensure(c, c->histCntVf, sizeof(int) * ((size_t)nvf + 2)));
+    CKR(ensure(c, c->histCntEe, sizeof(int) * ((size_t)nee + 2)));
+    CKR(ensure(c, c->histOffVf, sizeof(long long) * ((size_t)nvf + 2)));
+    CKR(ensure(c, c->histOffEe, sizeof(long long) * ((size_t)nee + 2)));
+    CKR(ensure(c, c->temp, ccdk_sort_temp_bytes((int)(nmax + 2))));
+    CK(cudaMemsetAsync(P<int>(c->histCntVf) + nvf, 0, sizeof(int), c->st));
+    CK(cudaMemsetAsync(P<int>(c->histCntEe) + nee, 0, sizeof(int), c->st));
+    ccdk_hist_count(c->st, nvf, d_vf, d_hoff, d_htime, d_hpos, P<int>(c->histCntVf));
+    ccdk_hist_count(c->st, nee, d_ee, d_hoff, d_htime, d_hpos, P<int>(c->histCntEe));
+    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, (int)nvf + 1, P<int>(c->histCntVf), P<long long>(c->histOffVf));
+    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, (int)nee + 1, P<int>(c->histCntEe), P<long long>(c->histOffEe));
+    long long ns[2] = {0, 0};
+    CK(cudaMemcpyAsync(&ns[0], P<long long>(c->histOffVf) + nvf, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(&ns[1], P<long long>(c->histOffEe) + nee, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const long long nsVf = ns[0], nsEe = ns[1], nsAll = nsVf + nsEe;
+    if (4 * nsAll >= (1ll << 31) - 8)
+    {
+        c->err = "narrowphase: more than 2^29 stitched segments in one call; split the stencil list";
+        return CCD_ERR_NOMEM;
+    }
+    c->launches += 4 + 4;
+    CKR(ensure(c, c->histQ0, sizeof(double) * 12 * ((size_t)nsAll + 1)));
+    CKR(ensure(c, c->histQ1, sizeof(double) * 12 * ((size_t)nsAll + 1)));
+    CKR(ensure(c, c->histVst, sizeof(int) * 4 * ((size_t)nsAll + 1)));
+    CKR(ensure(c, c->histEta, sizeof(double) * ((size_t)nsAll + 1)));
+    CKR(ensure(c, c->histTime, sizeof(double) * 2 * ((size_t)nsAll + 1)));
+    int *vstVf = P<int>(c->histVst), *vstEe = vstVf + 4 * nsVf;
+    double *etaVf = P<double>(c->histEta), *etaEe = etaVf + nsVf;
+    double *timeVf = P<double>(c->histTime), *timeEe = timeVf + 2 * nsVf;
+    ccdk_hist_fill(c->st, nvf, d_vf, d_vf_eta, eta_all_vf, d_hoff, d_htime, d_hpos, P<long long>(c->histOffVf), 0, P<double>(c->histQ0), P<double>(c->histQ1),
+                   vstVf, etaVf, timeVf);
+    ccdk_hist_fill(c->st, nee, d_ee, d_ee_eta, eta_all_ee, d_hoff, d_htime, d_hpos, P<long long>(c->histOffEe), nsVf, P<double>(c->histQ0), P<double>(c->histQ1),
+                   vstEe, etaEe, timeEe);
+    // the result buffers are shared with the virtual run: size them for both before anything is written
+    CKR(ensure(c, c->vfHit, (size_t)(nvf > nsVf ? nvf : nsVf) + 16));
+    CKR(ensure(c, c->eeHit, (size_t)(nee > nsEe ? nee : nsEe) + 16));
+    CKR(ensure(c, c->vfStage, (size_t)(nvf > nsVf ? nvf : nsVf) + 16));
+    CKR(ensure(c, c->eeStage, (size_t)(nee > nsEe ? nee : nsEe) + 16));
+    CKR(ensure(c, c->vfToi, sizeof(double) * ((size_t)(nvf > nsVf ? nvf : nsVf) + 2)));
+    CKR(ensure(c, c->eeToi, sizeof(double) * ((size_t)(nee > nsEe ? nee : nsEe) + 2)));
+    CKR(ensure(c, c->histHit, (size_t)(nvf + nee) + 16));
+    CKR(ensure(c, c->histStage, (size_t)(nvf + nee) + 16));
+    CKR(ensure(c, c->histToi, sizeof(double) * ((size_t)(nvf + nee) + 2)));
+    const int launches_before = c->launches;
+    ccd_np_summary virt;
+    CKR(narrowphase_device(c, (int)(4 * nsAll), nsVf, vstVf, etaVf, nsEe, vstEe, etaEe, 0.0, 0.0, P<double>(c->histQ0), P<double>(c->histQ1), 3, nullptr, nullptr,
+                           nullptr, &virt));
+    (void)launches_before;
+    // per stencil: the first hitting segment; the counters of the virtual run are replaced by the stencils' own
+    unsigned long long init[4] = {0xFFFFFFFFFFFFFFFFull, 0ull, 0xFFFFFFFFFFFFFFFFull, 0ull};
+    memcpy(c->h_counters + 8, init, sizeof(init));
+    CK(cudaMemcpyAsync(ctr + C_EARLY_VF, c->h_counters + 8, sizeof(init), cudaMemcpyHostToDevice, c->st));
+    unsigned char *hHit = P<unsigned char>(c->histHit), *hStage = P<unsigned char>(c->histStage);
+    double *hToi = P<double>(c->histToi);
+    ccdk_hist_reduce(c->st, nvf, P<long long>(c->histOffVf), P<unsigned char>(c->vfHit), P<double>(c->vfToi), P<unsigned char>(c->vfStage), timeVf, hHit, hToi,
+                     hStage, ctr + C_EARLY_VF, ctr + C_NHIT_VF);
+    ccdk_hist_reduce(c->st, nee, P<long long>(c->histOffEe), P<unsigned char>(c->eeHit), P<double>(c->eeToi), P<unsigned char>(c->eeStage), timeEe, hHit + nvf,
+                     hToi + nvf, hStage + nvf, ctr + C_EARLY_EE, ctr + C_NHIT_EE);
+    c->launches += 2;
+    if (nvf > 0)
+    {
+        CK(cudaMemcpyAsync(c->vfHit.p, hHit, (size_t)nvf, cudaMemcpyDeviceToDevice, c->st));
+        CK(cudaMemcpyAsync(c->vfStage.p, hStage, (size_t)nvf, cudaMemcpyDeviceToDevice, c->st));
+        CK(cudaMemcpyAsync(c->vfToi.p, hToi, sizeof(double) * (size_t)nvf, cudaMemcpyDeviceToDevice, c->st));
+    }
+    if (nee > 0)
+    {
+        CK(cudaMemcpyAsync(c->eeHit.p, hHit + nvf, (size_t)nee, cudaMemcpyDeviceToDevice, c->st));
+        CK(cudaMemcpyAsync(c->eeStage.p, hStage + nvf, (size_t)nee, cudaMemcpyDeviceToDevice, c->st));
+        CK(cudaMemcpyAsync(c->eeToi.p, hToi + nvf, sizeof(double) * (size_t)nee, cudaMemcpyDeviceToDevice, c->st));
+    }
+    cudaEventRecord(c->sev[CCD_N_STAGES], c->st);
+    CKR(sync_counters(c));
+    if (sum)
+    {
+        sum->n_vf_hits = (int64_t)c->h_counters[C_NHIT_VF];
+        sum->n_ee_hits = (int64_t)c->h_counters[C_NHIT_EE];
+        unsigned long long b = c->h_counters[C_EARLY_VF] < c->h_counters[C_EARLY_EE] ? c->h_counters[C_EARLY_VF] : c->h_counters[C_EARLY_EE];
+        double t;
+        memcpy(&t, &b, sizeof(t));
+        sum->earliest_toi = (b == 0xFFFFFFFFFFFFFFFFull) ? INFINITY : t;
+    }
+    return CCD_OK;
+}
+
 static int download_stencils(ccd_context *c, const DBuf &src, long long n, int32_t **out)
 {
     int32_t *h = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)(n > 0 ? n : 1));
@@ -780,10 +878,14 @@ int ccd_narrowphase(ccd_context *c, int V, const int64_t *hoff, const double *ht
     ccd_np_summary s;
     // two entries per vertex = one linear segment: read q0/q1 straight out of hpos (stride 6)
     const bool single = history_is_single_step(V, hoff);
-    CKR(narrowphase_device(c, V, nvf, P<int>(c->vf_in), uvf ? nullptr : P<double>(c->vf_eta), nee, P<int>(c->ee_in), uee ? nullptr : P<double>(c->ee_eta),
-                           uvf ? vf_eta[0] : 0.0, uee ? ee_eta[0] : 0.0,
-                           single ? P<double>(c->hpos) : nullptr, single ? P<double>(c->hpos) + 3 : nullptr, 6, P<long long>(c->hoff),
-                           P<double>(c->htime), P<double>(c->hpos), &s));
+    if (single)
+        CKR(narrowphase_device(c, V, nvf, P<int>(c->vf_in), uvf ? nullptr : P<double>(c->vf_eta), nee, P<int>(c->ee_in), uee ? nullptr : P<double>(c->ee_eta),
+                               uvf ? vf_eta[0] : 0.0, uee ? ee_eta[0] : 0.0, P<double>(c->hpos), P<double>(c->hpos) + 3, 6, P<long long>(c->hoff),
+                               P<double>(c->htime), P<double>(c->hpos), &s));
+    else
+        CKR(narrowphase_history_device(c, V, nvf, P<int>(c->vf_in), uvf ? nullptr : P<double>(c->vf_eta), nee, P<int>(c->ee_in),
+                                       uee ? nullptr : P<double>(c->ee_eta), uvf ? vf_eta[0] : 0.0, uee ? ee_eta[0] : 0.0, P<long long>(c->hoff),
+                                       P<double>(c->htime), P<double>(c->hpos), &s));
     if (nvf > 0)
     {
         CK(cudaMemcpyAsync(vf_hit, c->vfHit.p, (size_t)nvf, cudaMemcpyDeviceToHost, c->st));

@@ -1082,6 +1082,81 @@ template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_history_ker
     reduce_block(stage != 0, toi, A.earliest_bits, A.nhit);
 }
 
+// ---- multi-entry History, staged --------------------------------------------------------------------------------------
+// Every stitched linear segment of a stencil (src/History.cpp:98-140) is an independent single-step test, and the stencil's
+// answer is the first segment (in time) that hits.  So instead of one thread walking all segments of its stencil with the
+// whole algorithm inlined (stencil_history_kernel: the one-thread-per-stencil shape the single-step path left behind at
+// 5.7 of 32 lanes), the (stencil, segment) pairs are EXPANDED into virtual single-step stencils — four virtual vertices
+// each, holding the stitched start and end positions — the dense single-step pipeline above runs on all of them at once,
+// and hist_reduce_kernel takes, per stencil, its first hitting segment and maps the time of impact back to History time.
+//   pass COUNT: segments per stencil;  pass fill (after the scan): positions, virtual stencils, thickness, segment times
+template <bool COUNT>
+__global__ void __launch_bounds__(128) hist_expand_kernel(long long n, const int *__restrict__ stencils, const double *__restrict__ eta_arr, double eta_all,
+                                                          const long long *__restrict__ hoff, const double *__restrict__ htime, const double *__restrict__ hpos,
+                                                          int *__restrict__ seg_count, const long long *__restrict__ seg_off, long long vbase,
+                                                          double *__restrict__ q0v, double *__restrict__ q1v, int *__restrict__ vst, double *__restrict__ veta,
+                                                          double *__restrict__ vtime)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 s = reinterpret_cast<const int4 *>(stencils)[i];
+    const int verts[4] = {s.x, s.y, s.z, s.w};
+    V3 a[4], b[4];
+    Stitcher st;
+    st.begin(hoff, htime, hpos, verts);
+    int k = 0;
+    if (st.next(a))
+    {
+        double ta = st.postime;
+        while (st.next(b))
+        {
+            if (!COUNT)
+            {
+                const long long sl = seg_off[i] + k, sg = vbase + sl;      // index inside this type's run / among all virtual stencils
+                for (int j = 0; j < 4; j++)
+                {
+                    double *o0 = q0v + 3 * (4 * sg + j), *o1 = q1v + 3 * (4 * sg + j);
+                    o0[0] = a[j].x; o0[1] = a[j].y; o0[2] = a[j].z;
+                    o1[0] = b[j].x; o1[1] = b[j].y; o1[2] = b[j].z;
+                    vst[4 * sl + j] = (int)(4 * sg + j);
+                }
+                veta[sl] = eta_arr ? eta_arr[i] : eta_all;
+                vtime[2 * sl] = ta;
+                vtime[2 * sl + 1] = st.postime;
+            }
+            k++;
+            for (int j = 0; j < 4; j++) a[j] = b[j];
+            ta = st.postime;
+        }
+    }
+    if (COUNT) seg_count[i] = k;
+}
+
+__global__ void __launch_bounds__(128) hist_reduce_kernel(long long n, const long long *__restrict__ seg_off, const unsigned char *__restrict__ hitv,
+                                                          const double *__restrict__ toiv, const unsigned char *__restrict__ stagev,
+                                                          const double *__restrict__ vtime, unsigned char *__restrict__ hit, double *__restrict__ toi,
+                                                          unsigned char *__restrict__ stage, unsigned long long *earliest_bits, unsigned long long *nhit)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int sg = 0;
+    double t = 0.0;
+    if (i < n)
+    {
+        for (long long k = seg_off[i]; k < seg_off[i + 1]; k++)
+            if (hitv[k])
+            {
+                const double ta = vtime[2 * k], tb = vtime[2 * k + 1];
+                t = ta + toiv[k] * (tb - ta);      // the primitives return the parameter inside the stitched segment
+                sg = stagev[k];
+                break;
+            }
+        hit[i] = sg != 0;
+        toi[i] = sg ? t : 0.0;
+        if (stage) stage[i] = (unsigned char)sg;
+    }
+    reduce_block(sg != 0, t, earliest_bits, nhit);
+}
+
 // ---- batched public primitives (include/CTCD.h:36-79): pts = start points then end points ------
 __global__ void __launch_bounds__(128) prim_kernel(int kind, long long n, const double *__restrict__ pts, const double *__restrict__ eta,
                                                    unsigned char *__restrict__ hit, double *__restrict__ t)
@@ -1330,6 +1405,23 @@ void ccdk_sepplane(cudaStream_t st, bool is_vf, long long n, const int *stencils
     H.hoff = hoff; H.htime = htime; H.hpos = hpos;
     if (is_vf) sepplane_kernel<true><<<grid_for(n, 128), 128, 0, st>>>(n, stencils, eta_arr, H, eps, hit, nhit, err);
     else sepplane_kernel<false><<<grid_for(n, 128), 128, 0, st>>>(n, stencils, eta_arr, H, eps, hit, nhit, err);
+}
+
+void ccdk_hist_count(cudaStream_t st, long long n, const int *stencils, const long long *hoff, const double *htime, const double *hpos, int *seg_count)
+{
+    if (n > 0) hist_expand_kernel<true><<<grid_for(n, 128), 128, 0, st>>>(n, stencils, nullptr, 0.0, hoff, htime, hpos, seg_count, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+void ccdk_hist_fill(cudaStream_t st, long long n, const int *stencils, const double *eta_arr, double eta_all, const long long *hoff, const double *htime,
+                    const double *hpos, const long long *seg_off, long long vbase, double *q0v, double *q1v, int *vst, double *veta, double *vtime)
+{
+    if (n > 0) hist_expand_kernel<false><<<grid_for(n, 128), 128, 0, st>>>(n, stencils, eta_arr, eta_all, hoff, htime, hpos, nullptr, seg_off, vbase, q0v, q1v, vst, veta, vtime);
+}
+
+void ccdk_hist_reduce(cudaStream_t st, long long n, const long long *seg_off, const unsigned char *hitv, const double *toiv, const unsigned char *stagev,
+                      const double *vtime, unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits, unsigned long long *nhit)
+{
+    if (n > 0) hist_reduce_kernel<<<grid_for(n, 128), 128, 0, st>>>(n, seg_off, hitv, toiv, stagev, vtime, hit, toi, stage, earliest_bits, nhit);
 }
 
 void ccdk_pack_positions(cudaStream_t st, int V, const double *q0, const double *q1, int vstride, double *qpack, float *vbox)
