@@ -47,7 +47,7 @@ struct ccd_context
     // emission
     DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut;
     // narrowphase
-    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, p1Ve, qpack, histCntVf, histCntEe, histOffVf, histOffEe, histQ0, histQ1, histVst, histEta, histTime, histHit, histStage, histToi, selTmp, selA, selB, selC, selD, selCount;
+    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, p1Ve, qpack, histCntVf, histCntEe, histOffVf, histOffEe, histQ0, histQ1, histVst, histEta, histTime, histHit, histStage, histToi, spCtr, spQst, spQlo, spQhi, spLeafSt, selTmp, selA, selB, selC, selD, selCount;
     // penalty forces (penalty.cu)
     DBuf penF, penGroup, penContrib, penKeysA, penKeysB, penItemsA, penItemsB, penFired, penNewVf, penNewEe, penCtr;
     // pinned host scratch
@@ -55,7 +55,7 @@ struct ccd_context
     // pinned host buffers for the hit lists returned by ccd_step (valid until the next call on the context)
     void *h_res[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t h_res_cap[4] = {0, 0, 0, 0};
-    size_t candCap = 0, pairCap = 0, taskCapVf = 0, taskCapEe = 0;
+    size_t candCap = 0, pairCap = 0, taskCapVf = 0, taskCapEe = 0, spQCap = 0, spLeafCapVf = 0, spLeafCapEe = 0;
     long long veUniqueEe = 0, veUniqueVf = 0;      // unique vertex-edge tests of the last single-step narrowphase call
     // sharding: ownership ranges chosen by the caller (ccd_set_shard_partition), load profile of the last sharded step
     std::vector<int> partP;      // ownership bounds over the sorted (Morton) positions of a sharded step (ccd_set_shard_partition)
@@ -254,7 +254,7 @@ void ccd_destroy(ccd_context *c)
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1Ve, &c->qpack, &c->histCntVf, &c->histCntEe, &c->histOffVf, &c->histOffEe, &c->histQ0, &c->histQ1, &c->histVst, &c->histEta, &c->histTime, &c->histHit, &c->histStage, &c->histToi, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->sbox, &c->sfaces, &c->unsure, &c->frontA, &c->frontB, &c->bigV, &c->bigE,
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1Ve, &c->qpack, &c->histCntVf, &c->histCntEe, &c->histOffVf, &c->histOffEe, &c->histQ0, &c->histQ1, &c->histVst, &c->histEta, &c->histTime, &c->histHit, &c->histStage, &c->histToi, &c->spCtr, &c->spQst, &c->spQlo, &c->spQhi, &c->spLeafSt, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->sbox, &c->sfaces, &c->unsure, &c->frontA, &c->frontB, &c->bigV, &c->bigE,
                    &c->penF, &c->penGroup, &c->penContrib, &c->penKeysA, &c->penKeysB, &c->penItemsA, &c->penItemsB, &c->penFired, &c->penNewVf, &c->penNewEe, &c->penCtr};
     for (DBuf *b : all)
         if (b->p)
@@ -878,7 +878,14 @@ int ccd_narrowphase(ccd_context *c, int V, const int64_t *hoff, const double *ht
     ccd_np_summary s;
     // two entries per vertex = one linear segment: read q0/q1 straight out of hpos (stride 6)
     const bool single = history_is_single_step(V, hoff);
-    if (single)
+    // a few thousand stencils (Model1_flow frames, one VelocityFilter pass on a small mesh): the ~90 launches of the dense
+    // pipeline cost more than the work; one thread per stencil runs the whole sequence in a single kernel (same bits)
+    const bool tiny = nvf + nee <= 8192 && !getenv("CCD_NP_NO_SMALL");
+    if (single && tiny)
+        CKR(narrowphase_device(c, V, nvf, P<int>(c->vf_in), uvf ? nullptr : P<double>(c->vf_eta), nee, P<int>(c->ee_in), uee ? nullptr : P<double>(c->ee_eta),
+                               uvf ? vf_eta[0] : 0.0, uee ? ee_eta[0] : 0.0, nullptr, nullptr, 0, P<long long>(c->hoff), P<double>(c->htime),
+                               P<double>(c->hpos), &s));
+    else if (single)
         CKR(narrowphase_device(c, V, nvf, P<int>(c->vf_in), uvf ? nullptr : P<double>(c->vf_eta), nee, P<int>(c->ee_in), uee ? nullptr : P<double>(c->ee_eta),
                                uvf ? vf_eta[0] : 0.0, uee ? ee_eta[0] : 0.0, P<double>(c->hpos), P<double>(c->hpos) + 3, 6, P<long long>(c->hoff),
                                P<double>(c->htime), P<double>(c->hpos), &s));
@@ -902,6 +909,103 @@ int ccd_narrowphase(ccd_context *c, int V, const int64_t *hoff, const double *ht
     if (summary)
         *summary = s;
     return CCD_OK;
+}
+
+// Staged SeparatingPlaneNarrowPhase (narrowphase.cu): rounds over a global queue of open intervals, leaves through the
+// single-step pipeline, flags OR-ed per stencil.  Inputs are the uploaded c->vf_in / ee_in / vf_eta / ee_eta / hoff / htime /
+// hpos; per-stencil flags end in c->histHit (vertex-face first), hit counts in the C_NHIT_* counters.
+#define SP_MAX_ROUNDS 192      // interval lengths at least halve per round; a search that straddles a History breakpoint runs down to ~2^-52
+#define SP_BATCH 12            // rounds launched between two looks at the queue counters
+#define SP_DIRECT_LEAVES 32768 // up to this many leaves the CTCD sequence runs in one kernel per type instead of the dense pipeline
+static int sepplane_staged(ccd_context *c, long long nvf, long long nee, double eps)
+{
+    unsigned long long *ctr = P<unsigned long long>(c->counters);
+    for (int attempt = 0; attempt < 8; attempt++)
+    {
+        if (c->spQCap < (size_t)(2 * (nvf + nee) + 4096)) c->spQCap = (size_t)(2 * (nvf + nee) + 4096);
+        if (c->spLeafCapVf < (size_t)(2 * nvf + 2048)) c->spLeafCapVf = (size_t)(2 * nvf + 2048);
+        if (c->spLeafCapEe < (size_t)(2 * nee + 2048)) c->spLeafCapEe = (size_t)(2 * nee + 2048);
+        const size_t qcap = c->spQCap, lcv = c->spLeafCapVf, lce = c->spLeafCapEe, lcap = lcv + lce;
+        CKR(ensure(c, c->spCtr, sizeof(unsigned long long) * (SP_MAX_ROUNDS + 2 + 8)));
+        CKR(ensure(c, c->spQst, sizeof(int) * 2 * qcap));
+        CKR(ensure(c, c->spQlo, sizeof(double) * 2 * qcap));
+        CKR(ensure(c, c->spQhi, sizeof(double) * 2 * qcap));
+        CKR(ensure(c, c->histQ0, sizeof(double) * 12 * (lcap + 1)));
+        CKR(ensure(c, c->histQ1, sizeof(double) * 12 * (lcap + 1)));
+        CKR(ensure(c, c->histVst, sizeof(int) * 4 * (lcap + 1)));
+        CKR(ensure(c, c->histEta, sizeof(double) * (lcap + 1)));
+        CKR(ensure(c, c->spLeafSt, sizeof(int) * (lcap + 1)));
+        CKR(ensure(c, c->histHit, (size_t)(nvf + nee) + 16));
+        unsigned long long *rc = P<unsigned long long>(c->spCtr);      // rc[r] = intervals entering round r
+        CK(cudaMemsetAsync(rc, 0, sizeof(unsigned long long) * (SP_MAX_ROUNDS + 2 + 8), c->st));
+        CK(cudaMemsetAsync(c->histHit.p, 0, (size_t)(nvf + nee) + 16, c->st));
+        unsigned long long *leafCtr = rc + SP_MAX_ROUNDS + 2;
+        unsigned char *hitVf = P<unsigned char>(c->histHit), *hitEe = hitVf + nvf;
+        int *qst = P<int>(c->spQst);
+        double *qlo = P<double>(c->spQlo), *qhi = P<double>(c->spQhi);
+        std::vector<unsigned long long> h(SP_MAX_ROUNDS + 2 + 8);
+        bool overflow = false, done = false;
+        int r = 0;
+        while (!done && r < SP_MAX_ROUNDS)
+        {
+            for (int b = 0; b < SP_BATCH && r < SP_MAX_ROUNDS; b++, r++)
+            {
+                const size_t in = (size_t)((r + 1) & 1) * qcap, out = (size_t)(r & 1) * qcap;
+                ccdk_sp_round(c->st, r == 0, nvf, nee, P<int>(c->vf_in), P<int>(c->ee_in), P<double>(c->vf_eta), P<double>(c->ee_eta), P<long long>(c->hoff),
+                              P<double>(c->htime), P<double>(c->hpos), eps, qst + in, qlo + in, qhi + in, rc + r, qst + out, qlo + out, qhi + out, rc + r + 1,
+                              qcap, hitVf, hitEe, leafCtr, lcv, lce, P<double>(c->histQ0), P<double>(c->histQ1), P<int>(c->histVst), P<double>(c->histEta),
+                              P<int>(c->spLeafSt));
+                c->launches += 1;
+            }
+            CK(cudaMemcpyAsync(h.data(), rc, sizeof(unsigned long long) * (SP_MAX_ROUNDS + 2 + 8), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            for (int k = 1; k <= r; k++)
+                if (h[k] > qcap) { overflow = true; if (h[k] + h[k] / 2 > c->spQCap) c->spQCap = (size_t)(h[k] + h[k] / 2 + 4096); }
+            const unsigned long long lv = h[SP_MAX_ROUNDS + 2], le = h[SP_MAX_ROUNDS + 3];
+            if (lv > lcv) { overflow = true; c->spLeafCapVf = (size_t)(lv + lv / 2 + 2048); }
+            if (le > lce) { overflow = true; c->spLeafCapEe = (size_t)(le + le / 2 + 2048); }
+            done = overflow || h[r] == 0;
+        }
+        if (getenv("CCD_SP_TRACE"))
+        {
+            fprintf(stderr, "[sp] rounds %d, leaves %llu + %llu, intervals per round:", r, h[SP_MAX_ROUNDS + 2], h[SP_MAX_ROUNDS + 3]);
+            for (int k = 1; k <= r && (k == 1 || h[k - 1]); k++) fprintf(stderr, " %llu", h[k]);
+            fprintf(stderr, "\n");
+        }
+        if (overflow) continue;
+        if (!done)
+        {
+            c->err = "narrowphase_sepplane: interval search did not finish (History with extremely small time gaps)";
+            return CCD_ERR_NOMEM;
+        }
+        // the leaves: CTCD on short linear pieces
+        const long long nlv = (long long)h[SP_MAX_ROUNDS + 2], nle = (long long)h[SP_MAX_ROUNDS + 3];
+        if (nlv + nle > 0 && nlv + nle <= SP_DIRECT_LEAVES)
+        {
+            ccdk_sp_leaf_direct(c->st, true, nlv, 0, P<double>(c->histQ0), P<double>(c->histQ1), P<double>(c->histEta), P<int>(c->spLeafSt), hitVf);
+            ccdk_sp_leaf_direct(c->st, false, nle, (long long)lcv, P<double>(c->histQ0), P<double>(c->histQ1), P<double>(c->histEta), P<int>(c->spLeafSt), hitEe);
+            c->launches += 2;
+        }
+        else if (nlv + nle > 0)
+        {
+            // through the dense single-step pipeline as virtual stencils (vertex-face leaves in [0, nlv), edge-edge leaves from lcv on)
+            if (4 * ((long long)lcv + nle) >= (1ll << 31) - 8) { c->err = "narrowphase_sepplane: too many leaf intervals in one call"; return CCD_ERR_NOMEM; }
+            ccd_np_summary virt;
+            CKR(narrowphase_device(c, (int)(4 * ((long long)lcv + nle)), nlv, P<int>(c->histVst), P<double>(c->histEta), nle, P<int>(c->histVst) + 4 * lcv,
+                                   P<double>(c->histEta) + lcv, 0.0, 0.0, P<double>(c->histQ0), P<double>(c->histQ1), 3, nullptr, nullptr, nullptr, &virt));
+            ccdk_sp_leaf_or(c->st, nlv, P<int>(c->spLeafSt), P<unsigned char>(c->vfHit), hitVf);
+            ccdk_sp_leaf_or(c->st, nle, P<int>(c->spLeafSt) + lcv, P<unsigned char>(c->eeHit), hitEe);
+            c->launches += 2;
+        }
+        CK(cudaMemsetAsync(ctr + C_EARLY_VF, 0, sizeof(unsigned long long) * 4, c->st));
+        ccdk_count_flags(c->st, nvf, hitVf, ctr + C_NHIT_VF);
+        ccdk_count_flags(c->st, nee, hitEe, ctr + C_NHIT_EE);
+        c->launches += 2;
+        CK(cudaGetLastError());
+        return CCD_OK;
+    }
+    c->err = "narrowphase_sepplane: interval queues kept overflowing";
+    return CCD_ERR_NOMEM;
 }
 
 // SeparatingPlaneNarrowPhase::findCollisions (src/SeparatingPlaneNarrowPhase.cpp:11-25)
@@ -931,6 +1035,17 @@ int ccd_narrowphase_sepplane(ccd_context *c, int V, const int64_t *hoff, const d
     CKR(upload(c, c->ee_in, ee, sizeof(int32_t) * 4 * (size_t)nee));
     CKR(upload(c, c->vf_eta, vf_eta, sizeof(double) * (size_t)nvf));
     CKR(upload(c, c->ee_eta, ee_eta, sizeof(double) * (size_t)nee));
+    if (!getenv("CCD_SEPPLANE_ONE_THREAD"))
+    {
+        // staged: interval queue across all stencils (CCD_SEPPLANE_ONE_THREAD=1 keeps the one-thread-per-stencil kernel; same flags)
+        CKR(sepplane_staged(c, nvf, nee, eps));
+        if (nvf > 0) CK(cudaMemcpyAsync(vf_hit, c->histHit.p, (size_t)nvf, cudaMemcpyDeviceToHost, c->st));
+        if (nee > 0) CK(cudaMemcpyAsync(ee_hit, P<unsigned char>(c->histHit) + nvf, (size_t)nee, cudaMemcpyDeviceToHost, c->st));
+        CKR(sync_counters(c));
+        if (n_vf_hits) *n_vf_hits = (int64_t)c->h_counters[C_NHIT_VF];
+        if (n_ee_hits) *n_ee_hits = (int64_t)c->h_counters[C_NHIT_EE];
+        return CCD_OK;
+    }
     CKR(ensure(c, c->vfHit, (size_t)nvf + 16));
     CKR(ensure(c, c->eeHit, (size_t)nee + 16));
     unsigned long long *ctr = P<unsigned long long>(c->counters);

@@ -27,6 +27,16 @@ void ccdk_find_intervals(cudaStream_t st, long long n, int degree, int pos, cons
 // SeparatingPlaneNarrowPhase: hit flags only; *nhit += hits, *err += stencils whose interval stack overflowed
 void ccdk_sepplane(cudaStream_t st, bool is_vf, long long n, const int *stencils, const double *eta_arr, const long long *hoff, const double *htime,
                    const double *hpos, double eps, unsigned char *hit, unsigned long long *nhit, unsigned long long *err);
+// staged SeparatingPlaneNarrowPhase (narrowphase.cu): interval queue rounds, leaves -> single-step pipeline, OR
+void ccdk_sp_round(cudaStream_t st, bool first, long long nvf, long long nee, const int *vf, const int *ee, const double *vf_eta, const double *ee_eta,
+                   const long long *hoff, const double *htime, const double *hpos, double eps, const int *in_st, const double *in_lo, const double *in_hi,
+                   const unsigned long long *nin, int *out_st, double *out_lo, double *out_hi, unsigned long long *nout, unsigned long long qcap,
+                   unsigned char *hit_vf, unsigned char *hit_ee, unsigned long long *nleaf, unsigned long long leaf_cap_vf, unsigned long long leaf_cap_ee,
+                   double *q0v, double *q1v, int *vst, double *veta, int *leaf_stencil);
+void ccdk_sp_leaf_direct(cudaStream_t st, bool is_vf, long long nleaf, long long vbase, const double *q0v, const double *q1v, const double *veta,
+                         const int *leaf_stencil, unsigned char *hit);
+void ccdk_sp_leaf_or(cudaStream_t st, long long nleaf, const int *leaf_stencil, const unsigned char *hitv, unsigned char *hit);
+void ccdk_count_flags(cudaStream_t st, long long n, const unsigned char *flag, unsigned long long *count);
 // penalty.cu: PenaltyGroup::addForce over device arrays (see the file header for the scratch layout)
 size_t ccdk_penalty_temp_bytes(long long nitems);
 int ccdk_penalty_group_force(cudaStream_t st, int V, const double *q, const double *v, long long nvf, const int *vf, const unsigned char *vf_isnew,

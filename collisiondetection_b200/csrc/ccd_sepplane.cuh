@@ -99,6 +99,91 @@ CCD_FN double sp_trajectory_intersect(const HistView &H, int vert, int startidx,
     return INFINITY;
 }
 
+// One step of SeparatingPlaneNarrowPhase::checkInterval (:47-218) on the interval [mint, maxt] of one stencil — the body of
+// the recursion, free of any stack or queue (sp_check_stencil below keeps the intervals on a per-thread stack; the staged
+// kernels of narrowphase.cu keep them in a global queue shared by all stencils).  Outcome:
+//   SP_DROP   nothing left to do for this interval
+//   SP_HIT    closer than eta at the midpoint
+//   SP_LEAF   shorter than 3 eps inside one History segment: oldpos / newpos go to the CTCD primitives
+//   SP_SPLIT  nsub (0..2) sub-intervals sub_lo / sub_hi remain to be searched
+enum { SP_DROP = 0, SP_HIT = 1, SP_LEAF = 2, SP_SPLIT = 3 };
+template <bool IS_VF>
+CCD_FN int sp_interval_step(const HistView &H, const int *verts, double eta, double eps, double mint, double maxt, V3 *oldpos, V3 *newpos, int &nsub,
+                            double *sub_lo, double *sub_hi)
+{
+    nsub = 0;
+    if (maxt < mint)
+        return SP_DROP;
+    if (maxt - mint < 3 * eps)
+    {
+        bool ok = true;
+        for (int i = 0; i < 4; i++)
+        {
+            int oldidx, newidx;
+            hist_pos_at(H, verts[i], mint, oldpos[i], oldidx);
+            hist_pos_at(H, verts[i], maxt, newpos[i], newidx);
+            if (oldidx != newidx)
+            {
+                ok = false;
+                break;
+            }
+        }
+        if (ok)
+            return SP_LEAF;
+    }
+    const double midt = 0.5 * (mint + maxt);
+    V3 midpos[4];
+    int mididx[4];
+    for (int i = 0; i < 4; i++)
+        hist_pos_at(H, verts[i], midt, midpos[i], mididx[i]);
+    double bary1, bary2, bary3, bary4 = 0;
+    V3 closest;
+    if (IS_VF)
+        closest = dist_vf(midpos[0], midpos[1], midpos[2], midpos[3], bary1, bary2, bary3);
+    else
+        closest = dist_ee(midpos[0], midpos[1], midpos[2], midpos[3], bary1, bary2, bary3, bary4);
+    const double distsq = dot(closest, closest);
+    if (distsq < eta * eta)
+        return SP_HIT;
+    // separating plane (:167-189): bary * (next - prev) / dt, term by term as the reference writes it
+    const double w[4] = {IS_VF ? 1.0 : bary1, IS_VF ? bary1 : bary2, IS_VF ? bary2 : bary3, IS_VF ? bary3 : bary4};
+    V3 term[4], wpos[4];
+    for (int i = 0; i < 4; i++)
+    {
+        const long long e0 = H.hoff[verts[i]] + mididx[i];
+        const V3 prevpos = ldv(H.hpos + 3 * e0), nextpos = ldv(H.hpos + 3 * (e0 + 1));
+        const double dts = H.htime[e0 + 1] - H.htime[e0];
+        V3 d = nextpos - prevpos;
+        if (!(IS_VF && i == 0)) d = w[i] * d;
+        term[i] = mk(d.x / dts, d.y / dts, d.z / dts);
+        wpos[i] = (IS_VF && i == 0) ? midpos[0] : w[i] * midpos[i];
+    }
+    const V3 planepos = 0.5 * (((wpos[0] + wpos[1]) + wpos[2]) + wpos[3]);
+    const V3 planevel = 0.5 * (((term[0] + term[1]) + term[2]) + term[3]);
+    const double cn = sqrt(dot(closest, closest));
+    const V3 normal = mk(closest.x / cn, closest.y / cn, closest.z / cn);
+    double tb = INFINITY, tf = INFINITY;
+    for (int vert = 0; vert < 4; vert++)
+    {
+        const double sign = (vert == 0 || (vert == 1 && !IS_VF)) ? -1.0 : 1.0;
+        tb = smin(tb, sp_trajectory_intersect(H, verts[vert], mididx[vert], false, planepos, planevel, sign * normal, midpos[vert], midt, eta));
+        tf = smin(tf, sp_trajectory_intersect(H, verts[vert], mididx[vert] + 1, true, planepos, planevel, sign * normal, midpos[vert], midt, eta));
+    }
+    if (tf < 1.0)
+    {
+        sub_lo[nsub] = midt + smax(0.0, tf - eps);
+        sub_hi[nsub] = maxt;
+        nsub++;
+    }
+    if (tb < 1.0)
+    {
+        sub_lo[nsub] = mint;
+        sub_hi[nsub] = midt - smax(0.0, tb - eps);
+        nsub++;
+    }
+    return SP_SPLIT;
+}
+
 #define SP_STACK 96
 // SeparatingPlaneNarrowPhase::checkInterval (:47-218) over [0,1].  Returns 1 hit, 0 miss, -1 when the interval stack
 // overflows (the caller reports an error; with eps = minimum gap / 4 the search is ~log2(1/eps) deep).
@@ -112,86 +197,29 @@ template <bool IS_VF> CCD_FN int sp_check_stencil(const HistView &H, const int *
     while (sp > 0)
     {
         sp--;
-        const double mint = smin_[sp], maxt = smax_[sp];
-        if (maxt < mint)
-            continue;
-        if (maxt - mint < 3 * eps)
-        {
-            bool ok = true;
-            V3 oldpos[4], newpos[4];
-            for (int i = 0; i < 4; i++)
-            {
-                int oldidx, newidx;
-                hist_pos_at(H, verts[i], mint, oldpos[i], oldidx);
-                hist_pos_at(H, verts[i], maxt, newpos[i], newidx);
-                if (oldidx != newidx)
-                {
-                    ok = false;
-                    break;
-                }
-            }
-            if (ok)
-            {
-                // the primitive, then the vertex-edge and vertex-vertex tests in the reference's order (:76-140): the same
-                // sequence as CTCDNarrowPhase's on this linear piece
-                double t;
-                if (stencil_segment_full<IS_VF>(oldpos, newpos, eta, t) != 0)
-                    return 1;
-                continue;
-            }
-        }
-        const double midt = 0.5 * (mint + maxt);
-        V3 midpos[4];
-        int mididx[4];
-        for (int i = 0; i < 4; i++)
-            hist_pos_at(H, verts[i], midt, midpos[i], mididx[i]);
-        double bary1, bary2, bary3, bary4 = 0;
-        V3 closest;
-        if (IS_VF)
-            closest = dist_vf(midpos[0], midpos[1], midpos[2], midpos[3], bary1, bary2, bary3);
-        else
-            closest = dist_ee(midpos[0], midpos[1], midpos[2], midpos[3], bary1, bary2, bary3, bary4);
-        const double distsq = dot(closest, closest);
-        if (distsq < eta * eta)
+        V3 oldpos[4], newpos[4];
+        int nsub;
+        double lo[2], hi[2];
+        const int r = sp_interval_step<IS_VF>(H, verts, eta, eps, smin_[sp], smax_[sp], oldpos, newpos, nsub, lo, hi);
+        if (r == SP_HIT)
             return 1;
-        // separating plane (:167-189)
-        // bary * (next - prev) / dt, term by term as the reference writes it (the scalar multiplies before the division)
-        const double w[4] = {IS_VF ? 1.0 : bary1, IS_VF ? bary1 : bary2, IS_VF ? bary2 : bary3, IS_VF ? bary3 : bary4};
-        V3 term[4], wpos[4];
-        for (int i = 0; i < 4; i++)
+        if (r == SP_LEAF)
         {
-            const long long e0 = H.hoff[verts[i]] + mididx[i];
-            const V3 prevpos = ldv(H.hpos + 3 * e0), nextpos = ldv(H.hpos + 3 * (e0 + 1));
-            const double dts = H.htime[e0 + 1] - H.htime[e0];
-            V3 d = nextpos - prevpos;
-            if (!(IS_VF && i == 0)) d = w[i] * d;
-            term[i] = mk(d.x / dts, d.y / dts, d.z / dts);
-            wpos[i] = (IS_VF && i == 0) ? midpos[0] : w[i] * midpos[i];
+            // the primitive, then the vertex-edge and vertex-vertex tests in the reference's order (:76-140): the same
+            // sequence as CTCDNarrowPhase's on this linear piece
+            double t;
+            if (stencil_segment_full<IS_VF>(oldpos, newpos, eta, t) != 0)
+                return 1;
+            continue;
         }
-        const V3 planepos = 0.5 * (((wpos[0] + wpos[1]) + wpos[2]) + wpos[3]);
-        const V3 planevel = 0.5 * (((term[0] + term[1]) + term[2]) + term[3]);
-        const double cn = sqrt(dot(closest, closest));
-        const V3 normal = mk(closest.x / cn, closest.y / cn, closest.z / cn);
-        // upper bound of the lower interval (:193-204), lower bound of the upper interval (:208-219)
-        double tb = INFINITY, tf = INFINITY;
-        for (int vert = 0; vert < 4; vert++)
-        {
-            const double sign = (vert == 0 || (vert == 1 && !IS_VF)) ? -1.0 : 1.0;
-            tb = smin(tb, sp_trajectory_intersect(H, verts[vert], mididx[vert], false, planepos, planevel, sign * normal, midpos[vert], midt, eta));
-            tf = smin(tf, sp_trajectory_intersect(H, verts[vert], mididx[vert] + 1, true, planepos, planevel, sign * normal, midpos[vert], midt, eta));
-        }
+        if (r == SP_DROP)
+            continue;
         if (sp + 2 > SP_STACK)
             return -1;
-        if (tf < 1.0)
+        for (int k = 0; k < nsub; k++)
         {
-            smin_[sp] = midt + smax(0.0, tf - eps);
-            smax_[sp] = maxt;
-            sp++;
-        }
-        if (tb < 1.0)
-        {
-            smin_[sp] = mint;
-            smax_[sp] = midt - smax(0.0, tb - eps);
+            smin_[sp] = lo[k];
+            smax_[sp] = hi[k];
             sp++;
         }
     }

@@ -1051,6 +1051,129 @@ __global__ void __launch_bounds__(128) sepplane_kernel(long long n, const int *_
     (void)o;
 }
 
+// ---- SeparatingPlaneNarrowPhase, staged ----------------------------------------------------------------------------------
+// The reference recurses on time intervals per stencil (src/SeparatingPlaneNarrowPhase.cpp:47-218); sepplane_kernel above keeps
+// that recursion on a 96-deep per-thread stack, one thread per stencil, and the stencil with the deepest search sets the
+// kernel's duration.  Staged: the open intervals of ALL stencils sit in one global queue and are processed in rounds — one
+// thread per interval runs one step of the search (sp_interval_step: midpoint distance, separating plane, first crossings
+// along the four trajectories), appends the sub-intervals that remain to the next round's queue, marks a stencil that comes
+// within eta at a midpoint, and turns an interval short enough for the CTCD primitives into a LEAF: a virtual single-step
+// stencil on four virtual vertices.  When the queue runs empty the dense single-step pipeline tests all leaves at once and
+// sp_leaf_or_kernel folds their flags into the stencils' (the result is a disjunction over intervals: order is irrelevant).
+struct SpRoundArgs
+{
+    HistView H;
+    const int *stencils[2];               // [0] vertex-face, [1] edge-edge
+    const double *eta_arr[2];
+    double eps;
+    long long n[2];                       // round 0: one interval [0,1] per stencil, vertex-face stencils first
+    const int *in_st;                     // later rounds: the queue the round before wrote; stencil index | type << 31
+    const double *in_lo, *in_hi;
+    const unsigned long long *nin;
+    int *out_st;
+    double *out_lo, *out_hi;
+    unsigned long long *nout;
+    unsigned long long qcap;              // counts keep running past the capacities (writes are guarded): the caller grows and reruns
+    unsigned char *hit[2];                // per stencil
+    unsigned long long *nleaf;            // [2]
+    unsigned long long leaf_cap[2];
+    long long vbase[2];                   // first virtual stencil of each type (two regions of the leaf arrays)
+    double *q0v, *q1v;                    // 12 doubles per leaf each
+    int *vst;                             // 4 virtual vertex ids per leaf
+    double *veta;
+    int *leaf_stencil;
+};
+
+template <bool FIRST> __global__ void __launch_bounds__(128) sp_round_kernel(SpRoundArgs G)
+{
+    const unsigned long long n = FIRST ? (unsigned long long)(G.n[0] + G.n[1]) : (*G.nin < G.qcap ? *G.nin : G.qcap);
+    const unsigned long long nround = block_rounded(n);
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nround; w += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        int r = SP_DROP, nsub = 0, st = 0, ty = 0;
+        double lo[2] = {0, 0}, hi[2] = {0, 0}, eta = 0;
+        V3 oldpos[4], newpos[4];
+        if (w < n)
+        {
+            if (FIRST)
+            {
+                ty = (long long)w >= G.n[0] ? 1 : 0;
+                st = (int)((long long)w - (ty ? G.n[0] : 0));
+            }
+            else
+            {
+                const unsigned e = (unsigned)G.in_st[w];
+                ty = (int)(e >> 31);
+                st = (int)(e & 0x7fffffffu);
+            }
+            if (!G.hit[ty][st])      // (a stale 0 only costs work: the flag is a disjunction)
+            {
+                const int4 s4 = reinterpret_cast<const int4 *>(G.stencils[ty])[st];
+                const int verts[4] = {s4.x, s4.y, s4.z, s4.w};
+                eta = G.eta_arr[ty][st];
+                const double mint = FIRST ? 0.0 : G.in_lo[w], maxt = FIRST ? 1.0 : G.in_hi[w];
+                if (ty == 0) r = sp_interval_step<true>(G.H, verts, eta, G.eps, mint, maxt, oldpos, newpos, nsub, lo, hi);
+                else r = sp_interval_step<false>(G.H, verts, eta, G.eps, mint, maxt, oldpos, newpos, nsub, lo, hi);
+                if (r == SP_HIT) G.hit[ty][st] = 1;
+            }
+        }
+        // (nothing to append anywhere in this block: skip the three reservations' barriers)
+        if (!__syncthreads_or(nsub != 0 || r == SP_LEAF)) continue;
+        const unsigned long long o = block_alloc((unsigned)nsub, G.nout);
+        const unsigned long long l0 = block_alloc((r == SP_LEAF && ty == 0) ? 1u : 0u, G.nleaf + 0);
+        const unsigned long long l1 = block_alloc((r == SP_LEAF && ty == 1) ? 1u : 0u, G.nleaf + 1);
+        for (int k = 0; k < nsub; k++)
+            if (o + k < G.qcap)
+            {
+                G.out_st[o + k] = (int)((unsigned)st | ((unsigned)ty << 31));
+                G.out_lo[o + k] = lo[k];
+                G.out_hi[o + k] = hi[k];
+            }
+        const unsigned long long l = ty ? l1 : l0;
+        if (r == SP_LEAF && l < G.leaf_cap[ty])
+        {
+            const long long sg = G.vbase[ty] + (long long)l;
+            for (int j = 0; j < 4; j++)
+            {
+                double *o0 = G.q0v + 3 * (4 * sg + j), *o1 = G.q1v + 3 * (4 * sg + j);
+                o0[0] = oldpos[j].x; o0[1] = oldpos[j].y; o0[2] = oldpos[j].z;
+                o1[0] = newpos[j].x; o1[1] = newpos[j].y; o1[2] = newpos[j].z;
+                G.vst[4 * sg + j] = (int)(4 * sg + j);
+            }
+            G.veta[sg] = eta;
+            G.leaf_stencil[sg] = st;
+        }
+    }
+}
+
+// a few leaves (a small mesh): the whole CTCD sequence per leaf in one kernel beats the ~45 launches of the dense pipeline
+template <bool IS_VF>
+__global__ void __launch_bounds__(128) sp_leaf_direct_kernel(long long nleaf, long long vbase, const double *__restrict__ q0v, const double *__restrict__ q1v,
+                                                             const double *__restrict__ veta, const int *__restrict__ leaf_stencil, unsigned char *hit)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nleaf) return;
+    const long long sg = vbase + k;
+    V3 a[4], b[4];
+    for (int j = 0; j < 4; j++) { a[j] = ldv(q0v + 3 * (4 * sg + j)); b[j] = ldv(q1v + 3 * (4 * sg + j)); }
+    double t;
+    if (stencil_segment_full<IS_VF>(a, b, veta[sg], t) != 0) hit[leaf_stencil[sg]] = 1;
+}
+
+__global__ void __launch_bounds__(256) sp_leaf_or_kernel(long long nleaf, const int *__restrict__ leaf_stencil, const unsigned char *__restrict__ hitv,
+                                                         unsigned char *hit)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nleaf && hitv[k]) hit[leaf_stencil[k]] = 1;
+}
+
+__global__ void __launch_bounds__(256) count_flags_kernel(long long n, const unsigned char *__restrict__ flag, unsigned long long *count)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long o = block_alloc((i < n && flag[i]) ? 1u : 0u, count);
+    (void)o;
+}
+
 // multi-entry History: stitched segments, full algorithm in one pass
 template <bool IS_VF> __global__ void __launch_bounds__(128) stencil_history_kernel(NpArgs A)
 {
@@ -1422,6 +1545,48 @@ void ccdk_hist_reduce(cudaStream_t st, long long n, const long long *seg_off, co
                       const double *vtime, unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits, unsigned long long *nhit)
 {
     if (n > 0) hist_reduce_kernel<<<grid_for(n, 128), 128, 0, st>>>(n, seg_off, hitv, toiv, stagev, vtime, hit, toi, stage, earliest_bits, nhit);
+}
+
+// one round of the staged SeparatingPlane search (first: round 0 over the stencils, vertex-face then edge-edge); see SpRoundArgs
+void ccdk_sp_round(cudaStream_t st, bool first, long long nvf, long long nee, const int *vf, const int *ee, const double *vf_eta, const double *ee_eta,
+                   const long long *hoff, const double *htime, const double *hpos, double eps, const int *in_st, const double *in_lo, const double *in_hi,
+                   const unsigned long long *nin, int *out_st, double *out_lo, double *out_hi, unsigned long long *nout, unsigned long long qcap,
+                   unsigned char *hit_vf, unsigned char *hit_ee, unsigned long long *nleaf, unsigned long long leaf_cap_vf, unsigned long long leaf_cap_ee,
+                   double *q0v, double *q1v, int *vst, double *veta, int *leaf_stencil)
+{
+    SpRoundArgs G;
+    G.H.hoff = hoff; G.H.htime = htime; G.H.hpos = hpos;
+    G.stencils[0] = vf; G.stencils[1] = ee; G.eta_arr[0] = vf_eta; G.eta_arr[1] = ee_eta; G.eps = eps; G.n[0] = nvf; G.n[1] = nee;
+    G.in_st = in_st; G.in_lo = in_lo; G.in_hi = in_hi; G.nin = nin;
+    G.out_st = out_st; G.out_lo = out_lo; G.out_hi = out_hi; G.nout = nout; G.qcap = qcap; G.hit[0] = hit_vf; G.hit[1] = hit_ee; G.nleaf = nleaf;
+    G.leaf_cap[0] = leaf_cap_vf; G.leaf_cap[1] = leaf_cap_ee; G.vbase[0] = 0; G.vbase[1] = (long long)leaf_cap_vf;
+    G.q0v = q0v; G.q1v = q1v; G.vst = vst; G.veta = veta; G.leaf_stencil = leaf_stencil;
+    if (first) sp_round_kernel<true><<<grid_for(nvf + nee > 0 ? nvf + nee : 1, 128), 128, 0, st>>>(G);
+    else
+    {
+        // the queue of a later round is rarely longer than the stencil list: no more blocks than that needs (a small mesh runs ~60
+        // rounds of a few thousand intervals each, and every block pays the round's barriers)
+        const unsigned want = grid_for(nvf + nee > 0 ? nvf + nee : 1, 128);
+        sp_round_kernel<false><<<want < 148u * 4u ? want : 148u * 4u, 128, 0, st>>>(G);
+    }
+}
+
+void ccdk_sp_leaf_direct(cudaStream_t st, bool is_vf, long long nleaf, long long vbase, const double *q0v, const double *q1v, const double *veta,
+                         const int *leaf_stencil, unsigned char *hit)
+{
+    if (nleaf <= 0) return;
+    if (is_vf) sp_leaf_direct_kernel<true><<<grid_for(nleaf, 128), 128, 0, st>>>(nleaf, vbase, q0v, q1v, veta, leaf_stencil, hit);
+    else sp_leaf_direct_kernel<false><<<grid_for(nleaf, 128), 128, 0, st>>>(nleaf, vbase, q0v, q1v, veta, leaf_stencil, hit);
+}
+
+void ccdk_sp_leaf_or(cudaStream_t st, long long nleaf, const int *leaf_stencil, const unsigned char *hitv, unsigned char *hit)
+{
+    if (nleaf > 0) sp_leaf_or_kernel<<<grid_for(nleaf, 256), 256, 0, st>>>(nleaf, leaf_stencil, hitv, hit);
+}
+
+void ccdk_count_flags(cudaStream_t st, long long n, const unsigned char *flag, unsigned long long *count)
+{
+    if (n > 0) count_flags_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, flag, count);
 }
 
 void ccdk_pack_positions(cudaStream_t st, int V, const double *q0, const double *q1, int vstride, double *qpack, float *vbox)

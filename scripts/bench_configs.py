@@ -98,12 +98,16 @@ def main():
         ms_bp = timed(lambda: ctx.findCollisionCandidates(13, f, *H, outer))
         ms_sp = timed(lambda: ctx.findCollisionsSeparatingPlane(*H, vf, ve, ee, ee_eta))
         ms_ctcd = timed(lambda: ctx.findCollisions(*H, vf, ve, ee, ee_eta))
-        os.environ["CCD_HISTORY_ONE_THREAD"] = "1"      # the one-thread-per-stencil kernel the staged path replaced (same bits)
+        os.environ["CCD_HISTORY_ONE_THREAD"] = "1"      # the one-thread-per-stencil kernels the staged paths replaced (same bits)
+        os.environ["CCD_SEPPLANE_ONE_THREAD"] = "1"
         ms_ctcd_1t = timed(lambda: ctx.findCollisions(*H, vf, ve, ee, ee_eta), reps=3, warm=1)
+        ms_sp_1t = timed(lambda: ctx.findCollisionsSeparatingPlane(*H, vf, ve, ee, ee_eta), reps=3, warm=1)
         del os.environ["CCD_HISTORY_ONE_THREAD"]
+        del os.environ["CCD_SEPPLANE_ONE_THREAD"]
         d = dict(config="C4", workload="VelocityFilter mesh1 -> mesh2, detection pass %d (History of %d entries)" % (p, len(H[1])),
                  triangles=int(len(f)), stencils=int(len(vf) + len(ee)), gpu_ms_broadphase=ms_bp, gpu_ms_sepplane_narrowphase=ms_sp,
-                 gpu_ms_ctcd_narrowphase_multi_entry=ms_ctcd, gpu_ms_ctcd_narrowphase_multi_entry_one_thread_per_stencil=ms_ctcd_1t)
+                 gpu_ms_ctcd_narrowphase_multi_entry=ms_ctcd, gpu_ms_ctcd_narrowphase_multi_entry_one_thread_per_stencil=ms_ctcd_1t,
+                 gpu_ms_sepplane_narrowphase_one_thread_per_stencil=ms_sp_1t)
         if ref is not None:
             _, _, bp_s = ref.broadphase(13, f, *H, outer)
             s = ref.narrowphase(*H, vf, ve, ee, ee_eta, which=1)
