@@ -27,6 +27,8 @@ struct ccd_context
     cudaStream_t st = nullptr;
     cudaStream_t st2 = nullptr;      // side stream: the edge-edge run's general routine overlaps the vertex-face run
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaStream_t st3 = nullptr;      // the vertex-face narrowphase run, beside the edge-edge run (narrowphase_device)
+    cudaEvent_t evPack = nullptr, evVf = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t sev[CCD_N_STAGES + 1];
     bool stage_valid = false;
@@ -47,7 +49,7 @@ struct ccd_context
     // emission
     DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut;
     // narrowphase
-    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, p1Ve, qpack, histCntVf, histCntEe, histOffVf, histOffEe, histQ0, histQ1, histVst, histEta, histTime, histHit, histStage, histToi, spCtr, spQst, spQlo, spQhi, spLeafSt, selTmp, selA, selB, selC, selD, selCount;
+    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, p1StatusB, p1SbaseB, p1QueuesB, p1SqB, p1XqB, p1Ve, qpack, histCntVf, histCntEe, histOffVf, histOffEe, histQ0, histQ1, histVst, histEta, histTime, histHit, histStage, histToi, spCtr, spQst, spQlo, spQhi, spLeafSt, selTmp, selA, selB, selC, selD, selCount;
     // penalty forces (penalty.cu)
     DBuf penF, penGroup, penContrib, penKeysA, penKeysB, penItemsA, penItemsB, penFired, penNewVf, penNewEe, penCtr;
     // pinned host scratch
@@ -212,6 +214,8 @@ int ccd_create(ccd_context **out, int device)
     for (int i = 0; i <= CCD_N_STAGES; i++) c->sev[i] = nullptr;
     bool ok = cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->st3, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->evPack, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&c->evVf, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 4 && ok; i++)
         ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
     for (int i = 0; i <= CCD_N_STAGES && ok; i++)
@@ -248,13 +252,14 @@ void ccd_destroy(ccd_context *c)
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->st2) cudaStreamSynchronize(c->st2);
+    if (c->st3) cudaStreamSynchronize(c->st3);
     DBuf *all[] = {&c->faces, &c->q0, &c->q1, &c->hoff, &c->htime, &c->hpos, &c->fixed, &c->vf_in, &c->ee_in, &c->vf_eta, &c->ee_eta,
                    &c->pts, &c->eta, &c->boxes, &c->faabb, &c->bounds, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->temp, &c->facePos, &c->cmark,
                    &c->cand, &c->counters, &c->pairL, &c->pairR, &c->deg, &c->adjOff,
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1Ve, &c->qpack, &c->histCntVf, &c->histCntEe, &c->histOffVf, &c->histOffEe, &c->histQ0, &c->histQ1, &c->histVst, &c->histEta, &c->histTime, &c->histHit, &c->histStage, &c->histToi, &c->spCtr, &c->spQst, &c->spQlo, &c->spQhi, &c->spLeafSt, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->sbox, &c->sfaces, &c->unsure, &c->frontA, &c->frontB, &c->bigV, &c->bigE,
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1StatusB, &c->p1SbaseB, &c->p1QueuesB, &c->p1SqB, &c->p1XqB, &c->p1Ve, &c->qpack, &c->histCntVf, &c->histCntEe, &c->histOffVf, &c->histOffEe, &c->histQ0, &c->histQ1, &c->histVst, &c->histEta, &c->histTime, &c->histHit, &c->histStage, &c->histToi, &c->spCtr, &c->spQst, &c->spQlo, &c->spQhi, &c->spLeafSt, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->sbox, &c->sfaces, &c->unsure, &c->frontA, &c->frontB, &c->bigV, &c->bigE,
                    &c->penF, &c->penGroup, &c->penContrib, &c->penKeysA, &c->penKeysB, &c->penItemsA, &c->penItemsB, &c->penFired, &c->penNewVf, &c->penNewEe, &c->penCtr};
     for (DBuf *b : all)
         if (b->p)
@@ -274,6 +279,9 @@ void ccd_destroy(ccd_context *c)
             cudaEventDestroy(c->sev[i]);
     if (c->evFork) cudaEventDestroy(c->evFork);
     if (c->evJoin) cudaEventDestroy(c->evJoin);
+    if (c->evPack) cudaEventDestroy(c->evPack);
+    if (c->evVf) cudaEventDestroy(c->evVf);
+    if (c->st3) cudaStreamDestroy(c->st3);
     if (c->st2) cudaStreamDestroy(c->st2);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
@@ -582,14 +590,28 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
     CKR(ensure(c, c->workTaskEe, sizeof(int) * ((size_t)nee + 32)));
     CKR(ensure(c, c->workSubVf, sizeof(int) * 5 * ((size_t)nvf + 32)));
     CKR(ensure(c, c->workSubEe, sizeof(int) * 5 * ((size_t)nee + 32)));
+    // Single step with both stencil types: the vertex-face run executes on a stream of its own BESIDE the edge-edge run (most
+    // kernels of either pipeline are latency- or bandwidth-bound and leave issue slots, registers and block slots free —
+    // profiles/) with pass-1 scratch of its own; each run then does its own vertex-edge tests (no look-up in the other run's
+    // table: that would chain the runs through three events).  CCD_NP_SEQUENTIAL=1 or CCD_NP_TRACE=1: one after the other.
+    const bool concurrent = d_q0 != nullptr && nvf > 0 && nee > 0 && !getenv("CCD_NP_SEQUENTIAL") && !getenv("CCD_NP_TRACE");
     {
-        // pass-1 scratch, shared by the VF and the EE run (they execute one after the other)
-        const size_t nmax = (size_t)(nvf > nee ? nvf : nee) + 32;
+        // pass-1 scratch: shared by the VF and the EE run when they execute one after the other
+        const size_t nmax = (size_t)(concurrent ? nee : (nvf > nee ? nvf : nee)) + 32;
         CKR(ensure(c, c->p1Status, sizeof(unsigned) * nmax));
         CKR(ensure(c, c->p1Sbase, sizeof(int) * 5 * nmax));
         CKR(ensure(c, c->p1Queues, sizeof(int) * 13 * nmax));
         CKR(ensure(c, c->p1Sq, sizeof(int) * 4 * nmax));
         CKR(ensure(c, c->p1Xq, sizeof(int) * 10 * nmax));
+        if (concurrent)
+        {
+            const size_t nv = (size_t)nvf + 32;
+            CKR(ensure(c, c->p1StatusB, sizeof(unsigned) * nv));
+            CKR(ensure(c, c->p1SbaseB, sizeof(int) * 5 * nv));
+            CKR(ensure(c, c->p1QueuesB, sizeof(int) * 13 * nv));
+            CKR(ensure(c, c->p1SqB, sizeof(int) * 4 * nv));
+            CKR(ensure(c, c->p1XqB, sizeof(int) * 10 * nv));
+        }
         // vertex-edge de-duplication scratch: one region per run (the vertex-face run consults the edge-edge run's table)
         CKR(ensure(c, c->p1Ve, 12 * (size_t)ccdk_np_ve_slots(nee) + 48 * ((size_t)nee + 32) + 12 * (size_t)ccdk_np_ve_slots(nvf) + 48 * ((size_t)nvf + 32) + 64));
     }
@@ -628,18 +650,32 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         if (c->veUniqueEe > 0) { const unsigned s2 = ccdk_np_ve_slots(4 * c->veUniqueEe); if (s2 < slotsEe) slotsEe = s2; }
         if (c->veUniqueVf > 0) { const unsigned s2 = ccdk_np_ve_slots(4 * c->veUniqueVf); if (s2 < slotsVf) slotsVf = s2; }
         const size_t ve_off_vf = (12 * (size_t)ccdk_np_ve_slots(nee) + 48 * ((size_t)nee + 32) + 15) & ~(size_t)15;
-        const bool share_ve = single_step && nee > 0 && nvf > 0 && !d_vf_eta && !d_ee_eta && eta_all_vf == eta_all_ee && !getenv("CCD_NO_VE_SHARE");
+        const bool share_ve = !concurrent && single_step && nee > 0 && nvf > 0 && !d_vf_eta && !d_ee_eta && eta_all_vf == eta_all_ee && !getenv("CCD_NO_VE_SHARE");
+        cudaStream_t svf = concurrent ? c->st3 : c->st;
+        if (concurrent)
+        {
+            // the vertex-face stream starts once the packed positions (and the counters reset above) are in place
+            CK(cudaEventRecord(c->evPack, c->st));
+            CK(cudaStreamWaitEvent(c->st3, c->evPack, 0));
+        }
         cudaEventRecord(c->sev[ST_NP_EE], c->st);
         nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all_ee, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
                                P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE, P<int>(c->workEe),
                                P<int>(c->workTaskEe), P<int>(c->workSubEe), P<double>(c->tasksEe), P<int>(c->tlistEe), c->taskCapEe, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
                                P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_EE, c->p1Ve.p, slotsEe, V, c->st2, c->evFork, c->evJoin, nullptr, 0, 0, nullptr);
-        cudaEventRecord(c->sev[ST_NP_VF], c->st);
-        nl += ccdk_narrowphase(c->st, true, nvf, d_vf, d_vf_eta, eta_all_vf, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
+        cudaEventRecord(c->sev[ST_NP_VF], c->st);      // concurrent runs: "np_ee" is the edge-edge run, "np_vf" what is left of the vertex-face run after it
+        nl += ccdk_narrowphase(svf, true, nvf, d_vf, d_vf_eta, eta_all_vf, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
                                P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF, P<int>(c->workVf),
-                               P<int>(c->workTaskVf), P<int>(c->workSubVf), P<double>(c->tasksVf), P<int>(c->tlistVf), c->taskCapVf, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
-                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_VF, (char *)c->p1Ve.p + ve_off_vf, slotsVf, V, nullptr, nullptr, nullptr,
+                               P<int>(c->workTaskVf), P<int>(c->workSubVf), P<double>(c->tasksVf), P<int>(c->tlistVf), c->taskCapVf,
+                               concurrent ? P<unsigned>(c->p1StatusB) : P<unsigned>(c->p1Status), concurrent ? P<int>(c->p1SbaseB) : P<int>(c->p1Sbase),
+                               concurrent ? P<int>(c->p1QueuesB) : P<int>(c->p1Queues), concurrent ? P<int>(c->p1SqB) : P<int>(c->p1Sq),
+                               concurrent ? P<int>(c->p1XqB) : P<int>(c->p1Xq), ctr + C_NP_VF, (char *)c->p1Ve.p + ve_off_vf, slotsVf, V, nullptr, nullptr, nullptr,
                                share_ve ? c->p1Ve.p : nullptr, share_ve ? slotsEe : 0u, nee, share_ve ? P<double>(c->tasksEe) : nullptr);
+        if (concurrent)
+        {
+            CK(cudaEventRecord(c->evVf, c->st3));
+            CK(cudaStreamWaitEvent(c->st, c->evVf, 0));
+        }
         if (single_step && nee > 0 && !getenv("CCD_NP_TRACE")) CK(cudaStreamWaitEvent(c->st, c->evJoin, 0));
         cudaEventRecord(c->sev[CCD_N_STAGES], c->st);
         CK(cudaGetLastError());
