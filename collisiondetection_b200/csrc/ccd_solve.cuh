@@ -1,9 +1,9 @@
 // Root isolation as a per-lane state machine + the interval rules of CTCD::findIntervals, for the dense solve kernels.
 //
-// Same steps and the same roundings as roots01_t (ccd_roots_t.cuh), roots01 (ccd_math.cuh) and orc_roots01 in the CPU
-// checker — only the control flow differs.  roots01_t inlines one bracketed Newton solve per monotone piece and per
-// derivative level, so lanes working on different pieces of different levels never share instructions (ncu: 6.7 of 32
-// lanes active in roots_kernel<6>, profiles/r01_narrowphase_v9_c5.txt).  Here a lane alternates between
+// Same steps and the same roundings as roots01 (ccd_math.cuh) and orc_roots01 in the CPU checker — only the control flow
+// differs.  A form that inlines one bracketed Newton solve per monotone piece and per derivative level never lets lanes on
+// different pieces of different levels share instructions (ncu: 6.7 of 32 lanes active in roots_kernel<6>,
+// profiles/r01_narrowphase_v9_c5.txt).  Here a lane alternates between
 //     advance()      walk its pieces / levels until the next sign change that needs a solve (or the end), and
 //     newton_step()  one iteration of that solve,
 // so a warp runs ONE copy of the Newton iteration for all lanes that have a solve pending, whatever level or piece
@@ -214,7 +214,7 @@ template <int D, int STRIDE = 0> struct RootLane
         f_lo = f_hi;
     }
 
-    // Bernstein sign variations down the derivative chain (roots01_t, first half): finds the first level to climb
+    // Bernstein sign variations down the derivative chain (roots01, first half): finds the first level to climb
     CCD_FN void prepare(const double (&coef)[D + 1])
     {
         double b[D + 1];
@@ -409,7 +409,7 @@ template <int D, int STRIDE = 0> struct RootLane
         }
     }
 
-    // one iteration of solve_bracket_t (same operations in the same order; the exits are folded into one flag)
+    // one iteration of solve_bracket (ccd_math.cuh; same operations in the same order; the exits are folded into one flag)
     CCD_FN void newton_step()
     {
         double f, df;

@@ -37,6 +37,16 @@ for rank in range(3):
     tot += rr["n_vf_hits"] + rr["n_ee_hits"]
 assert tot == r["n_vf_hits"] + r["n_ee_hits"], (tot, r["n_vf_hits"] + r["n_ee_hits"])
 d = ctx.meshSelfDistance(q0, f)
+# PenaltyGroup::addForce (penalty.cu), the staged multi-entry / SeparatingPlane paths ran above (outm, sp); their one-thread forms:
+pg = np.load(os.path.join(G, "penalty.npz"))
+dt_, outer_, inner_, k_, cor_ = [float(x) for x in pg["thick_params"]]
+ctx.penaltyGroupAddForce(pg["thick_q"], pg["thick_v"], pg["thick_vf"], pg["thick_ee"], dt_, outer_, inner_, k_, cor_, pg["thick_F0"])
+os.environ["CCD_HISTORY_ONE_THREAD"] = "1"
+os.environ["CCD_SEPPLANE_ONE_THREAD"] = "1"
+ctx.findCollisions(*Hm, vfm, 1e-8, eem, 1e-8)
+ctx.findCollisionsSeparatingPlane(*Hm, vfm, 1e-8, eem, 1e-8)
+del os.environ["CCD_HISTORY_ONE_THREAD"], os.environ["CCD_SEPPLANE_ONE_THREAD"]
+spm = ctx.findCollisionsSeparatingPlane(*Hm, vfm, 1e-8, eem, 1e-8)
 print("sanitize run ok: %d+%d candidates, %d+%d hits, cloth41 hits %d, self distance %r" % (
     len(vf), len(ee), out["n_vf_hits"], out["n_ee_hits"], tot, d))
 ctx.close()
