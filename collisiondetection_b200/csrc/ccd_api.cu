@@ -375,6 +375,7 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         return CCD_ERR_ARG;
     }
     *res = BpResult();
+    c->stage_valid = false;      // only a complete step (ccd_step_device) leaves a consistent set of stage events
     CKR(ensure(c, c->vfOut, 16));
     CKR(ensure(c, c->eeOut, 16));
     if (F == 0 || V == 0)
@@ -578,6 +579,7 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
                               const double *d_htime, const double *d_hpos, ccd_np_summary *sum)
 {
     unsigned long long *ctr = P<unsigned long long>(c->counters);
+    c->stage_valid = false;
     CKR(ensure(c, c->vfHit, (size_t)nvf + 16));
     CKR(ensure(c, c->eeHit, (size_t)nee + 16));
     CKR(ensure(c, c->vfStage, (size_t)nvf + 16));

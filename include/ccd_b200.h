@@ -38,8 +38,10 @@ extern "C" {
 
 typedef struct ccd_context ccd_context;
 
-/* One context per process / GPU: owns a stream and a growable pool of device buffers that is reused
- * across calls (the reference keeps no state between calls; neither do results here). */
+/* One context per process / GPU: owns its streams and a growable pool of device buffers that is reused
+ * across calls (the reference keeps no state between calls; neither do results here).  Every call on a context makes
+ * the context's device the calling thread's current CUDA device (cudaSetDevice) and leaves it so.  Not thread-safe:
+ * one call at a time per context. */
 int ccd_create(ccd_context **ctx, int device);
 void ccd_destroy(ccd_context *ctx);
 const char *ccd_last_error(const ccd_context *ctx);
