@@ -29,6 +29,7 @@ struct ccd_context
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     cudaStream_t st3 = nullptr;      // the vertex-face narrowphase run, beside the edge-edge run (narrowphase_device)
     cudaEvent_t evPack = nullptr, evVf = nullptr;
+    cudaEvent_t evVe[3] = {nullptr, nullptr, nullptr};      // vertex-edge tests shared by the two concurrent runs (narrowphase.cu: launch_single_step)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t sev[CCD_N_STAGES + 1];
     bool stage_valid = false;
@@ -216,6 +217,7 @@ int ccd_create(ccd_context **out, int device)
     ok = ok && cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&c->st3, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->evPack, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&c->evVf, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 3; i++) ok = ok && cudaEventCreateWithFlags(&c->evVe[i], cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 4 && ok; i++)
         ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
     for (int i = 0; i <= CCD_N_STAGES && ok; i++)
@@ -279,6 +281,8 @@ void ccd_destroy(ccd_context *c)
             cudaEventDestroy(c->sev[i]);
     if (c->evFork) cudaEventDestroy(c->evFork);
     if (c->evJoin) cudaEventDestroy(c->evJoin);
+    for (int i = 0; i < 3; i++)
+        if (c->evVe[i]) cudaEventDestroy(c->evVe[i]);
     if (c->evPack) cudaEventDestroy(c->evPack);
     if (c->evVf) cudaEventDestroy(c->evVf);
     if (c->st3) cudaStreamDestroy(c->st3);
@@ -594,8 +598,7 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
     CKR(ensure(c, c->workSubEe, sizeof(int) * 5 * ((size_t)nee + 32)));
     // Single step with both stencil types: the vertex-face run executes on a stream of its own BESIDE the edge-edge run (most
     // kernels of either pipeline are latency- or bandwidth-bound and leave issue slots, registers and block slots free —
-    // profiles/) with pass-1 scratch of its own; each run then does its own vertex-edge tests (no look-up in the other run's
-    // table: that would chain the runs through three events).  CCD_NP_SEQUENTIAL=1 or CCD_NP_TRACE=1: one after the other.
+    // profiles/) with pass-1 scratch of its own.  CCD_NP_SEQUENTIAL=1 or CCD_NP_TRACE=1: one after the other.
     const bool concurrent = d_q0 != nullptr && nvf > 0 && nee > 0 && !getenv("CCD_NP_SEQUENTIAL") && !getenv("CCD_NP_TRACE");
     {
         // pass-1 scratch: shared by the VF and the EE run when they execute one after the other
@@ -652,7 +655,10 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         if (c->veUniqueEe > 0) { const unsigned s2 = ccdk_np_ve_slots(4 * c->veUniqueEe); if (s2 < slotsEe) slotsEe = s2; }
         if (c->veUniqueVf > 0) { const unsigned s2 = ccdk_np_ve_slots(4 * c->veUniqueVf); if (s2 < slotsVf) slotsVf = s2; }
         const size_t ve_off_vf = (12 * (size_t)ccdk_np_ve_slots(nee) + 48 * ((size_t)nee + 32) + 15) & ~(size_t)15;
-        const bool share_ve = !concurrent && single_step && nee > 0 && nvf > 0 && !d_vf_eta && !d_ee_eta && eta_all_vf == eta_all_ee && !getenv("CCD_NO_VE_SHARE");
+        // the vertex-face run looks its vertex-edge tests up in the edge-edge run's table first (same eta): side by side, the
+        // runs are then chained through three events at the points where the table, the results and the records are needed
+        const bool share_ve = single_step && nee > 0 && nvf > 0 && !d_vf_eta && !d_ee_eta && eta_all_vf == eta_all_ee && !getenv("CCD_NO_VE_SHARE");
+        const int role_ee = (concurrent && share_ve) ? 1 : 0, role_vf = (concurrent && share_ve) ? 2 : 0;
         cudaStream_t svf = concurrent ? c->st3 : c->st;
         if (concurrent)
         {
@@ -664,7 +670,7 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all_ee, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
                                P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE, P<int>(c->workEe),
                                P<int>(c->workTaskEe), P<int>(c->workSubEe), P<double>(c->tasksEe), P<int>(c->tlistEe), c->taskCapEe, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
-                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_EE, c->p1Ve.p, slotsEe, V, c->st2, c->evFork, c->evJoin, nullptr, 0, 0, nullptr);
+                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_EE, c->p1Ve.p, slotsEe, V, c->st2, c->evFork, c->evJoin, nullptr, 0, 0, nullptr, c->evVe, role_ee);
         cudaEventRecord(c->sev[ST_NP_VF], c->st);      // concurrent runs: "np_ee" is the edge-edge run, "np_vf" what is left of the vertex-face run after it
         nl += ccdk_narrowphase(svf, true, nvf, d_vf, d_vf_eta, eta_all_vf, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
                                P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF, P<int>(c->workVf),
@@ -672,7 +678,7 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
                                concurrent ? P<unsigned>(c->p1StatusB) : P<unsigned>(c->p1Status), concurrent ? P<int>(c->p1SbaseB) : P<int>(c->p1Sbase),
                                concurrent ? P<int>(c->p1QueuesB) : P<int>(c->p1Queues), concurrent ? P<int>(c->p1SqB) : P<int>(c->p1Sq),
                                concurrent ? P<int>(c->p1XqB) : P<int>(c->p1Xq), ctr + C_NP_VF, (char *)c->p1Ve.p + ve_off_vf, slotsVf, V, nullptr, nullptr, nullptr,
-                               share_ve ? c->p1Ve.p : nullptr, share_ve ? slotsEe : 0u, nee, share_ve ? P<double>(c->tasksEe) : nullptr);
+                               share_ve ? c->p1Ve.p : nullptr, share_ve ? slotsEe : 0u, nee, share_ve ? P<double>(c->tasksEe) : nullptr, c->evVe, role_vf);
         if (concurrent)
         {
             CK(cudaEventRecord(c->evVf, c->st3));

@@ -68,6 +68,8 @@ template <int RD, int LEVEL> CCD_FN unsigned dyadic_sub(const double (&b)[RD + 1
     // below this node would report "possible" — no need to split any further
     if (LEVEL == 0 || everywhere)
         return (1u << (1 << LEVEL)) - 1u;
+    if constexpr (LEVEL > 0)
+    {
     double l[RD + 1], r[RD + 1], t[RD + 1];
 #pragma unroll
     for (int i = 0; i <= RD; i++)
@@ -84,6 +86,8 @@ template <int RD, int LEVEL> CCD_FN unsigned dyadic_sub(const double (&b)[RD + 1
     const unsigned ml = dyadic_sub<RD, (LEVEL > 0 ? LEVEL - 1 : 0)>(l, pos, want);
     const unsigned mr = dyadic_sub<RD, (LEVEL > 0 ? LEVEL - 1 : 0)>(r, pos, want >> (1 << (LEVEL > 0 ? LEVEL - 1 : 0)));
     return ml | (mr << (1 << (LEVEL > 0 ? LEVEL - 1 : 0)));
+    }
+    return 1u;      // (LEVEL == 0 returned above)
 }
 
 template <int RD> CCD_FN unsigned dyadic_mask(const double *c, bool pos, unsigned want = 0xffu)

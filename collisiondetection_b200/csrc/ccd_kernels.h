@@ -10,7 +10,7 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
                      unsigned long long *nhit, int *w_stencil, int *w_meta, int *w_base, double *tasks, int *tlists,
                      unsigned long long task_cap, unsigned *status, int *sbase, int *queues, int *sq, int *xq, unsigned long long *ctr,
                      void *ve_scratch, unsigned ve_slots, int V, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join,
-                     const void *prev_ve_scratch, unsigned prev_ve_slots, long long prev_n, const double *prev_tasks);
+                     const void *prev_ve_scratch, unsigned prev_ve_slots, long long prev_n, const double *prev_tasks, cudaEvent_t *sync, int sync_role);
 unsigned ccdk_np_ve_slots(long long n);
 // multi-entry History, staged: (stencil, stitched segment) pairs -> virtual single-step stencils -> per-stencil first hit
 void ccdk_hist_count(cudaStream_t st, long long n, const int *stencils, const long long *hoff, const double *htime, const double *hpos, int *seg_count);

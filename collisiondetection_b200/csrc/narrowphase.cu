@@ -826,8 +826,13 @@ template <int D> __global__ void __launch_bounds__(128) prepare_kernel(double *t
     }
 }
 
-#define SOLVE_MINB(D) ((D) <= 4 ? 6 : 5)
+#ifndef SOLVE_MINB6
+#define SOLVE_MINB6 6      // sextic solve: 6 resident blocks (85 registers) beat 5 (86 needed, 102 allowed) by 4 %, measured
+#endif
+#define SOLVE_MINB(D) ((D) <= 4 ? 6 : SOLVE_MINB6)
+#ifndef SOLVE_CHUNK
 #define SOLVE_CHUNK 64
+#endif
 #ifndef SOLVE_KEEP_NUM
 #define SOLVE_KEEP_NUM 2      // a Newton round ends when fewer than SOLVE_KEEP_NUM/4 of its lanes are still iterating
 #endif
@@ -1375,8 +1380,11 @@ template <int D> static void launch_solve(cudaStream_t st, double *tasks, const 
     finalize_kernel<D><<<148 * 8, 128, 0, st>>>(tasks, list, count);
 }
 
+// sync / sync_role: two runs of one step on two streams that share vertex-edge tests.  Role 1 (the run whose table is consulted)
+// records sync[0] once its hash set is complete, sync[1] once the results of its unique tests are known, sync[2] once their
+// records are final; role 2 (the run that consults) waits for them right before it needs them.  Role 0: nothing.
 template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Args &Q, long long n, int *tlists, cudaStream_t side, cudaEvent_t ev_fork,
-                                                    cudaEvent_t ev_join)
+                                                    cudaEvent_t ev_join, cudaEvent_t *sync, int sync_role)
 {
     const NpArgs &A = Q.A;
     const int B = 128;
@@ -1408,10 +1416,14 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
     np_export_kernel<IS_VF, 1><<<gq, B, 0, st>>>(Q);
     np_export_kernel<IS_VF, 2><<<gq, B, 0, st>>>(Q);
     g_trace.mark(st, "export");
+    if (sync_role == 2) cudaStreamWaitEvent(st, sync[0], 0);
     np_ve_key_kernel<IS_VF><<<148 * 8, 256, 0, st>>>(Q);
+    if (sync_role == 1) cudaEventRecord(sync[0], st);
     g_trace.mark(st, "ve_key");
     np_ve_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
     np_ve_rec_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
+    if (sync_role == 1) cudaEventRecord(sync[1], st);
+    if (sync_role == 2) cudaStreamWaitEvent(st, sync[1], 0);
     np_ve_resolve_kernel<IS_VF><<<148 * 8, 256, 0, st>>>(Q);
     g_trace.mark(st, "ve");
     np_vv_kernel<IS_VF><<<gq, 256, 0, st>>>(Q);
@@ -1430,8 +1442,10 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
         g_trace.mark(st, "solve5");
         launch_solve<6>(st, A.tasks, tlists + 3 * A.task_cap, nd + 3, cu + 3);
         g_trace.mark(st, "solve6");
+        if (phase == 0 && sync_role == 1) cudaEventRecord(sync[2], st);      // the distance polynomials (vertex-edge quartics among them) are final
         if (phase == 0) { np_window_kernel<IS_VF><<<gq, B, 0, st>>>(Q); g_trace.mark(st, "window"); }
     }
+    if (sync_role == 2) cudaStreamWaitEvent(st, sync[2], 0);
     np_combine_kernel<IS_VF><<<gq, B, 0, st>>>(Q);
     g_trace.mark(st, "combine");
     if (side && !g_trace.on)
@@ -1466,7 +1480,7 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
                      unsigned long long *nhit, int *w_stencil, int *w_meta, int *w_base, double *tasks, int *tlists,
                      unsigned long long task_cap, unsigned *status, int *sbase, int *queues, int *sq, int *xq, unsigned long long *ctr,
                      void *ve_scratch, unsigned ve_slots, int V, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join,
-                     const void *prev_ve_scratch, unsigned prev_ve_slots, long long prev_n, const double *prev_tasks)
+                     const void *prev_ve_scratch, unsigned prev_ve_slots, long long prev_n, const double *prev_tasks, cudaEvent_t *sync, int sync_role)
 {
     static_assert(K_COUNT <= CCD_NP_COUNTERS, "counter block too small");
     if (n <= 0) return 0;
@@ -1508,7 +1522,7 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
         Q.pslotval = reinterpret_cast<const int *>(Q.pkeys + prev_ve_slots);
         Q.pures = Q.pslotval + prev_ve_slots + 8 * prev_n;      // behind that run's vitem and vulist (4 n ints each)
     }
-    return is_vf ? launch_single_step<true>(st, Q, n, tlists, side, ev_fork, ev_join) : launch_single_step<false>(st, Q, n, tlists, side, ev_fork, ev_join);
+    return is_vf ? launch_single_step<true>(st, Q, n, tlists, side, ev_fork, ev_join, sync, sync_role) : launch_single_step<false>(st, Q, n, tlists, side, ev_fork, ev_join, sync, sync_role);
 }
 
 // hash-set size for the vertex-edge de-duplication of a run over n stencils: the unique tests number ~0.15 n (4M-triangle
