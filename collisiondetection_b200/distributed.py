@@ -115,6 +115,43 @@ def gather_positions(d_q0, d_q1, h_q0, h_q1, rank, world, group=None):
             d.copy_(buf[:n])
 
 
+def _exchange(world, rank, head_vals, vf_hist, ee_hist, npos, device, group, rebalance):
+    """The all-gather and the arithmetic of exchange_step, free of the context: returns (toi, hits, stencils, bounds or None)."""
+    nb = len(vf_hist)
+    nh = len(head_vals)
+    mine = np.empty(nh + 2 * nb, dtype=np.float64)      # counts up to 2^53 are exact in float64
+    mine[:nh] = head_vals
+    mine[nh:nh + nb] = vf_hist
+    mine[nh + nb:] = ee_hist
+    send = torch.from_numpy(mine).to(device)
+    recv = torch.empty(world * len(mine), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    allr = recv.cpu().numpy().reshape(world, -1)
+    pb = None
+    if rebalance:
+        tot_vf, tot_ee, tot_owned = allr[:, 2].sum(), allr[:, 3].sum(), allr[:, 4].sum()
+        emit_per_stencil = allr[:, 6].sum() / max(tot_vf + tot_ee, 1.0)
+        a = allr[:, 5].sum() / max(tot_owned, 1.0)
+        b = allr[:, 7].sum() / max(tot_vf, 1.0) + emit_per_stencil
+        c = allr[:, 8].sum() / max(tot_ee, 1.0) + emit_per_stencil
+        if not (a > 0 and b > 0 and c > 0):      # no timings (CPU tests): the fixed model
+            a, b, c = VERTEX_WEIGHT, 1.0, 1.0
+        items = np.diff(_bucket_first(npos, nb)).astype(np.float64)
+        load = b * allr[:, nh:nh + nb].sum(axis=0) + c * allr[:, nh + nb:].sum(axis=0) + a * items
+        pb = balanced_bounds(load, npos, world)
+    toi = allr[:, 0].min()
+    return (float(toi) if np.isfinite(toi) else float("inf")), int(allr[:, 1].sum()), int(allr[:, 2].sum() + allr[:, 3].sum()), pb
+
+
+def _exchange_head(ctx, world, rank, earliest_toi, n_hits, n_vf, n_ee, npos, stage_ms):
+    t_item = stage_ms.get("traverse_exact", 0.0) + stage_ms.get("adjacency", 0.0)
+    t_emit = stage_ms.get("emit_count", 0.0) + stage_ms.get("emit_write", 0.0)
+    part = getattr(ctx, "shard_partition", None)
+    owned = float(part[rank + 1] - part[rank]) if part is not None and len(part) == world + 1 else float(npos) / world
+    return [earliest_toi if np.isfinite(earliest_toi) else np.inf, float(n_hits), float(n_vf), float(n_ee), owned, t_item, t_emit,
+            stage_ms.get("np_vf", 0.0), stage_ms.get("np_ee", 0.0)]
+
+
 def exchange_step(ctx, earliest_toi, n_hits, n_vf, n_ee=0, device="cpu", group=None, rebalance=True, stage_ms=None):
     """The step's only exchange: ONE all-gather of a small vector per rank — earliest TOI, hit / stencil counts, the rank's
     measured stage times and its load profile (stencils per bucket of sorted positions).
@@ -128,36 +165,62 @@ def exchange_step(ctx, earliest_toi, n_hits, n_vf, n_ee=0, device="cpu", group=N
         return float(earliest_toi), int(n_hits), int(n_vf + n_ee)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     vf_hist, ee_hist, npos = ctx.shard_histogram()
-    nb = len(vf_hist)
     if stage_ms is None:
         stage_ms = ctx.stage_times()
-    t_item = stage_ms.get("traverse_exact", 0.0) + stage_ms.get("adjacency", 0.0)
-    t_emit = stage_ms.get("emit_count", 0.0) + stage_ms.get("emit_write", 0.0)
-    part = getattr(ctx, "shard_partition", None)
-    owned = float(part[rank + 1] - part[rank]) if part is not None and len(part) == world + 1 else float(npos) / world
-    head = [earliest_toi if np.isfinite(earliest_toi) else np.inf, float(n_hits), float(n_vf), float(n_ee), owned, t_item, t_emit,
-            stage_ms.get("np_vf", 0.0), stage_ms.get("np_ee", 0.0)]
-    nh = len(head)
-    mine = np.empty(nh + 2 * nb, dtype=np.float64)      # counts up to 2^53 are exact in float64
-    mine[:nh] = head
-    mine[nh:nh + nb] = vf_hist
-    mine[nh + nb:] = ee_hist
-    send = torch.from_numpy(mine).to(device)
-    recv = torch.empty(world * len(mine), dtype=torch.float64, device=device)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    allr = recv.cpu().numpy().reshape(world, -1)
-    if rebalance:
-        tot_vf, tot_ee, tot_owned = allr[:, 2].sum(), allr[:, 3].sum(), allr[:, 4].sum()
-        emit_per_stencil = allr[:, 6].sum() / max(tot_vf + tot_ee, 1.0)
-        a = allr[:, 5].sum() / max(tot_owned, 1.0)
-        b = allr[:, 7].sum() / max(tot_vf, 1.0) + emit_per_stencil
-        c = allr[:, 8].sum() / max(tot_ee, 1.0) + emit_per_stencil
-        if not (a > 0 and b > 0 and c > 0):      # no timings (CPU tests): the fixed model
-            a, b, c = VERTEX_WEIGHT, 1.0, 1.0
-        items = np.diff(_bucket_first(npos, nb)).astype(np.float64)
-        load = b * allr[:, nh:nh + nb].sum(axis=0) + c * allr[:, nh + nb:].sum(axis=0) + a * items
-        pb = balanced_bounds(load, npos, world)
+    head = _exchange_head(ctx, world, rank, earliest_toi, n_hits, n_vf, n_ee, npos, stage_ms)
+    toi, hits, stencils, pb = _exchange(world, rank, head, vf_hist, ee_hist, npos, device, group, rebalance)
+    if pb is not None:
         ctx.set_shard_partition(pb)
         ctx.shard_partition = list(map(int, pb))
-    toi = allr[:, 0].min()
-    return (float(toi) if np.isfinite(toi) else float("inf")), int(allr[:, 1].sum()), int(allr[:, 2].sum() + allr[:, 3].sum())
+    return toi, hits, stencils
+
+
+class StepExchange(object):
+    """exchange_step, pipelined: the all-gather of step k runs in a worker thread BESIDE step k + 1 (the step call blocks the
+    calling thread inside the C library with the GIL released), and the ranges it yields are installed before step k + 2 —
+    the load profile is one step stale, the GPUs never wait for the exchange or for each other between steps.  The global
+    summary of step k is available from result() once the following submit() — or result() itself — has joined the worker.
+    Every rank issues its collectives from its worker in step order, so they match across ranks."""
+
+    def __init__(self, ctx, device="cpu", group=None, rebalance=True, cuda_index=None):
+        import threading
+        self._threading = threading
+        self.ctx, self.device, self.group, self.rebalance, self.cuda_index = ctx, device, group, rebalance, cuda_index
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.thread, self.out, self.last = None, None, None
+
+    def _join(self):
+        if self.thread is not None:
+            self.thread.join()
+            self.thread = None
+            toi, hits, stencils, pb = self.out
+            if pb is not None:
+                self.ctx.set_shard_partition(pb)
+                self.ctx.shard_partition = list(map(int, pb))
+            self.last = (toi, hits, stencils)
+
+    def submit(self, earliest_toi, n_hits, n_vf, n_ee, stage_ms):
+        """Call right after a step: takes the step's load profile off the context, joins the exchange of the step before
+        (installing its ranges for the NEXT step) and starts this step's exchange in the background."""
+        if not self.active:
+            self.last = (float(earliest_toi), int(n_hits), int(n_vf + n_ee))
+            return
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        vf_hist, ee_hist, npos = self.ctx.shard_histogram()
+        vf_hist, ee_hist = np.array(vf_hist), np.array(ee_hist)      # the context reuses its buffers in the next step
+        head = _exchange_head(self.ctx, world, rank, earliest_toi, n_hits, n_vf, n_ee, npos, stage_ms)
+        self._join()
+
+        def run():
+            if self.cuda_index is not None:
+                torch.cuda.set_device(self.cuda_index)      # the current device is per thread
+            self.out = _exchange(world, rank, head, vf_hist, ee_hist, npos, self.device, self.group, self.rebalance)
+        self.thread = self._threading.Thread(target=run)
+        self.thread.start()
+
+    def result(self):
+        """Global (earliest TOI, hits, stencils) of the last submitted step."""
+        self._join()
+        return self.last
+
+

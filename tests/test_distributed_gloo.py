@@ -146,3 +146,34 @@ def test_exchange_step_gathers_and_rebalances(world):
         toi, nh, ns, _ = results[r]
         assert toi == (0.35 if world > 1 else float("inf"))
         assert nh == sum(10 + k for k in range(world)) and ns == sum(1000 * (k + 1) for k in range(world))
+
+
+def _pipelined_worker(rank, world, port_no, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from collisiondetection_b200 import distributed as D
+    ctx = _FakeCtx(rank, world, 100000)
+    x = D.StepExchange(ctx)
+    seen = []
+    for step in range(3):
+        x.submit(0.5 - 0.1 * step + 0.01 * rank, 10 * (step + 1) + rank, 600 * (rank + 1), 400 * (rank + 1), {})
+        seen.append(ctx.partition)      # the ranges of step k are installed one submit later
+    last = x.result()
+    results[rank] = (last, seen, ctx.partition)
+    dist.destroy_process_group()
+
+
+def test_pipelined_exchange_is_one_step_stale_and_consistent():
+    """StepExchange: the exchange of step k overlaps step k + 1; its ranges arrive before step k + 2, the same on every rank,
+    and result() returns the summary of the last submitted step."""
+    world = 2
+    mgr = mp.get_context("spawn").Manager()
+    results = mgr.dict()
+    mp.spawn(_pipelined_worker, args=(world, 29671, results), nprocs=world, join=True)
+    for r in range(world):
+        (toi, nh, ns), seen, final = results[r]
+        assert seen[0] is None                      # nothing installed by the first submit
+        assert seen[1] is not None and seen[1] == seen[2] == final      # same profile every step -> same ranges
+        assert abs(toi - 0.3) < 1e-12 and nh == 30 + 31 and ns == 1000 * 3
+    assert results[0][2] == results[1][2]
