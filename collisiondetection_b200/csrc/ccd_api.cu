@@ -59,6 +59,8 @@ struct ccd_context
     void *h_res[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t h_res_cap[4] = {0, 0, 0, 0};
     size_t candCap = 0, pairCap = 0, taskCapVf = 0, taskCapEe = 0, spQCap = 0, spLeafCapVf = 0, spLeafCapEe = 0;
+    unsigned npSkipVf = 0, npSkipEe = 0;      // degrees / phases without records in the last single-step call (of npLastVf + npLastEe stencils)
+    long long npLastVf = -1, npLastEe = -1;
     long long veUniqueEe = 0, veUniqueVf = 0;      // unique vertex-edge tests of the last single-step narrowphase call
     // sharding: ownership ranges chosen by the caller (ccd_set_shard_partition), load profile of the last sharded step
     std::vector<int> partP;      // ownership bounds over the sorted (Morton) positions of a sharded step (ccd_set_shard_partition)
@@ -659,6 +661,12 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         // runs are then chained through three events at the points where the table, the results and the records are needed
         const bool share_ve = single_step && nee > 0 && nvf > 0 && !d_vf_eta && !d_ee_eta && eta_all_vf == eta_all_ee && !getenv("CCD_NO_VE_SHARE");
         const int role_ee = (concurrent && share_ve) ? 1 : 0, role_vf = (concurrent && share_ve) ? 2 : 0;
+        // root-isolation kernels of a degree and phase that had no record in the previous call of (nearly) the same size are not launched
+        // (3 launches each; never the distance sextics of the first phase): see launch_single_step
+        unsigned skipEe = 0, skipVf = 0;
+        auto near = [](long long a, long long b) { const long long d = a > b ? a - b : b - a; return b >= 0 && d <= b / 32; };      // a shard's lists move a little with every rebalancing
+        if (single_step && near(nvf, c->npLastVf) && near(nee, c->npLastEe) && !getenv("CCD_NP_NO_SKIP")) { skipEe = c->npSkipEe; skipVf = c->npSkipVf; }
+        if (const char *fs = getenv("CCD_NP_FORCE_SKIP")) skipEe = skipVf = (unsigned)strtoul(fs, nullptr, 0);      // tests: the fall-back of records left pending
         cudaStream_t svf = concurrent ? c->st3 : c->st;
         if (concurrent)
         {
@@ -670,7 +678,7 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         nl += ccdk_narrowphase(c->st, false, nee, d_ee, d_ee_eta, eta_all_ee, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->eeHit),
                                P<double>(c->eeToi), P<unsigned char>(c->eeStage), ctr + C_EARLY_EE, ctr + C_NHIT_EE, P<int>(c->workEe),
                                P<int>(c->workTaskEe), P<int>(c->workSubEe), P<double>(c->tasksEe), P<int>(c->tlistEe), c->taskCapEe, P<unsigned>(c->p1Status), P<int>(c->p1Sbase),
-                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_EE, c->p1Ve.p, slotsEe, V, c->st2, c->evFork, c->evJoin, nullptr, 0, 0, nullptr, c->evVe, role_ee);
+                               P<int>(c->p1Queues), P<int>(c->p1Sq), P<int>(c->p1Xq), ctr + C_NP_EE, c->p1Ve.p, slotsEe, V, c->st2, c->evFork, c->evJoin, nullptr, 0, 0, nullptr, c->evVe, role_ee, skipEe);
         cudaEventRecord(c->sev[ST_NP_VF], c->st);      // concurrent runs: "np_ee" is the edge-edge run, "np_vf" what is left of the vertex-face run after it
         nl += ccdk_narrowphase(svf, true, nvf, d_vf, d_vf_eta, eta_all_vf, d_q0, d_q1, vstride, d_vbox, d_hoff, d_htime, d_hpos, P<unsigned char>(c->vfHit),
                                P<double>(c->vfToi), P<unsigned char>(c->vfStage), ctr + C_EARLY_VF, ctr + C_NHIT_VF, P<int>(c->workVf),
@@ -678,7 +686,7 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
                                concurrent ? P<unsigned>(c->p1StatusB) : P<unsigned>(c->p1Status), concurrent ? P<int>(c->p1SbaseB) : P<int>(c->p1Sbase),
                                concurrent ? P<int>(c->p1QueuesB) : P<int>(c->p1Queues), concurrent ? P<int>(c->p1SqB) : P<int>(c->p1Sq),
                                concurrent ? P<int>(c->p1XqB) : P<int>(c->p1Xq), ctr + C_NP_VF, (char *)c->p1Ve.p + ve_off_vf, slotsVf, V, nullptr, nullptr, nullptr,
-                               share_ve ? c->p1Ve.p : nullptr, share_ve ? slotsEe : 0u, nee, share_ve ? P<double>(c->tasksEe) : nullptr, c->evVe, role_vf);
+                               share_ve ? c->p1Ve.p : nullptr, share_ve ? slotsEe : 0u, nee, share_ve ? P<double>(c->tasksEe) : nullptr, c->evVe, role_vf, skipVf);
         if (concurrent)
         {
             CK(cudaEventRecord(c->evVf, c->st3));
@@ -693,6 +701,14 @@ static int narrowphase_device(ccd_context *c, int V, long long nvf, const int *d
         {
             c->veUniqueEe = nee > 0 ? (long long)c->h_counters[C_NP_EE + CCD_NP_KVEU] : 0;
             c->veUniqueVf = nvf > 0 ? (long long)c->h_counters[C_NP_VF + CCD_NP_KVEU] : 0;
+            unsigned m[2] = {0, 0};
+            for (int run = 0; run < 2; run++)
+                for (int phase = 0; phase < 2; phase++)
+                    for (int d = 0; d < 4; d++)
+                        if (!(phase == 0 && d == 3) && c->h_counters[(run ? C_NP_EE : C_NP_VF) + (phase ? CCD_NP_KNDEG2 : CCD_NP_KNDEG) + d] == 0)
+                            m[run] |= 1u << (4 * phase + d);
+            c->npSkipVf = m[0]; c->npSkipEe = m[1];
+            c->npLastVf = nvf; c->npLastEe = nee;
         }
         const unsigned long long tv = single ? c->h_counters[C_NTASK_VF] : 0, te = single ? c->h_counters[C_NTASK_EE] : 0;
         if (tv + 5 <= c->taskCapVf && te + 5 <= c->taskCapEe)

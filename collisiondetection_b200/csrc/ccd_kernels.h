@@ -10,7 +10,7 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
                      unsigned long long *nhit, int *w_stencil, int *w_meta, int *w_base, double *tasks, int *tlists,
                      unsigned long long task_cap, unsigned *status, int *sbase, int *queues, int *sq, int *xq, unsigned long long *ctr,
                      void *ve_scratch, unsigned ve_slots, int V, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join,
-                     const void *prev_ve_scratch, unsigned prev_ve_slots, long long prev_n, const double *prev_tasks, cudaEvent_t *sync, int sync_role);
+                     const void *prev_ve_scratch, unsigned prev_ve_slots, long long prev_n, const double *prev_tasks, cudaEvent_t *sync, int sync_role, unsigned skip_mask);
 unsigned ccdk_np_ve_slots(long long n);
 // multi-entry History, staged: (stencil, stitched segment) pairs -> virtual single-step stencils -> per-stencil first hit
 void ccdk_hist_count(cudaStream_t st, long long n, const int *stencils, const long long *hoff, const double *htime, const double *hpos, int *seg_count);
@@ -19,6 +19,8 @@ void ccdk_hist_fill(cudaStream_t st, long long n, const int *stencils, const dou
 void ccdk_hist_reduce(cudaStream_t st, long long n, const long long *seg_off, const unsigned char *hitv, const double *toiv, const unsigned char *stagev,
                       const double *vtime, unsigned char *hit, double *toi, unsigned char *stage, unsigned long long *earliest_bits, unsigned long long *nhit);
 #define CCD_NP_COUNTERS 40      // counters per narrowphase run (narrowphase.cu: K_*)
+#define CCD_NP_KNDEG 2          // pending records of degree 3..6, first root-isolation phase; second phase: CCD_NP_KNDEG2
+#define CCD_NP_KNDEG2 23
 #define CCD_NP_KVEU 32          // unique vertex-edge tests of the run
 // {x0,y0,z0,-,x1,y1,z1,-} per vertex (8 doubles) for the single-step narrowphase kernels
 void ccdk_pack_positions(cudaStream_t st, int V, const double *q0, const double *q1, int vstride, double *qpack, float *vbox);

@@ -1383,8 +1383,12 @@ template <int D> static void launch_solve(cudaStream_t st, double *tasks, const 
 // sync / sync_role: two runs of one step on two streams that share vertex-edge tests.  Role 1 (the run whose table is consulted)
 // records sync[0] once its hash set is complete, sync[1] once the results of its unique tests are known, sync[2] once their
 // records are final; role 2 (the run that consults) waits for them right before it needs them.  Role 0: nothing.
+// skip_mask: bit 4 * phase + (degree - 3) set = the root-isolation kernels of that degree and phase are not launched (the caller
+// saw no such record in the same run of its previous, equally sized call).  Should records of that kind turn up after all
+// they stay pending, the combine step sees a record that is not final and hands the stencil to the general routine: slower,
+// same bits.
 template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Args &Q, long long n, int *tlists, cudaStream_t side, cudaEvent_t ev_fork,
-                                                    cudaEvent_t ev_join, cudaEvent_t *sync, int sync_role)
+                                                    cudaEvent_t ev_join, cudaEvent_t *sync, int sync_role, unsigned skip_mask)
 {
     const NpArgs &A = Q.A;
     const int B = 128;
@@ -1434,13 +1438,13 @@ template <bool IS_VF> static int launch_single_step(cudaStream_t st, const P1Arg
         unsigned long long *nd = Q.ctr + (phase ? K_NDEG2 : K_NDEG), *cu = Q.ctr + (phase ? K_CURSOR2 : K_CURSOR);
         bucket_tasks_kernel<<<148 * 4, 256, 0, st>>>(A.rtag, A.ntask, A.task_cap, tlists, nd, phase);
         g_trace.mark(st, "bucket");
-        launch_solve<3>(st, A.tasks, tlists + 0 * A.task_cap, nd + 0, cu + 0);
+        if (!((skip_mask >> (4 * phase + 0)) & 1u)) launch_solve<3>(st, A.tasks, tlists + 0 * A.task_cap, nd + 0, cu + 0);
         g_trace.mark(st, "solve3");
-        launch_solve<4>(st, A.tasks, tlists + 1 * A.task_cap, nd + 1, cu + 1);
+        if (!((skip_mask >> (4 * phase + 1)) & 1u)) launch_solve<4>(st, A.tasks, tlists + 1 * A.task_cap, nd + 1, cu + 1);
         g_trace.mark(st, "solve4");
-        launch_solve<5>(st, A.tasks, tlists + 2 * A.task_cap, nd + 2, cu + 2);
+        if (!((skip_mask >> (4 * phase + 2)) & 1u)) launch_solve<5>(st, A.tasks, tlists + 2 * A.task_cap, nd + 2, cu + 2);
         g_trace.mark(st, "solve5");
-        launch_solve<6>(st, A.tasks, tlists + 3 * A.task_cap, nd + 3, cu + 3);
+        if (!((skip_mask >> (4 * phase + 3)) & 1u)) launch_solve<6>(st, A.tasks, tlists + 3 * A.task_cap, nd + 3, cu + 3);
         g_trace.mark(st, "solve6");
         if (phase == 0 && sync_role == 1) cudaEventRecord(sync[2], st);      // the distance polynomials (vertex-edge quartics among them) are final
         if (phase == 0) { np_window_kernel<IS_VF><<<gq, B, 0, st>>>(Q); g_trace.mark(st, "window"); }
@@ -1480,7 +1484,7 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
                      unsigned long long *nhit, int *w_stencil, int *w_meta, int *w_base, double *tasks, int *tlists,
                      unsigned long long task_cap, unsigned *status, int *sbase, int *queues, int *sq, int *xq, unsigned long long *ctr,
                      void *ve_scratch, unsigned ve_slots, int V, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join,
-                     const void *prev_ve_scratch, unsigned prev_ve_slots, long long prev_n, const double *prev_tasks, cudaEvent_t *sync, int sync_role)
+                     const void *prev_ve_scratch, unsigned prev_ve_slots, long long prev_n, const double *prev_tasks, cudaEvent_t *sync, int sync_role, unsigned skip_mask)
 {
     static_assert(K_COUNT <= CCD_NP_COUNTERS, "counter block too small");
     if (n <= 0) return 0;
@@ -1522,7 +1526,7 @@ int ccdk_narrowphase(cudaStream_t st, bool is_vf, long long n, const int *stenci
         Q.pslotval = reinterpret_cast<const int *>(Q.pkeys + prev_ve_slots);
         Q.pures = Q.pslotval + prev_ve_slots + 8 * prev_n;      // behind that run's vitem and vulist (4 n ints each)
     }
-    return is_vf ? launch_single_step<true>(st, Q, n, tlists, side, ev_fork, ev_join, sync, sync_role) : launch_single_step<false>(st, Q, n, tlists, side, ev_fork, ev_join, sync, sync_role);
+    return is_vf ? launch_single_step<true>(st, Q, n, tlists, side, ev_fork, ev_join, sync, sync_role, skip_mask) : launch_single_step<false>(st, Q, n, tlists, side, ev_fork, ev_join, sync, sync_role, skip_mask);
 }
 
 // hash-set size for the vertex-edge de-duplication of a run over n stencils: the unique tests number ~0.15 n (4M-triangle

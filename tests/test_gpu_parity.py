@@ -537,3 +537,24 @@ def test_reference_drivers_with_gpu_detection(tmp_path, driver):
     want = str(g["seq_stdout"]).splitlines()
     got = _run_lines(exe, ["1e-3", "1e-4", "coarse.obj", "fine_"], d, 600)
     assert got == want
+
+
+def test_skipped_root_isolation_falls_back_to_general_routine(ctx, port):
+    """The root-isolation kernels of a degree / phase that had no record in the previous equally sized call are not launched.
+    Records of that kind that turn up after all stay pending, and every stencil that needs one must come out of the general
+    routine with the same bits.  Forced here: everything but the first-phase sextics is skipped (0xf7)."""
+    import os
+    g = golden("alec_prob11_835.npz")
+    eta = float(g["eta"])
+    H = _single(g)
+    ref = ctx.findCollisions(*H, g["ref_vf"], eta, g["ref_ee"], eta)
+    os.environ["CCD_NP_FORCE_SKIP"] = "0xf7"
+    try:
+        out = ctx.findCollisions(*H, g["ref_vf"], eta, g["ref_ee"], eta)
+    finally:
+        del os.environ["CCD_NP_FORCE_SKIP"]
+    for k in ("vf", "ee"):
+        assert np.array_equal(out[k + "_hit"], ref[k + "_hit"])
+        assert np.array_equal(out[k + "_toi"].view(np.uint64), ref[k + "_toi"].view(np.uint64))
+        assert np.array_equal(out[k + "_stage"], ref[k + "_stage"])
+    assert out["n_vf_hits"] == ref["n_vf_hits"] and out["n_ee_hits"] == ref["n_ee_hits"]
