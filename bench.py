@@ -263,12 +263,15 @@ def main():
     ap.add_argument("--workload", default="cloth1415")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--pipeline-exchange", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    config = dict(workload=args.workload, kind="KDOP-13", sharding="ownership by Morton (LBVH subtree) range over %d rank(s), rebalanced every step from the load profile of the step before the previous one (the exchange overlaps the next step); replicated cluster tree, sharded tree intersection / emission / narrowphase" % world,
+    # a sharded job needs a few steps for the ownership ranges (rebalanced every step) and with them the buffer sizes to settle:
+    # at least 8 untimed steps there, 3 on one GPU; the number actually run is the one printed
+    warmup = max(args.warmup, 8 if world > 1 else 3) if args.impl == "ours" else args.warmup
+    config = dict(workload=args.workload, kind="KDOP-13", sharding="ownership by Morton (LBVH subtree) range over %d rank(s), rebalanced every step from the previous step's load profile; replicated cluster tree, sharded tree intersection / emission / narrowphase" % world,
                   l2="working set (inputs 144 MB at cloth1415 + GBs of intermediates) exceeds the 126 MB L2; nothing is reused across steps")
 
     if args.impl == "reference":
@@ -313,15 +316,20 @@ def main():
         D.broadcast_positions(d_q0, d_q1, src=0)
         ctx.wait_stream(torch.cuda.current_stream().cuda_stream)      # the context's private stream must not read before the broadcast lands
     summary = {}
-    # the path's only exchange: earliest TOI, hit / stencil counts and the load profile that balances the ownership ranges — one
-    # small all-gather per step, pipelined: it runs in a worker thread beside the NEXT step (distributed.StepExchange), so the
-    # GPUs wait neither for it nor for each other between steps; the ranges it yields apply one step later
-    xch = D.StepExchange(ctx, device="cuda", cuda_index=local_rank)
+    # the path's only exchange: earliest TOI, hit / stencil counts and the load profile that balances the next step's ownership
+    # ranges — one small all-gather per step.  --pipeline-exchange runs it in a worker thread beside the NEXT step
+    # (distributed.StepExchange; the ranges then apply one step later).  Measured: 0.1 ms per step at N = 2, but at N = 4 the
+    # delayed feedback makes the rebalancing oscillate (ranges jump, buffers regrow, 7.8 instead of 6.3 ms), so it is off by default.
+    xch = D.StepExchange(ctx, device="cuda", cuda_index=local_rank) if args.pipeline_exchange else None
 
     def step_dev():
         r = ctx.step_device(api.KDOP, V, F, d_f.data_ptr(), d_q0.data_ptr(), d_q1.data_ptr(), wl["outer_eta"], wl["eta"], 0, rank, world)
         st = ctx.stage_times()
-        xch.submit(r.earliest_toi, r.n_vf_hits + r.n_ee_hits, r.n_vf_candidates, r.n_ee_candidates, st)
+        if xch is not None:
+            xch.submit(r.earliest_toi, r.n_vf_hits + r.n_ee_hits, r.n_vf_candidates, r.n_ee_candidates, st)
+        else:
+            summary["toi"], summary["hits"], summary["stencils"] = D.exchange_step(
+                ctx, r.earliest_toi, r.n_vf_hits + r.n_ee_hits, r.n_vf_candidates, r.n_ee_candidates, device="cuda", stage_ms=st)
         summary["stage_ms"] = st
         return r
 
@@ -354,7 +362,8 @@ def main():
         kern_ms += r.ms_broadphase + r.ms_narrowphase
         for k, v in summary["stage_ms"].items():
             stage_sum[k] = stage_sum.get(k, 0.0) + v
-    summary["toi"], summary["hits"], summary["stencils"] = xch.result()      # joins the last step's exchange: inside the timed region
+    if xch is not None:
+        summary["toi"], summary["hits"], summary["stencils"] = xch.result()      # joins the last step's exchange: inside the timed region
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None

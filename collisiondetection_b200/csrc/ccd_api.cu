@@ -50,7 +50,7 @@ struct ccd_context
     // emission
     DBuf vfCounts, vfOffsets, eeCounts, eeOffsets, vfOut, eeOut;
     // narrowphase
-    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, p1StatusB, p1SbaseB, p1QueuesB, p1SqB, p1XqB, p1Ve, qpack, histCntVf, histCntEe, histOffVf, histOffEe, histQ0, histQ1, histVst, histEta, histTime, histHit, histStage, histToi, spCtr, spQst, spQlo, spQhi, spLeafSt, selTmp, selA, selB, selC, selD, selCount;
+    DBuf vfHit, eeHit, vfToi, eeToi, vfStage, eeStage, workVf, workEe, workTaskVf, workTaskEe, workSubVf, workSubEe, tasksVf, tasksEe, tlistVf, tlistEe, p1Status, p1Sbase, p1Queues, p1Sq, p1Xq, tempB, p1StatusB, p1SbaseB, p1QueuesB, p1SqB, p1XqB, p1Ve, qpack, histCntVf, histCntEe, histOffVf, histOffEe, histQ0, histQ1, histVst, histEta, histTime, histHit, histStage, histToi, spCtr, spQst, spQlo, spQhi, spLeafSt, selTmp, selA, selB, selC, selD, selCount;
     // penalty forces (penalty.cu)
     DBuf penF, penGroup, penContrib, penKeysA, penKeysB, penItemsA, penItemsB, penFired, penNewVf, penNewEe, penCtr;
     // pinned host scratch
@@ -263,7 +263,7 @@ void ccd_destroy(ccd_context *c)
                    &c->cursor, &c->adj, &c->k32A, &c->k32B, &c->scanFlags, &c->scanIds, &c->edgeVerts, &c->edgeStart, &c->faceEdge,
                    &c->heFace, &c->faceRank, &c->rankFace, &c->vdeg, &c->starOff, &c->starCur, &c->star, &c->topoHash, &c->vfCounts,
                    &c->vfOffsets, &c->eeCounts, &c->eeOffsets, &c->vfOut, &c->eeOut, &c->vfHit, &c->eeHit, &c->vfToi, &c->eeToi,
-                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->p1StatusB, &c->p1SbaseB, &c->p1QueuesB, &c->p1SqB, &c->p1XqB, &c->p1Ve, &c->qpack, &c->histCntVf, &c->histCntEe, &c->histOffVf, &c->histOffEe, &c->histQ0, &c->histQ1, &c->histVst, &c->histEta, &c->histTime, &c->histHit, &c->histStage, &c->histToi, &c->spCtr, &c->spQst, &c->spQlo, &c->spQhi, &c->spLeafSt, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->sbox, &c->sfaces, &c->unsure, &c->frontA, &c->frontB, &c->bigV, &c->bigE,
+                   &c->vfStage, &c->eeStage, &c->workVf, &c->workEe, &c->workTaskVf, &c->workTaskEe, &c->workSubVf, &c->workSubEe, &c->tasksVf, &c->tlistVf, &c->tlistEe, &c->p1Status, &c->p1Sbase, &c->p1Queues, &c->p1Sq, &c->p1Xq, &c->tempB, &c->p1StatusB, &c->p1SbaseB, &c->p1QueuesB, &c->p1SqB, &c->p1XqB, &c->p1Ve, &c->qpack, &c->histCntVf, &c->histCntEe, &c->histOffVf, &c->histOffEe, &c->histQ0, &c->histQ1, &c->histVst, &c->histEta, &c->histTime, &c->histHit, &c->histStage, &c->histToi, &c->spCtr, &c->spQst, &c->spQlo, &c->spQhi, &c->spLeafSt, &c->qlist, &c->hist, &c->needed, &c->neededPre, &c->alistV, &c->alistE, &c->kstartV, &c->kstartE, &c->keysV, &c->keysE, &c->tasksEe, &c->selTmp, &c->selA, &c->selB, &c->selC, &c->selD, &c->selCount, &c->heap, &c->srec, &c->sbox, &c->sfaces, &c->unsure, &c->frontA, &c->frontB, &c->bigV, &c->bigE,
                    &c->penF, &c->penGroup, &c->penContrib, &c->penKeysA, &c->penKeysB, &c->penItemsA, &c->penItemsB, &c->penFired, &c->penNewVf, &c->penNewEe, &c->penCtr};
     for (DBuf *b : all)
         if (b->p)
@@ -533,9 +533,13 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         CK(cudaMemsetAsync(ctr + C_NBIG, 0, sizeof(unsigned long long) * 2, c->st));
         CKR(ensure(c, c->bigV, sizeof(int) * (size_t)(V + 32)));
         CKR(ensure(c, c->bigE, sizeof(int) * (size_t)(E + 32)));
-        ccdk_active_list(c->st, 0, V, P<long long>(c->starOff), nullptr, P<int>(c->star), P<int>(c->deg), P<int>(c->vfCounts), P<int>(c->alistV), ctr + C_NA_VF, facePos, p0, p1);
+        // the vertex-face chain (active list, key sets, scan of the counts) on the second stream beside the edge-edge chain:
+        // nothing on one GPU at full size, a shorter stage on a shard (small grids leave most of the machine idle)
+        CK(cudaEventRecord(c->evPack, c->st));
+        CK(cudaStreamWaitEvent(c->st3, c->evPack, 0));
+        ccdk_active_list(c->st3, 0, V, P<long long>(c->starOff), nullptr, P<int>(c->star), P<int>(c->deg), P<int>(c->vfCounts), P<int>(c->alistV), ctr + C_NA_VF, facePos, p0, p1);
         ccdk_active_list(c->st, 0, E, nullptr, P<int>(c->edgeStart), P<int>(c->heFace), P<int>(c->deg), P<int>(c->eeCounts), P<int>(c->alistE), ctr + C_NA_EE, facePos, p0, p1);
-        ccdk_emit_sort(c->st, true, P<int>(c->alistV), ctr + C_NA_VF, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
+        ccdk_emit_sort(c->st3, true, P<int>(c->alistV), ctr + C_NA_VF, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
                        P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceRank), P<int>(c->rankFace), P<int>(c->faceEdge),
                        c->edgeVerts.p, d_fixed, P<int>(c->vfCounts), P<long long>(c->kstartV), P<int>(c->keysV), ctr + C_KCUR_VF, P<int>(c->bigV), ctr + C_NBIG);
         ccdk_emit_sort(c->st, false, P<int>(c->alistE), ctr + C_NA_EE, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
@@ -544,8 +548,11 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
         c->launches += 6;
     }
     // the scan reads one element past the range (never added to anything it outputs)
-    ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, V + 1, P<int>(c->vfCounts), P<long long>(c->vfOffsets));
+    CKR(ensure(c, c->tempB, ccdk_sort_temp_bytes(V + 1)));
+    ccdk_exclusive_sum64(c->st3, c->tempB.p, c->tempB.cap, V + 1, P<int>(c->vfCounts), P<long long>(c->vfOffsets));
     ccdk_exclusive_sum64(c->st, c->temp.p, c->temp.cap, E + 1, P<int>(c->eeCounts), P<long long>(c->eeOffsets));
+    CK(cudaEventRecord(c->evVf, c->st3));
+    CK(cudaStreamWaitEvent(c->st, c->evVf, 0));
     c->launches += 4;
     c->hist_valid = false;
     if (sharded)
@@ -568,12 +575,16 @@ static int broadphase_device(ccd_context *c, int kind, int V, int F, const int *
     CKR(ensure(c, c->vfOut, sizeof(int) * 4 * (size_t)(res->nvf + 1)));
     CKR(ensure(c, c->eeOut, sizeof(int) * 4 * (size_t)(res->nee + 1)));
     cudaEventRecord(c->sev[ST_EMIT_WRITE], c->st);
-    ccdk_emit_write(c->st, true, P<int>(c->alistV), ctr + C_NA_VF, 0, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
+    CK(cudaEventRecord(c->evPack, c->st));
+    CK(cudaStreamWaitEvent(c->st3, c->evPack, 0));
+    ccdk_emit_write(c->st3, true, P<int>(c->alistV), ctr + C_NA_VF, 0, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
                     P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceRank), P<int>(c->rankFace), P<int>(c->faceEdge),
                     c->edgeVerts.p, d_fixed, P<int>(c->vfCounts), P<long long>(c->kstartV), P<int>(c->keysV), P<long long>(c->vfOffsets), P<int>(c->vfOut));
     ccdk_emit_write(c->st, false, P<int>(c->alistE), ctr + C_NA_EE, 0, d_faces, P<long long>(c->starOff), P<int>(c->star), P<int>(c->edgeStart),
                     P<int>(c->heFace), P<long long>(c->adjOff), P<int>(c->adj), P<int>(c->faceRank), P<int>(c->rankFace), P<int>(c->faceEdge),
                     c->edgeVerts.p, d_fixed, P<int>(c->eeCounts), P<long long>(c->kstartE), P<int>(c->keysE), P<long long>(c->eeOffsets), P<int>(c->eeOut));
+    CK(cudaEventRecord(c->evVf, c->st3));
+    CK(cudaStreamWaitEvent(c->st, c->evVf, 0));
     c->launches += 2;
     CK(cudaGetLastError());
     return CCD_OK;
