@@ -475,6 +475,11 @@ def main():
                e2e=dict(value=n_stencils / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
                gpu_launches=int(launches) * args.steps,
                roofline=roof, phases=phases,
+               roofline_broadphase=dict(kernel="broadphase kernel group (boxes, Morton sort, cluster tree, pair traversal, face-pair tests, adjacency, emission)",
+                                        bound="hbm", achieved=phases["broadphase"]["achieved_gbs"], peak=hbm_peak, unit="GB/s",
+                                        frac=(phases["broadphase"]["achieved_gbs"] / hbm_peak) if phases["broadphase"]["achieved_gbs"] else None,
+                                        traffic=traffic.get("broadphase_bytes"), traffic_source=traffic.get("source"), peak_source=hbm_src,
+                                        algorithmic="892 B/face + 48 B/raw stencil + 16 B/unique stencil (SURVEY.md 8d)", group_ms=bp_ms),
                stages_ms=stages, stages_ms_max_over_ranks={k: float(st_all[:, i].max()) for i, k in enumerate(stage_names)},
                stencils_per_rank=[int(x) for x in st_all[:, -1]], stages_ms_per_rank={k: [round(float(x), 3) for x in st_all[:, i]] for i, k in enumerate(stage_names)}, kernel_ms_per_step=kern_ms / args.steps,
                counts=dict(vertices=V, faces=F, stencils=n_stencils, vf_rank0=int(nvf), ee_rank0=int(nee), hits=n_hits,
