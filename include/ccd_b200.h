@@ -171,9 +171,12 @@ int ccd_shard_histogram(ccd_context *ctx, int64_t *vf_hist, int64_t *ee_hist, in
  * memory, and a measured FP64 roofline denominator (dependent-free DFMA streams on every SM) in TFLOP/s. */
 int ccd_memcpy_d2h(ccd_context *ctx, void *h_dst, const void *d_src, uint64_t bytes);
 /* Device time (ms, CUDA events on the context's stream) of the stages of the last ccd_step_device / ccd_step call:
- * 0 topology tables (cached after the first call on a mesh), 1 leaf boxes, 2 Morton + sort + LBVH + refit,
- * 3 traversal + exact pair test, 4 adjacency CSR, 5 stencil count pass, 6 stencil write pass,
- * 7 VF narrowphase kernel, 8 EE narrowphase kernel.  n must be >= 9. */
+ * 0 topology tables (cached after the first call on a mesh; a hash of the faces is checked every call), 1 face boxes,
+ * 2 Morton codes + radix sort + cluster tree, 3 pair traversal + cluster-pair / k-DOP face-pair tests, 4 adjacency CSR,
+ * 5 stencil count pass, 6 stencil write pass, 7 and 8 the narrowphase: the edge-edge run (8) and the vertex-face run (7).
+ * When both stencil types are present the two runs execute side by side on two streams: 8 then is the time until the
+ * edge-edge run has finished and 7 what is left of the vertex-face run after that; their sum is the narrowphase.
+ * Zero after any call that was not a complete step.  n must be >= 9. */
 #define CCD_N_STAGE_TIMES 9
 int ccd_stage_times(ccd_context *ctx, float *ms, int n);
 int ccd_fp64_peak(ccd_context *ctx, double *tflops);
