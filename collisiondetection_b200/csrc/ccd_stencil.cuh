@@ -163,10 +163,41 @@ CCD_FN float box_scale_f(const BoxF &b)
     return r;
 }
 
+// Extent of a group of vertices along the ten diagonal k-DOP directions (x+-y, x+-z, y+-z, x+-y+-z; NOT normalised: lengths
+// sqrt 2 and sqrt 3), in float, bounded from the vertices' swept BOXES: a vertex moves on a segment inside its box, so its
+// projection on x+y stays within [lo.x + lo.y, hi.x + hi.y], and so on: no position is read.  Two groups separated along a
+// direction by more than 2 m (> m times the direction's length) stay further than m apart: the same argument as for the
+// coordinate axes, and with m >= 4e-5 of the coordinate scale the float roundings of the sums (~1e-7 of the scale) are two
+// orders below the margin.  At the 4M-triangle cloth half of the edge pairs whose swept boxes overlap are separated along one
+// of these directions (bounding the projections by the box corners instead of the two end points costs 1 % of that).
+struct DopF { float lo[10], hi[10]; };
+CCD_FN void dopf_init(DopF &d)
+{
+#pragma unroll
+    for (int k = 0; k < 10; k++) { d.lo[k] = INFINITY; d.hi[k] = -INFINITY; }
+}
+CCD_FN void dopf_add_box(DopF &d, const BoxF &b)
+{
+    const float lx = b.lo[0], ly = b.lo[1], lz = b.lo[2], hx = b.hi[0], hy = b.hi[1], hz = b.hi[2];
+    const float lxy = lx + ly, lxmy = lx - hy, hxy = hx + hy, hxmy = hx - ly;
+    const float lo[10] = {lxy, lxmy, lx + lz, lx - hz, ly + lz, ly - hz, lxy + lz, lxy - hz, lxmy + lz, lxmy - hz};
+    const float hi[10] = {hxy, hxmy, hx + hz, hx - lz, hy + hz, hy - lz, hxy + hz, hxy - lz, hxmy + hz, hxmy - lz};
+#pragma unroll
+    for (int k = 0; k < 10; k++) { d.lo[k] = fminf(d.lo[k], lo[k]); d.hi[k] = fmaxf(d.hi[k], hi[k]); }
+}
+CCD_FN bool dopf_apart(const DopF &a, const DopF &b, float m2)
+{
+    bool r = false;
+#pragma unroll
+    for (int k = 0; k < 10; k++) r = r || (b.lo[k] - a.hi[k] > m2) || (a.lo[k] - b.hi[k] > m2);
+    return r;
+}
+
 template <bool IS_VF> struct CullF
 {
     BoxF bx[4], g0, g1;
     float m;
+    bool far13 = false;      // the two parts are separated along a diagonal direction (init13)
     CCD_FN void init(double eta)
     {
         if (IS_VF) { g0 = bx[0]; g1 = join_f(join_f(bx[1], bx[2]), bx[3]); }
@@ -174,6 +205,20 @@ template <bool IS_VF> struct CullF
         m = f_add_up(f_up(eta), f_mul_up(4.0001e-5f, fmaxf(box_scale_f(g0), box_scale_f(g1))));
     }
     CCD_FN bool stencil_apart() const { return apart_f(g0, g1, m); }
+    // call after init(); only worth it when !stencil_apart()
+    CCD_FN void init13()
+    {
+        DopF d0, d1;
+        dopf_init(d0);
+        dopf_init(d1);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            const bool first = IS_VF ? (i == 0) : (i < 2);
+            if (first) dopf_add_box(d0, bx[i]); else dopf_add_box(d1, bx[i]);
+        }
+        far13 = dopf_apart(d0, d1, f_mul_up(2.0f, m));
+    }
     CCD_FN bool ve_apart(int sub) const
     {
         int iv, i1, i2;
@@ -190,7 +235,7 @@ template <bool IS_VF> struct CullF
     CCD_FN unsigned todo() const
     {
         constexpr int NVE = Subs<IS_VF>::NVE, NVV = Subs<IS_VF>::NVV;
-        const bool far = stencil_apart();
+        const bool far = stencil_apart() || far13;
         unsigned t = (IS_VF || !far) ? 1u : 0u;
         if (!far)
         {

@@ -313,6 +313,7 @@ template <bool IS_VF> __global__ void __launch_bounds__(256) np_cull_kernel(P1Ar
         c.bx[2] = ldbox(A.vbox, s.z);
         c.bx[3] = ldbox(A.vbox, s.w);
         c.init(A.eta_arr ? A.eta_arr[i] : A.eta_all);
+        if (!c.stencil_apart()) c.init13();      // the swept boxes overlap: the ten diagonal directions, still from the boxes alone
         todo = c.todo();
         Q.status[i] = 0u;
     }

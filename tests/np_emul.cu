@@ -131,6 +131,7 @@ void run(long long n, const int *stencils, const double *q0, const double *q1, i
         CullF<IS_VF> c;
         for (int k = 0; k < 4; k++) c.bx[k] = swept_box_f(a[k], b[k]);
         c.init(eta);
+        if (!c.stencil_apart()) c.init13();      // as np_cull_kernel
         const unsigned todo = c.todo();
         if (g_stats)
         {
